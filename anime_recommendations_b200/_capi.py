@@ -1,0 +1,122 @@
+"""ctypes binding of libanimerec.so (include/animerec.h).
+
+The product path has no CPU fallback: if the library is missing or a call fails this module
+raises.  PyTorch is only used by callers to own device memory and streams.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+PKG = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(PKG, "lib", "libanimerec.so")
+ABI_VERSION = 1
+
+AR_MAX_BATCH = 16384
+AR_HEAVY_LEN = 64
+ADAM_REPLAY, ADAM_DENSE, ADAM_TOUCHED = 0, 1, 2
+ADAM_MODES = {"replay": ADAM_REPLAY, "dense": ADAM_DENSE, "touched": ADAM_TOUCHED}
+MAX_K = 32
+
+c_f32p = C.c_void_p  # device pointers travel as integers
+c_i32p = C.c_void_p
+
+
+class ArTable(C.Structure):
+    _fields_ = [("n_rows", C.c_int32), ("dim", C.c_int32), ("W", C.c_void_p), ("m", C.c_void_p),
+                ("v", C.c_void_p), ("last_step", C.c_void_p)]
+
+
+class ArPlan(C.Structure):
+    _fields_ = [("batch_cap", C.c_int32), ("heavy_cap", C.c_int32), ("n_slots", C.c_int32),
+                ("order", C.c_void_p), ("uniq", C.c_void_p), ("off", C.c_void_p), ("meta", C.c_void_p),
+                ("heavy", C.c_void_p)]
+
+
+class ArTrainCtx(C.Structure):
+    _fields_ = [("users", ArTable), ("anime", ArTable),
+                ("head", C.c_void_p), ("head_m", C.c_void_p), ("head_v", C.c_void_p),
+                ("bn_moving", C.c_void_p), ("alpha", C.c_void_p),
+                ("iu", C.c_void_p), ("ia", C.c_void_p), ("label", C.c_void_p),
+                ("n_samples", C.c_int64), ("batch", C.c_int32), ("l2", C.c_float), ("mode", C.c_int32),
+                ("plan_u", ArPlan), ("plan_a", ArPlan),
+                ("uh", C.c_void_p), ("ah", C.c_void_p), ("c", C.c_void_p), ("ru", C.c_void_p),
+                ("ra", C.c_void_p), ("dc", C.c_void_p),
+                ("metrics", C.c_void_p), ("reg_sumsq", C.c_void_p)]
+
+
+class AnimerecError(RuntimeError):
+    pass
+
+
+_P = C.c_void_p
+_I32, _I64, _F = C.c_int32, C.c_int64, C.c_float
+
+# name -> (restype, argtypes); every symbol include/animerec.h declares
+SIGNATURES = {
+    "ar_last_error": (C.c_char_p, []),
+    "ar_abi_version": (C.c_int, []),
+    "ar_check_device": (C.c_int, []),
+    "ar_plan_build": (C.c_int, [_P, _I64, _I32, _I64, _I32, C.POINTER(ArPlan), _P]),
+    "ar_train_steps": (C.c_int, [C.POINTER(ArTrainCtx), _I64, _I32, _I64, _I32, _P]),
+    "ar_table_flush": (C.c_int, [C.POINTER(ArTable), _P, _F, _I64, _P]),
+    "ar_embed_fwd": (C.c_int, [_P, _P, _I32, _P, _P, _I32, _P, _P, _P, _P, _P, _P]),
+    "ar_head_step": (C.c_int, [_P, _P, _I32, _P, _P, _P, _P, _P, _I64, _P, _P, _P]),
+    "ar_rows_catchup": (C.c_int, [C.POINTER(ArTable), C.POINTER(ArPlan), _I32, _P, _F, _I64, _P]),
+    "ar_rows_update": (C.c_int, [C.POINTER(ArTable), C.POINTER(ArPlan), _I32, _P, _P, _P, _P, _P, _F,
+                                 _I64, _I32, _P, _P]),
+    "ar_predict": (C.c_int, [_P, _P, _I32, _P, _P, _P, _P, _I64, _P, _P]),
+    "ar_eval_sums": (C.c_int, [_P, _P, _I32, _P, _P, _P, _P, _P, _I64, _P, _P]),
+    "ar_sumsq": (C.c_int, [_P, _I64, _P, _P]),
+    "ar_rownorm": (C.c_int, [_P, _I64, _I32, _P, _P]),
+    "ar_topk_query_workspace": (C.c_int64, [_I64, _I32]),
+    "ar_cosine_topk_query": (C.c_int, [_P, _I64, _I32, _I64, _P, _I64, _I32, _P, _P, _P, _P]),
+    "ar_topk_merge": (C.c_int, [_P, _P, _I32, _I64, _I32, _I32, _P, _P, _P]),
+    "ar_cosine_rerank": (C.c_int, [_P, _I64, _I64, _P, _I32, _P, _I32, _I32, _P, _P, _P]),
+    "ar_rownorm_bf16": (C.c_int, [_P, _I64, _I32, _P, _P]),
+    "ar_allpairs_workspace": (C.c_int64, [_I64, _I32]),
+    "ar_cosine_topk_allpairs": (C.c_int, [_P, _I64, _I64, _P, _I64, _I64, _I64, _I32, _I32, _I32, _P,
+                                          _I64, _F, _P, _P, _P, _P]),
+}
+
+_lib = None
+
+
+def lib():
+    """Load libanimerec.so (once).  Raises if it has not been built -- there is no fallback."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise AnimerecError(
+                "libanimerec.so is missing (%s); run `python -c 'import __graft_entry__ as g; g.build()'` "
+                "or `python -m anime_recommendations_b200.build` -- there is no CPU fallback" % LIB_PATH)
+        l = C.CDLL(LIB_PATH)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(l, name)
+            fn.restype = res
+            fn.argtypes = args
+        if l.ar_abi_version() != ABI_VERSION:
+            raise AnimerecError("libanimerec.so ABI %d != binding ABI %d; rebuild" % (l.ar_abi_version(), ABI_VERSION))
+        _lib = l
+    return _lib
+
+
+def check(rc, what=""):
+    if rc != 0:
+        msg = lib().ar_last_error().decode("utf-8", "replace")
+        raise AnimerecError("%s failed (%d): %s" % (what or "libanimerec call", rc, msg))
+
+
+def ptr(t):
+    """Device pointer of a torch tensor (must be contiguous) or None."""
+    if t is None:
+        return None
+    if not t.is_contiguous():
+        raise AnimerecError("tensor passed to libanimerec must be contiguous")
+    return C.c_void_p(t.data_ptr())
+
+
+def stream_ptr(stream=None):
+    import torch
+    s = stream if stream is not None else torch.cuda.current_stream()
+    return C.c_void_p(s.cuda_stream)

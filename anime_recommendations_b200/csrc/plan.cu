@@ -1,0 +1,174 @@
+// Per-step dedup plan: group the samples of each training step by embedding row.
+//
+// Replaces TF's IndexedSlices -> UnsortedSegmentSum gradient aggregation with a
+// sort-based, atomic-free plan: one CTA sorts one step's (row, sample) pairs entirely in shared
+// memory (bitonic network over 64-bit packed keys), then emits the distinct rows, the segment
+// offsets and the list of "heavy" rows.  Many steps are planned per launch (one CTA each), so
+// the cost is amortised off the per-step critical path.
+#include <stdarg.h>
+
+#include "common.cuh"
+
+namespace ar {
+
+static thread_local char g_err[512] = "";
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+constexpr int kPlanThreads = 1024;
+
+__global__ void __launch_bounds__(kPlanThreads, 1)
+plan_build_kernel(const int32_t* __restrict__ idx, int64_t n_total, int batch, int64_t step0,
+                  ar_plan plan, int pow2) {
+  extern __shared__ unsigned long long keys[];  // pow2 entries
+  __shared__ int warp_tot[kPlanThreads / 32];
+  __shared__ int n_heavy_s;
+  const int slot = blockIdx.x;
+  const int tid = threadIdx.x;
+  const int64_t base = (step0 + slot) * (int64_t)batch;
+  int n = 0;
+  if (base < n_total) n = (int)min((int64_t)batch, n_total - base);
+
+  for (int i = tid; i < pow2; i += kPlanThreads) {
+    unsigned long long k = ~0ull;
+    if (i < n) k = ((unsigned long long)(uint32_t)idx[base + i] << 32) | (uint32_t)i;
+    keys[i] = k;
+  }
+  if (tid == 0) n_heavy_s = 0;
+  __syncthreads();
+
+  // bitonic sort, ascending; (row, sample) packed so equal rows keep sample order
+  for (int k = 2; k <= pow2; k <<= 1) {
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      for (int p = tid; p < (pow2 >> 1); p += kPlanThreads) {
+        // p-th compare-exchange pair of this stage
+        int i = ((p & ~(j - 1)) << 1) | (p & (j - 1));
+        int l = i | j;
+        bool up = ((i & k) == 0);
+        unsigned long long a = keys[i], b = keys[l];
+        if ((a > b) == up) {
+          keys[i] = b;
+          keys[l] = a;
+        }
+      }
+      __syncthreads();
+    }
+  }
+
+  int32_t* order = plan.order + (int64_t)slot * plan.batch_cap;
+  int32_t* uniq = plan.uniq + (int64_t)slot * plan.batch_cap;
+  int32_t* off = plan.off + (int64_t)slot * (plan.batch_cap + 1);
+  int32_t* meta = plan.meta + (int64_t)slot * 4;
+  int32_t* heavy = plan.heavy + (int64_t)slot * plan.heavy_cap;
+
+  // segment heads: blocked arrangement, per = pow2 / threads consecutive elements per thread
+  const int per = (pow2 + kPlanThreads - 1) / kPlanThreads;
+  const int lo = tid * per;
+  int cnt = 0;
+  for (int e = 0; e < per; ++e) {
+    int i = lo + e;
+    if (i < n) {
+      uint32_t r = (uint32_t)(keys[i] >> 32);
+      bool head = (i == 0) || ((uint32_t)(keys[i - 1] >> 32) != r);
+      cnt += head ? 1 : 0;
+    }
+  }
+  // block exclusive scan of cnt
+  int incl = cnt;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    int t = __shfl_up_sync(0xffffffffu, incl, o);
+    if ((tid & 31) >= o) incl += t;
+  }
+  if ((tid & 31) == 31) warp_tot[tid >> 5] = incl;
+  __syncthreads();
+  if (tid < 32) {
+    int w = warp_tot[tid];
+    int wi = w;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      int t = __shfl_up_sync(0xffffffffu, wi, o);
+      if (tid >= o) wi += t;
+    }
+    warp_tot[tid] = wi - w;  // exclusive
+  }
+  __syncthreads();
+  int seg = warp_tot[tid >> 5] + incl - cnt;
+  for (int e = 0; e < per; ++e) {
+    int i = lo + e;
+    if (i < n) {
+      unsigned long long kv = keys[i];
+      uint32_t r = (uint32_t)(kv >> 32);
+      bool head = (i == 0) || ((uint32_t)(keys[i - 1] >> 32) != r);
+      order[i] = (int32_t)(uint32_t)kv;
+      if (head) {
+        uniq[seg] = (int32_t)r;
+        off[seg] = i;
+        ++seg;
+      }
+    }
+  }
+  __shared__ int n_uniq_s;
+  if (tid == kPlanThreads - 1) {
+    n_uniq_s = seg;  // last thread's running count == total
+    off[seg] = n;
+  }
+  __syncthreads();
+  const int n_uniq = n_uniq_s;
+  for (int s = tid; s < n_uniq; s += kPlanThreads) {
+    int len = off[s + 1] - off[s];
+    if (len > AR_HEAVY_LEN) {
+      int pos = atomicAdd(&n_heavy_s, 1);
+      if (pos < plan.heavy_cap) heavy[pos] = s;
+    }
+  }
+  __syncthreads();
+  if (tid == 0) {
+    meta[0] = n_uniq;
+    meta[1] = min(n_heavy_s, plan.heavy_cap);
+    meta[2] = n;
+    meta[3] = 0;
+  }
+}
+
+}  // namespace ar
+
+extern "C" const char* ar_last_error(void) { return ar::g_err; }
+extern "C" int ar_abi_version(void) { return 1; }
+
+extern "C" int ar_check_device(void) {
+  int dev = 0;
+  AR_CUDA(cudaGetDevice(&dev));
+  cudaDeviceProp p;
+  AR_CUDA(cudaGetDeviceProperties(&p, dev));
+  if (p.major != 10) {
+    ar::set_error("libanimerec is built for sm_100a only; current device is sm_%d%d", p.major, p.minor);
+    return AR_ERR_UNSUPPORTED;
+  }
+  return AR_OK;
+}
+
+extern "C" int ar_plan_build(const int32_t* idx, int64_t n_total, int32_t batch, int64_t step0,
+                             int32_t n_steps, const ar_plan* plan, void* stream) {
+  AR_REQUIRE(idx && plan, "ar_plan_build: null pointer");
+  AR_REQUIRE(batch > 0 && batch <= AR_MAX_BATCH, "ar_plan_build: batch %d outside (0, %d]", batch, AR_MAX_BATCH);
+  AR_REQUIRE(plan->batch_cap >= batch, "ar_plan_build: plan.batch_cap %d < batch %d", plan->batch_cap, batch);
+  AR_REQUIRE(n_steps >= 0 && n_steps <= plan->n_slots, "ar_plan_build: n_steps %d > plan.n_slots %d", n_steps, plan->n_slots);
+  AR_REQUIRE(plan->heavy_cap >= batch / AR_HEAVY_LEN + 1, "ar_plan_build: heavy_cap too small");
+  if (n_steps == 0) return AR_OK;
+  int pow2 = 2;
+  while (pow2 < batch) pow2 <<= 1;
+  size_t smem = (size_t)pow2 * sizeof(unsigned long long);
+  static bool attr_set = false;
+  if (!attr_set) {
+    AR_CUDA(cudaFuncSetAttribute(ar::plan_build_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, AR_MAX_BATCH * 8));
+    attr_set = true;
+  }
+  ar::plan_build_kernel<<<n_steps, ar::kPlanThreads, smem, (cudaStream_t)stream>>>(idx, n_total, batch, step0, *plan, pow2);
+  AR_LAUNCH_CHECK();
+  return AR_OK;
+}

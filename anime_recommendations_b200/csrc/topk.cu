@@ -1,0 +1,360 @@
+// Half B, memory-bound part: row normalisation, single-query cosine GEMV fused with a warp
+// top-k (similar_anime.py:404-468, similar_users.py:293-312), partial-list merge and the exact
+// fp32 re-rank used after the tensor-core candidate pass.
+//
+// Ranking order everywhere: higher score first, equal scores -> lower row index first; NaN scores
+// (zero-norm rows) never rank (oracle/similarity.py rank_desc).
+#include <algorithm>
+#include <cuda_bf16.h>
+#include <math_constants.h>
+
+#include "common.cuh"
+
+namespace ar {
+
+constexpr int kTopkThreads = 256;
+constexpr int kTopkWarps = kTopkThreads / 32;
+constexpr int kMaxK = 32;
+
+__device__ __forceinline__ bool better(float as, int ai, float bs, int bi) {
+  return (as > bs) || (as == bs && ai < bi);
+}
+
+// Sorted top-32 list distributed over a warp: lane l holds the l-th best (score, idx).
+struct WarpList {
+  float s;
+  int i;
+  __device__ __forceinline__ void init() {
+    s = -CUDART_INF_F;
+    i = 0x7fffffff;
+  }
+  // warp-uniform candidate; dedup = ignore a row id the list already holds
+  __device__ __forceinline__ void insert(float cs, int ci, int lane, bool dedup = false) {
+    if (dedup && __ballot_sync(0xffffffffu, i == ci)) return;
+    const unsigned worse = __ballot_sync(0xffffffffu, better(cs, ci, s, i));
+    if (!worse) return;
+    const int pos = __ffs(worse) - 1;
+    const float ps = __shfl_up_sync(0xffffffffu, s, 1);
+    const int pi = __shfl_up_sync(0xffffffffu, i, 1);
+    if (lane > pos) {
+      s = ps;
+      i = pi;
+    } else if (lane == pos) {
+      s = cs;
+      i = ci;
+    }
+  }
+  // every lane offers its own candidate (valid = has one); k-th entry is the admission threshold
+  __device__ __forceinline__ void insert_lanes(float cs, int ci, bool valid, int k, int lane) {
+    float ts = __shfl_sync(0xffffffffu, s, k - 1);
+    int ti = __shfl_sync(0xffffffffu, i, k - 1);
+    unsigned pend = __ballot_sync(0xffffffffu, valid && better(cs, ci, ts, ti));
+    while (pend) {
+      const int src = __ffs(pend) - 1;
+      const float bs = __shfl_sync(0xffffffffu, cs, src);
+      const int bi = __shfl_sync(0xffffffffu, ci, src);
+      insert(bs, bi, lane);
+      ts = __shfl_sync(0xffffffffu, s, k - 1);
+      ti = __shfl_sync(0xffffffffu, i, k - 1);
+      pend &= pend - 1;
+      pend &= __ballot_sync(0xffffffffu, valid && better(cs, ci, ts, ti));
+    }
+  }
+};
+
+// Merge the lists of all warps of a CTA through shared memory; result in warp 0's list.
+// sm_s / sm_i: [nwarps][32]
+__device__ __forceinline__ void cta_merge(WarpList& wl, float* sm_s, int* sm_i, int k, int nwarps) {
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  sm_s[wid * 32 + lane] = wl.s;
+  sm_i[wid * 32 + lane] = wl.i;
+  __syncthreads();
+  if (wid == 0) {
+    for (int w = 1; w < nwarps; ++w) {
+      const float cs = sm_s[w * 32 + lane];
+      const int ci = sm_i[w * 32 + lane];
+      wl.insert_lanes(cs, ci, lane < k && ci != 0x7fffffff, k, lane);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) rownorm_kernel(const float* __restrict__ W, int64_t n, int dim,
+                                                      float* __restrict__ out, __nv_bfloat16* __restrict__ out_bf) {
+  const int lane = threadIdx.x & 31;
+  const int d4 = dim >> 2;
+  for (int64_t row = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5); row < n; row += (int64_t)gridDim.x * 8) {
+    const float* src = W + row * dim;
+    float ss = 0.f;
+    for (int j = lane; j < d4; j += 32) {
+      float4 x = ld4_nc(src + 4 * j);
+      ss += dot4(x, x);
+    }
+    ss = warp_sum(ss);
+    const float nrm = sqrtf(ss);
+    for (int j = lane; j < d4; j += 32) {
+      float4 x = ld4(src + 4 * j);
+      x.x /= nrm; x.y /= nrm; x.z /= nrm; x.w /= nrm;
+      if (out) st4(out + row * dim + 4 * j, x);
+      if (out_bf) {
+        __nv_bfloat162 lo = __floats2bfloat162_rn(x.x, x.y);
+        __nv_bfloat162 hi = __floats2bfloat162_rn(x.z, x.w);
+        uint2 pk;
+        pk.x = *reinterpret_cast<uint32_t*>(&lo);
+        pk.y = *reinterpret_cast<uint32_t*>(&hi);
+        *reinterpret_cast<uint2*>(out_bf + row * dim + 4 * j) = pk;
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Single-query GEMV + top-k.  8 lanes per row, 4 rows per warp iteration, 2 iterations in flight.
+// NQ = float4 per lane = ceil(dim/4/8).
+template <int NQ>
+__global__ void __launch_bounds__(kTopkThreads)
+query_topk_kernel(const float* __restrict__ W, int64_t n, int dim, int64_t q,
+                  const uint32_t* __restrict__ cand_mask, int64_t exclude, int k,
+                  int* __restrict__ part_idx, float* __restrict__ part_score) {
+  __shared__ float sm_s[kTopkWarps * 32];
+  __shared__ int sm_i[kTopkWarps * 32];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const int sub = lane & 7, grp = lane >> 3;
+  const int d4 = dim >> 2;
+
+  // normalised query row chunk owned by this lane: q_hat = W[q] / ||W[q]||
+  float4 qv[NQ];
+  float qs = 0.f;
+#pragma unroll
+  for (int i = 0; i < NQ; ++i) {
+    const int j = sub + 8 * i;
+    qv[i] = (j < d4) ? ld4(W + q * dim + 4 * j) : make_float4(0.f, 0.f, 0.f, 0.f);
+    qs += dot4(qv[i], qv[i]);
+  }
+  qs += __shfl_xor_sync(0xffffffffu, qs, 1);
+  qs += __shfl_xor_sync(0xffffffffu, qs, 2);
+  qs += __shfl_xor_sync(0xffffffffu, qs, 4);
+  const float qn = sqrtf(qs);
+#pragma unroll
+  for (int i = 0; i < NQ; ++i) {
+    qv[i].x /= qn; qv[i].y /= qn; qv[i].z /= qn; qv[i].w /= qn;
+  }
+
+  WarpList wl;
+  wl.init();
+  const int64_t warp_global = (int64_t)blockIdx.x * kTopkWarps + wid;
+  const int64_t n_warps = (int64_t)gridDim.x * kTopkWarps;
+  for (int64_t r0 = warp_global * 4; r0 < n; r0 += n_warps * 4) {
+    const int64_t row = r0 + grp;
+    float dot = 0.f, ss = 0.f;
+    if (row < n) {
+      const float* src = W + row * dim;
+      float4 x[NQ];
+#pragma unroll
+      for (int i = 0; i < NQ; ++i) {
+        const int j = sub + 8 * i;
+        x[i] = (j < d4) ? ld4_nc(src + 4 * j) : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+#pragma unroll
+      for (int i = 0; i < NQ; ++i) {
+        dot += dot4(x[i], qv[i]);
+        ss += dot4(x[i], x[i]);
+      }
+    }
+#pragma unroll
+    for (int o = 1; o < 8; o <<= 1) {
+      dot += __shfl_xor_sync(0xffffffffu, dot, o);
+      ss += __shfl_xor_sync(0xffffffffu, ss, o);
+    }
+    float sc = dot / sqrtf(ss);  // 0/0 -> NaN for zero rows, rejected below
+    bool ok = (row < n) && (sc == sc) && (row != exclude);
+    if (ok && cand_mask) ok = (cand_mask[row >> 5] >> (row & 31)) & 1u;
+    // one candidate per 8-lane group: lanes 0, 8, 16, 24 offer theirs
+    wl.insert_lanes(sc, (int)row, ok && sub == 0, k, lane);
+  }
+  cta_merge(wl, sm_s, sm_i, k, kTopkWarps);
+  if (wid == 0 && lane < k) {
+    part_idx[(int64_t)blockIdx.x * k + lane] = (wl.i == 0x7fffffff) ? -1 : wl.i;
+    part_score[(int64_t)blockIdx.x * k + lane] = wl.s;
+  }
+}
+
+// Merge n_lists partial lists per query.  idx/score layout: [list][query][k_in].  One CTA per query.
+__global__ void __launch_bounds__(kTopkThreads)
+topk_merge_kernel(const int* __restrict__ idx, const float* __restrict__ score, int n_lists,
+                  int64_t n_queries, int k_in, int k_out, int* __restrict__ out_idx,
+                  float* __restrict__ out_score) {
+  __shared__ float sm_s[kTopkWarps * 32];
+  __shared__ int sm_i[kTopkWarps * 32];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const int64_t qy = blockIdx.x;
+  WarpList wl;
+  wl.init();
+  const int total = n_lists * k_in;
+  for (int e0 = wid * 32; e0 < total; e0 += kTopkWarps * 32) {
+    const int e = e0 + lane;
+    float cs = -CUDART_INF_F;
+    int ci = -1;
+    if (e < total) {
+      const int l = e / k_in, j = e - l * k_in;
+      const int64_t o = ((int64_t)l * n_queries + qy) * k_in + j;
+      ci = idx[o];
+      cs = score[o];
+    }
+    wl.insert_lanes(cs, ci, ci >= 0 && cs == cs, k_out, lane);
+  }
+  cta_merge(wl, sm_s, sm_i, k_out, kTopkWarps);
+  if (wid == 0 && lane < k_out) {
+    out_idx[qy * k_out + lane] = (wl.i == 0x7fffffff) ? -1 : wl.i;
+    out_score[qy * k_out + lane] = wl.s;
+  }
+}
+
+// Exact fp32 re-rank: warp per query row, candidates gathered one by one.
+template <int NV>
+__global__ void __launch_bounds__(kTopkThreads)
+rerank_kernel(const float* __restrict__ Wq, int64_t q0, int64_t n_queries, const float* __restrict__ Wc,
+              int dim, const int* __restrict__ cand, int n_cand, int k, int* __restrict__ out_idx,
+              float* __restrict__ out_score) {
+  const int lane = threadIdx.x & 31;
+  const int d4 = dim >> 2;
+  const int64_t qi = (int64_t)blockIdx.x * kTopkWarps + (threadIdx.x >> 5);
+  if (qi >= n_queries) return;
+  float4 qv[NV];
+  float qs = 0.f;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const int j = lane + 32 * i;
+    qv[i] = (j < d4) ? ld4(Wq + (q0 + qi) * dim + 4 * j) : make_float4(0.f, 0.f, 0.f, 0.f);
+    qs += dot4(qv[i], qv[i]);
+  }
+  const float qn = sqrtf(warp_sum(qs));
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    qv[i].x /= qn; qv[i].y /= qn; qv[i].z /= qn; qv[i].w /= qn;
+  }
+  WarpList wl;
+  wl.init();
+  const int* cl = cand + qi * n_cand;
+  for (int j0 = 0; j0 < n_cand; j0 += 32) {
+    const int mine = (j0 + lane < n_cand) ? cl[j0 + lane] : -1;
+    const int cnt = min(32, n_cand - j0);
+    for (int j = 0; j < cnt; ++j) {
+      const int r = __shfl_sync(0xffffffffu, mine, j);
+      if (r < 0) continue;
+      float dot = 0.f, ss = 0.f;
+#pragma unroll
+      for (int i = 0; i < NV; ++i) {
+        const int jj = lane + 32 * i;
+        if (jj < d4) {
+          float4 x = ld4_nc(Wc + (int64_t)r * dim + 4 * jj);
+          dot += dot4(x, qv[i]);
+          ss += dot4(x, x);
+        }
+      }
+      dot = warp_sum(dot);
+      ss = warp_sum(ss);
+      const float sc = dot / sqrtf(ss);
+      if (sc == sc) wl.insert(sc, r, lane, true);
+    }
+  }
+  if (lane < k) {
+    out_idx[qi * k + lane] = (wl.i == 0x7fffffff) ? -1 : wl.i;
+    out_score[qi * k + lane] = wl.s;
+  }
+}
+
+static int sm_count() {
+  static int n = 0;
+  if (!n) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    if (n <= 0) n = 148;
+  }
+  return n;
+}
+static bool dim_ok(int dim) { return dim > 0 && dim <= 512 && (dim % 4) == 0; }
+static int query_blocks(int64_t n_rows) {
+  int64_t need = (n_rows + kTopkWarps * 4 - 1) / (kTopkWarps * 4);
+  return (int)std::max<int64_t>(1, std::min<int64_t>(need, (int64_t)sm_count() * 4));
+}
+
+}  // namespace ar
+
+using namespace ar;
+
+extern "C" int ar_rownorm(const float* W, int64_t n_rows, int32_t dim, float* out, void* stream) {
+  AR_REQUIRE(W && out, "ar_rownorm: null pointer");
+  AR_REQUIRE(dim_ok(dim), "ar_rownorm: dim %d unsupported", dim);
+  if (n_rows <= 0) return AR_OK;
+  int blocks = (int)std::min<int64_t>((n_rows + 7) / 8, (int64_t)sm_count() * 8);
+  rownorm_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(W, n_rows, dim, out, nullptr);
+  AR_LAUNCH_CHECK();
+  return AR_OK;
+}
+
+extern "C" int ar_rownorm_bf16(const float* W, int64_t n_rows, int32_t dim, void* out_bf16, void* stream) {
+  AR_REQUIRE(W && out_bf16, "ar_rownorm_bf16: null pointer");
+  AR_REQUIRE(dim_ok(dim), "ar_rownorm_bf16: dim %d unsupported", dim);
+  if (n_rows <= 0) return AR_OK;
+  int blocks = (int)std::min<int64_t>((n_rows + 7) / 8, (int64_t)sm_count() * 8);
+  rownorm_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(W, n_rows, dim, nullptr, (__nv_bfloat16*)out_bf16);
+  AR_LAUNCH_CHECK();
+  return AR_OK;
+}
+
+extern "C" int64_t ar_topk_query_workspace(int64_t n_rows, int32_t k) {
+  if (k <= 0 || k > kMaxK || n_rows <= 0) return 0;
+  return (int64_t)query_blocks(n_rows) * k * 8;
+}
+
+extern "C" int ar_cosine_topk_query(const float* W, int64_t n_rows, int32_t dim, int64_t q,
+                                    const uint32_t* cand_mask, int64_t exclude, int32_t k, int32_t* out_idx,
+                                    float* out_score, void* workspace, void* stream) {
+  AR_REQUIRE(W && out_idx && out_score && workspace, "ar_cosine_topk_query: null pointer");
+  AR_REQUIRE(dim_ok(dim), "ar_cosine_topk_query: dim %d unsupported", dim);
+  AR_REQUIRE(k > 0 && k <= kMaxK, "ar_cosine_topk_query: k %d outside [1,%d]", k, kMaxK);
+  AR_REQUIRE(n_rows > 0 && q >= 0 && q < n_rows, "ar_cosine_topk_query: query row %lld outside [0,%lld)", (long long)q, (long long)n_rows);
+  const int blocks = query_blocks(n_rows);
+  int* pidx = (int*)workspace;
+  float* pscore = (float*)workspace + (int64_t)blocks * k;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int nq = ((dim >> 2) + 7) / 8;
+  if (nq <= 4) query_topk_kernel<4><<<blocks, kTopkThreads, 0, st>>>(W, n_rows, dim, q, cand_mask, exclude, k, pidx, pscore);
+  else if (nq <= 8) query_topk_kernel<8><<<blocks, kTopkThreads, 0, st>>>(W, n_rows, dim, q, cand_mask, exclude, k, pidx, pscore);
+  else query_topk_kernel<16><<<blocks, kTopkThreads, 0, st>>>(W, n_rows, dim, q, cand_mask, exclude, k, pidx, pscore);
+  AR_LAUNCH_CHECK();
+  topk_merge_kernel<<<1, kTopkThreads, 0, st>>>(pidx, pscore, blocks, 1, k, k, out_idx, out_score);
+  AR_LAUNCH_CHECK();
+  return AR_OK;
+}
+
+extern "C" int ar_topk_merge(const int32_t* idx, const float* score, int32_t n_lists, int64_t n_queries,
+                             int32_t k_in, int32_t k_out, int32_t* out_idx, float* out_score, void* stream) {
+  AR_REQUIRE(idx && score && out_idx && out_score, "ar_topk_merge: null pointer");
+  AR_REQUIRE(k_out > 0 && k_out <= kMaxK && k_in > 0 && n_lists > 0, "ar_topk_merge: bad k/n_lists");
+  if (n_queries <= 0) return AR_OK;
+  topk_merge_kernel<<<(unsigned)n_queries, kTopkThreads, 0, (cudaStream_t)stream>>>(idx, score, n_lists, n_queries, k_in, k_out, out_idx, out_score);
+  AR_LAUNCH_CHECK();
+  return AR_OK;
+}
+
+extern "C" int ar_cosine_rerank(const float* Wq, int64_t q0, int64_t n_queries, const float* Wc, int32_t dim,
+                                const int32_t* cand, int32_t n_cand, int32_t k, int32_t* out_idx,
+                                float* out_score, void* stream) {
+  AR_REQUIRE(Wq && Wc && cand && out_idx && out_score, "ar_cosine_rerank: null pointer");
+  AR_REQUIRE(dim_ok(dim), "ar_cosine_rerank: dim %d unsupported", dim);
+  AR_REQUIRE(k > 0 && k <= kMaxK && n_cand > 0, "ar_cosine_rerank: bad k/n_cand");
+  if (n_queries <= 0) return AR_OK;
+  const int blocks = (int)((n_queries + kTopkWarps - 1) / kTopkWarps);
+  cudaStream_t st = (cudaStream_t)stream;
+  switch ((dim + 127) / 128) {
+    case 1: rerank_kernel<1><<<blocks, kTopkThreads, 0, st>>>(Wq, q0, n_queries, Wc, dim, cand, n_cand, k, out_idx, out_score); break;
+    case 2: rerank_kernel<2><<<blocks, kTopkThreads, 0, st>>>(Wq, q0, n_queries, Wc, dim, cand, n_cand, k, out_idx, out_score); break;
+    case 3: rerank_kernel<3><<<blocks, kTopkThreads, 0, st>>>(Wq, q0, n_queries, Wc, dim, cand, n_cand, k, out_idx, out_score); break;
+    default: rerank_kernel<4><<<blocks, kTopkThreads, 0, st>>>(Wq, q0, n_queries, Wc, dim, cand, n_cand, k, out_idx, out_score); break;
+  }
+  AR_LAUNCH_CHECK();
+  return AR_OK;
+}

@@ -1,0 +1,721 @@
+// Half A: the training step of the neural_network.py embedding model on sm_100a.
+//
+// Step t (global, 1-based) runs four launches on one stream:
+//   1. rows_catchup   (AR_ADAM_REPLAY only) bring the step's distinct rows to optimizer step t-1
+//                     by replaying their missed pure-L2 Adam steps in registers
+//   2. embed_fwd      warp per sample: gather both rows (128-bit loads), l2-normalise, dot
+//   3. head_step      one CTA: Dense(1) + BatchNorm(train) + sigmoid + BCE, its backward, Adam on
+//                     the 4 head scalars, moving statistics, per-step metrics
+//   4. rows_update    warp per distinct row: atomic-free segment reduction of the row gradient
+//                     over the plan's sorted samples + L2 term + Adam, one RMW of (W, m, v)
+// AR_ADAM_DENSE appends a flush of every other row to step t (the reference-literal dense Adam).
+//
+// Arithmetic follows oracle/train.py (the restatement of neural_network.py:66-106 under
+// Keras-2.12 semantics); citations there.
+#include <algorithm>
+
+#include "common.cuh"
+
+namespace ar {
+
+constexpr int kRowThreads = 256;               // 8 warps per CTA, one row / sample per warp
+constexpr int kRowWarps = kRowThreads / 32;
+constexpr int kHeadThreads = 1024;
+
+// ---------------------------------------------------------------------------------------------
+// Row register tile: a warp owns one row, lane l holds float4 #(l + 32*k), k < NV.
+template <int NV>
+struct RowTile {
+  float4 x[NV];
+  __device__ __forceinline__ void load(const float* row, int d4, int lane) {
+#pragma unroll
+    for (int k = 0; k < NV; ++k) {
+      int j = lane + 32 * k;
+      x[k] = (j < d4) ? ld4(row + 4 * j) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+  }
+  __device__ __forceinline__ void store(float* row, int d4, int lane) const {
+#pragma unroll
+    for (int k = 0; k < NV; ++k) {
+      int j = lane + 32 * k;
+      if (j < d4) st4(row + 4 * j, x[k]);
+    }
+  }
+  __device__ __forceinline__ void zero() {
+#pragma unroll
+    for (int k = 0; k < NV; ++k) x[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+};
+
+template <int NV>
+__device__ __forceinline__ float tile_dot(const RowTile<NV>& a, const RowTile<NV>& b) {
+  float s = 0.f;
+#pragma unroll
+  for (int k = 0; k < NV; ++k) s += dot4(a.x[k], b.x[k]);
+  return warp_sum(s);
+}
+
+// Replay pure-L2 Adam steps (from, to] of one row held in registers.
+template <int NV>
+__device__ __forceinline__ void replay_l2(RowTile<NV>& w, RowTile<NV>& m, RowTile<NV>& v,
+                                          const float* __restrict__ alpha, int64_t from, int64_t to,
+                                          float l2x2, int lane) {
+  for (int64_t t0 = from + 1; t0 <= to; t0 += 32) {
+    int64_t tl = t0 + lane;
+    float a_l = (tl <= to) ? __ldg(alpha + tl) : 0.f;
+    int cnt = (int)min((int64_t)32, to - t0 + 1);
+    for (int s = 0; s < cnt; ++s) {
+      float a = __shfl_sync(0xffffffffu, a_l, s);
+#pragma unroll
+      for (int k = 0; k < NV; ++k) {
+        float4 g = make_float4(__fmul_rn(l2x2, w.x[k].x), __fmul_rn(l2x2, w.x[k].y),
+                               __fmul_rn(l2x2, w.x[k].z), __fmul_rn(l2x2, w.x[k].w));
+        adam4(w.x[k], m.x[k], v.x[k], g, a);
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// 1. catch-up of the step's distinct rows (both tables in one launch)
+struct CatchupArgs {
+  ar_table tab[2];
+  const int32_t* uniq[2];
+  const int32_t* meta[2];
+  int blocks0;  // CTAs assigned to table 0
+};
+
+template <int NV>
+__global__ void __launch_bounds__(kRowThreads)
+rows_catchup_kernel(CatchupArgs a, const float* __restrict__ alpha, float l2x2, int64_t t_target) {
+  const int which = (blockIdx.x >= a.blocks0) ? 1 : 0;
+  const int blk = which ? blockIdx.x - a.blocks0 : blockIdx.x;
+  const int lane = threadIdx.x & 31;
+  const int seg = blk * kRowWarps + (threadIdx.x >> 5);
+  if (seg >= a.meta[which][0]) return;
+  const ar_table& tb = a.tab[which];
+  const int row = a.uniq[which][seg];
+  const int64_t last = tb.last_step[row];
+  if (last >= t_target) return;
+  const int d4 = tb.dim >> 2;
+  const size_t o = (size_t)row * tb.dim;
+  RowTile<NV> w, m, v;
+  w.load(tb.W + o, d4, lane);
+  m.load(tb.m + o, d4, lane);
+  v.load(tb.v + o, d4, lane);
+  replay_l2<NV>(w, m, v, alpha, last, t_target, l2x2, lane);
+  w.store(tb.W + o, d4, lane);
+  m.store(tb.m + o, d4, lane);
+  v.store(tb.v + o, d4, lane);
+  if (lane == 0) tb.last_step[row] = (int32_t)t_target;
+}
+
+// whole-table flush: every row to t_target
+template <int NV>
+__global__ void __launch_bounds__(kRowThreads)
+table_flush_kernel(ar_table tb, const float* __restrict__ alpha, float l2x2, int64_t t_target,
+                   double* sumsq_out) {
+  __shared__ double ss_red[kRowWarps];
+  const int lane = threadIdx.x & 31;
+  const int d4 = tb.dim >> 2;
+  double ss = 0.0;
+  for (int64_t row = (int64_t)blockIdx.x * kRowWarps + (threadIdx.x >> 5); row < tb.n_rows;
+       row += (int64_t)gridDim.x * kRowWarps) {
+    const int64_t last = tb.last_step[row];
+    if (last >= t_target) continue;
+    const size_t o = (size_t)row * tb.dim;
+    RowTile<NV> w, m, v;
+    w.load(tb.W + o, d4, lane);
+    m.load(tb.m + o, d4, lane);
+    v.load(tb.v + o, d4, lane);
+    if (sumsq_out) ss += (double)tile_dot<NV>(w, w);
+    replay_l2<NV>(w, m, v, alpha, last, t_target, l2x2, lane);
+    w.store(tb.W + o, d4, lane);
+    m.store(tb.m + o, d4, lane);
+    v.store(tb.v + o, d4, lane);
+    if (lane == 0) tb.last_step[row] = (int32_t)t_target;
+  }
+  if (sumsq_out) {
+    if (lane == 0) ss_red[threadIdx.x >> 5] = ss;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      double a = 0.0;
+      for (int i = 0; i < kRowWarps; ++i) a += ss_red[i];
+      atomicAdd(sumsq_out + (blockIdx.x & 31), a);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// 2. forward: gather + l2_normalize + dot (neural_network.py:75-96; oracle forward())
+template <int NV>
+__global__ void __launch_bounds__(kRowThreads)
+embed_fwd_kernel(const float* __restrict__ U, const float* __restrict__ A, int dim,
+                 const int32_t* __restrict__ iu, const int32_t* __restrict__ ia, int n,
+                 const int32_t* __restrict__ meta_n, float* __restrict__ uh, float* __restrict__ ah,
+                 float* __restrict__ c, float* __restrict__ ru, float* __restrict__ ra) {
+  if (meta_n) n = min(n, meta_n[2]);
+  const int s = blockIdx.x * kRowWarps + (threadIdx.x >> 5);
+  if (s >= n) return;
+  const int lane = threadIdx.x & 31;
+  const int d4 = dim >> 2;
+  RowTile<NV> u, a;
+  u.load(U + (size_t)iu[s] * dim, d4, lane);
+  a.load(A + (size_t)ia[s] * dim, d4, lane);
+  const float su = tile_dot<NV>(u, u);
+  const float sa = tile_dot<NV>(a, a);
+  const float r_u = 1.0f / sqrtf(fmaxf(su, kL2NormEps));
+  const float r_a = 1.0f / sqrtf(fmaxf(sa, kL2NormEps));
+#pragma unroll
+  for (int k = 0; k < NV; ++k) {
+    u.x[k] = scale4(u.x[k], r_u);
+    a.x[k] = scale4(a.x[k], r_a);
+  }
+  const float cs = tile_dot<NV>(u, a);
+  if (uh) u.store(uh + (size_t)s * dim, d4, lane);
+  if (ah) a.store(ah + (size_t)s * dim, d4, lane);
+  if (lane == 0) {
+    c[s] = cs;
+    if (ru) ru[s] = r_u;
+    if (ra) ra[s] = r_a;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// 3. head: Dense(1) -> BatchNorm(train) -> sigmoid -> BCE, backward, Adam on (w,b,gamma,beta)
+//    (neural_network.py:97-104; oracle forward()/head_backward()).  One CTA; sums in double.
+template <int NVAL>
+__device__ __forceinline__ void block_sum(double (&v)[NVAL], double* smem /* [NVAL][32] */) {
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+#pragma unroll
+  for (int i = 0; i < NVAL; ++i) v[i] = warp_sum(v[i]);
+  __syncthreads();  // protect smem reuse between consecutive calls
+  if (lane == 0) {
+#pragma unroll
+    for (int i = 0; i < NVAL; ++i) smem[i * 32 + wid] = v[i];
+  }
+  __syncthreads();
+  const int nw = blockDim.x >> 5;
+#pragma unroll
+  for (int i = 0; i < NVAL; ++i) {
+    double x = (lane < nw) ? smem[i * 32 + lane] : 0.0;
+    v[i] = warp_sum(x);
+  }
+}
+
+__device__ __forceinline__ float sigmoidf_(float y) {
+  if (y >= 0.f) return 1.0f / (1.0f + expf(-y));
+  float e = expf(y);
+  return e / (1.0f + e);
+}
+__device__ __forceinline__ float bce_logits(float y, float t) {
+  return fmaxf(y, 0.f) - y * t + log1pf(expf(-fabsf(y)));
+}
+
+__global__ void __launch_bounds__(kHeadThreads, 1)
+head_step_kernel(const float* __restrict__ c, const float* __restrict__ label, int n,
+                 const int32_t* __restrict__ meta_n, float* __restrict__ head, float* __restrict__ head_m,
+                 float* __restrict__ head_v, float* __restrict__ bn_moving,
+                 const float* __restrict__ alpha, int64_t t, float* __restrict__ dc,
+                 float* __restrict__ metrics_row) {
+  __shared__ double red[4 * 32];
+  if (meta_n) n = min(n, meta_n[2]);
+  if (n <= 0) return;
+  const int tid = threadIdx.x;
+  const float w = head[0], b = head[1], gamma = head[2], beta = head[3];
+  const float fn = (float)n;
+
+  double s1[1] = {0.0};
+  for (int i = tid; i < n; i += kHeadThreads) s1[0] += (double)(w * c[i] + b);
+  block_sum<1>(s1, red);
+  const float mu = (float)(s1[0] / n);
+
+  double s2[1] = {0.0};
+  for (int i = tid; i < n; i += kHeadThreads) {
+    float d = (w * c[i] + b) - mu;
+    s2[0] += (double)(d * d);
+  }
+  block_sum<1>(s2, red);
+  const float var = (float)(s2[0] / n);
+  const float inv = 1.0f / sqrtf(var + kBnEps);
+
+  double s3[4] = {0.0, 0.0, 0.0, 0.0};  // sum bce, sum sq err, sum dy, sum dy*zh
+  for (int i = tid; i < n; i += kHeadThreads) {
+    float zh = ((w * c[i] + b) - mu) * inv;
+    float y = gamma * zh + beta;
+    float p = sigmoidf_(y);
+    float tg = label[i];
+    float dy = (p - tg) / fn;
+    s3[0] += (double)bce_logits(y, tg);
+    s3[1] += (double)((tg - p) * (tg - p));
+    s3[2] += (double)dy;
+    s3[3] += (double)(dy * zh);
+  }
+  block_sum<4>(s3, red);
+  const float dgamma = (float)s3[3];
+  const float dbeta = (float)s3[2];
+  const float sdzh = gamma * dbeta;     // sum dzh
+  const float sdzhzh = gamma * dgamma;  // sum dzh*zh
+
+  double s4[2] = {0.0, 0.0};  // sum dz*c, sum dz
+  for (int i = tid; i < n; i += kHeadThreads) {
+    float ci = c[i];
+    float zh = ((w * ci + b) - mu) * inv;
+    float y = gamma * zh + beta;
+    float p = sigmoidf_(y);
+    float dzh = gamma * ((p - label[i]) / fn);
+    float dz = inv / fn * (fn * dzh - sdzh - zh * sdzhzh);
+    dc[i] = w * dz;
+    s4[0] += (double)(dz * ci);
+    s4[1] += (double)dz;
+  }
+  block_sum<2>(s4, red);
+
+  if (tid == 0) {
+    const float a = alpha[t];
+    float g[4] = {(float)s4[0], (float)s4[1], dgamma, dbeta};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      float th = head[i], m = head_m[i], v = head_v[i];
+      adam1(th, m, v, g[i], a);
+      head[i] = th;
+      head_m[i] = m;
+      head_v[i] = v;
+    }
+    float mm = bn_moving[0], mv = bn_moving[1];
+    bn_moving[0] = mm - (mm - mu) * kBnOneMinusMomentum;
+    bn_moving[1] = mv - (mv - var) * kBnOneMinusMomentum;
+    if (metrics_row) {
+      metrics_row[0] = (float)(s3[0] / n);
+      metrics_row[1] = (float)(s3[1] / n);
+      metrics_row[2] = fn;
+      metrics_row[3] = mu;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// 4. row update: segment-reduce the row gradient over the plan's sorted samples, add the L2 term,
+//    apply Adam step t.   g_r = r * (sum_s dc_s*o_s - (sum_s dc_s*c_s) * (W_r*r)) + 2*l2*W_r
+//    where o_s is the normalised row of the OTHER table for sample s and r = 1/||W_r||
+//    (= oracle du/da summed per row, factored).
+struct UpdateArgs {
+  ar_table tab[2];
+  const int32_t* order[2];
+  const int32_t* uniq[2];
+  const int32_t* off[2];
+  const int32_t* meta[2];
+  const int32_t* heavy[2];
+  const float* other[2];  // (batch, dim) normalised rows of the other table
+  const float* rinv[2];   // (batch) 1/||row|| per sample of THIS table
+  int blocks_norm[2];     // warp-per-row CTAs per table
+  int blocks_heavy[2];    // CTA-per-heavy-row CTAs per table
+};
+
+template <int NV>
+__device__ __forceinline__ void finish_row(const ar_table& tb, int row, RowTile<NV>& acc, float q,
+                                           float rinv, const float* __restrict__ alpha, float l2x2,
+                                           int64_t t, int replay, double* sumsq_out, int lane) {
+  const int d4 = tb.dim >> 2;
+  const size_t o = (size_t)row * tb.dim;
+  RowTile<NV> w, m, v;
+  w.load(tb.W + o, d4, lane);
+  m.load(tb.m + o, d4, lane);
+  v.load(tb.v + o, d4, lane);
+  if (replay) {
+    const int64_t last = tb.last_step[row];
+    if (last < t - 1) replay_l2<NV>(w, m, v, alpha, last, t - 1, l2x2, lane);
+  }
+  if (sumsq_out) {
+    float ss = tile_dot<NV>(w, w);
+    if (lane == 0) atomicAdd(sumsq_out + ((blockIdx.x * kRowWarps + (threadIdx.x >> 5)) & 31), (double)ss);
+  }
+  const float a = alpha[t];
+#pragma unroll
+  for (int k = 0; k < NV; ++k) {
+    float4 wk = w.x[k], ak = acc.x[k], g;
+    g.x = __fadd_rn(rinv * (ak.x - q * (wk.x * rinv)), __fmul_rn(l2x2, wk.x));
+    g.y = __fadd_rn(rinv * (ak.y - q * (wk.y * rinv)), __fmul_rn(l2x2, wk.y));
+    g.z = __fadd_rn(rinv * (ak.z - q * (wk.z * rinv)), __fmul_rn(l2x2, wk.z));
+    g.w = __fadd_rn(rinv * (ak.w - q * (wk.w * rinv)), __fmul_rn(l2x2, wk.w));
+    adam4(w.x[k], m.x[k], v.x[k], g, a);
+  }
+  w.store(tb.W + o, d4, lane);
+  m.store(tb.m + o, d4, lane);
+  v.store(tb.v + o, d4, lane);
+  if (lane == 0) tb.last_step[row] = (int32_t)t;
+}
+
+template <int NV>
+__global__ void __launch_bounds__(kRowThreads)
+rows_update_kernel(UpdateArgs a, const float* __restrict__ c, const float* __restrict__ dc,
+                   const float* __restrict__ alpha, float l2x2, int64_t t, int replay,
+                   double* sumsq_out) {
+  extern __shared__ float red[];  // heavy path: [kRowWarps][dim] + [kRowWarps]
+  int b = blockIdx.x;
+  int which, heavy_path;
+  if (b < a.blocks_norm[0]) { which = 0; heavy_path = 0; }
+  else if ((b -= a.blocks_norm[0]) < a.blocks_norm[1]) { which = 1; heavy_path = 0; }
+  else if ((b -= a.blocks_norm[1]) < a.blocks_heavy[0]) { which = 0; heavy_path = 1; }
+  else { b -= a.blocks_heavy[0]; which = 1; heavy_path = 1; }
+
+  const ar_table& tb = a.tab[which];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const int dim = tb.dim, d4 = dim >> 2;
+  const int32_t* __restrict__ order = a.order[which];
+  const int32_t* __restrict__ off = a.off[which];
+  const float* __restrict__ other = a.other[which];
+
+  if (!heavy_path) {
+    const int seg = b * kRowWarps + wid;
+    if (seg >= a.meta[which][0]) return;
+    const int beg = off[seg], end = off[seg + 1];
+    if (end - beg > AR_HEAVY_LEN) return;  // CTA path handles it
+    RowTile<NV> acc;
+    acc.zero();
+    float q = 0.f;
+    int j = beg;
+    for (; j + 1 < end; j += 2) {  // two samples in flight
+      const int s0 = order[j], s1 = order[j + 1];
+      RowTile<NV> o0, o1;
+      o0.load(other + (size_t)s0 * dim, d4, lane);
+      o1.load(other + (size_t)s1 * dim, d4, lane);
+      const float d0 = dc[s0], d1 = dc[s1];
+      q = fmaf(d0, c[s0], q);
+      q = fmaf(d1, c[s1], q);
+#pragma unroll
+      for (int k = 0; k < NV; ++k) {
+        acc.x[k] = fma4(d0, o0.x[k], acc.x[k]);
+        acc.x[k] = fma4(d1, o1.x[k], acc.x[k]);
+      }
+    }
+    if (j < end) {
+      const int s0 = order[j];
+      RowTile<NV> o0;
+      o0.load(other + (size_t)s0 * dim, d4, lane);
+      const float d0 = dc[s0];
+      q = fmaf(d0, c[s0], q);
+#pragma unroll
+      for (int k = 0; k < NV; ++k) acc.x[k] = fma4(d0, o0.x[k], acc.x[k]);
+    }
+    finish_row<NV>(tb, a.uniq[which][seg], acc, q, a.rinv[which][order[beg]], alpha, l2x2, t, replay,
+                   sumsq_out, lane);
+    return;
+  }
+
+  // heavy row: the whole CTA reduces one long segment; warp w takes samples beg+w, beg+w+8, ...
+  if (b >= a.meta[which][1]) return;
+  const int seg = a.heavy[which][b];
+  const int beg = off[seg], end = off[seg + 1];
+  RowTile<NV> acc;
+  acc.zero();
+  float q = 0.f;
+  for (int j = beg + wid; j < end; j += kRowWarps) {
+    const int s0 = order[j];
+    RowTile<NV> o0;
+    o0.load(other + (size_t)s0 * dim, d4, lane);
+    const float d0 = dc[s0];
+    q = fmaf(d0, c[s0], q);
+#pragma unroll
+    for (int k = 0; k < NV; ++k) acc.x[k] = fma4(d0, o0.x[k], acc.x[k]);
+  }
+  acc.store(red + (size_t)wid * dim, d4, lane);
+  float* qred = red + (size_t)kRowWarps * dim;
+  if (lane == 0) qred[wid] = q;
+  __syncthreads();
+  if (wid != 0) return;
+  acc.zero();
+  q = 0.f;
+  for (int w8 = 0; w8 < kRowWarps; ++w8) {  // fixed order: deterministic
+    RowTile<NV> p;
+    p.load(red + (size_t)w8 * dim, d4, lane);
+#pragma unroll
+    for (int k = 0; k < NV; ++k) {
+      acc.x[k].x += p.x[k].x; acc.x[k].y += p.x[k].y; acc.x[k].z += p.x[k].z; acc.x[k].w += p.x[k].w;
+    }
+    q += qred[w8];
+  }
+  finish_row<NV>(tb, a.uniq[which][seg], acc, q, a.rinv[which][order[beg]], alpha, l2x2, t, replay,
+                 sumsq_out, lane);
+}
+
+// ---------------------------------------------------------------------------------------------
+// inference forward / validation sums (Keras predict / test_step; oracle predict()/evaluate())
+template <int NV, bool EVAL>
+__global__ void __launch_bounds__(kRowThreads)
+predict_kernel(const float* __restrict__ U, const float* __restrict__ A, int dim,
+               const float* __restrict__ head, const float* __restrict__ bn_moving,
+               const int32_t* __restrict__ iu, const int32_t* __restrict__ ia,
+               const float* __restrict__ label, int64_t n, float* __restrict__ out,
+               double* __restrict__ sums) {
+  __shared__ double red[2 * kRowWarps];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const int d4 = dim >> 2;
+  const float w = head[0], b = head[1], gamma = head[2], beta = head[3];
+  const float mu = bn_moving[0];
+  const float inv = 1.0f / sqrtf(bn_moving[1] + kBnEps);
+  double sb = 0.0, sm = 0.0;
+  for (int64_t s = (int64_t)blockIdx.x * kRowWarps + wid; s < n; s += (int64_t)gridDim.x * kRowWarps) {
+    RowTile<NV> u, a;
+    u.load(U + (size_t)iu[s] * dim, d4, lane);
+    a.load(A + (size_t)ia[s] * dim, d4, lane);
+    const float su = tile_dot<NV>(u, u);
+    const float sa = tile_dot<NV>(a, a);
+    const float r_u = 1.0f / sqrtf(fmaxf(su, kL2NormEps));
+    const float r_a = 1.0f / sqrtf(fmaxf(sa, kL2NormEps));
+#pragma unroll
+    for (int k = 0; k < NV; ++k) {
+      u.x[k] = scale4(u.x[k], r_u);
+      a.x[k] = scale4(a.x[k], r_a);
+    }
+    const float cs = tile_dot<NV>(u, a);
+    const float y = gamma * (((w * cs + b) - mu) * inv) + beta;
+    const float p = sigmoidf_(y);
+    if (EVAL) {
+      const float tg = label[s];
+      sb += (double)bce_logits(y, tg);
+      sm += (double)((tg - p) * (tg - p));
+    } else if (lane == 0) {
+      out[s] = p;
+    }
+  }
+  if (EVAL) {
+    if (lane == 0) { red[wid] = sb; red[kRowWarps + wid] = sm; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      double a0 = 0.0, a1 = 0.0;
+      for (int i = 0; i < kRowWarps; ++i) { a0 += red[i]; a1 += red[kRowWarps + i]; }
+      atomicAdd(sums, a0);
+      atomicAdd(sums + 1, a1);
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256) sumsq_kernel(const float* __restrict__ W, int64_t n4, double* out) {
+  __shared__ double red[8];
+  double s = 0.0;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
+    float4 x = ld4_nc(W + 4 * i);
+    s += (double)(x.x * x.x + x.y * x.y + x.z * x.z + x.w * x.w);
+  }
+  s = warp_sum(s);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double a = 0.0;
+    for (int i = 0; i < 8; ++i) a += red[i];
+    atomicAdd(out, a);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+static int nv_of(int dim) { return (dim + 127) / 128; }
+static bool dim_ok(int dim) { return dim > 0 && dim <= 512 && (dim % 4) == 0; }
+static int num_sms() {
+  static int n = 0;
+  if (!n) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    if (n <= 0) n = 148;
+  }
+  return n;
+}
+
+#define AR_DISPATCH_NV(dim, ...)                     \
+  switch (nv_of(dim)) {                              \
+    case 1: { constexpr int NV = 1; __VA_ARGS__; } break; \
+    case 2: { constexpr int NV = 2; __VA_ARGS__; } break; \
+    case 3: { constexpr int NV = 3; __VA_ARGS__; } break; \
+    default: { constexpr int NV = 4; __VA_ARGS__; } break; \
+  }
+
+static int launch_catchup(const ar_table* t0, const ar_plan* p0, int slot0, const ar_table* t1,
+                          const ar_plan* p1, int slot1, const float* alpha, float l2, int64_t t_target,
+                          cudaStream_t st) {
+  CatchupArgs a{};
+  a.tab[0] = *t0;
+  a.uniq[0] = p0->uniq + (int64_t)slot0 * p0->batch_cap;
+  a.meta[0] = p0->meta + (int64_t)slot0 * 4;
+  a.blocks0 = ceil_div(p0->batch_cap, kRowWarps);
+  int blocks = a.blocks0;
+  if (t1) {
+    a.tab[1] = *t1;
+    a.uniq[1] = p1->uniq + (int64_t)slot1 * p1->batch_cap;
+    a.meta[1] = p1->meta + (int64_t)slot1 * 4;
+    blocks += ceil_div(p1->batch_cap, kRowWarps);
+  }
+  const float l2x2 = (float)(2.0 * (double)l2);
+  AR_DISPATCH_NV(t0->dim, rows_catchup_kernel<NV><<<blocks, kRowThreads, 0, st>>>(a, alpha, l2x2, t_target));
+  AR_LAUNCH_CHECK();
+  return AR_OK;
+}
+
+static void fill_update(UpdateArgs& a, int w, const ar_table* tab, const ar_plan* p, int slot,
+                        const float* other, const float* rinv, int batch_hint) {
+  a.tab[w] = *tab;
+  a.order[w] = p->order + (int64_t)slot * p->batch_cap;
+  a.uniq[w] = p->uniq + (int64_t)slot * p->batch_cap;
+  a.off[w] = p->off + (int64_t)slot * (p->batch_cap + 1);
+  a.meta[w] = p->meta + (int64_t)slot * 4;
+  a.heavy[w] = p->heavy + (int64_t)slot * p->heavy_cap;
+  a.other[w] = other;
+  a.rinv[w] = rinv;
+  int b = batch_hint > 0 ? batch_hint : p->batch_cap;
+  a.blocks_norm[w] = ceil_div(b, kRowWarps);
+  a.blocks_heavy[w] = b / AR_HEAVY_LEN;  // at most this many segments can exceed AR_HEAVY_LEN
+}
+
+static int launch_update(UpdateArgs& a, bool two, const float* c, const float* dc, const float* alpha,
+                         float l2, int64_t t, int replay, double* sumsq_out, cudaStream_t st) {
+  if (!two) { a.blocks_norm[1] = 0; a.blocks_heavy[1] = 0; a.tab[1] = a.tab[0]; }
+  int blocks = a.blocks_norm[0] + a.blocks_norm[1] + a.blocks_heavy[0] + a.blocks_heavy[1];
+  const int dim = a.tab[0].dim;
+  size_t smem = (size_t)kRowWarps * dim * sizeof(float) + kRowWarps * sizeof(float);
+  const float l2x2 = (float)(2.0 * (double)l2);
+  AR_DISPATCH_NV(dim, rows_update_kernel<NV><<<blocks, kRowThreads, smem, st>>>(a, c, dc, alpha, l2x2, t, replay, sumsq_out));
+  AR_LAUNCH_CHECK();
+  return AR_OK;
+}
+
+static int launch_flush(const ar_table* tab, const float* alpha, float l2, int64_t t_target,
+                        double* sumsq_out, cudaStream_t st) {
+  const float l2x2 = (float)(2.0 * (double)l2);
+  int blocks = (int)std::min<int64_t>(ceil_div(tab->n_rows, kRowWarps), (int64_t)num_sms() * 8);
+  if (blocks <= 0) return AR_OK;
+  AR_DISPATCH_NV(tab->dim, table_flush_kernel<NV><<<blocks, kRowThreads, 0, st>>>(*tab, alpha, l2x2, t_target, sumsq_out));
+  AR_LAUNCH_CHECK();
+  return AR_OK;
+}
+
+}  // namespace ar
+
+using namespace ar;
+
+extern "C" int ar_table_flush(const ar_table* tab, const float* alpha, float l2, int64_t t_target, void* stream) {
+  AR_REQUIRE(tab && alpha, "ar_table_flush: null pointer");
+  AR_REQUIRE(dim_ok(tab->dim), "ar_table_flush: dim %d unsupported", tab->dim);
+  return launch_flush(tab, alpha, l2, t_target, nullptr, (cudaStream_t)stream);
+}
+
+extern "C" int ar_embed_fwd(const float* U, const float* A, int32_t dim, const int32_t* iu, const int32_t* ia,
+                            int32_t n, float* uh, float* ah, float* c, float* ru, float* ra, void* stream) {
+  AR_REQUIRE(U && A && iu && ia && c, "ar_embed_fwd: null pointer");
+  AR_REQUIRE(dim_ok(dim), "ar_embed_fwd: dim %d unsupported", dim);
+  if (n <= 0) return AR_OK;
+  AR_DISPATCH_NV(dim, embed_fwd_kernel<NV><<<ceil_div(n, kRowWarps), kRowThreads, 0, (cudaStream_t)stream>>>(
+                          U, A, dim, iu, ia, n, nullptr, uh, ah, c, ru, ra));
+  AR_LAUNCH_CHECK();
+  return AR_OK;
+}
+
+extern "C" int ar_head_step(const float* c, const float* label, int32_t n, float* head, float* head_m,
+                            float* head_v, float* bn_moving, const float* alpha, int64_t t, float* dc,
+                            float* metrics_row, void* stream) {
+  AR_REQUIRE(c && label && head && head_m && head_v && bn_moving && alpha && dc, "ar_head_step: null pointer");
+  AR_REQUIRE(n > 0, "ar_head_step: n must be positive");
+  head_step_kernel<<<1, kHeadThreads, 0, (cudaStream_t)stream>>>(c, label, n, nullptr, head, head_m, head_v,
+                                                                  bn_moving, alpha, t, dc, metrics_row);
+  AR_LAUNCH_CHECK();
+  return AR_OK;
+}
+
+extern "C" int ar_rows_catchup(const ar_table* tab, const ar_plan* plan, int32_t slot, const float* alpha,
+                               float l2, int64_t t, void* stream) {
+  AR_REQUIRE(tab && plan && alpha, "ar_rows_catchup: null pointer");
+  AR_REQUIRE(dim_ok(tab->dim), "ar_rows_catchup: dim %d unsupported", tab->dim);
+  AR_REQUIRE(slot >= 0 && slot < plan->n_slots, "ar_rows_catchup: slot out of range");
+  return launch_catchup(tab, plan, slot, nullptr, nullptr, 0, alpha, l2, t - 1, (cudaStream_t)stream);
+}
+
+extern "C" int ar_rows_update(const ar_table* tab, const ar_plan* plan, int32_t slot, const float* other_hat,
+                              const float* c, const float* dc, const float* rinv, const float* alpha, float l2,
+                              int64_t t, int32_t replay, double* sumsq_out, void* stream) {
+  AR_REQUIRE(tab && plan && other_hat && c && dc && rinv && alpha, "ar_rows_update: null pointer");
+  AR_REQUIRE(dim_ok(tab->dim), "ar_rows_update: dim %d unsupported", tab->dim);
+  AR_REQUIRE(slot >= 0 && slot < plan->n_slots, "ar_rows_update: slot out of range");
+  UpdateArgs a{};
+  fill_update(a, 0, tab, plan, slot, other_hat, rinv, 0);
+  return launch_update(a, false, c, dc, alpha, l2, t, replay, sumsq_out, (cudaStream_t)stream);
+}
+
+extern "C" int ar_train_steps(const ar_train_ctx* ctx, int64_t epoch_step0, int32_t slot0, int64_t t0,
+                              int32_t n_steps, void* stream) {
+  AR_REQUIRE(ctx, "ar_train_steps: null ctx");
+  const ar_train_ctx& x = *ctx;
+  AR_REQUIRE(x.users.W && x.anime.W && x.head && x.alpha && x.iu && x.ia && x.label, "ar_train_steps: null pointer in ctx");
+  AR_REQUIRE(x.users.dim == x.anime.dim && dim_ok(x.users.dim), "ar_train_steps: dim %d/%d unsupported", x.users.dim, x.anime.dim);
+  AR_REQUIRE(x.batch > 0 && x.batch <= AR_MAX_BATCH, "ar_train_steps: batch %d outside (0,%d]", x.batch, AR_MAX_BATCH);
+  AR_REQUIRE(x.uh && x.ah && x.c && x.ru && x.ra && x.dc && x.metrics, "ar_train_steps: null scratch");
+  AR_REQUIRE(slot0 >= 0 && slot0 + n_steps <= x.plan_u.n_slots && slot0 + n_steps <= x.plan_a.n_slots,
+             "ar_train_steps: plan slots [%d,%d) exceed plan size", slot0, slot0 + n_steps);
+  AR_REQUIRE(x.mode >= AR_ADAM_REPLAY && x.mode <= AR_ADAM_TOUCHED, "ar_train_steps: bad mode %d", x.mode);
+  cudaStream_t st = (cudaStream_t)stream;
+  const int dim = x.users.dim;
+  for (int s = 0; s < n_steps; ++s) {
+    const int64_t e = epoch_step0 + s;
+    const int64_t base = e * (int64_t)x.batch;
+    if (base >= x.n_samples) break;
+    const int n = (int)std::min<int64_t>(x.batch, x.n_samples - base);
+    const int slot = slot0 + s;
+    const int64_t t = t0 + s + 1;
+    const int32_t* meta_u = x.plan_u.meta + (int64_t)slot * 4;
+    if (x.mode == AR_ADAM_REPLAY) {
+      int rc = launch_catchup(&x.users, &x.plan_u, slot, &x.anime, &x.plan_a, slot, x.alpha, x.l2, t - 1, st);
+      if (rc) return rc;
+    }
+    AR_DISPATCH_NV(dim, embed_fwd_kernel<NV><<<ceil_div(n, kRowWarps), kRowThreads, 0, st>>>(
+                            x.users.W, x.anime.W, dim, x.iu + base, x.ia + base, n, meta_u, x.uh, x.ah, x.c, x.ru, x.ra));
+    AR_LAUNCH_CHECK();
+    head_step_kernel<<<1, kHeadThreads, 0, st>>>(x.c, x.label + base, n, meta_u, x.head, x.head_m, x.head_v,
+                                                 x.bn_moving, x.alpha, t, x.dc, x.metrics + t * 4);
+    AR_LAUNCH_CHECK();
+    UpdateArgs a{};
+    fill_update(a, 0, &x.users, &x.plan_u, slot, x.ah, x.ru, n);
+    fill_update(a, 1, &x.anime, &x.plan_a, slot, x.uh, x.ra, n);
+    double* ss = (x.mode == AR_ADAM_DENSE && x.reg_sumsq) ? x.reg_sumsq + t * 32 : nullptr;
+    int rc = launch_update(a, true, x.c, x.dc, x.alpha, x.l2, t, 0, ss, st);
+    if (rc) return rc;
+    if (x.mode == AR_ADAM_DENSE) {
+      // every row the batch did not touch takes the same Adam step with the pure L2 gradient
+      if ((rc = launch_flush(&x.users, x.alpha, x.l2, t, ss, st))) return rc;
+      if ((rc = launch_flush(&x.anime, x.alpha, x.l2, t, ss, st))) return rc;
+    }
+  }
+  return AR_OK;
+}
+
+extern "C" int ar_predict(const float* U, const float* A, int32_t dim, const float* head, const float* bn_moving,
+                          const int32_t* iu, const int32_t* ia, int64_t n, float* out, void* stream) {
+  AR_REQUIRE(U && A && head && bn_moving && iu && ia && out, "ar_predict: null pointer");
+  AR_REQUIRE(dim_ok(dim), "ar_predict: dim %d unsupported", dim);
+  if (n <= 0) return AR_OK;
+  int blocks = (int)std::min<int64_t>(ceil_div(n, kRowWarps), (int64_t)num_sms() * 8);
+  AR_DISPATCH_NV(dim, predict_kernel<NV, false><<<blocks, kRowThreads, 0, (cudaStream_t)stream>>>(
+                          U, A, dim, head, bn_moving, iu, ia, nullptr, n, out, nullptr));
+  AR_LAUNCH_CHECK();
+  return AR_OK;
+}
+
+extern "C" int ar_eval_sums(const float* U, const float* A, int32_t dim, const float* head, const float* bn_moving,
+                            const int32_t* iu, const int32_t* ia, const float* label, int64_t n, double* sums,
+                            void* stream) {
+  AR_REQUIRE(U && A && head && bn_moving && iu && ia && label && sums, "ar_eval_sums: null pointer");
+  AR_REQUIRE(dim_ok(dim), "ar_eval_sums: dim %d unsupported", dim);
+  if (n <= 0) return AR_OK;
+  int blocks = (int)std::min<int64_t>(ceil_div(n, kRowWarps), (int64_t)num_sms() * 8);
+  AR_DISPATCH_NV(dim, predict_kernel<NV, true><<<blocks, kRowThreads, 0, (cudaStream_t)stream>>>(
+                          U, A, dim, head, bn_moving, iu, ia, label, n, nullptr, sums));
+  AR_LAUNCH_CHECK();
+  return AR_OK;
+}
+
+extern "C" int ar_sumsq(const float* W, int64_t n_elems, double* out, void* stream) {
+  AR_REQUIRE(W && out, "ar_sumsq: null pointer");
+  AR_REQUIRE(n_elems % 4 == 0, "ar_sumsq: n_elems must be a multiple of 4");
+  if (n_elems == 0) return AR_OK;
+  int blocks = (int)std::min<int64_t>(ceil_div(n_elems / 4, 256), (int64_t)num_sms() * 8);
+  sumsq_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(W, n_elems / 4, out);
+  AR_LAUNCH_CHECK();
+  return AR_OK;
+}

@@ -1,0 +1,407 @@
+"""Keras-like facade over the CUDA training path (host-side mirror of the reference interface).
+
+Mirrors the object surface the reference's components use:
+`Model.fit(x=[users, animes], y, batch_size, epochs, verbose, validation_data, callbacks)` ->
+`.history` (neural_network.py:210-217,223), `Model.save(path)` (:221), `load_model(path)`
+(similar_anime.py:132), `Model.get_layer(name).get_weights()[0]` (similar_anime.py:155-157),
+`Model.predict([user_arr, anime_arr])` -> (M,1) float32 (model_recs.py:394).
+
+All arithmetic runs in libanimerec.so (hand-written sm_100a CUDA); torch only owns the device
+buffers.  There is no CPU fallback: constructing a model without a CUDA device raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+import time
+
+import numpy as np
+import torch
+
+from . import _capi
+from ._capi import ArPlan, ArTable, ArTrainCtx, check, lib, ptr, stream_ptr
+from . import weights_io
+
+BETA1, BETA2 = 0.9, 0.999
+PLAN_CHUNK = 256
+
+
+def adam_alpha_table(lr, t_first, count):
+    """alpha_t = lr*sqrt(1-b2^t)/(1-b1^t) in float32 for t = t_first .. t_first+count-1 (Keras Adam)."""
+    t = np.arange(t_first, t_first + count, dtype=np.float32)
+    b1p = np.power(np.float32(BETA1), t)
+    b2p = np.power(np.float32(BETA2), t)
+    return (np.float32(lr) * np.sqrt(np.float32(1) - b2p) / (np.float32(1) - b1p)).astype(np.float32)
+
+
+def he_normal_scalar(rng):
+    """Dense(1) kernel (1,1) under kernel_initializer='he_normal' (config.yaml:56)."""
+    sd = math.sqrt(2.0) / 0.87962566103423978
+    while True:
+        x = rng.standard_normal()
+        if abs(x) <= 2.0:
+            return np.float32(x * sd)
+
+
+class History:
+    def __init__(self):
+        self.history = {}
+        self.epoch = []
+
+
+class _EmbeddingLayer:
+    def __init__(self, model, which, name):
+        self._model, self._which, self.name = model, which, name
+
+    def get_weights(self):
+        self._model._sync_tables()
+        t = self._model.U if self._which == "user" else self._model.A
+        return [t.detach().cpu().numpy()]
+
+
+class _ScalarLayer:
+    def __init__(self, name, getter):
+        self.name, self._getter = name, getter
+
+    def get_weights(self):
+        return self._getter()
+
+
+class EmbeddingDotModel:
+    """The model of neural_network.py:66-106 with its optimizer state, resident in HBM."""
+
+    def __init__(self, n_users, n_anime, embedding_size=128, l2_reg_factor=1e-4,
+                 kernel_initializer="he_normal", ID_emb_name="user_embedding",
+                 anime_emb_name="anime_embedding", merged_name="dot_product", seed=None,
+                 device=None, adam_mode="replay", dense_kernel=None):
+        if not torch.cuda.is_available():
+            raise _capi.AnimerecError("EmbeddingDotModel needs a CUDA device (sm_100a); there is no CPU fallback")
+        lib()
+        check(lib().ar_check_device(), "ar_check_device")
+        if adam_mode not in _capi.ADAM_MODES:
+            raise ValueError("adam_mode must be one of %s" % list(_capi.ADAM_MODES))
+        D = int(embedding_size)
+        if D % 4 or not 0 < D <= 512:
+            raise ValueError("embedding_size must be a multiple of 4 in (0, 512]")
+        self.device = torch.device(device or "cuda:%d" % torch.cuda.current_device())
+        self.n_users, self.n_anime, self.dim = int(n_users), int(n_anime), D
+        self.l2 = float(l2_reg_factor)
+        self.adam_mode = adam_mode
+        self.names = dict(user=ID_emb_name, anime=anime_emb_name, merged=merged_name)
+        rng = np.random.RandomState(seed)
+        if kernel_initializer != "he_normal" and dense_kernel is None:
+            raise ValueError("only kernel_initializer='he_normal' (config.yaml:56) or an explicit dense_kernel")
+        U = rng.uniform(-0.05, 0.05, size=(self.n_users, D)).astype(np.float32)
+        A = rng.uniform(-0.05, 0.05, size=(self.n_anime, D)).astype(np.float32)
+        w = he_normal_scalar(rng) if dense_kernel is None else np.float32(dense_kernel)
+        self._alloc(U, A, np.array([w, 0.0, 1.0, 0.0], np.float32), np.array([0.0, 1.0], np.float32))
+        self.iterations = 0
+        self.lr = 1e-3                      # Keras Adam default until a LearningRateScheduler sets it
+        self.stop_training = False
+        self.history = None
+        self._alpha = None                  # device alpha table, index = global step
+        self._alpha_host = np.zeros(1, np.float32)
+        self.timings = {}
+
+    # ------------------------------------------------------------------ state
+    def _alloc(self, U, A, head, bn):
+        dev = self.device
+        f = dict(dtype=torch.float32, device=dev)
+        self.U = torch.from_numpy(np.ascontiguousarray(U, np.float32)).to(dev)
+        self.A = torch.from_numpy(np.ascontiguousarray(A, np.float32)).to(dev)
+        self.mU, self.vU = torch.zeros_like(self.U), torch.zeros_like(self.U)
+        self.mA, self.vA = torch.zeros_like(self.A), torch.zeros_like(self.A)
+        self.lastU = torch.zeros(self.n_users, dtype=torch.int32, device=dev)
+        self.lastA = torch.zeros(self.n_anime, dtype=torch.int32, device=dev)
+        self.head = torch.from_numpy(np.asarray(head, np.float32)).to(dev)
+        self.head_m = torch.zeros(4, **f)
+        self.head_v = torch.zeros(4, **f)
+        self.bn_moving = torch.from_numpy(np.asarray(bn, np.float32)).to(dev)
+
+    def _table(self, which):
+        t = ArTable()
+        if which == "user":
+            t.n_rows, t.dim = self.n_users, self.dim
+            t.W, t.m, t.v, t.last_step = (x.data_ptr() for x in (self.U, self.mU, self.vU, self.lastU))
+        else:
+            t.n_rows, t.dim = self.n_anime, self.dim
+            t.W, t.m, t.v, t.last_step = (x.data_ptr() for x in (self.A, self.mA, self.vA, self.lastA))
+        return t
+
+    def _ensure_alpha(self, upto):
+        """Device alpha table covering global steps [0, upto]."""
+        if self._alpha is None or self._alpha.numel() <= upto:
+            n = max(upto + 1, 2 * (0 if self._alpha is None else self._alpha.numel()))
+            host = np.zeros(n, np.float32)
+            host[:len(self._alpha_host)] = self._alpha_host
+            self._alpha_host = host
+            self._alpha = torch.from_numpy(host).to(self.device)
+
+    def _set_alpha(self, lr, t_first, count):
+        self._ensure_alpha(t_first + count)
+        vals = adam_alpha_table(lr, t_first, count)
+        self._alpha_host[t_first:t_first + count] = vals
+        self._alpha[t_first:t_first + count].copy_(torch.from_numpy(vals), non_blocking=False)
+
+    def _sync_tables(self):
+        """In replay mode rows lag behind; replay every row up to the current optimizer step."""
+        if self.adam_mode != "replay" or self.iterations == 0:
+            return
+        self._ensure_alpha(self.iterations)
+        st = stream_ptr()
+        for which in ("user", "anime"):
+            t = self._table(which)
+            check(lib().ar_table_flush(C.byref(t), ptr(self._alpha), self.l2, self.iterations, st), "ar_table_flush")
+
+    def reg_sumsq(self):
+        """sum U^2 + sum A^2 of the current (synchronised) tables, float64 on host."""
+        self._sync_tables()
+        out = torch.zeros(1, dtype=torch.float64, device=self.device)
+        st = stream_ptr()
+        check(lib().ar_sumsq(ptr(self.U), self.U.numel(), ptr(out), st), "ar_sumsq")
+        check(lib().ar_sumsq(ptr(self.A), self.A.numel(), ptr(out), st), "ar_sumsq")
+        return float(out.item())
+
+    # ------------------------------------------------------------------ Keras surface
+    def get_layer(self, name):
+        if name == self.names["user"]:
+            return _EmbeddingLayer(self, "user", name)
+        if name == self.names["anime"]:
+            return _EmbeddingLayer(self, "anime", name)
+        if name == "dense":
+            return _ScalarLayer(name, lambda: [self.head[0:1].cpu().numpy().reshape(1, 1), self.head[1:2].cpu().numpy()])
+        if name == "batch_normalization":
+            return _ScalarLayer(name, lambda: [self.head[2:3].cpu().numpy(), self.head[3:4].cpu().numpy(),
+                                               self.bn_moving[0:1].cpu().numpy(), self.bn_moving[1:2].cpu().numpy()])
+        raise ValueError("No such layer: %s. Existing layers are: %s" % (
+            name, [self.names["user"], self.names["anime"], self.names["merged"], "dense", "batch_normalization"]))
+
+    def get_weights(self):
+        """[user table, anime table, dense kernel, dense bias, gamma, beta, moving_mean, moving_variance]."""
+        self._sync_tables()
+        h, b = self.head.cpu().numpy(), self.bn_moving.cpu().numpy()
+        return [self.U.cpu().numpy(), self.A.cpu().numpy(), h[0:1].reshape(1, 1), h[1:2], h[2:3], h[3:4],
+                b[0:1], b[1:2]]
+
+    def set_weights(self, w):
+        self._sync_tables()
+        self.U.copy_(torch.from_numpy(np.ascontiguousarray(w[0], np.float32)))
+        self.A.copy_(torch.from_numpy(np.ascontiguousarray(w[1], np.float32)))
+        head = np.array([np.ravel(w[2])[0], np.ravel(w[3])[0], np.ravel(w[4])[0], np.ravel(w[5])[0]], np.float32)
+        self.head.copy_(torch.from_numpy(head))
+        self.bn_moving.copy_(torch.from_numpy(np.array([np.ravel(w[6])[0], np.ravel(w[7])[0]], np.float32)))
+
+    def _device_weights(self):
+        self._sync_tables()
+        return [self.U.clone(), self.A.clone(), self.head.clone(), self.bn_moving.clone()]
+
+    def _restore_device_weights(self, w):
+        self._sync_tables()
+        self.U.copy_(w[0]); self.A.copy_(w[1]); self.head.copy_(w[2]); self.bn_moving.copy_(w[3])
+
+    @staticmethod
+    def _as_idx(a, dev):
+        if isinstance(a, torch.Tensor):
+            return a.to(device=dev, dtype=torch.int32).reshape(-1).contiguous()
+        a = np.asarray(a).reshape(-1)
+        if a.dtype.kind == "f":          # Keras Input(shape=[1]) carries ids as float32
+            a = a.astype(np.int64)
+        return torch.from_numpy(np.ascontiguousarray(a, np.int32)).to(dev)
+
+    @staticmethod
+    def _as_f32(a, dev):
+        if isinstance(a, torch.Tensor):
+            return a.to(device=dev, dtype=torch.float32).reshape(-1).contiguous()
+        return torch.from_numpy(np.ascontiguousarray(np.asarray(a, np.float64).reshape(-1), np.float32)).to(dev)
+
+    def predict(self, x, verbose=0, batch_size=None):
+        """model.predict([user_arr, anime_arr]) -> (M,1) float32, inference-mode BatchNorm."""
+        self._sync_tables()
+        iu, ia = self._as_idx(x[0], self.device), self._as_idx(x[1], self.device)
+        if iu.numel() != ia.numel():
+            raise ValueError("user and anime index arrays differ in length")
+        self._check_range(iu, ia)
+        out = torch.empty(iu.numel(), dtype=torch.float32, device=self.device)
+        check(lib().ar_predict(ptr(self.U), ptr(self.A), self.dim, ptr(self.head), ptr(self.bn_moving),
+                               ptr(iu), ptr(ia), iu.numel(), ptr(out), stream_ptr()), "ar_predict")
+        return out.cpu().numpy().reshape(-1, 1)
+
+    def _check_range(self, iu, ia):
+        if iu.numel() and (int(iu.min()) < 0 or int(iu.max()) >= self.n_users):
+            raise IndexError("user index outside [0, %d)" % self.n_users)
+        if ia.numel() and (int(ia.min()) < 0 or int(ia.max()) >= self.n_anime):
+            raise IndexError("anime index outside [0, %d)" % self.n_anime)
+
+    def evaluate(self, x, y, batch_size=None, verbose=0, return_dict=True):
+        """Keras test pass: inference BN, loss = mean BCE + l2*(sum U^2 + sum A^2), mse."""
+        self._sync_tables()
+        iu, ia = self._as_idx(x[0], self.device), self._as_idx(x[1], self.device)
+        t = self._as_f32(y, self.device)
+        self._check_range(iu, ia)
+        sums = torch.zeros(2, dtype=torch.float64, device=self.device)
+        check(lib().ar_eval_sums(ptr(self.U), ptr(self.A), self.dim, ptr(self.head), ptr(self.bn_moving),
+                                 ptr(iu), ptr(ia), ptr(t), iu.numel(), ptr(sums), stream_ptr()), "ar_eval_sums")
+        s = sums.cpu().numpy()
+        n = max(1, iu.numel())
+        reg = self.l2 * self.reg_sumsq()
+        out = dict(loss=s[0] / n + reg, mse=s[1] / n, bce=s[0] / n, reg=reg)
+        return out if return_dict else [out["loss"], out["mse"]]
+
+    # ------------------------------------------------------------------ training
+    def _make_plan(self, n_slots, batch):
+        dev = self.device
+        hc = batch // _capi.AR_HEAVY_LEN + 1
+        bufs = dict(order=torch.empty((n_slots, batch), dtype=torch.int32, device=dev),
+                    uniq=torch.empty((n_slots, batch), dtype=torch.int32, device=dev),
+                    off=torch.empty((n_slots, batch + 1), dtype=torch.int32, device=dev),
+                    meta=torch.zeros((n_slots, 4), dtype=torch.int32, device=dev),
+                    heavy=torch.empty((n_slots, hc), dtype=torch.int32, device=dev))
+        p = ArPlan()
+        p.batch_cap, p.heavy_cap, p.n_slots = batch, hc, n_slots
+        for k, v in bufs.items():
+            setattr(p, k, v.data_ptr())
+        return p, bufs
+
+    def fit(self, x, y, batch_size=10000, epochs=1, verbose=0, validation_data=None, callbacks=None,
+            shuffle="numpy", shuffle_seed=0, initial_epoch=0):
+        """model.fit of neural_network.py:210-217.
+
+        shuffle: "numpy"  -> np.random.RandomState(shuffle_seed + epoch).permutation(n) (the oracle's
+                             documented rule; Keras' own shuffle is unseeded),
+                 "device" -> torch.randperm on the GPU (fast path for 1e8 samples),
+                 False    -> keep the given order.
+        """
+        dev = self.device
+        iu_all, ia_all = self._as_idx(x[0], dev), self._as_idx(x[1], dev)
+        y_all = self._as_f32(y, dev)
+        N = iu_all.numel()
+        if not (ia_all.numel() == N == y_all.numel()) or N == 0:
+            raise ValueError("x[0], x[1] and y must be non-empty and of equal length")
+        B = int(batch_size)
+        if not 0 < B <= _capi.AR_MAX_BATCH:
+            raise ValueError("batch_size must be in (0, %d]" % _capi.AR_MAX_BATCH)
+        self._check_range(iu_all, ia_all)
+        steps = (N + B - 1) // B
+        D = self.dim
+        n_slots = min(steps, PLAN_CHUNK)
+        plan_u, keep_u = self._make_plan(n_slots, B)
+        plan_a, keep_a = self._make_plan(n_slots, B)
+        f = dict(dtype=torch.float32, device=dev)
+        uh, ah = torch.empty((B, D), **f), torch.empty((B, D), **f)
+        c, ru, ra, dc = (torch.empty(B, **f) for _ in range(4))
+        t_end = self.iterations + epochs * steps
+        self._ensure_alpha(t_end)
+        metrics = torch.zeros((t_end + 1, 4), **f)
+        dense = self.adam_mode == "dense"
+        reg_ss = torch.zeros((t_end + 1, 32), dtype=torch.float64, device=dev) if dense else None
+
+        callbacks = list(callbacks or [])
+        for cb in callbacks:
+            cb.set_model(self)
+        hist = History()
+        self.history = hist
+        self.stop_training = False
+        for cb in callbacks:
+            cb.on_train_begin()
+        val = None
+        if validation_data is not None:
+            (vx, vy) = validation_data[0], validation_data[1]
+            val = (self._as_idx(vx[0], dev), self._as_idx(vx[1], dev), self._as_f32(vy, dev))
+            self._check_range(val[0], val[1])
+        st = stream_ptr()
+        L = lib()
+        for epoch in range(initial_epoch, epochs):
+            t_epoch = time.perf_counter()
+            for cb in callbacks:
+                cb.on_epoch_begin(epoch)
+            lr = float(self.lr)
+            t0 = self.iterations
+            self._set_alpha(lr, t0 + 1, steps)
+            if shuffle == "numpy":
+                perm = torch.from_numpy(np.random.RandomState(shuffle_seed + epoch).permutation(N)).to(dev)
+            elif shuffle == "device":
+                g = torch.Generator(device=dev)
+                g.manual_seed(shuffle_seed + epoch)
+                perm = torch.randperm(N, device=dev, generator=g)
+            elif shuffle in (False, None, "none"):
+                perm = None
+            else:
+                raise ValueError("shuffle must be 'numpy', 'device' or False")
+            if perm is None:
+                iu_e, ia_e, y_e = iu_all, ia_all, y_all
+            else:
+                iu_e, ia_e, y_e = iu_all[perm].contiguous(), ia_all[perm].contiguous(), y_all[perm].contiguous()
+            reg0 = None if dense else self.l2 * self.reg_sumsq()
+
+            ctx = ArTrainCtx()
+            ctx.users, ctx.anime = self._table("user"), self._table("anime")
+            ctx.head, ctx.head_m, ctx.head_v = self.head.data_ptr(), self.head_m.data_ptr(), self.head_v.data_ptr()
+            ctx.bn_moving, ctx.alpha = self.bn_moving.data_ptr(), self._alpha.data_ptr()
+            ctx.iu, ctx.ia, ctx.label = iu_e.data_ptr(), ia_e.data_ptr(), y_e.data_ptr()
+            ctx.n_samples, ctx.batch, ctx.l2 = N, B, self.l2
+            ctx.mode = _capi.ADAM_MODES[self.adam_mode]
+            ctx.plan_u, ctx.plan_a = plan_u, plan_a
+            ctx.uh, ctx.ah, ctx.c, ctx.ru, ctx.ra, ctx.dc = (z.data_ptr() for z in (uh, ah, c, ru, ra, dc))
+            ctx.metrics = metrics.data_ptr()
+            ctx.reg_sumsq = reg_ss.data_ptr() if dense else None
+            for s0 in range(0, steps, n_slots):
+                ns = min(n_slots, steps - s0)
+                check(L.ar_plan_build(ptr(iu_e), N, B, s0, ns, C.byref(plan_u), st), "ar_plan_build(users)")
+                check(L.ar_plan_build(ptr(ia_e), N, B, s0, ns, C.byref(plan_a), st), "ar_plan_build(anime)")
+                check(L.ar_train_steps(C.byref(ctx), s0, 0, t0 + s0, ns, st), "ar_train_steps")
+            self.iterations = t0 + steps
+            self._sync_tables()
+
+            m = metrics[t0 + 1:t0 + steps + 1].cpu().numpy().astype(np.float64)
+            w = m[:, 2]
+            bce = float((m[:, 0] * w).sum() / N)
+            mse = float((m[:, 1] * w).sum() / N)
+            reg1 = self.l2 * self.reg_sumsq()
+            if dense:
+                r = self.l2 * reg_ss[t0 + 1:t0 + steps + 1].sum(dim=1).cpu().numpy()
+                reg = float((r * w).sum() / N)
+            else:
+                reg = 0.5 * (reg0 + reg1)   # regulariser is only evaluated at the epoch's flush points
+            logs = dict(loss=bce + reg, mse=mse)
+            if val is not None:
+                sums = torch.zeros(2, dtype=torch.float64, device=dev)
+                check(L.ar_eval_sums(ptr(self.U), ptr(self.A), D, ptr(self.head), ptr(self.bn_moving),
+                                     ptr(val[0]), ptr(val[1]), ptr(val[2]), val[0].numel(), ptr(sums), st),
+                      "ar_eval_sums")
+                sv = sums.cpu().numpy()
+                nv = max(1, val[0].numel())
+                logs["val_loss"] = float(sv[0] / nv + reg1)
+                logs["val_mse"] = float(sv[1] / nv)
+            logs["lr"] = float(np.float32(lr))
+            self.timings.setdefault("epoch_s", []).append(time.perf_counter() - t_epoch)
+            self.last_epoch_parts = dict(bce=bce, reg=reg, reg_end=reg1)
+            for k, v in logs.items():
+                hist.history.setdefault(k, []).append(v)
+            hist.epoch.append(epoch)
+            if verbose:
+                print("Epoch %d/%d - %.2fs - %s" % (epoch + 1, epochs, self.timings["epoch_s"][-1],
+                                                     " - ".join("%s: %.6g" % kv for kv in logs.items())))
+            for cb in callbacks:
+                cb.on_epoch_end(epoch, logs)
+            if self.stop_training:
+                break
+        for cb in callbacks:
+            cb.on_train_end()
+        del keep_u, keep_a
+        return hist
+
+    # ------------------------------------------------------------------ persistence
+    def save(self, path, include_optimizer=True):
+        """model.save(path): full model in the Keras-2.12 H5 name layout (SURVEY §5 checkpoint row)."""
+        weights_io.save_model(self, path, include_optimizer=include_optimizer)
+
+    def save_weights(self, path):
+        weights_io.save_model(self, path, include_optimizer=False, weights_only=True)
+
+    def load_weights(self, path):
+        weights_io.load_into(self, path)
+
+
+def load_model(path, device=None, adam_mode="replay"):
+    """tf.keras.models.load_model replacement (similar_anime.py:132, model_recs.py:204)."""
+    return weights_io.load_model(path, device=device, adam_mode=adam_mode)

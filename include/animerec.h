@@ -1,0 +1,194 @@
+/*
+ * animerec.h -- C-ABI of libanimerec.so: the B200 (sm_100a) hot path of
+ * Dyrutter/anime_recommendations.
+ *
+ * The reference has no FFI of its own (it is pure Python on TensorFlow/NumPy,
+ * SURVEY.md §8b), so every entry point below names the reference call site whose
+ * arithmetic it replaces.  Conventions:
+ *   - plain C types only; every pointer is a DEVICE pointer owned by the caller
+ *     (torch tensors on the Python side) unless it is marked "host";
+ *   - `stream` is a cudaStream_t passed as void*; calls are asynchronous on it and
+ *     never synchronise unless documented;
+ *   - return 0 on success, a negative ar_status otherwise; ar_last_error() returns
+ *     a thread-local message; nothing throws;
+ *   - tables are row-major float32 (n_rows, dim), dim % 4 == 0, dim <= 512,
+ *     16-byte aligned.
+ */
+#ifndef ANIMEREC_H_
+#define ANIMEREC_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum {
+  AR_OK = 0,
+  AR_ERR_INVALID = -1,     /* bad argument (null pointer, dim, k, batch too large ...) */
+  AR_ERR_CUDA = -2,        /* a CUDA runtime call or launch failed */
+  AR_ERR_UNSUPPORTED = -3, /* valid request this build cannot serve */
+  AR_ERR_NCCL = -4
+} ar_status;
+
+const char* ar_last_error(void);
+/* version of this ABI; bumped on any signature change */
+int ar_abi_version(void);
+/* 0 when a device with compute capability 10.x is current, AR_ERR_UNSUPPORTED otherwise */
+int ar_check_device(void);
+
+/* ------------------------------------------------------------------ Half A: training
+ * Replaces the TensorFlow train_step behind `model.fit` (neural_network.py:210-217) for the
+ * model of neural_network.py:66-106.
+ */
+
+#define AR_MAX_BATCH 16384   /* per-step samples the in-shared-memory plan sort handles */
+#define AR_HEAVY_LEN 64      /* rows hit by more than this many samples of one step take the CTA path */
+
+/* One embedding table and its Adam slots (Keras: Embedding.embeddings + optimizer m, v). */
+typedef struct {
+  int32_t n_rows;
+  int32_t dim;
+  float* W;
+  float* m;
+  float* v;
+  int32_t* last_step; /* (n_rows) optimizer step (1-based) already applied to the row; 0 = none */
+} ar_table;
+
+/* Per-step dedup plan of one table: samples grouped by row (stable, ascending row).
+ * Arrays hold `n_slots` consecutive steps. */
+typedef struct {
+  int32_t batch_cap;  /* stride of order/uniq; off has stride batch_cap+1 */
+  int32_t heavy_cap;  /* stride of heavy */
+  int32_t n_slots;
+  int32_t* order;     /* [slot][batch_cap]  sample id within the step, sorted by (row, sample) */
+  int32_t* uniq;      /* [slot][batch_cap]  distinct rows ascending */
+  int32_t* off;       /* [slot][batch_cap+1] segment starts into order; off[n_uniq] = n */
+  int32_t* meta;      /* [slot][4]  n_uniq, n_heavy, n (samples in the step), 0 */
+  int32_t* heavy;     /* [slot][heavy_cap] segment ids longer than AR_HEAVY_LEN */
+} ar_plan;
+
+/* Build the plan of `n_steps` consecutive steps of one table.  Step s (0-based within the
+ * call) covers idx[(step0+s)*batch : min(n_total, (step0+s+1)*batch)] and is written to slot s.
+ * idx values must lie in [0, n_rows).  batch <= AR_MAX_BATCH.
+ * Replaces TF's IndexedSlices -> UnsortedSegmentSum aggregation. */
+int ar_plan_build(const int32_t* idx, int64_t n_total, int32_t batch, int64_t step0,
+                  int32_t n_steps, const ar_plan* plan, void* stream);
+
+typedef enum {
+  AR_ADAM_REPLAY = 0,  /* reference-equivalent: missed dense steps of a row are replayed when it is next touched */
+  AR_ADAM_DENSE = 1,   /* reference-literal: every row of both tables is updated every step */
+  AR_ADAM_TOUCHED = 2  /* north-star literal: rows absent from the batch are left alone (NOT the reference's arithmetic) */
+} ar_adam_mode;
+
+/* Everything one training run needs; all pointers are device pointers. */
+typedef struct {
+  ar_table users;
+  ar_table anime;
+  float* head;         /* [4] Dense kernel w, Dense bias b, BN gamma, BN beta  (neural_network.py:97-99) */
+  float* head_m;       /* [4] Adam m */
+  float* head_v;       /* [4] Adam v */
+  float* bn_moving;    /* [2] moving_mean, moving_variance */
+  const float* alpha;  /* alpha[t] = lr_t*sqrt(1-b2^t)/(1-b1^t) for global 1-based step t (alpha[0] unused) */
+  const int32_t* iu;   /* (n_samples) user row per sample, epoch visit order */
+  const int32_t* ia;   /* (n_samples) anime row per sample */
+  const float* label;  /* (n_samples) rating in [0,1] */
+  int64_t n_samples;
+  int32_t batch;
+  float l2;            /* embeddings_regularizer factor (config l2_reg_factor) */
+  int32_t mode;        /* ar_adam_mode */
+  ar_plan plan_u;
+  ar_plan plan_a;
+  /* per-step scratch, each sized for `batch` samples */
+  float* uh;           /* (batch, dim) normalised user rows of the step */
+  float* ah;           /* (batch, dim) normalised anime rows */
+  float* c;            /* (batch) cosine */
+  float* ru;           /* (batch) 1/||u|| */
+  float* ra;           /* (batch) 1/||a|| */
+  float* dc;           /* (batch) dLoss/dc */
+  /* per-step outputs, indexed by global step t (1-based): metrics[t*4 + {0: mean BCE, 1: mean
+   * squared error, 2: n, 3: batch mean of z}] ; reg_sumsq[t] = sum U^2 + sum A^2 BEFORE step t
+   * (written in AR_ADAM_DENSE only; may be null) */
+  float* metrics;
+  double* reg_sumsq;
+} ar_train_ctx;
+
+/* Run `n_steps` consecutive training steps.  Epoch-local step e = epoch_step0 + s reads samples
+ * [e*batch, min(n_samples,(e+1)*batch)) and plan slot `slot0 + s`; its global Adam step is
+ * t = t0 + s + 1.  Replaces Keras Model.train_step x n_steps. */
+int ar_train_steps(const ar_train_ctx* ctx, int64_t epoch_step0, int32_t slot0, int64_t t0,
+                   int32_t n_steps, void* stream);
+
+/* Bring every row of the table to optimizer step t_target by replaying its missed pure-L2 steps
+ * (no-op per row when last_step >= t_target).  Used at epoch end / before validation, saving and
+ * similarity in AR_ADAM_REPLAY, and as the "all other rows" half of a dense step. */
+int ar_table_flush(const ar_table* tab, const float* alpha, float l2, int64_t t_target, void* stream);
+
+/* Individual stages (the kernels ar_train_steps chains), exported for unit parity tests. */
+int ar_embed_fwd(const float* U, const float* A, int32_t dim, const int32_t* iu, const int32_t* ia,
+                 int32_t n, float* uh, float* ah, float* c, float* ru, float* ra, void* stream);
+int ar_head_step(const float* c, const float* label, int32_t n, float* head, float* head_m,
+                 float* head_v, float* bn_moving, const float* alpha, int64_t t, float* dc,
+                 float* metrics_row, void* stream);
+int ar_rows_catchup(const ar_table* tab, const ar_plan* plan, int32_t slot, const float* alpha,
+                    float l2, int64_t t, void* stream);
+int ar_rows_update(const ar_table* tab, const ar_plan* plan, int32_t slot, const float* other_hat,
+                   const float* c, const float* dc, const float* rinv, const float* alpha, float l2,
+                   int64_t t, int32_t replay, double* sumsq_out, void* stream);
+
+/* Inference forward, Keras `model.predict([users, animes])` (model_recs.py:394): BN uses the
+ * moving statistics.  out: (n) float32 probabilities. */
+int ar_predict(const float* U, const float* A, int32_t dim, const float* head, const float* bn_moving,
+               const int32_t* iu, const int32_t* ia, int64_t n, float* out, void* stream);
+/* Validation pass (Keras test_step): adds sum of BCE-from-logits and of squared error over the n
+ * samples to sums[0], sums[1] (double, caller zeroes them). */
+int ar_eval_sums(const float* U, const float* A, int32_t dim, const float* head, const float* bn_moving,
+                 const int32_t* iu, const int32_t* ia, const float* label, int64_t n, double* sums,
+                 void* stream);
+/* out[0] += sum of squares of the table (L2 regulariser term, neural_network.py:73). */
+int ar_sumsq(const float* W, int64_t n_elems, double* out, void* stream);
+
+/* ------------------------------------------------------------------ Half B: cosine top-k */
+
+/* out = W / ||W||_2 per row, the reference's get_weights (similar_anime.py:159-170).  Only used to
+ * export normalised tables; the top-k kernels fuse the normalisation. */
+int ar_rownorm(const float* W, int64_t n_rows, int32_t dim, float* out, void* stream);
+
+/* Single-query cosine top-k: dists = np.dot(Wn, Wn[q]); rank (similar_anime.py:404-468,
+ * similar_users.py:293-312).  cand_mask: optional bitmask, bit r set = row r is a candidate
+ * ((n_rows+31)/32 words).  exclude: row to drop (-1 none).  Results sorted by (score desc, row asc);
+ * unfilled slots hold idx -1 / score -inf.  workspace: >= ar_topk_query_workspace(n_rows,k) bytes. */
+int64_t ar_topk_query_workspace(int64_t n_rows, int32_t k);
+int ar_cosine_topk_query(const float* W, int64_t n_rows, int32_t dim, int64_t q,
+                         const uint32_t* cand_mask, int64_t exclude, int32_t k, int32_t* out_idx,
+                         float* out_score, void* workspace, void* stream);
+
+/* Merge `n_lists` partial top-k lists per query (lists[l][query][k], global row ids) into one. */
+int ar_topk_merge(const int32_t* idx, const float* score, int32_t n_lists, int64_t n_queries,
+                  int32_t k_in, int32_t k_out, int32_t* out_idx, float* out_score, void* stream);
+
+/* Exact fp32 re-rank: for each query row, score the n_cand candidate rows (cand[query][n_cand],
+ * -1 = empty) with fp32 cosine and keep the best k.  Q rows come from Wq[q0 + i], candidates from Wc. */
+int ar_cosine_rerank(const float* Wq, int64_t q0, int64_t n_queries, const float* Wc, int32_t dim,
+                     const int32_t* cand, int32_t n_cand, int32_t k, int32_t* out_idx,
+                     float* out_score, void* stream);
+
+/* All-pairs / many-query cosine candidates on the tensor cores (tcgen05, bf16 operands, fp32
+ * accumulation in TMEM): for query rows [q0, q0+n_q) of Qn and candidate rows [c0, c0+n_c) of Cn
+ * (both ROW-NORMALISED bf16, produced by ar_rownorm_bf16), keep per query the kprime best
+ * candidates by bf16 score.  exclude_self: drop candidate == query row id (same-table case).
+ * watched (optional): bit matrix [n_q][ (n_c_total+31)/32 ] words, bit set = drop.  sign: +1/-1,
+ * ranks by sign*score (model_recs with a negative Dense kernel).
+ * out_idx/out_score: [n_q][kprime].  workspace from ar_allpairs_workspace(). */
+int ar_rownorm_bf16(const float* W, int64_t n_rows, int32_t dim, void* out_bf16, void* stream);
+int64_t ar_allpairs_workspace(int64_t n_q, int32_t kprime);
+int ar_cosine_topk_allpairs(const void* Qn_bf16, int64_t q0, int64_t n_q, const void* Cn_bf16,
+                            int64_t c0, int64_t n_c, int64_t c_total, int32_t dim, int32_t kprime,
+                            int32_t exclude_self, const uint32_t* watched, int64_t watched_stride,
+                            float sign, int32_t* out_idx, float* out_score, void* workspace,
+                            void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ANIMEREC_H_ */

@@ -1,0 +1,263 @@
+"""GPU parity: the CUDA training path (through the C-ABI) against oracle/train.py.
+
+Tolerances (stated once, used everywhere below):
+  per-step loss / mse          |d| <= 2e-6 + 2e-6*|x|   (fp32 sums of ~1e4 terms, double accum on GPU)
+  updated table rows, m, v     |d| <= 2e-7 + 2e-5*|x|   after a few steps (fp32 reassociation in the
+                                                         D-length and per-row segment sums)
+  head w, gamma, beta          same as rows; Dense bias b only loosely (its gradient is 0 + noise)
+  replay mode vs dense mode    BIT-EXACT (same op order, tests/test_oracle_train.py proves the identity)
+"""
+import ctypes as C
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import train as ot
+
+pytestmark = pytest.mark.gpu
+
+if torch.cuda.is_available():
+    import anime_recommendations_b200 as ar
+    from anime_recommendations_b200 import _capi
+    from gpu_util import DEV, dev, make_plan, make_table, check, lib, ptr, stream_ptr
+
+ROW_TOL = dict(rtol=2e-5, atol=2e-7)
+
+
+def np_plan(idx):
+    order = np.argsort(idx, kind="stable")
+    rows = idx[order]
+    head = np.r_[True, rows[1:] != rows[:-1]]
+    uniq = rows[head]
+    off = np.r_[np.nonzero(head)[0], len(idx)]
+    return order, uniq, off
+
+
+@pytest.mark.parametrize("batch,n_total,n_rows", [(1000, 3500, 300), (10000, 25000, 350000), (64, 64, 5),
+                                                   (16384, 16384 * 2, 18000), (1, 3, 10)])
+def test_plan_build_matches_numpy(batch, n_total, n_rows):
+    rng = np.random.RandomState(batch)
+    idx = rng.randint(0, n_rows, n_total).astype(np.int32)
+    if batch == 10000:
+        idx[:300] = 7                                   # a heavy row in step 0
+    steps = (n_total + batch - 1) // batch
+    plan, bufs = make_plan(steps, batch)
+    d_idx = dev(idx)
+    check(lib().ar_plan_build(ptr(d_idx), n_total, batch, 0, steps, C.byref(plan), stream_ptr()), "plan")
+    torch.cuda.synchronize()
+    b = {k: v.cpu().numpy() for k, v in bufs.items()}
+    for s in range(steps):
+        part = idx[s * batch:(s + 1) * batch]
+        order, uniq, off = np_plan(part)
+        nu, nh, n, _ = b["meta"][s]
+        assert n == len(part) and nu == len(uniq)
+        np.testing.assert_array_equal(b["order"][s, :n], order)
+        np.testing.assert_array_equal(b["uniq"][s, :nu], uniq)
+        np.testing.assert_array_equal(b["off"][s, :nu + 1], off)
+        heavy = set(np.nonzero(np.diff(off) > _capi.AR_HEAVY_LEN)[0].tolist())
+        assert set(b["heavy"][s, :nh].tolist()) == heavy
+
+
+def test_plan_build_rejects_oversized_batch():
+    plan, _ = make_plan(1, 64)
+    d_idx = dev(np.zeros(10, np.int32))
+    rc = lib().ar_plan_build(ptr(d_idx), 10, _capi.AR_MAX_BATCH + 1, 0, 1, C.byref(plan), stream_ptr())
+    assert rc == -1 and b"batch" in lib().ar_last_error()
+
+
+@pytest.mark.parametrize("dim", [16, 100, 128, 256, 512])
+def test_embed_fwd_matches_oracle(dim):
+    rng = np.random.RandomState(dim)
+    st = ot.init_state(500, 300, dim, seed=1, w=1.0)
+    st.U[3] = 0.0                                       # zero row: hits the 1e-12 clamp
+    st.A[5] *= 1e-8
+    B = 777
+    iu = rng.randint(0, 500, B).astype(np.int32)
+    ia = rng.randint(0, 300, B).astype(np.int32)
+    iu[:4] = 3
+    ia[:9] = 5
+    fw = ot.forward(st, iu, ia, training=True)
+    U, A = dev(st.U), dev(st.A)
+    uh, ah = torch.empty((B, dim), device=DEV), torch.empty((B, dim), device=DEV)
+    c, ru, ra = (torch.empty(B, device=DEV) for _ in range(3))
+    check(lib().ar_embed_fwd(ptr(U), ptr(A), dim, ptr(dev(iu)), ptr(dev(ia)), B, ptr(uh), ptr(ah), ptr(c),
+                             ptr(ru), ptr(ra), stream_ptr()), "fwd")
+    np.testing.assert_allclose(c.cpu().numpy(), fw["c"], rtol=0, atol=1e-6)
+    np.testing.assert_allclose(ru.cpu().numpy(), fw["ru"], rtol=2e-6)
+    np.testing.assert_allclose(ra.cpu().numpy(), fw["ra"], rtol=2e-6)
+    np.testing.assert_allclose(uh.cpu().numpy(), fw["uh"], rtol=2e-6, atol=1e-9)
+    np.testing.assert_allclose(ah.cpu().numpy(), fw["ah"], rtol=2e-6, atol=1e-9)
+
+
+@pytest.mark.parametrize("n", [1, 37, 10000, 16384])
+def test_head_step_matches_oracle(n):
+    rng = np.random.RandomState(n)
+    c = rng.uniform(-1, 1, n).astype(np.float32)
+    t = (rng.randint(0, 11, n) / 10.0).astype(np.float32)
+    head0 = np.array([-1.7, 0.3, 0.8, -0.2], np.float32)
+    st = ot.State(U=np.zeros((1, 4)), A=np.zeros((1, 4)), head=head0, mov_mean=0.1, mov_var=0.9)
+    st.mh[:] = [1e-3, 0, -2e-3, 1e-4]
+    st.vh[:] = [1e-5, 0, 3e-5, 1e-6]
+    w, b, g, be = head0
+    z = w * c + b
+    mu = np.mean(z, dtype=np.float32)
+    var = np.mean((z - mu) ** 2, dtype=np.float32)
+    inv = np.float32(1) / np.sqrt(var + np.float32(1e-3))
+    zh = (z - mu) * inv
+    y = g * zh + be
+    fw = dict(c=c, zh=zh, y=y, p=ot._sigmoid(y), inv=inv)
+    hb = ot.head_backward(fw, t, head0, n)
+    tstep = 17
+    alpha = np.zeros(32, np.float32)
+    alpha[tstep] = ot.adam_alpha(3e-4, tstep)
+    head, hm, hv = st.head.copy(), st.mh.copy(), st.vh.copy()
+    ot._adam_apply(head, hm, hv, hb["ghead"], alpha[tstep], np.float32)
+
+    d = dict(head=dev(head0), hm=dev(st.mh), hv=dev(st.vh), bn=dev(np.array([0.1, 0.9], np.float32)),
+             dc=torch.empty(n, device=DEV), met=torch.zeros(4, device=DEV))
+    check(lib().ar_head_step(ptr(dev(c)), ptr(dev(t)), n, ptr(d["head"]), ptr(d["hm"]), ptr(d["hv"]), ptr(d["bn"]),
+                             ptr(dev(alpha)), tstep, ptr(d["dc"]), ptr(d["met"]), stream_ptr()), "head")
+    scale = np.abs(hb["dc"]).max() + 1e-30
+    np.testing.assert_allclose(d["dc"].cpu().numpy() / scale, hb["dc"] / scale, rtol=0, atol=5e-6)
+    met = d["met"].cpu().numpy()
+    bce = np.mean(ot.bce_from_logits(y, t), dtype=np.float64)
+    mse = np.mean((t - fw["p"]) ** 2, dtype=np.float64)
+    assert abs(met[0] - bce) <= 2e-6 + 2e-6 * abs(bce)
+    assert abs(met[1] - mse) <= 2e-6 + 2e-6 * abs(mse)
+    assert met[2] == n
+    if n > 1:
+        got = d["head"].cpu().numpy()
+        np.testing.assert_allclose(np.delete(got, 1), np.delete(head, 1), rtol=1e-4, atol=1e-7)
+        assert abs(got[1] - head[1]) <= 2 * alpha[tstep] + 1e-7     # bias: noise gradient, bounded by ~alpha
+    bn = d["bn"].cpu().numpy()
+    np.testing.assert_allclose(bn, [0.1 - (0.1 - mu) * 0.01, 0.9 - (0.9 - var) * 0.01], rtol=1e-5, atol=1e-7)
+
+
+def _problem(seed, n_users, n_anime, n, heavy=False):
+    rng = np.random.RandomState(seed)
+    iu = rng.randint(0, n_users, n).astype(np.int32)
+    ia = rng.randint(0, n_anime, n).astype(np.int32)
+    if heavy:
+        ia[rng.rand(n) < 0.3] = 2                       # one anime takes ~30% of every batch (CTA path)
+        iu[rng.rand(n) < 0.1] = 1
+    y = (rng.randint(0, 11, n) / 10.0).astype(np.float32)
+    return iu, ia, y
+
+
+def _model_from_state(st, mode):
+    m = ar.EmbeddingDotModel(st.U.shape[0], st.A.shape[0], st.U.shape[1], l2_reg_factor=1e-4, seed=0,
+                             adam_mode=mode, dense_kernel=1.0)
+    m.set_weights([st.U, st.A, st.head[0:1], st.head[1:2], st.head[2:3], st.head[3:4],
+                   np.array([st.mov_mean]), np.array([st.mov_var])])
+    return m
+
+
+def _compare_model_state(m, st, check_slots=True):
+    w = m.get_weights()
+    np.testing.assert_allclose(w[0], st.U, **ROW_TOL)
+    np.testing.assert_allclose(w[1], st.A, **ROW_TOL)
+    head = np.array([w[2].ravel()[0], w[3][0], w[4][0], w[5][0]])
+    np.testing.assert_allclose(np.delete(head, 1), np.delete(st.head, 1), rtol=1e-4, atol=1e-7)
+    np.testing.assert_allclose([w[6][0], w[7][0]], [st.mov_mean, st.mov_var], rtol=1e-5, atol=1e-7)
+    if check_slots:
+        np.testing.assert_allclose(m.mU.cpu().numpy(), st.mU, rtol=2e-5, atol=1e-9)
+        np.testing.assert_allclose(m.vU.cpu().numpy(), st.vU, rtol=4e-5, atol=1e-14)
+        np.testing.assert_allclose(m.mA.cpu().numpy(), st.mA, rtol=2e-5, atol=1e-9)
+        np.testing.assert_allclose(m.vA.cpu().numpy(), st.vA, rtol=4e-5, atol=1e-14)
+
+
+@pytest.mark.parametrize("mode", ["dense", "replay"])
+@pytest.mark.parametrize("dim,heavy", [(128, False), (64, True), (256, False)])
+def test_fit_matches_reference_arithmetic(mode, dim, heavy):
+    """dense AND replay mode reproduce the oracle's dense Keras step (loss per epoch, rows, slots)."""
+    n_users, n_anime, n, B = 700, 90, 5300, 1000        # 6 steps/epoch, last one partial (300)
+    iu, ia, y = _problem(11, n_users, n_anime, n, heavy)
+    vu, va, vy = _problem(12, n_users, n_anime, 500)
+    st = ot.init_state(n_users, n_anime, dim, seed=5, w=-1.3)
+    lr_kw = dict(start_lr=1e-3, min_lr=1e-3, max_lr=3e-3, rampup_epochs=2, sustain_epochs=0, exp_decay=0.8)
+    m = _model_from_state(st, mode)
+    sched = ar.LearningRateScheduler(lambda e: ar.lrfn(e, **lr_kw))
+    h = m.fit([iu, ia], y, batch_size=B, epochs=3, validation_data=([vu, va], vy), callbacks=[sched],
+              shuffle="numpy", shuffle_seed=0)
+    oh, _ = ot.fit(st, [iu, ia], y, B, 3, ([vu, va], vy), lr_kwargs=lr_kw, shuffle_seed=0, patience=99)
+    assert m.iterations == st.iterations == 18
+    _compare_model_state(m, st)
+    for k in ("mse", "val_loss", "val_mse", "lr"):
+        np.testing.assert_allclose(h.history[k], oh[k], rtol=3e-6, atol=2e-6, err_msg=k)
+    # `loss` = BCE + L2 term; the L2 term is exact per step only in dense mode
+    np.testing.assert_allclose(h.history["loss"], oh["loss"], rtol=3e-6 if mode == "dense" else 2e-4, atol=2e-6)
+    p = m.predict([vu, va])
+    np.testing.assert_allclose(p, ot.predict(st, vu, va), rtol=0, atol=2e-6)
+    assert p.shape == (500, 1) and p.dtype == np.float32
+
+
+def test_touched_mode_matches_its_own_oracle():
+    n_users, n_anime, n, B = 400, 60, 2000, 512
+    iu, ia, y = _problem(21, n_users, n_anime, n)
+    st = ot.init_state(n_users, n_anime, 32, seed=6, w=0.9)
+    m = _model_from_state(st, "touched")
+    m.lr = 2e-3
+    m.fit([iu, ia], y, batch_size=B, epochs=2, shuffle=False)
+    for epoch in range(2):
+        for s in range(0, n, B):
+            ot.train_step_touched_only(st, iu[s:s + B], ia[s:s + B], y[s:s + B], 2e-3)
+    _compare_model_state(m, st)
+
+
+def test_replay_is_bit_identical_to_dense_at_full_table_size():
+    """Size-independent property at cfg2's table shapes: lazy replay == dense Adam, bit for bit."""
+    n_users, n_anime, dim, B = 350000, 18000, 128, 10000
+    n = 4 * B + 1234
+    iu, ia, y = _problem(31, n_users, n_anime, n)
+    out = {}
+    for mode in ("dense", "replay"):
+        m = ar.EmbeddingDotModel(n_users, n_anime, dim, seed=3, adam_mode=mode, dense_kernel=1.0)
+        m.lr = 5e-5
+        h = m.fit([iu, ia], y, batch_size=B, epochs=2, shuffle="device", shuffle_seed=4)
+        m._sync_tables()
+        out[mode] = [t.cpu().numpy() for t in (m.U, m.mU, m.vU, m.A, m.mA, m.vA, m.head, m.bn_moving)]
+        out[mode + "_h"] = h.history
+    for a, b in zip(out["dense"], out["replay"]):
+        np.testing.assert_array_equal(a, b)
+    np.testing.assert_array_equal(out["dense_h"]["mse"], out["replay_h"]["mse"])
+    # rows never touched still moved (dense L2 pull), i.e. the replay really ran
+    assert np.abs(out["replay"][1]).min() > 0
+
+
+def test_early_stopping_checkpoint_and_container_roundtrip(tmp_path):
+    n_users, n_anime, n, B = 300, 50, 3000, 500
+    iu, ia, y = _problem(41, n_users, n_anime, n)
+    vu, va, vy = _problem(42, n_users, n_anime, 400)
+    m = ar.EmbeddingDotModel(n_users, n_anime, 16, seed=1)
+    ck = str(tmp_path / "wandb_main_weights.h5")
+    cbs = [ar.ModelCheckpoint(filepath=ck, save_weights_only=True, monitor="val_loss", mode="min",
+                              save_best_only=True, save_freq="epoch"),
+           ar.LearningRateScheduler(lambda e: 0.05),           # large lr: val_loss turns around quickly
+           ar.EarlyStopping(patience=3, monitor="val_loss", mode="min", restore_best_weights=True)]
+    h = m.fit([iu, ia], y, batch_size=B, epochs=40, validation_data=([vu, va], vy), callbacks=cbs)
+    vl = h.history["val_loss"]
+    assert list(h.history) == ["loss", "mse", "val_loss", "val_mse", "lr"]
+    assert len(vl) < 40 and len(vl) - 1 - int(np.argmin(vl)) == 3     # stopped 3 epochs after the best
+    best = ar.load_model(ck)
+    np.testing.assert_array_equal(best.get_weights()[0], m.get_weights()[0])   # restored best == checkpoint
+    full = str(tmp_path / "wandb_anime_nn.h5")
+    m.save(full)
+    m2 = ar.load_model(full)
+    for a, b in zip(m.get_weights(), m2.get_weights()):
+        np.testing.assert_array_equal(a, b)
+    assert m2.iterations == m.iterations
+    np.testing.assert_array_equal(m2.get_layer("user_embedding").get_weights()[0], m.get_weights()[0])
+    np.testing.assert_array_equal(m.predict([vu, va]), m2.predict([vu, va]))
+    with pytest.raises(ValueError):
+        m.get_layer("nope")
+
+
+def test_index_range_and_batch_limits_raise():
+    m = ar.EmbeddingDotModel(10, 10, 8, seed=1)
+    with pytest.raises(IndexError):
+        m.fit([[0, 10], [0, 1]], [0.5, 0.5], batch_size=2)
+    with pytest.raises(ValueError):
+        m.fit([[0, 1], [0, 1]], [0.5, 0.5], batch_size=_capi.AR_MAX_BATCH + 1)
+    with pytest.raises(IndexError):
+        m.predict([[0], [11]])
