@@ -13,6 +13,7 @@
 // Arithmetic follows oracle/train.py (the restatement of neural_network.py:66-106 under
 // Keras-2.12 semantics); citations there.
 #include <algorithm>
+#include <vector>
 
 #include "common.cuh"
 
@@ -639,18 +640,27 @@ extern "C" int ar_rows_update(const ar_table* tab, const ar_plan* plan, int32_t 
   return launch_update(a, false, c, dc, alpha, l2, t, replay, sumsq_out, (cudaStream_t)stream);
 }
 
-extern "C" int ar_train_steps(const ar_train_ctx* ctx, int64_t epoch_step0, int32_t slot0, int64_t t0,
-                              int32_t n_steps, void* stream) {
-  AR_REQUIRE(ctx, "ar_train_steps: null ctx");
-  const ar_train_ctx& x = *ctx;
-  AR_REQUIRE(x.users.W && x.anime.W && x.head && x.alpha && x.iu && x.ia && x.label, "ar_train_steps: null pointer in ctx");
-  AR_REQUIRE(x.users.dim == x.anime.dim && dim_ok(x.users.dim), "ar_train_steps: dim %d/%d unsupported", x.users.dim, x.anime.dim);
-  AR_REQUIRE(x.batch > 0 && x.batch <= AR_MAX_BATCH, "ar_train_steps: batch %d outside (0,%d]", x.batch, AR_MAX_BATCH);
-  AR_REQUIRE(x.uh && x.ah && x.c && x.ru && x.ra && x.dc && x.metrics, "ar_train_steps: null scratch");
-  AR_REQUIRE(slot0 >= 0 && slot0 + n_steps <= x.plan_u.n_slots && slot0 + n_steps <= x.plan_a.n_slots,
-             "ar_train_steps: plan slots [%d,%d) exceed plan size", slot0, slot0 + n_steps);
-  AR_REQUIRE(x.mode >= AR_ADAM_REPLAY && x.mode <= AR_ADAM_TOUCHED, "ar_train_steps: bad mode %d", x.mode);
-  cudaStream_t st = (cudaStream_t)stream;
+namespace ar {
+// Optional per-stage timing: events bracket every launch of the step (bench.py roofline leg).
+struct StageTimer {
+  std::vector<cudaEvent_t> ev;  // per step: 0 start, 1 after catch-up, 2 after fwd, 3 after head, 4 after update, 5 after dense flush
+  cudaStream_t st;
+  int rec(int) {
+    cudaEvent_t e;
+    AR_CUDA(cudaEventCreate(&e));
+    AR_CUDA(cudaEventRecord(e, st));
+    ev.push_back(e);
+    return AR_OK;
+  }
+};
+#define AR_TICK(i)                          \
+  if (timer) {                              \
+    int rc__ = timer->rec(i);               \
+    if (rc__) return rc__;                  \
+  }
+
+static int run_steps(const ar_train_ctx& x, int64_t epoch_step0, int32_t slot0, int64_t t0, int32_t n_steps,
+                     cudaStream_t st, StageTimer* timer) {
   const int dim = x.users.dim;
   for (int s = 0; s < n_steps; ++s) {
     const int64_t e = epoch_step0 + s;
@@ -660,29 +670,82 @@ extern "C" int ar_train_steps(const ar_train_ctx* ctx, int64_t epoch_step0, int3
     const int slot = slot0 + s;
     const int64_t t = t0 + s + 1;
     const int32_t* meta_u = x.plan_u.meta + (int64_t)slot * 4;
+    AR_TICK(0);
     if (x.mode == AR_ADAM_REPLAY) {
       int rc = launch_catchup(&x.users, &x.plan_u, slot, &x.anime, &x.plan_a, slot, x.alpha, x.l2, t - 1, st);
       if (rc) return rc;
     }
+    AR_TICK(1);
     AR_DISPATCH_NV(dim, embed_fwd_kernel<NV><<<ceil_div(n, kRowWarps), kRowThreads, 0, st>>>(
                             x.users.W, x.anime.W, dim, x.iu + base, x.ia + base, n, meta_u, x.uh, x.ah, x.c, x.ru, x.ra));
     AR_LAUNCH_CHECK();
+    AR_TICK(2);
     head_step_kernel<<<1, kHeadThreads, 0, st>>>(x.c, x.label + base, n, meta_u, x.head, x.head_m, x.head_v,
                                                  x.bn_moving, x.alpha, t, x.dc, x.metrics + t * 4);
     AR_LAUNCH_CHECK();
+    AR_TICK(3);
     UpdateArgs a{};
     fill_update(a, 0, &x.users, &x.plan_u, slot, x.ah, x.ru, n);
     fill_update(a, 1, &x.anime, &x.plan_a, slot, x.uh, x.ra, n);
     double* ss = (x.mode == AR_ADAM_DENSE && x.reg_sumsq) ? x.reg_sumsq + t * 32 : nullptr;
     int rc = launch_update(a, true, x.c, x.dc, x.alpha, x.l2, t, 0, ss, st);
     if (rc) return rc;
+    AR_TICK(4);
     if (x.mode == AR_ADAM_DENSE) {
       // every row the batch did not touch takes the same Adam step with the pure L2 gradient
       if ((rc = launch_flush(&x.users, x.alpha, x.l2, t, ss, st))) return rc;
       if ((rc = launch_flush(&x.anime, x.alpha, x.l2, t, ss, st))) return rc;
     }
+    AR_TICK(5);
   }
   return AR_OK;
+}
+
+static int check_ctx(const ar_train_ctx* ctx, int32_t slot0, int32_t n_steps) {
+  AR_REQUIRE(ctx, "ar_train_steps: null ctx");
+  const ar_train_ctx& x = *ctx;
+  AR_REQUIRE(x.users.W && x.anime.W && x.head && x.alpha && x.iu && x.ia && x.label, "ar_train_steps: null pointer in ctx");
+  AR_REQUIRE(x.users.dim == x.anime.dim && dim_ok(x.users.dim), "ar_train_steps: dim %d/%d unsupported", x.users.dim, x.anime.dim);
+  AR_REQUIRE(x.batch > 0 && x.batch <= AR_MAX_BATCH, "ar_train_steps: batch %d outside (0,%d]", x.batch, AR_MAX_BATCH);
+  AR_REQUIRE(x.uh && x.ah && x.c && x.ru && x.ra && x.dc && x.metrics, "ar_train_steps: null scratch");
+  AR_REQUIRE(slot0 >= 0 && slot0 + n_steps <= x.plan_u.n_slots && slot0 + n_steps <= x.plan_a.n_slots,
+             "ar_train_steps: plan slots [%d,%d) exceed plan size", slot0, slot0 + n_steps);
+  AR_REQUIRE(x.mode >= AR_ADAM_REPLAY && x.mode <= AR_ADAM_TOUCHED, "ar_train_steps: bad mode %d", x.mode);
+  return AR_OK;
+}
+}  // namespace ar
+
+extern "C" int ar_train_steps(const ar_train_ctx* ctx, int64_t epoch_step0, int32_t slot0, int64_t t0,
+                              int32_t n_steps, void* stream) {
+  int rc = check_ctx(ctx, slot0, n_steps);
+  if (rc) return rc;
+  return run_steps(*ctx, epoch_step0, slot0, t0, n_steps, (cudaStream_t)stream, nullptr);
+}
+
+extern "C" int ar_train_steps_profile(const ar_train_ctx* ctx, int64_t epoch_step0, int32_t slot0, int64_t t0,
+                                      int32_t n_steps, float* stage_ms_host, void* stream) {
+  int rc = check_ctx(ctx, slot0, n_steps);
+  if (rc) return rc;
+  AR_REQUIRE(stage_ms_host, "ar_train_steps_profile: null stage_ms_host");
+  StageTimer tm;
+  tm.st = (cudaStream_t)stream;
+  rc = run_steps(*ctx, epoch_step0, slot0, t0, n_steps, tm.st, &tm);
+  if (rc == AR_OK) {
+    cudaError_t e = cudaStreamSynchronize(tm.st);
+    if (e != cudaSuccess) { ar::set_error("ar_train_steps_profile: %s", cudaGetErrorString(e)); rc = AR_ERR_CUDA; }
+  }
+  for (int i = 0; i < 5; ++i) stage_ms_host[i] = 0.f;
+  if (rc == AR_OK) {
+    for (size_t b = 0; b + 5 < tm.ev.size() + 0 && b + 5 <= tm.ev.size() - 1; b += 6) {
+      for (int i = 0; i < 5; ++i) {
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, tm.ev[b + i], tm.ev[b + i + 1]);
+        stage_ms_host[i] += ms;
+      }
+    }
+  }
+  for (cudaEvent_t e : tm.ev) cudaEventDestroy(e);
+  return rc;
 }
 
 extern "C" int ar_predict(const float* U, const float* A, int32_t dim, const float* head, const float* bn_moving,

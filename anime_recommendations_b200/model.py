@@ -248,20 +248,6 @@ class EmbeddingDotModel:
         return out if return_dict else [out["loss"], out["mse"]]
 
     # ------------------------------------------------------------------ training
-    def _make_plan(self, n_slots, batch):
-        dev = self.device
-        hc = batch // _capi.AR_HEAVY_LEN + 1
-        bufs = dict(order=torch.empty((n_slots, batch), dtype=torch.int32, device=dev),
-                    uniq=torch.empty((n_slots, batch), dtype=torch.int32, device=dev),
-                    off=torch.empty((n_slots, batch + 1), dtype=torch.int32, device=dev),
-                    meta=torch.zeros((n_slots, 4), dtype=torch.int32, device=dev),
-                    heavy=torch.empty((n_slots, hc), dtype=torch.int32, device=dev))
-        p = ArPlan()
-        p.batch_cap, p.heavy_cap, p.n_slots = batch, hc, n_slots
-        for k, v in bufs.items():
-            setattr(p, k, v.data_ptr())
-        return p, bufs
-
     def fit(self, x, y, batch_size=10000, epochs=1, verbose=0, validation_data=None, callbacks=None,
             shuffle="numpy", shuffle_seed=0, initial_epoch=0):
         """model.fit of neural_network.py:210-217.
@@ -282,18 +268,8 @@ class EmbeddingDotModel:
             raise ValueError("batch_size must be in (0, %d]" % _capi.AR_MAX_BATCH)
         self._check_range(iu_all, ia_all)
         steps = (N + B - 1) // B
-        D = self.dim
-        n_slots = min(steps, PLAN_CHUNK)
-        plan_u, keep_u = self._make_plan(n_slots, B)
-        plan_a, keep_a = self._make_plan(n_slots, B)
-        f = dict(dtype=torch.float32, device=dev)
-        uh, ah = torch.empty((B, D), **f), torch.empty((B, D), **f)
-        c, ru, ra, dc = (torch.empty(B, **f) for _ in range(4))
-        t_end = self.iterations + epochs * steps
-        self._ensure_alpha(t_end)
-        metrics = torch.zeros((t_end + 1, 4), **f)
+        sess = TrainSession(self, B, total_steps=max(0, epochs - initial_epoch) * steps)
         dense = self.adam_mode == "dense"
-        reg_ss = torch.zeros((t_end + 1, 32), dtype=torch.float64, device=dev) if dense else None
 
         callbacks = list(callbacks or [])
         for cb in callbacks:
@@ -308,15 +284,12 @@ class EmbeddingDotModel:
             (vx, vy) = validation_data[0], validation_data[1]
             val = (self._as_idx(vx[0], dev), self._as_idx(vx[1], dev), self._as_f32(vy, dev))
             self._check_range(val[0], val[1])
-        st = stream_ptr()
-        L = lib()
         for epoch in range(initial_epoch, epochs):
             t_epoch = time.perf_counter()
             for cb in callbacks:
                 cb.on_epoch_begin(epoch)
             lr = float(self.lr)
             t0 = self.iterations
-            self._set_alpha(lr, t0 + 1, steps)
             if shuffle == "numpy":
                 perm = torch.from_numpy(np.random.RandomState(shuffle_seed + epoch).permutation(N)).to(dev)
             elif shuffle == "device":
@@ -332,42 +305,25 @@ class EmbeddingDotModel:
             else:
                 iu_e, ia_e, y_e = iu_all[perm].contiguous(), ia_all[perm].contiguous(), y_all[perm].contiguous()
             reg0 = None if dense else self.l2 * self.reg_sumsq()
-
-            ctx = ArTrainCtx()
-            ctx.users, ctx.anime = self._table("user"), self._table("anime")
-            ctx.head, ctx.head_m, ctx.head_v = self.head.data_ptr(), self.head_m.data_ptr(), self.head_v.data_ptr()
-            ctx.bn_moving, ctx.alpha = self.bn_moving.data_ptr(), self._alpha.data_ptr()
-            ctx.iu, ctx.ia, ctx.label = iu_e.data_ptr(), ia_e.data_ptr(), y_e.data_ptr()
-            ctx.n_samples, ctx.batch, ctx.l2 = N, B, self.l2
-            ctx.mode = _capi.ADAM_MODES[self.adam_mode]
-            ctx.plan_u, ctx.plan_a = plan_u, plan_a
-            ctx.uh, ctx.ah, ctx.c, ctx.ru, ctx.ra, ctx.dc = (z.data_ptr() for z in (uh, ah, c, ru, ra, dc))
-            ctx.metrics = metrics.data_ptr()
-            ctx.reg_sumsq = reg_ss.data_ptr() if dense else None
-            for s0 in range(0, steps, n_slots):
-                ns = min(n_slots, steps - s0)
-                check(L.ar_plan_build(ptr(iu_e), N, B, s0, ns, C.byref(plan_u), st), "ar_plan_build(users)")
-                check(L.ar_plan_build(ptr(ia_e), N, B, s0, ns, C.byref(plan_a), st), "ar_plan_build(anime)")
-                check(L.ar_train_steps(C.byref(ctx), s0, 0, t0 + s0, ns, st), "ar_train_steps")
-            self.iterations = t0 + steps
+            sess.run(iu_e, ia_e, y_e, lr)
             self._sync_tables()
 
-            m = metrics[t0 + 1:t0 + steps + 1].cpu().numpy().astype(np.float64)
+            m = sess.metrics[t0 + 1:t0 + steps + 1].cpu().numpy().astype(np.float64)
             w = m[:, 2]
             bce = float((m[:, 0] * w).sum() / N)
             mse = float((m[:, 1] * w).sum() / N)
             reg1 = self.l2 * self.reg_sumsq()
             if dense:
-                r = self.l2 * reg_ss[t0 + 1:t0 + steps + 1].sum(dim=1).cpu().numpy()
+                r = self.l2 * sess.reg_ss[t0 + 1:t0 + steps + 1].sum(dim=1).cpu().numpy()
                 reg = float((r * w).sum() / N)
             else:
                 reg = 0.5 * (reg0 + reg1)   # regulariser is only evaluated at the epoch's flush points
             logs = dict(loss=bce + reg, mse=mse)
             if val is not None:
                 sums = torch.zeros(2, dtype=torch.float64, device=dev)
-                check(L.ar_eval_sums(ptr(self.U), ptr(self.A), D, ptr(self.head), ptr(self.bn_moving),
-                                     ptr(val[0]), ptr(val[1]), ptr(val[2]), val[0].numel(), ptr(sums), st),
-                      "ar_eval_sums")
+                check(lib().ar_eval_sums(ptr(self.U), ptr(self.A), self.dim, ptr(self.head), ptr(self.bn_moving),
+                                         ptr(val[0]), ptr(val[1]), ptr(val[2]), val[0].numel(), ptr(sums),
+                                         stream_ptr()), "ar_eval_sums")
                 sv = sums.cpu().numpy()
                 nv = max(1, val[0].numel())
                 logs["val_loss"] = float(sv[0] / nv + reg1)
@@ -387,7 +343,6 @@ class EmbeddingDotModel:
                 break
         for cb in callbacks:
             cb.on_train_end()
-        del keep_u, keep_a
         return hist
 
     # ------------------------------------------------------------------ persistence
@@ -400,6 +355,87 @@ class EmbeddingDotModel:
 
     def load_weights(self, path):
         weights_io.load_into(self, path)
+
+
+class TrainSession:
+    """Device-side buffers of one training run: dedup plans (PLAN_CHUNK steps at a time), the per-step
+    scratch, the per-step metrics and the ar_train_ctx handed to libanimerec."""
+
+    def __init__(self, model, batch, total_steps):
+        self.model, self.B = model, int(batch)
+        dev, D, B = model.device, model.dim, int(batch)
+        self.n_slots = max(1, min(int(total_steps) if total_steps else PLAN_CHUNK, PLAN_CHUNK))
+        self.plan_u, self._keep_u = self._make_plan(self.n_slots, B, dev)
+        self.plan_a, self._keep_a = self._make_plan(self.n_slots, B, dev)
+        f = dict(dtype=torch.float32, device=dev)
+        self.uh, self.ah = torch.empty((B, D), **f), torch.empty((B, D), **f)
+        self.c, self.ru, self.ra, self.dc = (torch.empty(B, **f) for _ in range(4))
+        self.t_cap = model.iterations + int(total_steps)
+        model._ensure_alpha(self.t_cap)
+        self.metrics = torch.zeros((self.t_cap + 1, 4), **f)
+        self.reg_ss = (torch.zeros((self.t_cap + 1, 32), dtype=torch.float64, device=dev)
+                       if model.adam_mode == "dense" else None)
+        self.launches = 0
+
+    @staticmethod
+    def _make_plan(n_slots, batch, dev):
+        hc = batch // _capi.AR_HEAVY_LEN + 1
+        bufs = dict(order=torch.empty((n_slots, batch), dtype=torch.int32, device=dev),
+                    uniq=torch.empty((n_slots, batch), dtype=torch.int32, device=dev),
+                    off=torch.empty((n_slots, batch + 1), dtype=torch.int32, device=dev),
+                    meta=torch.zeros((n_slots, 4), dtype=torch.int32, device=dev),
+                    heavy=torch.empty((n_slots, hc), dtype=torch.int32, device=dev))
+        p = ArPlan()
+        p.batch_cap, p.heavy_cap, p.n_slots = batch, hc, n_slots
+        for k, v in bufs.items():
+            setattr(p, k, v.data_ptr())
+        return p, bufs
+
+    def _ctx(self, iu, ia, y):
+        m = self.model
+        ctx = ArTrainCtx()
+        ctx.users, ctx.anime = m._table("user"), m._table("anime")
+        ctx.head, ctx.head_m, ctx.head_v = m.head.data_ptr(), m.head_m.data_ptr(), m.head_v.data_ptr()
+        ctx.bn_moving, ctx.alpha = m.bn_moving.data_ptr(), m._alpha.data_ptr()
+        ctx.iu, ctx.ia, ctx.label = iu.data_ptr(), ia.data_ptr(), y.data_ptr()
+        ctx.n_samples, ctx.batch, ctx.l2 = iu.numel(), self.B, m.l2
+        ctx.mode = _capi.ADAM_MODES[m.adam_mode]
+        ctx.plan_u, ctx.plan_a = self.plan_u, self.plan_a
+        ctx.uh, ctx.ah, ctx.c, ctx.ru, ctx.ra, ctx.dc = (z.data_ptr() for z in (
+            self.uh, self.ah, self.c, self.ru, self.ra, self.dc))
+        ctx.metrics = self.metrics.data_ptr()
+        ctx.reg_sumsq = self.reg_ss.data_ptr() if self.reg_ss is not None else None
+        return ctx
+
+    def run(self, iu, ia, y, lr, profile=None):
+        """Train on every sample of (iu, ia, y) (device int32/int32/float32, visit order) at learning
+        rate `lr`: ceil(n/B) optimizer steps.  Asynchronous on the current stream unless `profile`
+        (a list) is given, in which case per-stage device times [ms] are accumulated into it."""
+        m, B = self.model, self.B
+        N = iu.numel()
+        steps = (N + B - 1) // B
+        t0 = m.iterations
+        if t0 + steps > self.t_cap:
+            raise _capi.AnimerecError("TrainSession sized for %d optimizer steps, %d requested" % (
+                self.t_cap, t0 + steps))
+        m._set_alpha(lr, t0 + 1, steps)
+        ctx = self._ctx(iu, ia, y)
+        st, L = stream_ptr(), lib()
+        per_step = {"replay": 4, "dense": 5, "touched": 3}[m.adam_mode]
+        for s0 in range(0, steps, self.n_slots):
+            ns = min(self.n_slots, steps - s0)
+            check(L.ar_plan_build(ptr(iu), N, B, s0, ns, C.byref(self.plan_u), st), "ar_plan_build(users)")
+            check(L.ar_plan_build(ptr(ia), N, B, s0, ns, C.byref(self.plan_a), st), "ar_plan_build(anime)")
+            if profile is None:
+                check(L.ar_train_steps(C.byref(ctx), s0, 0, t0 + s0, ns, st), "ar_train_steps")
+            else:
+                ms = (C.c_float * 5)()
+                check(L.ar_train_steps_profile(C.byref(ctx), s0, 0, t0 + s0, ns, ms, st), "ar_train_steps_profile")
+                for i in range(5):
+                    profile[i] += ms[i]
+            self.launches += 2 + ns * per_step
+        m.iterations = t0 + steps
+        return steps
 
 
 def load_model(path, device=None, adam_mode="replay"):

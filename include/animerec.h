@@ -107,7 +107,7 @@ typedef struct {
   float* ra;           /* (batch) 1/||a|| */
   float* dc;           /* (batch) dLoss/dc */
   /* per-step outputs, indexed by global step t (1-based): metrics[t*4 + {0: mean BCE, 1: mean
-   * squared error, 2: n, 3: batch mean of z}] ; reg_sumsq[t] = sum U^2 + sum A^2 BEFORE step t
+   * squared error, 2: n, 3: batch mean of z}] ; reg_sumsq[t*32 + j], j<32: partial sums whose total is sum U^2 + sum A^2 BEFORE step t
    * (written in AR_ADAM_DENSE only; may be null) */
   float* metrics;
   double* reg_sumsq;
@@ -118,6 +118,12 @@ typedef struct {
  * t = t0 + s + 1.  Replaces Keras Model.train_step x n_steps. */
 int ar_train_steps(const ar_train_ctx* ctx, int64_t epoch_step0, int32_t slot0, int64_t t0,
                    int32_t n_steps, void* stream);
+
+/* Same as ar_train_steps with CUDA events around every launch; synchronises the stream and writes the
+ * summed device time (ms) of the five stages to the HOST array stage_ms_host[5]:
+ * 0 catch-up, 1 forward, 2 head, 3 row update, 4 dense flush.  Measurement aid for bench.py. */
+int ar_train_steps_profile(const ar_train_ctx* ctx, int64_t epoch_step0, int32_t slot0, int64_t t0,
+                           int32_t n_steps, float* stage_ms_host, void* stream);
 
 /* Bring every row of the table to optimizer step t_target by replaying its missed pure-L2 steps
  * (no-op per row when last_step >= t_target).  Used at epoch end / before validation, saving and

@@ -117,7 +117,7 @@ def test_merge_and_rerank():
     Wn = osim.get_weights(W)
     ti, ts = osim.allpairs_topk_fast(W, k, q0=100, q1=164)
     cand = np.concatenate([ti[:, ::-1], rng.randint(0, 3000, (64, 20)).astype(np.int32)], axis=1)
-    cand[:, 5] = -1
+    cand[:, 15] = -1
     cand[np.arange(64), 12] = np.arange(100, 164)             # the query itself sneaks in: caller filters
     Wd = sim.as_table(W)
     gi, gs = sim.rerank(Wd, 100, 64, Wd, dev(cand), k + 1)

@@ -148,3 +148,18 @@ def test_predict_uses_moving_statistics():
     st.mov_mean, st.mov_var = np.float32(0.5), np.float32(4.0)
     p1 = ot.predict(st, [0, 1, 2], [3, 4, 5])
     assert not np.allclose(p0, p1)
+
+
+def test_torch_cpu_port_matches_numpy_oracle():
+    from oracle import train_torch as tt
+    rng = np.random.RandomState(8)
+    st = ot.init_state(60, 40, 16, seed=9, w=1.2)
+    ts = tt.TorchState(st)
+    for _ in range(4):
+        iu, ia = rng.randint(0, 60, 128), rng.randint(0, 40, 128)
+        t = (rng.randint(0, 11, 128) / 10.0).astype(np.float32)
+        m0 = ot.train_step(st, iu, ia, t, 2e-3)
+        m1 = tt.train_step(ts, iu, ia, t, 2e-3)
+        assert abs(m0["loss"] - m1["loss"]) < 2e-6 and abs(m0["mse"] - m1["mse"]) < 2e-6
+    np.testing.assert_allclose(ts.U.numpy(), st.U, rtol=2e-5, atol=2e-7)
+    np.testing.assert_allclose(ts.A.numpy(), st.A, rtol=2e-5, atol=2e-7)
