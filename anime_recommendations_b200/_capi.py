@@ -10,7 +10,7 @@ import os
 
 PKG = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(PKG, "lib", "libanimerec.so")
-ABI_VERSION = 1
+ABI_VERSION = 2
 
 AR_MAX_BATCH = 16384
 AR_HEAVY_LEN = 64
@@ -41,7 +41,8 @@ class ArTrainCtx(C.Structure):
                 ("n_samples", C.c_int64), ("batch", C.c_int32), ("l2", C.c_float), ("mode", C.c_int32),
                 ("plan_u", ArPlan), ("plan_a", ArPlan),
                 ("uh", C.c_void_p), ("ah", C.c_void_p), ("c", C.c_void_p), ("ru", C.c_void_p),
-                ("ra", C.c_void_p), ("dc", C.c_void_p),
+                ("ra", C.c_void_p), ("dy", C.c_void_p), ("fwd_part", C.c_void_p), ("head_part", C.c_void_p),
+                ("stepc", C.c_void_p), ("ticket", C.c_void_p),
                 ("metrics", C.c_void_p), ("reg_sumsq", C.c_void_p)]
 
 
@@ -64,7 +65,7 @@ SIGNATURES = {
     "ar_embed_fwd": (C.c_int, [_P, _P, _I32, _P, _P, _I32, _P, _P, _P, _P, _P, _P]),
     "ar_head_step": (C.c_int, [_P, _P, _I32, _P, _P, _P, _P, _P, _I64, _P, _P, _P]),
     "ar_rows_catchup": (C.c_int, [C.POINTER(ArTable), C.POINTER(ArPlan), _I32, _P, _F, _I64, _P]),
-    "ar_rows_update": (C.c_int, [C.POINTER(ArTable), C.POINTER(ArPlan), _I32, _P, _P, _P, _P, _P, _F,
+    "ar_rows_update": (C.c_int, [C.POINTER(ArTable), C.POINTER(ArPlan), _I32, _P, _P, _P, _P, _P, _P, _F,
                                  _I64, _I32, _P, _P]),
     "ar_predict": (C.c_int, [_P, _P, _I32, _P, _P, _P, _P, _I64, _P, _P]),
     "ar_eval_sums": (C.c_int, [_P, _P, _I32, _P, _P, _P, _P, _P, _I64, _P, _P]),

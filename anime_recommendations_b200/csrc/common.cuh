@@ -75,12 +75,29 @@ __device__ __forceinline__ float4 fma4(float s, float4 a, float4 acc) {
   return make_float4(fmaf(s, a.x, acc.x), fmaf(s, a.y, acc.y), fmaf(s, a.z, acc.z), fmaf(s, a.w, acc.w));
 }
 
-// One Keras-2.12 Adam update of a single element (oracle/train.py::_adam_apply, assumption A6).
-// Op order is kept identical to the oracle so that the deferred replay is bit-reproducible.
+__device__ __forceinline__ float sqrt_approx(float x) {
+  float r;
+  asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+__device__ __forceinline__ float rcp_approx(float x) {
+  float r;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+
+// One Keras-2.12 Adam update of a single element (oracle/train.py::_adam_apply, assumption A6):
+//   m += (g-m)(1-b1);  v += (g^2-v)(1-b2);  w -= (m*alpha)/(sqrt(v)+eps)
+// Every operation is spelled as an explicit intrinsic (no compiler contraction), so the SAME bits come
+// out wherever this is inlined -- that is what makes the deferred replay bit-identical to the dense
+// mode.  sqrt and the reciprocal use the MUFU approximations (<= 2 ulp each, ~3e-7 relative on a step of
+// size ~alpha, i.e. ~1e-11 absolute): 2 MUFU + 9 FP32 ops per element-step instead of ~40 for the IEEE
+// sequences, which is what bounds the replay (DESIGN.md "rows_catchup").
 __device__ __forceinline__ void adam1(float& w, float& m, float& v, float g, float alpha) {
-  m = __fadd_rn(m, __fmul_rn(__fsub_rn(g, m), kOneMinusBeta1));
-  v = __fadd_rn(v, __fmul_rn(__fsub_rn(__fmul_rn(g, g), v), kOneMinusBeta2));
-  w = __fsub_rn(w, __fdiv_rn(__fmul_rn(m, alpha), __fadd_rn(__fsqrt_rn(v), kAdamEps)));
+  m = __fmaf_rn(__fsub_rn(g, m), kOneMinusBeta1, m);
+  v = __fmaf_rn(__fmaf_rn(g, g, -v), kOneMinusBeta2, v);
+  const float r = rcp_approx(__fadd_rn(sqrt_approx(v), kAdamEps));
+  w = __fmaf_rn(-__fmul_rn(m, alpha), r, w);
 }
 __device__ __forceinline__ void adam4(float4& w, float4& m, float4& v, float4 g, float alpha) {
   adam1(w.x, m.x, v.x, g.x, alpha);

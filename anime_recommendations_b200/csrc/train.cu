@@ -4,8 +4,12 @@
 //   1. rows_catchup   (AR_ADAM_REPLAY only) bring the step's distinct rows to optimizer step t-1
 //                     by replaying their missed pure-L2 Adam steps in registers
 //   2. embed_fwd      warp per sample: gather both rows (128-bit loads), l2-normalise, dot
-//   3. head_step      one CTA: Dense(1) + BatchNorm(train) + sigmoid + BCE, its backward, Adam on
-//                     the 4 head scalars, moving statistics, per-step metrics
+//   3. head_step      thread per sample over ceil(n/256) CTAs: Dense(1) + BatchNorm(train) + sigmoid +
+//                     BCE and dLoss/dy; the batch statistics come from the forward's per-CTA partial
+//                     sums, the backward's from this kernel's own partials; the last CTA to finish
+//                     (ticket) reduces them in a fixed order and applies Adam to the 4 head scalars,
+//                     the moving statistics and the per-step metrics.  No atomics on data => the step
+//                     is bit-reproducible.
 //   4. rows_update    warp per distinct row: atomic-free segment reduction of the row gradient
 //                     over the plan's sorted samples + L2 term + Adam, one RMW of (W, m, v)
 // AR_ADAM_DENSE appends a flush of every other row to step t (the reference-literal dense Adam).
@@ -21,7 +25,7 @@ namespace ar {
 
 constexpr int kRowThreads = 256;               // 8 warps per CTA, one row / sample per warp
 constexpr int kRowWarps = kRowThreads / 32;
-constexpr int kHeadThreads = 1024;
+constexpr int kHeadThreads = 256;
 
 // ---------------------------------------------------------------------------------------------
 // Row register tile: a warp owns one row, lane l holds float4 #(l + 32*k), k < NV.
@@ -89,13 +93,19 @@ struct CatchupArgs {
 template <int NV>
 __global__ void __launch_bounds__(kRowThreads)
 rows_catchup_kernel(CatchupArgs a, const float* __restrict__ alpha, float l2x2, int64_t t_target) {
-  const int which = (blockIdx.x >= a.blocks0) ? 1 : 0;
-  const int blk = which ? blockIdx.x - a.blocks0 : blockIdx.x;
+  const bool second = blockIdx.x >= a.blocks0;
+  const int blk = second ? blockIdx.x - a.blocks0 : blockIdx.x;
   const int lane = threadIdx.x & 31;
   const int seg = blk * kRowWarps + (threadIdx.x >> 5);
-  if (seg >= a.meta[which][0]) return;
-  const ar_table& tb = a.tab[which];
-  const int row = a.uniq[which][seg];
+  const int32_t* meta = second ? a.meta[1] : a.meta[0];
+  if (seg >= meta[0]) return;
+  ar_table tb;
+  tb.dim = a.tab[0].dim;
+  tb.W = second ? a.tab[1].W : a.tab[0].W;
+  tb.m = second ? a.tab[1].m : a.tab[0].m;
+  tb.v = second ? a.tab[1].v : a.tab[0].v;
+  tb.last_step = second ? a.tab[1].last_step : a.tab[0].last_step;
+  const int row = (second ? a.uniq[1] : a.uniq[0])[seg];
   const int64_t last = tb.last_step[row];
   if (last >= t_target) return;
   const int d4 = tb.dim >> 2;
@@ -154,11 +164,16 @@ __global__ void __launch_bounds__(kRowThreads)
 embed_fwd_kernel(const float* __restrict__ U, const float* __restrict__ A, int dim,
                  const int32_t* __restrict__ iu, const int32_t* __restrict__ ia, int n,
                  const int32_t* __restrict__ meta_n, float* __restrict__ uh, float* __restrict__ ah,
-                 float* __restrict__ c, float* __restrict__ ru, float* __restrict__ ra) {
+                 float* __restrict__ c, float* __restrict__ ru, float* __restrict__ ra,
+                 double* __restrict__ fwd_part) {
+  __shared__ float cs_s[kRowWarps];
   if (meta_n) n = min(n, meta_n[2]);
   const int s = blockIdx.x * kRowWarps + (threadIdx.x >> 5);
-  if (s >= n) return;
   const int lane = threadIdx.x & 31;
+  if (fwd_part) {  // (sum c, sum c^2) of this CTA's samples, summed in a fixed order by one thread
+    if (lane == 0) cs_s[threadIdx.x >> 5] = 0.f;
+  }
+  if (s < n) {
   const int d4 = dim >> 2;
   RowTile<NV> u, a;
   u.load(U + (size_t)iu[s] * dim, d4, lane);
@@ -179,6 +194,22 @@ embed_fwd_kernel(const float* __restrict__ U, const float* __restrict__ A, int d
     c[s] = cs;
     if (ru) ru[s] = r_u;
     if (ra) ra[s] = r_a;
+    cs_s[threadIdx.x >> 5] = cs;
+  }
+  }
+  if (fwd_part) {
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      double a0 = 0.0, a1 = 0.0;
+#pragma unroll
+      for (int i = 0; i < kRowWarps; ++i) {
+        const double x = (double)cs_s[i];
+        a0 += x;
+        a1 += x * x;
+      }
+      fwd_part[2 * blockIdx.x] = a0;
+      fwd_part[2 * blockIdx.x + 1] = a1;
+    }
   }
 }
 
@@ -213,86 +244,136 @@ __device__ __forceinline__ float bce_logits(float y, float t) {
   return fmaxf(y, 0.f) - y * t + log1pf(expf(-fabsf(y)));
 }
 
-__global__ void __launch_bounds__(kHeadThreads, 1)
+// Per-step scalars the head hands to the row-update kernel: dc_s = K_COEF*(dy_s - K_S1N - zh_s*K_S2N),
+// zh_s = ((w*c_s + b) - mu)*inv   (oracle head_backward(): dz, dc)
+enum { K_COEF = 0, K_S1N, K_S2N, K_MU, K_INV, K_W, K_B, K_PAD, K_STEPC };
+constexpr int kHeadSums = 7;  // sum bce, sq err, dy, dy*zh, zh, dy*c, zh*c
+
+__device__ __forceinline__ float dc_of(float dy, float c, const float* __restrict__ k) {
+  const float zh = ((k[K_W] * c + k[K_B]) - k[K_MU]) * k[K_INV];
+  return k[K_COEF] * (dy - k[K_S1N] - zh * k[K_S2N]);
+}
+
+__global__ void __launch_bounds__(kHeadThreads)
 head_step_kernel(const float* __restrict__ c, const float* __restrict__ label, int n,
-                 const int32_t* __restrict__ meta_n, float* __restrict__ head, float* __restrict__ head_m,
-                 float* __restrict__ head_v, float* __restrict__ bn_moving,
-                 const float* __restrict__ alpha, int64_t t, float* __restrict__ dc,
-                 float* __restrict__ metrics_row) {
-  __shared__ double red[4 * 32];
+                 const int32_t* __restrict__ meta_n, const double* __restrict__ fwd_part,
+                 float* __restrict__ head, float* __restrict__ head_m, float* __restrict__ head_v,
+                 float* __restrict__ bn_moving, const float* __restrict__ alpha, int64_t t,
+                 float* __restrict__ dy_out, double* __restrict__ head_part, float* __restrict__ stepc,
+                 unsigned int* __restrict__ ticket, float* __restrict__ metrics_row) {
+  __shared__ double red[kHeadSums * 32];
+  __shared__ int is_last;
   if (meta_n) n = min(n, meta_n[2]);
   if (n <= 0) return;
+  const int nblk = (n + kHeadThreads - 1) / kHeadThreads;
+  if ((int)blockIdx.x >= nblk) return;
   const int tid = threadIdx.x;
   const float w = head[0], b = head[1], gamma = head[2], beta = head[3];
   const float fn = (float)n;
 
-  double s1[1] = {0.0};
-  for (int i = tid; i < n; i += kHeadThreads) s1[0] += (double)(w * c[i] + b);
-  block_sum<1>(s1, red);
-  const float mu = (float)(s1[0] / n);
-
-  double s2[1] = {0.0};
-  for (int i = tid; i < n; i += kHeadThreads) {
-    float d = (w * c[i] + b) - mu;
-    s2[0] += (double)(d * d);
+  // batch statistics from the forward's per-CTA partials (fixed summation order in every CTA)
+  const int nfp = (n + kRowWarps - 1) / kRowWarps;
+  double s0[2] = {0.0, 0.0};
+  for (int i = tid; i < nfp; i += kHeadThreads) {
+    s0[0] += __ldcg(fwd_part + 2 * i);
+    s0[1] += __ldcg(fwd_part + 2 * i + 1);
   }
-  block_sum<1>(s2, red);
-  const float var = (float)(s2[0] / n);
+  block_sum<2>(s0, red);
+  const double mean_c = s0[0] / n;
+  const double var_c = fmax(s0[1] / n - mean_c * mean_c, 0.0);
+  const float mu = (float)((double)w * mean_c + (double)b);
+  const float var = (float)((double)w * (double)w * var_c);
   const float inv = 1.0f / sqrtf(var + kBnEps);
 
-  double s3[4] = {0.0, 0.0, 0.0, 0.0};  // sum bce, sum sq err, sum dy, sum dy*zh
-  for (int i = tid; i < n; i += kHeadThreads) {
-    float zh = ((w * c[i] + b) - mu) * inv;
-    float y = gamma * zh + beta;
-    float p = sigmoidf_(y);
-    float tg = label[i];
-    float dy = (p - tg) / fn;
-    s3[0] += (double)bce_logits(y, tg);
-    s3[1] += (double)((tg - p) * (tg - p));
-    s3[2] += (double)dy;
-    s3[3] += (double)(dy * zh);
-  }
-  block_sum<4>(s3, red);
-  const float dgamma = (float)s3[3];
-  const float dbeta = (float)s3[2];
-  const float sdzh = gamma * dbeta;     // sum dzh
-  const float sdzhzh = gamma * dgamma;  // sum dzh*zh
-
-  double s4[2] = {0.0, 0.0};  // sum dz*c, sum dz
-  for (int i = tid; i < n; i += kHeadThreads) {
-    float ci = c[i];
-    float zh = ((w * ci + b) - mu) * inv;
-    float y = gamma * zh + beta;
-    float p = sigmoidf_(y);
-    float dzh = gamma * ((p - label[i]) / fn);
-    float dz = inv / fn * (fn * dzh - sdzh - zh * sdzhzh);
-    dc[i] = w * dz;
-    s4[0] += (double)(dz * ci);
-    s4[1] += (double)dz;
-  }
-  block_sum<2>(s4, red);
-
-  if (tid == 0) {
-    const float a = alpha[t];
-    float g[4] = {(float)s4[0], (float)s4[1], dgamma, dbeta};
+  double s1[kHeadSums];
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      float th = head[i], m = head_m[i], v = head_v[i];
-      adam1(th, m, v, g[i], a);
-      head[i] = th;
-      head_m[i] = m;
-      head_v[i] = v;
+  for (int i = 0; i < kHeadSums; ++i) s1[i] = 0.0;
+  const int i = blockIdx.x * kHeadThreads + tid;
+  if (i < n) {
+    const float ci = c[i];
+    const float zh = ((w * ci + b) - mu) * inv;
+    const float y = gamma * zh + beta;
+    const float p = sigmoidf_(y);
+    const float tg = label[i];
+    const float dy = (p - tg) / fn;
+    dy_out[i] = dy;
+    s1[0] = (double)bce_logits(y, tg);
+    s1[1] = (double)((tg - p) * (tg - p));
+    s1[2] = (double)dy;
+    s1[3] = (double)dy * (double)zh;
+    s1[4] = (double)zh;
+    s1[5] = (double)dy * (double)ci;
+    s1[6] = (double)zh * (double)ci;
+  }
+  block_sum<kHeadSums>(s1, red);
+  if (tid == 0) {
+#pragma unroll
+    for (int k = 0; k < kHeadSums; ++k) head_part[blockIdx.x * 8 + k] = s1[k];
+    __threadfence();
+    const unsigned int old = atomicAdd(ticket, 1u);
+    is_last = (old == (unsigned int)(nblk - 1));
+  }
+  __syncthreads();
+  if (!is_last) return;
+  __threadfence();
+  double s2[kHeadSums];
+#pragma unroll
+  for (int k = 0; k < kHeadSums; ++k) s2[k] = (tid < nblk) ? __ldcg(head_part + tid * 8 + k) : 0.0;
+  block_sum<kHeadSums>(s2, red);
+  if (tid == 0) {
+    const double S1 = s2[2], S2 = s2[3], Szh = s2[4], Sdyc = s2[5], Szhc = s2[6], Sc = s0[0];
+    const double ig = (double)inv * (double)gamma;
+    // oracle head_backward(): dgamma = sum dy*zh, dbeta = sum dy, dz_i = inv*gamma*(dy_i - S1/n - zh_i*S2/n)
+    const float g[4] = {(float)(ig * (Sdyc - S1 / n * Sc - S2 / n * Szhc)),  // dw = sum dz*c
+                        (float)(-ig * (S2 / n) * Szh),                       // db = sum dz (0 up to rounding)
+                        (float)S2, (float)S1};
+    const float a = alpha[t];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      float th = head[k], m = head_m[k], v = head_v[k];
+      adam1(th, m, v, g[k], a);
+      head[k] = th;
+      head_m[k] = m;
+      head_v[k] = v;
     }
-    float mm = bn_moving[0], mv = bn_moving[1];
+    const float mm = bn_moving[0], mv = bn_moving[1];
     bn_moving[0] = mm - (mm - mu) * kBnOneMinusMomentum;
     bn_moving[1] = mv - (mv - var) * kBnOneMinusMomentum;
+    stepc[K_COEF] = (float)((double)w * ig);
+    stepc[K_S1N] = (float)(S1 / n);
+    stepc[K_S2N] = (float)(S2 / n);
+    stepc[K_MU] = mu;
+    stepc[K_INV] = inv;
+    stepc[K_W] = w;
+    stepc[K_B] = b;
+    stepc[K_PAD] = 0.f;
     if (metrics_row) {
-      metrics_row[0] = (float)(s3[0] / n);
-      metrics_row[1] = (float)(s3[1] / n);
+      metrics_row[0] = (float)(s2[0] / n);
+      metrics_row[1] = (float)(s2[1] / n);
       metrics_row[2] = fn;
       metrics_row[3] = mu;
     }
+    *ticket = 0u;  // ready for the next step
   }
+}
+
+// helpers behind the stand-alone ar_head_step entry point (unit tests): partials from c, dc from dy
+__global__ void c_partials_kernel(const float* __restrict__ c, int n, double* __restrict__ fwd_part) {
+  const int blk = blockIdx.x * blockDim.x + threadIdx.x;
+  if (blk * kRowWarps >= n) return;
+  double a0 = 0.0, a1 = 0.0;
+  for (int i = blk * kRowWarps; i < min(n, (blk + 1) * kRowWarps); ++i) {
+    const double x = (double)c[i];
+    a0 += x;
+    a1 += x * x;
+  }
+  fwd_part[2 * blk] = a0;
+  fwd_part[2 * blk + 1] = a1;
+}
+__global__ void dc_from_dy_kernel(const float* __restrict__ dy, const float* __restrict__ c, int n,
+                                  const float* __restrict__ stepc, float* __restrict__ dc) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) dc[i] = dc_of(dy[i], c[i], stepc);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -349,9 +430,9 @@ __device__ __forceinline__ void finish_row(const ar_table& tb, int row, RowTile<
 
 template <int NV>
 __global__ void __launch_bounds__(kRowThreads)
-rows_update_kernel(UpdateArgs a, const float* __restrict__ c, const float* __restrict__ dc,
-                   const float* __restrict__ alpha, float l2x2, int64_t t, int replay,
-                   double* sumsq_out) {
+rows_update_kernel(UpdateArgs a, const float* __restrict__ c, const float* __restrict__ dy,
+                   const float* __restrict__ stepc, const float* __restrict__ alpha, float l2x2, int64_t t,
+                   int replay, double* sumsq_out) {
   extern __shared__ float red[];  // heavy path: [kRowWarps][dim] + [kRowWarps]
   int b = blockIdx.x;
   int which, heavy_path;
@@ -360,16 +441,29 @@ rows_update_kernel(UpdateArgs a, const float* __restrict__ c, const float* __res
   else if ((b -= a.blocks_norm[1]) < a.blocks_heavy[0]) { which = 0; heavy_path = 1; }
   else { b -= a.blocks_heavy[0]; which = 1; heavy_path = 1; }
 
-  const ar_table& tb = a.tab[which];
+  ar_table tb;
+  tb.dim = a.tab[0].dim;
+  tb.n_rows = which ? a.tab[1].n_rows : a.tab[0].n_rows;
+  tb.W = which ? a.tab[1].W : a.tab[0].W;
+  tb.m = which ? a.tab[1].m : a.tab[0].m;
+  tb.v = which ? a.tab[1].v : a.tab[0].v;
+  tb.last_step = which ? a.tab[1].last_step : a.tab[0].last_step;
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   const int dim = tb.dim, d4 = dim >> 2;
-  const int32_t* __restrict__ order = a.order[which];
-  const int32_t* __restrict__ off = a.off[which];
-  const float* __restrict__ other = a.other[which];
+  const int32_t* __restrict__ order = which ? a.order[1] : a.order[0];
+  const int32_t* __restrict__ off = which ? a.off[1] : a.off[0];
+  const int32_t* __restrict__ uniq = which ? a.uniq[1] : a.uniq[0];
+  const int32_t* __restrict__ meta = which ? a.meta[1] : a.meta[0];
+  const int32_t* __restrict__ heavy = which ? a.heavy[1] : a.heavy[0];
+  const float* __restrict__ other = which ? a.other[1] : a.other[0];
+  const float* __restrict__ rinv = which ? a.rinv[1] : a.rinv[0];
+  float kk[K_STEPC];
+#pragma unroll
+  for (int i = 0; i < K_STEPC; ++i) kk[i] = stepc[i];
 
   if (!heavy_path) {
     const int seg = b * kRowWarps + wid;
-    if (seg >= a.meta[which][0]) return;
+    if (seg >= meta[0]) return;
     const int beg = off[seg], end = off[seg + 1];
     if (end - beg > AR_HEAVY_LEN) return;  // CTA path handles it
     RowTile<NV> acc;
@@ -381,9 +475,10 @@ rows_update_kernel(UpdateArgs a, const float* __restrict__ c, const float* __res
       RowTile<NV> o0, o1;
       o0.load(other + (size_t)s0 * dim, d4, lane);
       o1.load(other + (size_t)s1 * dim, d4, lane);
-      const float d0 = dc[s0], d1 = dc[s1];
-      q = fmaf(d0, c[s0], q);
-      q = fmaf(d1, c[s1], q);
+      const float c0 = c[s0], c1 = c[s1];
+      const float d0 = dc_of(dy[s0], c0, kk), d1 = dc_of(dy[s1], c1, kk);
+      q = fmaf(d0, c0, q);
+      q = fmaf(d1, c1, q);
 #pragma unroll
       for (int k = 0; k < NV; ++k) {
         acc.x[k] = fma4(d0, o0.x[k], acc.x[k]);
@@ -394,19 +489,19 @@ rows_update_kernel(UpdateArgs a, const float* __restrict__ c, const float* __res
       const int s0 = order[j];
       RowTile<NV> o0;
       o0.load(other + (size_t)s0 * dim, d4, lane);
-      const float d0 = dc[s0];
-      q = fmaf(d0, c[s0], q);
+      const float c0 = c[s0];
+      const float d0 = dc_of(dy[s0], c0, kk);
+      q = fmaf(d0, c0, q);
 #pragma unroll
       for (int k = 0; k < NV; ++k) acc.x[k] = fma4(d0, o0.x[k], acc.x[k]);
     }
-    finish_row<NV>(tb, a.uniq[which][seg], acc, q, a.rinv[which][order[beg]], alpha, l2x2, t, replay,
-                   sumsq_out, lane);
+    finish_row<NV>(tb, uniq[seg], acc, q, rinv[order[beg]], alpha, l2x2, t, replay, sumsq_out, lane);
     return;
   }
 
   // heavy row: the whole CTA reduces one long segment; warp w takes samples beg+w, beg+w+8, ...
-  if (b >= a.meta[which][1]) return;
-  const int seg = a.heavy[which][b];
+  if (b >= meta[1]) return;
+  const int seg = heavy[b];
   const int beg = off[seg], end = off[seg + 1];
   RowTile<NV> acc;
   acc.zero();
@@ -415,8 +510,9 @@ rows_update_kernel(UpdateArgs a, const float* __restrict__ c, const float* __res
     const int s0 = order[j];
     RowTile<NV> o0;
     o0.load(other + (size_t)s0 * dim, d4, lane);
-    const float d0 = dc[s0];
-    q = fmaf(d0, c[s0], q);
+    const float c0 = c[s0];
+    const float d0 = dc_of(dy[s0], c0, kk);
+    q = fmaf(d0, c0, q);
 #pragma unroll
     for (int k = 0; k < NV; ++k) acc.x[k] = fma4(d0, o0.x[k], acc.x[k]);
   }
@@ -436,8 +532,7 @@ rows_update_kernel(UpdateArgs a, const float* __restrict__ c, const float* __res
     }
     q += qred[w8];
   }
-  finish_row<NV>(tb, a.uniq[which][seg], acc, q, a.rinv[which][order[beg]], alpha, l2x2, t, replay,
-                 sumsq_out, lane);
+  finish_row<NV>(tb, uniq[seg], acc, q, rinv[order[beg]], alpha, l2x2, t, replay, sumsq_out, lane);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -567,14 +662,14 @@ static void fill_update(UpdateArgs& a, int w, const ar_table* tab, const ar_plan
   a.blocks_heavy[w] = b / AR_HEAVY_LEN;  // at most this many segments can exceed AR_HEAVY_LEN
 }
 
-static int launch_update(UpdateArgs& a, bool two, const float* c, const float* dc, const float* alpha,
-                         float l2, int64_t t, int replay, double* sumsq_out, cudaStream_t st) {
+static int launch_update(UpdateArgs& a, bool two, const float* c, const float* dy, const float* stepc,
+                         const float* alpha, float l2, int64_t t, int replay, double* sumsq_out, cudaStream_t st) {
   if (!two) { a.blocks_norm[1] = 0; a.blocks_heavy[1] = 0; a.tab[1] = a.tab[0]; }
   int blocks = a.blocks_norm[0] + a.blocks_norm[1] + a.blocks_heavy[0] + a.blocks_heavy[1];
   const int dim = a.tab[0].dim;
   size_t smem = (size_t)kRowWarps * dim * sizeof(float) + kRowWarps * sizeof(float);
   const float l2x2 = (float)(2.0 * (double)l2);
-  AR_DISPATCH_NV(dim, rows_update_kernel<NV><<<blocks, kRowThreads, smem, st>>>(a, c, dc, alpha, l2x2, t, replay, sumsq_out));
+  AR_DISPATCH_NV(dim, rows_update_kernel<NV><<<blocks, kRowThreads, smem, st>>>(a, c, dy, stepc, alpha, l2x2, t, replay, sumsq_out));
   AR_LAUNCH_CHECK();
   return AR_OK;
 }
@@ -605,7 +700,7 @@ extern "C" int ar_embed_fwd(const float* U, const float* A, int32_t dim, const i
   AR_REQUIRE(dim_ok(dim), "ar_embed_fwd: dim %d unsupported", dim);
   if (n <= 0) return AR_OK;
   AR_DISPATCH_NV(dim, embed_fwd_kernel<NV><<<ceil_div(n, kRowWarps), kRowThreads, 0, (cudaStream_t)stream>>>(
-                          U, A, dim, iu, ia, n, nullptr, uh, ah, c, ru, ra));
+                          U, A, dim, iu, ia, n, nullptr, uh, ah, c, ru, ra, nullptr));
   AR_LAUNCH_CHECK();
   return AR_OK;
 }
@@ -615,9 +710,26 @@ extern "C" int ar_head_step(const float* c, const float* label, int32_t n, float
                             float* metrics_row, void* stream) {
   AR_REQUIRE(c && label && head && head_m && head_v && bn_moving && alpha && dc, "ar_head_step: null pointer");
   AR_REQUIRE(n > 0, "ar_head_step: n must be positive");
-  head_step_kernel<<<1, kHeadThreads, 0, (cudaStream_t)stream>>>(c, label, n, nullptr, head, head_m, head_v,
-                                                                  bn_moving, alpha, t, dc, metrics_row);
+  cudaStream_t st = (cudaStream_t)stream;
+  const int nfp = ceil_div(n, kRowWarps), nhb = ceil_div(n, kHeadThreads);
+  // stand-alone call: temporary scratch on the stream (ar_train_steps uses the caller's ctx buffers)
+  const size_t bytes = (size_t)nfp * 16 + (size_t)nhb * 64 + (size_t)n * 4 + K_STEPC * 4 + 16;
+  char* buf = nullptr;
+  AR_CUDA(cudaMallocAsync((void**)&buf, bytes, st));
+  double* fwd_part = (double*)buf;
+  double* head_part = fwd_part + 2 * (size_t)nfp;
+  float* dy = (float*)(head_part + 8 * (size_t)nhb);
+  float* stepc = dy + n;
+  unsigned int* ticket = (unsigned int*)(stepc + K_STEPC);
+  AR_CUDA(cudaMemsetAsync(ticket, 0, 4, st));
+  c_partials_kernel<<<ceil_div(nfp, 128), 128, 0, st>>>(c, n, fwd_part);
   AR_LAUNCH_CHECK();
+  head_step_kernel<<<nhb, kHeadThreads, 0, st>>>(c, label, n, nullptr, fwd_part, head, head_m, head_v, bn_moving,
+                                                  alpha, t, dy, head_part, stepc, ticket, metrics_row);
+  AR_LAUNCH_CHECK();
+  dc_from_dy_kernel<<<ceil_div(n, 256), 256, 0, st>>>(dy, c, n, stepc, dc);
+  AR_LAUNCH_CHECK();
+  AR_CUDA(cudaFreeAsync(buf, st));
   return AR_OK;
 }
 
@@ -630,14 +742,15 @@ extern "C" int ar_rows_catchup(const ar_table* tab, const ar_plan* plan, int32_t
 }
 
 extern "C" int ar_rows_update(const ar_table* tab, const ar_plan* plan, int32_t slot, const float* other_hat,
-                              const float* c, const float* dc, const float* rinv, const float* alpha, float l2,
-                              int64_t t, int32_t replay, double* sumsq_out, void* stream) {
-  AR_REQUIRE(tab && plan && other_hat && c && dc && rinv && alpha, "ar_rows_update: null pointer");
+                              const float* c, const float* dy, const float* stepc, const float* rinv,
+                              const float* alpha, float l2, int64_t t, int32_t replay, double* sumsq_out,
+                              void* stream) {
+  AR_REQUIRE(tab && plan && other_hat && c && dy && stepc && rinv && alpha, "ar_rows_update: null pointer");
   AR_REQUIRE(dim_ok(tab->dim), "ar_rows_update: dim %d unsupported", tab->dim);
   AR_REQUIRE(slot >= 0 && slot < plan->n_slots, "ar_rows_update: slot out of range");
   UpdateArgs a{};
   fill_update(a, 0, tab, plan, slot, other_hat, rinv, 0);
-  return launch_update(a, false, c, dc, alpha, l2, t, replay, sumsq_out, (cudaStream_t)stream);
+  return launch_update(a, false, c, dy, stepc, alpha, l2, t, replay, sumsq_out, (cudaStream_t)stream);
 }
 
 namespace ar {
@@ -677,18 +790,19 @@ static int run_steps(const ar_train_ctx& x, int64_t epoch_step0, int32_t slot0, 
     }
     AR_TICK(1);
     AR_DISPATCH_NV(dim, embed_fwd_kernel<NV><<<ceil_div(n, kRowWarps), kRowThreads, 0, st>>>(
-                            x.users.W, x.anime.W, dim, x.iu + base, x.ia + base, n, meta_u, x.uh, x.ah, x.c, x.ru, x.ra));
+                            x.users.W, x.anime.W, dim, x.iu + base, x.ia + base, n, meta_u, x.uh, x.ah, x.c, x.ru, x.ra, x.fwd_part));
     AR_LAUNCH_CHECK();
     AR_TICK(2);
-    head_step_kernel<<<1, kHeadThreads, 0, st>>>(x.c, x.label + base, n, meta_u, x.head, x.head_m, x.head_v,
-                                                 x.bn_moving, x.alpha, t, x.dc, x.metrics + t * 4);
+    head_step_kernel<<<ceil_div(n, kHeadThreads), kHeadThreads, 0, st>>>(
+        x.c, x.label + base, n, meta_u, x.fwd_part, x.head, x.head_m, x.head_v, x.bn_moving, x.alpha, t, x.dy,
+        x.head_part, x.stepc, x.ticket, x.metrics + t * 4);
     AR_LAUNCH_CHECK();
     AR_TICK(3);
     UpdateArgs a{};
     fill_update(a, 0, &x.users, &x.plan_u, slot, x.ah, x.ru, n);
     fill_update(a, 1, &x.anime, &x.plan_a, slot, x.uh, x.ra, n);
     double* ss = (x.mode == AR_ADAM_DENSE && x.reg_sumsq) ? x.reg_sumsq + t * 32 : nullptr;
-    int rc = launch_update(a, true, x.c, x.dc, x.alpha, x.l2, t, 0, ss, st);
+    int rc = launch_update(a, true, x.c, x.dy, x.stepc, x.alpha, x.l2, t, 0, ss, st);
     if (rc) return rc;
     AR_TICK(4);
     if (x.mode == AR_ADAM_DENSE) {
@@ -707,7 +821,8 @@ static int check_ctx(const ar_train_ctx* ctx, int32_t slot0, int32_t n_steps) {
   AR_REQUIRE(x.users.W && x.anime.W && x.head && x.alpha && x.iu && x.ia && x.label, "ar_train_steps: null pointer in ctx");
   AR_REQUIRE(x.users.dim == x.anime.dim && dim_ok(x.users.dim), "ar_train_steps: dim %d/%d unsupported", x.users.dim, x.anime.dim);
   AR_REQUIRE(x.batch > 0 && x.batch <= AR_MAX_BATCH, "ar_train_steps: batch %d outside (0,%d]", x.batch, AR_MAX_BATCH);
-  AR_REQUIRE(x.uh && x.ah && x.c && x.ru && x.ra && x.dc && x.metrics, "ar_train_steps: null scratch");
+  AR_REQUIRE(x.uh && x.ah && x.c && x.ru && x.ra && x.dy && x.fwd_part && x.head_part && x.stepc && x.ticket && x.metrics,
+             "ar_train_steps: null scratch");
   AR_REQUIRE(slot0 >= 0 && slot0 + n_steps <= x.plan_u.n_slots && slot0 + n_steps <= x.plan_a.n_slots,
              "ar_train_steps: plan slots [%d,%d) exceed plan size", slot0, slot0 + n_steps);
   AR_REQUIRE(x.mode >= AR_ADAM_REPLAY && x.mode <= AR_ADAM_TOUCHED, "ar_train_steps: bad mode %d", x.mode);

@@ -369,7 +369,11 @@ class TrainSession:
         self.plan_a, self._keep_a = self._make_plan(self.n_slots, B, dev)
         f = dict(dtype=torch.float32, device=dev)
         self.uh, self.ah = torch.empty((B, D), **f), torch.empty((B, D), **f)
-        self.c, self.ru, self.ra, self.dc = (torch.empty(B, **f) for _ in range(4))
+        self.c, self.ru, self.ra, self.dy = (torch.empty(B, **f) for _ in range(4))
+        self.fwd_part = torch.zeros(2 * ((B + 7) // 8), dtype=torch.float64, device=dev)
+        self.head_part = torch.zeros(8 * ((B + 255) // 256), dtype=torch.float64, device=dev)
+        self.stepc = torch.zeros(8, **f)
+        self.ticket = torch.zeros(1, dtype=torch.int32, device=dev)
         self.t_cap = model.iterations + int(total_steps)
         model._ensure_alpha(self.t_cap)
         self.metrics = torch.zeros((self.t_cap + 1, 4), **f)
@@ -401,8 +405,10 @@ class TrainSession:
         ctx.n_samples, ctx.batch, ctx.l2 = iu.numel(), self.B, m.l2
         ctx.mode = _capi.ADAM_MODES[m.adam_mode]
         ctx.plan_u, ctx.plan_a = self.plan_u, self.plan_a
-        ctx.uh, ctx.ah, ctx.c, ctx.ru, ctx.ra, ctx.dc = (z.data_ptr() for z in (
-            self.uh, self.ah, self.c, self.ru, self.ra, self.dc))
+        ctx.uh, ctx.ah, ctx.c, ctx.ru, ctx.ra, ctx.dy = (z.data_ptr() for z in (
+            self.uh, self.ah, self.c, self.ru, self.ra, self.dy))
+        ctx.fwd_part, ctx.head_part = self.fwd_part.data_ptr(), self.head_part.data_ptr()
+        ctx.stepc, ctx.ticket = self.stepc.data_ptr(), self.ticket.data_ptr()
         ctx.metrics = self.metrics.data_ptr()
         ctx.reg_sumsq = self.reg_ss.data_ptr() if self.reg_ss is not None else None
         return ctx

@@ -74,6 +74,18 @@ def cosine_topk_query(W, q, k, mask=None, exclude=None):
     return oi[keep], os_[keep]
 
 
+def cosine_topk_query_device(W, q, k, mask_bits=None, exclude=-1):
+    """Same kernel, device tensors in and out (idx int32[k] with -1 padding, score float32[k]); no host copy."""
+    n, D = W.shape
+    L = lib()
+    ws = torch.empty(max(8, L.ar_topk_query_workspace(n, k)), dtype=torch.uint8, device=W.device)
+    oi = torch.empty(k, dtype=torch.int32, device=W.device)
+    os_ = torch.empty(k, dtype=torch.float32, device=W.device)
+    check(L.ar_cosine_topk_query(ptr(W), n, D, int(q), ptr(mask_bits), int(exclude), k, ptr(oi), ptr(os_), ptr(ws),
+                                 stream_ptr()), "ar_cosine_topk_query")
+    return oi, os_
+
+
 def find_similar_users(W_users, q, n_users):
     """similar_users.py:293-312 / user_recs.py:475-488: top-(n+1) of ALL rows, then drop the query."""
     idx, sc = cosine_topk_query(W_users, q, n_users + 1)

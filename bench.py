@@ -1,0 +1,321 @@
+#!/usr/bin/env python
+"""bench.py -- headline measurement of the hot path on B200 (see DESIGN.md "Measurement").
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
+    python bench.py --impl reference --steps K --warmup W    # reference arithmetic on the host cores
+
+Workload (BASELINE.json configs[1]): synthetic 350 000 users x 18 000 anime, dim 128, batch 10 000,
+fp32 training; a "step" is one optimizer step over one batch.  One JSON line on stdout (rank 0).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+N_USERS, N_ANIME, DIM, BATCH = 350_000, 18_000, 128, 10_000
+L2 = 1e-4
+LR = 1e-5                      # lrfn(0) of the reference's schedule
+METRIC = "train_samples_per_s"
+UNIT = "samples/s"
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return dict(hbm_gbs=float(d["hbm_gbs"]), bf16_tflops=float(d["bf16_tflops"]),
+                    bf16_tflops_sustained=float(d.get("bf16_tflops_sustained", d["bf16_tflops"])), source="measured")
+    return dict(hbm_gbs=6650.0, bf16_tflops=1590.0, bf16_tflops_sustained=1400.0, source="fallback")
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks + throttle reasons while the timed region runs."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        super().__init__(daemon=True)
+        self.gpu, self.rows, self._halt = gpu_index, [], threading.Event()
+
+    def run(self):
+        while not self._halt.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q,
+                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
+                for line in out.strip().splitlines():
+                    self.rows.append([x.strip() for x in line.split(",")])
+            except Exception:  # noqa: BLE001
+                pass
+            self._halt.wait(0.2)
+
+    def stop(self):
+        self._halt.set()
+        self.join(timeout=3)
+        sm = [float(r[1]) for r in self.rows if len(r) > 8 and r[1].replace(".", "").isdigit()]
+        mx = [float(r[2]) for r in self.rows if len(r) > 8 and r[2].replace(".", "").isdigit()]
+        reasons = set()
+        for r in self.rows:
+            if len(r) > 8:
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
+                    if v.lower() == "active":
+                        reasons.add(name)
+        return dict(sm_mhz=float(np.median(sm)) if sm else None, sm_max_mhz=max(mx) if mx else None,
+                    reasons=sorted(reasons), samples=len(sm))
+
+
+def synth(n_samples, seed, device, zipf=False):
+    """SURVEY §8(d) cfg2 inputs: users uniform, anime uniform (or Zipf s~1), labels on {0,0.1,..,1}."""
+    import torch
+    g = torch.Generator(device=device)
+    g.manual_seed(seed)
+    iu = torch.randint(0, N_USERS, (n_samples,), generator=g, device=device, dtype=torch.int32)
+    if zipf:
+        w = 1.0 / torch.arange(1, N_ANIME + 1, device=device, dtype=torch.float64)
+        ia = torch.multinomial((w / w.sum()).float(), n_samples, replacement=True, generator=g).to(torch.int32)
+    else:
+        ia = torch.randint(0, N_ANIME, (n_samples,), generator=g, device=device, dtype=torch.int32)
+    y = torch.randint(0, 11, (n_samples,), generator=g, device=device).float() / 10.0
+    return iu, ia, y
+
+
+def unique_rows_per_step(idx, steps):
+    import torch
+    tot = 0
+    for s in range(steps):
+        tot += int(torch.unique(idx[s * BATCH:(s + 1) * BATCH]).numel())
+    return tot / max(1, steps)
+
+
+# ------------------------------------------------------------------------------------------ CPU arm
+def cpu_reference_run(steps, warmup, seed=42, budget_s=120.0):
+    """The reference's arithmetic (dense gradient + dense Keras Adam, what TF-2.12 executes for
+    neural_network.py:66-106) restated with PyTorch-CPU ops on all host cores (oracle/train_torch.py);
+    TensorFlow itself is not installable in this image."""
+    import torch
+    from oracle import train as ot, train_torch as tt
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    st = ot.init_state(N_USERS, N_ANIME, DIM, seed=1, w=1.0)
+    ts = tt.TorchState(st)
+    rng = np.random.RandomState(seed)
+    times = []
+    t_begin = time.perf_counter()
+    for s in range(warmup + steps):
+        iu = rng.randint(0, N_USERS, BATCH)
+        ia = rng.randint(0, N_ANIME, BATCH)
+        y = (rng.randint(0, 11, BATCH) / 10.0).astype(np.float32)
+        t0 = time.perf_counter()
+        tt.train_step(ts, iu, ia, y, LR, L2)
+        dt = time.perf_counter() - t0
+        if s >= warmup:
+            times.append(dt)
+        if time.perf_counter() - t_begin > budget_s and len(times) >= 2:
+            break
+    ms = 1e3 * float(np.mean(times))
+    return dict(value=BATCH / (ms / 1e3), ms_per_step=ms, steps=len(times), cores=cores)
+
+
+def reference_main(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    r = cpu_reference_run(args.steps, args.warmup)
+    sample = "%d dense steps of batch %d at cfg2 table shapes (after %d warm-up)" % (r["steps"], BATCH, args.warmup)
+    line = dict(impl="reference", metric=METRIC, value=r["value"], unit=UNIT, n_gpus=args.gpus, steps=r["steps"],
+                warmup=args.warmup, ms_per_step=r["ms_per_step"], higher_is_better=True, scaling="weak",
+                vs_baseline=None, dtype="f32", data="synthetic",
+                config=workload_config("dense (reference arithmetic)", 1),
+                cpu_baseline=dict(value=r["value"], unit=UNIT, cores=r["cores"], kind="port", sample=sample),
+                e2e=dict(value=r["value"], unit=UNIT, h2d_bytes_per_step=0, d2h_bytes_per_step=0),
+                note="CPU restatement of the reference's TF-2.12 train step (oracle/train_torch.py); "
+                     "TensorFlow is not installable in this image")
+    print(json.dumps(line))
+    return 0
+
+
+def workload_config(mode, n_gpus):
+    return dict(workload="cfg2: synthetic 350k users x 18k anime, dim 128, batch 10000/GPU, fp32 embedding-model "
+                         "training step (neural_network.py:66-106)",
+                n_users=N_USERS, n_anime=N_ANIME, dim=DIM, batch_per_gpu=BATCH, global_batch=BATCH * n_gpus,
+                adam_mode=mode, l2=L2, lr=LR,
+                l2_flush="inputs larger than L2: 3 x 188 MB of table+Adam state, rows drawn at random each step",
+                parallelism="dp%d" % n_gpus)
+
+
+# ------------------------------------------------------------------------------------------ GPU arm
+def gpu_main(args):
+    import torch
+    import torch.distributed as dist
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    import anime_recommendations_b200 as ar
+    from anime_recommendations_b200.model import TrainSession
+    pk = peaks()
+    K, W = args.steps, args.warmup
+    mode = args.mode
+
+    model = ar.EmbeddingDotModel(N_USERS, N_ANIME, DIM, l2_reg_factor=L2, seed=1, adam_mode=mode, dense_kernel=1.0)
+    iu, ia, y = synth((W + K) * BATCH, 42 + rank, dev, zipf=args.zipf)
+    if world > 1:
+        from anime_recommendations_b200 import dist as ardist
+        sess = ardist.DistTrainSession(model, BATCH, total_steps=2 * (W + K) + 8)
+    else:
+        sess = TrainSession(model, BATCH, total_steps=2 * (W + K) + 8)
+    # warm-up (untimed)
+    sess.run(iu[:W * BATCH], ia[:W * BATCH], y[:W * BATCH], LR)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    sampler = ClockSampler(local) if rank == 0 else None
+    if sampler:
+        sampler.start()
+    l0 = sess.launches
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    e0.record()
+    sess.run(iu[W * BATCH:], ia[W * BATCH:], y[W * BATCH:], LR)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    launches = sess.launches - l0
+    if world > 1:
+        t = torch.tensor([ms], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+        dist.barrier()
+    clocks = sampler.stop() if sampler else None
+    value = world * K * BATCH / (ms / 1e3)
+
+    line = dict(metric=METRIC, value=value, unit=UNIT, n_gpus=world, steps=K, warmup=W, ms_per_step=ms / K,
+                higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f32", data="synthetic",
+                config=workload_config(mode, world), gpu_launches=int(launches), clocks=clocks)
+
+    if rank == 0 and world == 1:
+        # ---- roofline of the dominant kernel: per-stage device time measured live with CUDA events
+        prof = [0.0] * 5
+        iu2, ia2, y2 = synth(K * BATCH, 4242, dev, zipf=args.zipf)
+        sess.run(iu2, ia2, y2, LR, profile=prof)
+        uu = unique_rows_per_step(iu2, min(K, 16))
+        ua = unique_rows_per_step(ia2, min(K, 16))
+        names = ["rows_catchup", "embed_fwd", "head_step", "rows_update", "dense_flush"]
+        row_b = DIM * 4
+        alg = dict(rows_catchup=(uu + ua) * row_b * 6,
+                   embed_fwd=BATCH * row_b * 2 * 2 + BATCH * 20,              # gather 2 rows, save 2 normalised rows
+                   head_step=BATCH * 12,
+                   rows_update=(uu + ua) * row_b * 6 + BATCH * row_b * 2 + BATCH * 24,
+                   dense_flush=(N_USERS + N_ANIME) * row_b * 6)
+        stage = {n: dict(ms_per_step=prof[i] / K, alg_bytes=alg[n],
+                         gbs=(alg[n] / (prof[i] / K * 1e-3) / 1e9 if prof[i] > 0 else 0.0)) for i, n in enumerate(names)}
+        dom = max(names, key=lambda n: stage[n]["ms_per_step"])
+        # step-level accounting of SURVEY §8(d): touched rows (replay/touched) or dense
+        if mode == "dense":
+            step_bytes = (N_USERS + N_ANIME) * row_b * 6 + BATCH * row_b * 2 + BATCH * 12
+        else:
+            step_bytes = BATCH * row_b * 2 + (uu + ua) * row_b * 6 + BATCH * 12
+        line["roofline"] = dict(bound="hbm", kernel=dom, achieved=stage[dom]["gbs"], peak=pk["hbm_gbs"], unit="GB/s",
+                                frac=stage[dom]["gbs"] / pk["hbm_gbs"], traffic=None, peak_source=pk["source"],
+                                accounting="dense" if mode == "dense" else "touched-rows",
+                                step=dict(alg_bytes=step_bytes, gbs=step_bytes / (ms / K * 1e-3) / 1e9,
+                                          frac=step_bytes / (ms / K * 1e-3) / 1e9 / pk["hbm_gbs"],
+                                          unique_user_rows=uu, unique_anime_rows=ua),
+                                stages=stage)
+
+        # ---- e2e: the public API (Model.fit) fed from pinned HOST buffers, copies inside the timed region
+        m2 = ar.EmbeddingDotModel(N_USERS, N_ANIME, DIM, l2_reg_factor=L2, seed=1, adam_mode=mode, dense_kernel=1.0)
+        m2.lr = LR
+        hu, ha, hy = (t.cpu().pin_memory() for t in synth(K * BATCH, 77, dev, zipf=args.zipf))
+        wu, wa, wy = (t.cpu().pin_memory() for t in synth(W * BATCH, 78, dev, zipf=args.zipf))
+        m2.fit([wu, wa], wy, batch_size=BATCH, epochs=1, shuffle=False)         # warm-up epoch
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        h = m2.fit([hu, ha], hy, batch_size=BATCH, epochs=1, shuffle=False)
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        line["e2e"] = dict(value=K * BATCH / dt, unit=UNIT, h2d_bytes_per_step=BATCH * 12, d2h_bytes_per_step=16,
+                           seconds=dt, loss=h.history["loss"][0],
+                           what="Model.fit([users, animes], ratings) from pinned host arrays: H2D of the step inputs, "
+                                "plan build, K steps, end-of-epoch flush + L2 term, D2H of per-step metrics")
+
+        # ---- CPU baseline (bounded sample) beside the GPU number
+        if not args.skip_cpu:
+            r = cpu_reference_run(steps=8, warmup=1, budget_s=25.0)
+            line["cpu_baseline"] = dict(value=r["value"], unit=UNIT, cores=r["cores"], kind="port",
+                                        sample="%d dense steps of batch %d at cfg2 table shapes, torch-CPU "
+                                               "restatement of the TF step" % (r["steps"], BATCH),
+                                        ms_per_step=r["ms_per_step"])
+        if not args.skip_extras:
+            line["extras"] = extras(dev, pk)
+    elif rank == 0:
+        line["e2e"] = None
+    if rank == 0:
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+def extras(dev, pk):
+    """Half-B numbers reported beside the headline: single-query cosine top-k over the user table."""
+    import torch
+    from anime_recommendations_b200 import similarity as sim
+    out = {}
+    g = torch.Generator(device=dev)
+    g.manual_seed(7)
+    Wt = torch.randn((N_USERS, DIM), generator=g, device=dev)
+    flush = torch.empty(256 * 1024 * 1024 // 4, device=dev)
+    qs = [int(x) for x in np.random.RandomState(0).randint(0, N_USERS, 20)]
+    sim.cosine_topk_query(Wt, qs[0], 11)
+    ts = []
+    for q in qs:
+        flush.fill_(0.0)                                # write 256 MB > L2 between timed iterations
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        sim.cosine_topk_query_device(Wt, q, 11)
+        e1.record()
+        torch.cuda.synchronize()
+        ts.append(e0.elapsed_time(e1))
+    ms = float(np.median(ts))
+    by = N_USERS * DIM * 4
+    out["query_topk_users"] = dict(rows=N_USERS, dim=DIM, k=11, ms=ms, rows_per_s=N_USERS / (ms / 1e3),
+                                   gbs=by / (ms / 1e3) / 1e9, frac_hbm=by / (ms / 1e3) / 1e9 / pk["hbm_gbs"],
+                                   l2_flush="256 MB write between iterations")
+    return out
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=20)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--mode", default="replay", choices=["replay", "dense", "touched"])
+    ap.add_argument("--zipf", action="store_true", help="Zipf(1) anime popularity instead of uniform")
+    ap.add_argument("--skip-cpu", action="store_true")
+    ap.add_argument("--skip-extras", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "b200" else max(args.warmup, 1)
+    if args.impl == "reference":
+        return reference_main(args)
+    return gpu_main(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -105,7 +105,11 @@ typedef struct {
   float* c;            /* (batch) cosine */
   float* ru;           /* (batch) 1/||u|| */
   float* ra;           /* (batch) 1/||a|| */
-  float* dc;           /* (batch) dLoss/dc */
+  float* dy;           /* (batch) dLoss/dy = (p - t)/n per sample */
+  double* fwd_part;    /* (2*ceil(batch/8)) per-CTA (sum c, sum c^2) of the forward kernel */
+  double* head_part;   /* (8*ceil(batch/256)) per-CTA partial sums of the head kernel */
+  float* stepc;        /* (8) per-step scalars the head hands to the row update */
+  uint32_t* ticket;    /* (1) zero-initialised arrival counter of the head kernel */
   /* per-step outputs, indexed by global step t (1-based): metrics[t*4 + {0: mean BCE, 1: mean
    * squared error, 2: n, 3: batch mean of z}] ; reg_sumsq[t*32 + j], j<32: partial sums whose total is sum U^2 + sum A^2 BEFORE step t
    * (written in AR_ADAM_DENSE only; may be null) */
@@ -139,8 +143,8 @@ int ar_head_step(const float* c, const float* label, int32_t n, float* head, flo
 int ar_rows_catchup(const ar_table* tab, const ar_plan* plan, int32_t slot, const float* alpha,
                     float l2, int64_t t, void* stream);
 int ar_rows_update(const ar_table* tab, const ar_plan* plan, int32_t slot, const float* other_hat,
-                   const float* c, const float* dc, const float* rinv, const float* alpha, float l2,
-                   int64_t t, int32_t replay, double* sumsq_out, void* stream);
+                   const float* c, const float* dy, const float* stepc, const float* rinv,
+                   const float* alpha, float l2, int64_t t, int32_t replay, double* sumsq_out, void* stream);
 
 /* Inference forward, Keras `model.predict([users, animes])` (model_recs.py:394): BN uses the
  * moving statistics.  out: (n) float32 probabilities. */
