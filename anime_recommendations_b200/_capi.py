@@ -46,6 +46,13 @@ class ArTrainCtx(C.Structure):
                 ("metrics", C.c_void_p), ("reg_sumsq", C.c_void_p)]
 
 
+class ArDistCtx(C.Structure):
+    _fields_ = [("comm", C.c_void_p), ("n_ranks", C.c_int32), ("rank", C.c_int32),
+                ("c_all", C.c_void_p), ("label_all", C.c_void_p), ("dy_all", C.c_void_p),
+                ("fwd_part_all", C.c_void_p), ("head_part_all", C.c_void_p),
+                ("send", C.c_void_p), ("recv", C.c_void_p)]
+
+
 class AnimerecError(RuntimeError):
     pass
 
@@ -61,6 +68,11 @@ SIGNATURES = {
     "ar_plan_build": (C.c_int, [_P, _I64, _I32, _I64, _I32, C.POINTER(ArPlan), _P]),
     "ar_train_steps": (C.c_int, [C.POINTER(ArTrainCtx), _I64, _I32, _I64, _I32, _P]),
     "ar_train_steps_profile": (C.c_int, [C.POINTER(ArTrainCtx), _I64, _I32, _I64, _I32, C.POINTER(C.c_float), _P]),
+    "ar_nccl_unique_id": (C.c_int, [_P]),
+    "ar_comm_init": (C.c_int, [_P, _I32, _I32, C.POINTER(C.c_void_p)]),
+    "ar_comm_destroy": (C.c_int, [_P]),
+    "ar_train_steps_dist": (C.c_int, [C.POINTER(ArTrainCtx), C.POINTER(ArDistCtx), _I64, _I32, _I64, _I32, _P]),
+    "ar_allgather_bytes": (C.c_int, [_P, _P, _P, _I64, _P]),
     "ar_table_flush": (C.c_int, [C.POINTER(ArTable), _P, _F, _I64, _P]),
     "ar_embed_fwd": (C.c_int, [_P, _P, _I32, _P, _P, _I32, _P, _P, _P, _P, _P, _P]),
     "ar_head_step": (C.c_int, [_P, _P, _I32, _P, _P, _P, _P, _P, _I64, _P, _P, _P]),

@@ -16,6 +16,8 @@
 //
 // Arithmetic follows oracle/train.py (the restatement of neural_network.py:66-106 under
 // Keras-2.12 semantics); citations there.
+#include <string.h>
+
 #include <algorithm>
 #include <vector>
 
@@ -90,13 +92,16 @@ struct CatchupArgs {
   int blocks0;  // CTAs assigned to table 0
 };
 
+// One warp per CTA: replay lengths are geometric (mean n_rows/unique-per-step, max ~10x that), and a CTA
+// only frees its SM slot when its slowest warp ends -- with 8 rows per CTA the SFU sat idle ~60% of the
+// time (measured 57 us vs a 20 us MUFU floor); single-warp CTAs let every finished row make room at once.
+constexpr int kCatchThreads = 32;
 template <int NV>
-__global__ void __launch_bounds__(kRowThreads)
+__global__ void __launch_bounds__(kCatchThreads)
 rows_catchup_kernel(CatchupArgs a, const float* __restrict__ alpha, float l2x2, int64_t t_target) {
   const bool second = blockIdx.x >= a.blocks0;
-  const int blk = second ? blockIdx.x - a.blocks0 : blockIdx.x;
+  const int seg = second ? blockIdx.x - a.blocks0 : blockIdx.x;
   const int lane = threadIdx.x & 31;
-  const int seg = blk * kRowWarps + (threadIdx.x >> 5);
   const int32_t* meta = second ? a.meta[1] : a.meta[0];
   if (seg >= meta[0]) return;
   ar_table tb;
@@ -318,7 +323,11 @@ head_step_kernel(const float* __restrict__ c, const float* __restrict__ label, i
   __threadfence();
   double s2[kHeadSums];
 #pragma unroll
-  for (int k = 0; k < kHeadSums; ++k) s2[k] = (tid < nblk) ? __ldcg(head_part + tid * 8 + k) : 0.0;
+  for (int k = 0; k < kHeadSums; ++k) s2[k] = 0.0;
+  for (int j = tid; j < nblk; j += kHeadThreads) {
+#pragma unroll
+    for (int k = 0; k < kHeadSums; ++k) s2[k] += __ldcg(head_part + j * 8 + k);
+  }
   block_sum<kHeadSums>(s2, red);
   if (tid == 0) {
     const double S1 = s2[2], S2 = s2[3], Szh = s2[4], Sdyc = s2[5], Szhc = s2[6], Sc = s0[0];
@@ -392,6 +401,11 @@ struct UpdateArgs {
   const float* rinv[2];   // (batch) 1/||row|| per sample of THIS table
   int blocks_norm[2];     // warp-per-row CTAs per table
   int blocks_heavy[2];    // CTA-per-heavy-row CTAs per table
+  // multi-GPU: instead of updating, emit (row id, q, P[dim]) per segment for the gradient exchange
+  int32_t* emit_ids[2];
+  float* emit_q[2];
+  float* emit_P[2];
+  int emit_cap;           // entries per table in the emit buffers; ids beyond n_uniq are set to INT_MAX
 };
 
 template <int NV>
@@ -412,6 +426,7 @@ __device__ __forceinline__ void finish_row(const ar_table& tb, int row, RowTile<
     float ss = tile_dot<NV>(w, w);
     if (lane == 0) atomicAdd(sumsq_out + ((blockIdx.x * kRowWarps + (threadIdx.x >> 5)) & 31), (double)ss);
   }
+  if (rinv < 0.f) rinv = 1.0f / sqrtf(fmaxf(tile_dot<NV>(w, w), kL2NormEps));  // same formula as embed_fwd
   const float a = alpha[t];
 #pragma unroll
   for (int k = 0; k < NV; ++k) {
@@ -457,13 +472,19 @@ rows_update_kernel(UpdateArgs a, const float* __restrict__ c, const float* __res
   const int32_t* __restrict__ heavy = which ? a.heavy[1] : a.heavy[0];
   const float* __restrict__ other = which ? a.other[1] : a.other[0];
   const float* __restrict__ rinv = which ? a.rinv[1] : a.rinv[0];
+  int32_t* __restrict__ emit_ids = which ? a.emit_ids[1] : a.emit_ids[0];
+  float* __restrict__ emit_q = which ? a.emit_q[1] : a.emit_q[0];
+  float* __restrict__ emit_P = which ? a.emit_P[1] : a.emit_P[0];
   float kk[K_STEPC];
 #pragma unroll
   for (int i = 0; i < K_STEPC; ++i) kk[i] = stepc[i];
 
   if (!heavy_path) {
     const int seg = b * kRowWarps + wid;
-    if (seg >= meta[0]) return;
+    if (seg >= meta[0]) {
+      if (emit_ids && seg < a.emit_cap && lane == 0) emit_ids[seg] = 0x7fffffff;
+      return;
+    }
     const int beg = off[seg], end = off[seg + 1];
     if (end - beg > AR_HEAVY_LEN) return;  // CTA path handles it
     RowTile<NV> acc;
@@ -494,6 +515,14 @@ rows_update_kernel(UpdateArgs a, const float* __restrict__ c, const float* __res
       q = fmaf(d0, c0, q);
 #pragma unroll
       for (int k = 0; k < NV; ++k) acc.x[k] = fma4(d0, o0.x[k], acc.x[k]);
+    }
+    if (emit_ids) {
+      acc.store(emit_P + (size_t)seg * dim, d4, lane);
+      if (lane == 0) {
+        emit_ids[seg] = uniq[seg];
+        emit_q[seg] = q;
+      }
+      return;
     }
     finish_row<NV>(tb, uniq[seg], acc, q, rinv[order[beg]], alpha, l2x2, t, replay, sumsq_out, lane);
     return;
@@ -531,6 +560,14 @@ rows_update_kernel(UpdateArgs a, const float* __restrict__ c, const float* __res
       acc.x[k].x += p.x[k].x; acc.x[k].y += p.x[k].y; acc.x[k].z += p.x[k].z; acc.x[k].w += p.x[k].w;
     }
     q += qred[w8];
+  }
+  if (emit_ids) {
+    acc.store(emit_P + (size_t)seg * dim, d4, lane);
+    if (lane == 0) {
+      emit_ids[seg] = uniq[seg];
+      emit_q[seg] = q;
+    }
+    return;
   }
   finish_row<NV>(tb, uniq[seg], acc, q, rinv[order[beg]], alpha, l2x2, t, replay, sumsq_out, lane);
 }
@@ -633,16 +670,16 @@ static int launch_catchup(const ar_table* t0, const ar_plan* p0, int slot0, cons
   a.tab[0] = *t0;
   a.uniq[0] = p0->uniq + (int64_t)slot0 * p0->batch_cap;
   a.meta[0] = p0->meta + (int64_t)slot0 * 4;
-  a.blocks0 = ceil_div(p0->batch_cap, kRowWarps);
+  a.blocks0 = p0->batch_cap;
   int blocks = a.blocks0;
   if (t1) {
     a.tab[1] = *t1;
     a.uniq[1] = p1->uniq + (int64_t)slot1 * p1->batch_cap;
     a.meta[1] = p1->meta + (int64_t)slot1 * 4;
-    blocks += ceil_div(p1->batch_cap, kRowWarps);
+    blocks += p1->batch_cap;
   }
   const float l2x2 = (float)(2.0 * (double)l2);
-  AR_DISPATCH_NV(t0->dim, rows_catchup_kernel<NV><<<blocks, kRowThreads, 0, st>>>(a, alpha, l2x2, t_target));
+  AR_DISPATCH_NV(t0->dim, rows_catchup_kernel<NV><<<blocks, kCatchThreads, 0, st>>>(a, alpha, l2x2, t_target));
   AR_LAUNCH_CHECK();
   return AR_OK;
 }
@@ -862,6 +899,8 @@ extern "C" int ar_train_steps_profile(const ar_train_ctx* ctx, int64_t epoch_ste
   for (cudaEvent_t e : tm.ev) cudaEventDestroy(e);
   return rc;
 }
+
+#include "dist.inl"
 
 extern "C" int ar_predict(const float* U, const float* A, int32_t dim, const float* head, const float* bn_moving,
                           const int32_t* iu, const int32_t* ia, int64_t n, float* out, void* stream) {

@@ -1,0 +1,93 @@
+"""Multi-GPU plumbing: one process per GPU (torchrun), torch.distributed for rendezvous, NCCL collectives
+issued from libanimerec on the kernels' stream.
+
+* DistTrainSession  -- replicated-table data-parallel training (BASELINE cfg2): every rank trains on its
+  own shard of each global batch; SyncBN + all-gathered, merged row gradients keep replicas bit-identical.
+* Comm              -- the library's own NCCL communicator (ncclCommInitRank with an id broadcast through
+  torch.distributed), also used by the candidate-sharded top-k.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+from . import _capi
+from ._capi import ArDistCtx, check, lib, ptr, stream_ptr
+from .model import TrainSession
+
+
+class Comm:
+    """ncclComm_t owned by libanimerec; world = the default torch.distributed group."""
+
+    def __init__(self):
+        if not dist.is_initialized():
+            raise _capi.AnimerecError("torch.distributed must be initialised (torchrun) before Comm()")
+        self.rank, self.world = dist.get_rank(), dist.get_world_size()
+        ident = (C.c_ubyte * 128)()
+        if self.rank == 0:
+            check(lib().ar_nccl_unique_id(ident), "ar_nccl_unique_id")
+        dev = torch.device("cuda", torch.cuda.current_device()) if dist.get_backend() == "nccl" else torch.device("cpu")
+        t = torch.tensor(list(bytes(ident)), dtype=torch.uint8, device=dev)
+        dist.broadcast(t, src=0)
+        ident = (C.c_ubyte * 128)(*t.cpu().tolist())
+        h = C.c_void_p()
+        check(lib().ar_comm_init(ident, self.world, self.rank, C.byref(h)), "ar_comm_init")
+        self.handle = h
+
+    def allgather(self, t):
+        """[world, *t.shape] tensor of every rank's `t` (equal shapes), on the current stream."""
+        t = t.contiguous()
+        out = torch.empty((self.world,) + tuple(t.shape), dtype=t.dtype, device=t.device)
+        check(lib().ar_allgather_bytes(self.handle, ptr(t), ptr(out), t.numel() * t.element_size(), stream_ptr()),
+              "ar_allgather_bytes")
+        return out
+
+    def close(self):
+        if self.handle:
+            check(lib().ar_comm_destroy(self.handle), "ar_comm_destroy")
+            self.handle = None
+
+
+class DistTrainSession(TrainSession):
+    """TrainSession whose steps run ar_train_steps_dist: `batch` is the PER-RANK batch."""
+
+    def __init__(self, model, batch, total_steps, comm=None):
+        super().__init__(model, batch, total_steps)
+        self.comm = comm or Comm()
+        G, B, D, dev = self.comm.world, self.B, model.dim, model.device
+        f = dict(dtype=torch.float32, device=dev)
+        self.c_all, self.label_all, self.dy_all = (torch.empty(G * B, **f) for _ in range(3))
+        self.fwd_part_all = torch.zeros(2 * ((G * B + 7) // 8), dtype=torch.float64, device=dev)
+        self.head_part_all = torch.zeros(8 * ((G * B + 255) // 256), dtype=torch.float64, device=dev)
+        words = 2 * B * (D + 2)
+        self.send = torch.zeros(words, **f)
+        self.recv = torch.zeros(G * words, **f)
+        d = ArDistCtx()
+        d.comm, d.n_ranks, d.rank = self.comm.handle, G, self.comm.rank
+        d.c_all, d.label_all, d.dy_all = self.c_all.data_ptr(), self.label_all.data_ptr(), self.dy_all.data_ptr()
+        d.fwd_part_all, d.head_part_all = self.fwd_part_all.data_ptr(), self.head_part_all.data_ptr()
+        d.send, d.recv = self.send.data_ptr(), self.recv.data_ptr()
+        self.dctx = d
+
+    def run(self, iu, ia, y, lr, profile=None):
+        m, B = self.model, self.B
+        N = iu.numel()
+        steps = (N + B - 1) // B
+        t0 = m.iterations
+        if t0 + steps > self.t_cap:
+            raise _capi.AnimerecError("DistTrainSession sized for %d optimizer steps, %d requested" % (self.t_cap, t0 + steps))
+        m._set_alpha(lr, t0 + 1, steps)
+        ctx = self._ctx(iu, ia, y)
+        st, L = stream_ptr(), lib()
+        per_step = {"replay": 6, "dense": 7, "touched": 5}[m.adam_mode]
+        for s0 in range(0, steps, self.n_slots):
+            ns = min(self.n_slots, steps - s0)
+            check(L.ar_plan_build(ptr(iu), N, B, s0, ns, C.byref(self.plan_u), st), "ar_plan_build(users)")
+            check(L.ar_plan_build(ptr(ia), N, B, s0, ns, C.byref(self.plan_a), st), "ar_plan_build(anime)")
+            check(L.ar_train_steps_dist(C.byref(ctx), C.byref(self.dctx), s0, 0, t0 + s0, ns, st), "ar_train_steps_dist")
+            self.launches += 2 + ns * per_step
+        m.iterations = t0 + steps
+        return steps

@@ -13,6 +13,7 @@ from __future__ import annotations
 
 import ctypes as C
 import math
+import os
 import time
 
 import numpy as np
@@ -304,9 +305,20 @@ class EmbeddingDotModel:
                 iu_e, ia_e, y_e = iu_all, ia_all, y_all
             else:
                 iu_e, ia_e, y_e = iu_all[perm].contiguous(), ia_all[perm].contiguous(), y_all[perm].contiguous()
+            dbg = os.environ.get("AR_FIT_TIMING") == "1"
+            tick = []
+
+            def _tk(name):
+                if dbg:
+                    torch.cuda.synchronize()
+                    tick.append((name, time.perf_counter()))
+            _tk("start")
             reg0 = None if dense else self.l2 * self.reg_sumsq()
+            _tk("reg0")
             sess.run(iu_e, ia_e, y_e, lr)
+            _tk("steps")
             self._sync_tables()
+            _tk("flush")
 
             m = sess.metrics[t0 + 1:t0 + steps + 1].cpu().numpy().astype(np.float64)
             w = m[:, 2]
@@ -329,6 +341,10 @@ class EmbeddingDotModel:
                 logs["val_loss"] = float(sv[0] / nv + reg1)
                 logs["val_mse"] = float(sv[1] / nv)
             logs["lr"] = float(np.float32(lr))
+            _tk("metrics+val")
+            if dbg:
+                self.timings.setdefault("sections", []).append(
+                    {b[0]: b[1] - a[1] for a, b in zip(tick[:-1], tick[1:])})
             self.timings.setdefault("epoch_s", []).append(time.perf_counter() - t_epoch)
             self.last_epoch_parts = dict(bce=bce, reg=reg, reg_end=reg1)
             for k, v in logs.items():

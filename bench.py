@@ -40,40 +40,61 @@ def peaks():
 
 
 class ClockSampler(threading.Thread):
-    """nvidia-smi clocks + throttle reasons while the timed region runs."""
+    """SM clock + throttle reasons while the timed region runs, read in-process through NVML (pynvml);
+    an external `nvidia-smi -lms` would contend for the driver lock and perturb a 15 ms timed region."""
 
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
-         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
-         "clocks_event_reasons.sw_power_cap")
-
-    def __init__(self, gpu_index):
+    def __init__(self, gpu_index, period_s=0.005):
         super().__init__(daemon=True)
-        self.gpu, self.rows, self._halt = gpu_index, [], threading.Event()
+        self.gpu, self.period, self.rows, self._halt = gpu_index, period_s, [], threading.Event()
+        self.nv = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(gpu_index)
+            self.max_sm = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+        except Exception:  # noqa: BLE001
+            self.nv = None
+
+    def _sample(self):
+        nv = self.nv
+        sm = float(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+        try:
+            r = int(nv.nvmlDeviceGetCurrentClocksEventReasons(self.h))
+        except Exception:  # noqa: BLE001
+            r = int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h))
+        try:
+            util = int(nv.nvmlDeviceGetUtilizationRates(self.h).gpu)
+        except Exception:  # noqa: BLE001
+            util = -1
+        self.rows.append((sm, r, util))
 
     def run(self):
+        if self.nv is None:
+            return
         while not self._halt.is_set():
             try:
-                out = subprocess.run(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q,
-                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
-                for line in out.strip().splitlines():
-                    self.rows.append([x.strip() for x in line.split(",")])
+                self._sample()
             except Exception:  # noqa: BLE001
                 pass
-            self._halt.wait(0.2)
+            self._halt.wait(self.period)
 
     def stop(self):
         self._halt.set()
         self.join(timeout=3)
-        sm = [float(r[1]) for r in self.rows if len(r) > 8 and r[1].replace(".", "").isdigit()]
-        mx = [float(r[2]) for r in self.rows if len(r) > 8 and r[2].replace(".", "").isdigit()]
-        reasons = set()
-        for r in self.rows:
-            if len(r) > 8:
-                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
-                    if v.lower() == "active":
-                        reasons.add(name)
-        return dict(sm_mhz=float(np.median(sm)) if sm else None, sm_max_mhz=max(mx) if mx else None,
-                    reasons=sorted(reasons), samples=len(sm))
+        if self.nv is None or not self.rows:
+            return dict(sm_mhz=None, sm_max_mhz=None, reasons=[], samples=0, source="nvml unavailable")
+        nv = self.nv
+        names = dict(hw_slowdown=0x8, sw_power_cap=0x4, sw_thermal_slowdown=0x20, hw_thermal_slowdown=0x40,
+                     hw_power_brake_slowdown=0x80)
+        seen = set()
+        for _, r, _ in self.rows:
+            for k, bit in names.items():
+                if r & bit:
+                    seen.add(k)
+        sm = [x[0] for x in self.rows]
+        return dict(sm_mhz=float(np.median(sm)), sm_min_mhz=float(min(sm)), sm_max_mhz=self.max_sm,
+                    reasons=sorted(seen), samples=len(sm), source="nvml, %.0f ms period" % (self.period * 1e3))
 
 
 def synth(n_samples, seed, device, zipf=False):

@@ -129,6 +129,37 @@ int ar_train_steps(const ar_train_ctx* ctx, int64_t epoch_step0, int32_t slot0, 
 int ar_train_steps_profile(const ar_train_ctx* ctx, int64_t epoch_step0, int32_t slot0, int64_t t0,
                            int32_t n_steps, float* stage_ms_host, void* stream);
 
+/* ---- multi-GPU training, replicated tables (one process per GPU, NCCL over NVLink) ----
+ * The reference's only data-parallel path is tf.distribute TPUStrategy (neural_network.py:142-147,
+ * 173-182: replicated variables, implicit gradient all-reduce); this is its B200 counterpart.
+ * NCCL is resolved with dlopen("libnccl.so.2") at run time. */
+int ar_nccl_unique_id(void* id_out_host /* 128 bytes, host */);
+int ar_comm_init(const void* id_host /* 128 bytes */, int32_t n_ranks, int32_t rank, void** comm_out);
+int ar_comm_destroy(void* comm);
+
+typedef struct {
+  void* comm;            /* from ar_comm_init */
+  int32_t n_ranks;
+  int32_t rank;
+  float* c_all;          /* (n_ranks*batch) cosines of the global batch, rank-major */
+  float* label_all;      /* (n_ranks*batch) */
+  float* dy_all;         /* (n_ranks*batch) */
+  double* fwd_part_all;  /* (2*ceil(n_ranks*batch/8)) */
+  double* head_part_all; /* (8*ceil(n_ranks*batch/256)) */
+  float* send;           /* (2*batch*(dim+2)) packed partial row gradients of this rank:
+                            [ids_u | q_u | P_u(batch,dim) | ids_a | q_a | P_a(batch,dim)], ids int32 */
+  float* recv;           /* n_ranks such blocks */
+} ar_dist_ctx;
+
+/* ar_train_steps for rank `d->rank` of `d->n_ranks`: ctx holds this rank's samples (every rank must
+ * pass the same n_samples and batch); global batch = n_ranks*batch; BatchNorm statistics and the head
+ * update are computed over the global batch, row gradients are all-gathered and merged, so all
+ * replicas stay bit-identical and equal to a single-GPU run on the concatenated batch. */
+int ar_train_steps_dist(const ar_train_ctx* ctx, const ar_dist_ctx* d, int64_t epoch_step0,
+                        int32_t slot0, int64_t t0, int32_t n_steps, void* stream);
+/* NCCL all-gather of equally sized byte buffers (sharded top-k lists before ar_topk_merge). */
+int ar_allgather_bytes(void* comm, const void* send, void* recv, int64_t bytes_per_rank, void* stream);
+
 /* Bring every row of the table to optimizer step t_target by replaying its missed pure-L2 steps
  * (no-op per row when last_step >= t_target).  Used at epoch end / before validation, saving and
  * similarity in AR_ADAM_REPLAY, and as the "all other rows" half of a dense step. */

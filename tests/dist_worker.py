@@ -1,0 +1,74 @@
+"""Worker for tests/test_gpu_dist.py (one process per GPU)."""
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+
+def main(mode):
+    rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+    torch.cuda.set_device(int(os.environ["LOCAL_RANK"]))
+    dev = torch.device("cuda", int(os.environ["LOCAL_RANK"]))
+    dist.init_process_group("nccl", device_id=dev)
+    import anime_recommendations_b200 as ar
+    from anime_recommendations_b200.dist import DistTrainSession
+    from anime_recommendations_b200.model import TrainSession
+    nu, na, D, B, steps = 5000, 700, 128, 1000, 6
+    rng = np.random.RandomState(5)
+    n_glob = world * B * steps - world * 300                      # last step partial (700 per rank)
+    iu = rng.randint(0, nu, n_glob).astype(np.int32)
+    ia = rng.randint(0, na, n_glob).astype(np.int32)
+    ia[rng.rand(n_glob) < 0.2] = 3                                # heavy anime row
+    y = (rng.randint(0, 11, n_glob) / 10.0).astype(np.float32)
+    # global step s = concatenation over ranks of each rank's s-th local batch
+    per = n_glob // world
+    sl = slice(rank * per, (rank + 1) * per)
+    m = ar.EmbeddingDotModel(nu, na, D, seed=2, adam_mode=mode, dense_kernel=-1.2)
+    sess = DistTrainSession(m, B, total_steps=steps)
+    sess.run(torch.from_numpy(iu[sl]).to(dev), torch.from_numpy(ia[sl]).to(dev), torch.from_numpy(y[sl]).to(dev), 2e-3)
+    m._sync_tables()
+    mine = [t.clone() for t in (m.U, m.A, m.mU, m.vU, m.mA, m.vA, m.head, m.bn_moving)]
+    # replicas identical?
+    for t in mine:
+        g = [torch.empty_like(t) for _ in range(world)]
+        dist.all_gather(g, t)
+        for o in g[1:]:
+            assert torch.equal(g[0], o), "replicas diverged"
+    if rank == 0:
+        # single-GPU reference: batch = world*B, samples ordered [rank0 batch s | rank1 batch s | ...]
+        order = []
+        for s in range(steps):
+            for r in range(world):
+                lo = r * per + s * B
+                order.append(np.arange(lo, min(lo + B, (r + 1) * per)))
+        order = np.concatenate(order)
+        m1 = ar.EmbeddingDotModel(nu, na, D, seed=2, adam_mode=mode, dense_kernel=-1.2)
+        s1 = TrainSession(m1, world * B, total_steps=steps)
+        s1.run(torch.from_numpy(iu[order]).to(dev), torch.from_numpy(ia[order]).to(dev),
+               torch.from_numpy(y[order]).to(dev), 2e-3)
+        m1._sync_tables()
+        ref = [m1.U, m1.A, m1.mU, m1.vU, m1.mA, m1.vA, m1.head, m1.bn_moving]
+        names = ["U", "A", "mU", "vU", "mA", "vA", "head", "bn"]
+        for n, a, b in zip(names, mine, ref):
+            a, b = a.cpu().numpy(), b.cpu().numpy()
+            if n == "head":
+                a, b = np.delete(a, 1), np.delete(b, 1)          # Dense bias: noise walk
+            tol = dict(rtol=1e-4, atol=3e-6) if n not in ("vU", "vA") else dict(rtol=2e-4, atol=1e-11)
+            if n == "bn":
+                tol = dict(rtol=1e-4, atol=1e-4)
+            np.testing.assert_allclose(a, b, err_msg=n, **tol)
+        mt = sess.metrics[1:steps + 1].cpu().numpy()
+        m1t = s1.metrics[1:steps + 1].cpu().numpy()
+        np.testing.assert_allclose(mt[:, :3], m1t[:, :3], rtol=2e-6, atol=2e-6)
+        print("DIST_OK", mode)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main(sys.argv[1])
