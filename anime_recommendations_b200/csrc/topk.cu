@@ -210,12 +210,17 @@ topk_merge_kernel(const int* __restrict__ idx, const float* __restrict__ score, 
   }
 }
 
-// Exact fp32 re-rank: warp per query row, candidates gathered one by one.
+// Exact fp32 re-rank: warp per query row.  Candidates come as n_lists lists of list_k entries per query
+// (layout [list][query][list_k], -1 = empty), e.g. the per-chunk bf16 lists of the tensor-core pass.
+// Certification (optional): a list that is full may have cut candidates off at its smallest bf16 score;
+// any row left out therefore has fp32 score <= that score + eps.  The fp32 top-k is provably exact when
+// the k-th re-ranked score clears max_l(min score of full list l) + eps; flag = 1 then, else 0.
 template <int NV>
 __global__ void __launch_bounds__(kTopkThreads)
 rerank_kernel(const float* __restrict__ Wq, int64_t q0, int64_t n_queries, const float* __restrict__ Wc,
-              int dim, const int* __restrict__ cand, int n_cand, int k, int* __restrict__ out_idx,
-              float* __restrict__ out_score) {
+              int dim, const int* __restrict__ cand, const float* __restrict__ cand_score, int n_lists,
+              int list_k, int k, float eps, int* __restrict__ out_idx, float* __restrict__ out_score,
+              unsigned char* __restrict__ certified) {
   const int lane = threadIdx.x & 31;
   const int d4 = dim >> 2;
   const int64_t qi = (int64_t)blockIdx.x * kTopkWarps + (threadIdx.x >> 5);
@@ -235,32 +240,63 @@ rerank_kernel(const float* __restrict__ Wq, int64_t q0, int64_t n_queries, const
   }
   WarpList wl;
   wl.init();
-  const int* cl = cand + qi * n_cand;
-  for (int j0 = 0; j0 < n_cand; j0 += 32) {
-    const int mine = (j0 + lane < n_cand) ? cl[j0 + lane] : -1;
-    const int cnt = min(32, n_cand - j0);
-    for (int j = 0; j < cnt; ++j) {
-      const int r = __shfl_sync(0xffffffffu, mine, j);
-      if (r < 0) continue;
-      float dot = 0.f, ss = 0.f;
+  float bound = -CUDART_INF_F;
+  for (int l = 0; l < n_lists; ++l) {
+    const int64_t lo = ((int64_t)l * n_queries + qi) * list_k;
+    bool full = true;
+    float lmin = CUDART_INF_F;
+    for (int j0 = 0; j0 < list_k; j0 += 32) {
+      const bool in = j0 + lane < list_k;
+      const int mine = in ? cand[lo + j0 + lane] : -1;
+      if (cand_score) {
+        const float ms = (in && mine >= 0) ? cand_score[lo + j0 + lane] : CUDART_INF_F;
+        float mm = ms;
 #pragma unroll
-      for (int i = 0; i < NV; ++i) {
-        const int jj = lane + 32 * i;
-        if (jj < d4) {
-          float4 x = ld4_nc(Wc + (int64_t)r * dim + 4 * jj);
-          dot += dot4(x, qv[i]);
-          ss += dot4(x, x);
-        }
+        for (int o = 16; o > 0; o >>= 1) mm = fminf(mm, __shfl_xor_sync(0xffffffffu, mm, o));
+        lmin = fminf(lmin, mm);
+        full = full && !__any_sync(0xffffffffu, in && mine < 0);
       }
-      dot = warp_sum(dot);
-      ss = warp_sum(ss);
-      const float sc = dot / sqrtf(ss);
-      if (sc == sc) wl.insert(sc, r, lane, true);
+      const int cnt = min(32, list_k - j0);
+      for (int j = 0; j < cnt; ++j) {
+        const int r = __shfl_sync(0xffffffffu, mine, j);
+        if (r < 0) continue;
+        float dot = 0.f, ss = 0.f;
+#pragma unroll
+        for (int i = 0; i < NV; ++i) {
+          const int jj = lane + 32 * i;
+          if (jj < d4) {
+            float4 x = ld4_nc(Wc + (int64_t)r * dim + 4 * jj);
+            dot += dot4(x, qv[i]);
+            ss += dot4(x, x);
+          }
+        }
+        dot = warp_sum(dot);
+        ss = warp_sum(ss);
+        const float sc = dot / sqrtf(ss);
+        if (sc == sc) wl.insert(sc, r, lane, true);
+      }
     }
+    if (cand_score && full) bound = fmaxf(bound, lmin);
   }
   if (lane < k) {
     out_idx[qi * k + lane] = (wl.i == 0x7fffffff) ? -1 : wl.i;
     out_score[qi * k + lane] = wl.s;
+  }
+  if (certified) {
+    const float kth = __shfl_sync(0xffffffffu, wl.s, k - 1);  // -inf when fewer than k candidates exist
+    if (lane == 0) certified[qi] = (bound == -CUDART_INF_F || kth >= bound + eps) ? 1 : 0;
+  }
+}
+
+// watched-bit matrix for the scoring path: set bit idx[j] of row r for j in [indptr[r], indptr[r+1])
+__global__ void bits_from_csr_kernel(const int64_t* __restrict__ indptr, const int32_t* __restrict__ idx,
+                                     int64_t n_rows, int64_t stride_words, int64_t n_bits,
+                                     uint32_t* __restrict__ out) {
+  const int64_t r = blockIdx.x;
+  if (r >= n_rows) return;
+  for (int64_t j = indptr[r] + threadIdx.x; j < indptr[r + 1]; j += blockDim.x) {
+    const int c = idx[j];
+    if (c >= 0 && c < n_bits) atomicOr(out + r * stride_words + (c >> 5), 1u << (c & 31));
   }
 }
 
@@ -341,20 +377,35 @@ extern "C" int ar_topk_merge(const int32_t* idx, const float* score, int32_t n_l
 }
 
 extern "C" int ar_cosine_rerank(const float* Wq, int64_t q0, int64_t n_queries, const float* Wc, int32_t dim,
-                                const int32_t* cand, int32_t n_cand, int32_t k, int32_t* out_idx,
-                                float* out_score, void* stream) {
+                                const int32_t* cand, const float* cand_score, int32_t n_lists, int32_t list_k,
+                                int32_t k, float eps, int32_t* out_idx, float* out_score, uint8_t* certified,
+                                void* stream) {
   AR_REQUIRE(Wq && Wc && cand && out_idx && out_score, "ar_cosine_rerank: null pointer");
   AR_REQUIRE(dim_ok(dim), "ar_cosine_rerank: dim %d unsupported", dim);
-  AR_REQUIRE(k > 0 && k <= kMaxK && n_cand > 0, "ar_cosine_rerank: bad k/n_cand");
+  AR_REQUIRE(k > 0 && k <= kMaxK && n_lists > 0 && list_k > 0, "ar_cosine_rerank: bad k/n_lists/list_k");
+  AR_REQUIRE(!certified || cand_score, "ar_cosine_rerank: certification needs the candidates' bf16 scores");
   if (n_queries <= 0) return AR_OK;
   const int blocks = (int)((n_queries + kTopkWarps - 1) / kTopkWarps);
   cudaStream_t st = (cudaStream_t)stream;
+#define AR_RERANK(NVV) rerank_kernel<NVV><<<blocks, kTopkThreads, 0, st>>>(Wq, q0, n_queries, Wc, dim, cand, cand_score, \
+                                                                            n_lists, list_k, k, eps, out_idx, out_score, certified)
   switch ((dim + 127) / 128) {
-    case 1: rerank_kernel<1><<<blocks, kTopkThreads, 0, st>>>(Wq, q0, n_queries, Wc, dim, cand, n_cand, k, out_idx, out_score); break;
-    case 2: rerank_kernel<2><<<blocks, kTopkThreads, 0, st>>>(Wq, q0, n_queries, Wc, dim, cand, n_cand, k, out_idx, out_score); break;
-    case 3: rerank_kernel<3><<<blocks, kTopkThreads, 0, st>>>(Wq, q0, n_queries, Wc, dim, cand, n_cand, k, out_idx, out_score); break;
-    default: rerank_kernel<4><<<blocks, kTopkThreads, 0, st>>>(Wq, q0, n_queries, Wc, dim, cand, n_cand, k, out_idx, out_score); break;
+    case 1: AR_RERANK(1); break;
+    case 2: AR_RERANK(2); break;
+    case 3: AR_RERANK(3); break;
+    default: AR_RERANK(4); break;
   }
+#undef AR_RERANK
+  AR_LAUNCH_CHECK();
+  return AR_OK;
+}
+
+extern "C" int ar_bits_from_csr(const int64_t* indptr, const int32_t* idx, int64_t n_rows, int64_t stride_words,
+                                int64_t n_bits, uint32_t* out, void* stream) {
+  AR_REQUIRE(indptr && idx && out, "ar_bits_from_csr: null pointer");
+  AR_REQUIRE(stride_words * 32 >= n_bits, "ar_bits_from_csr: stride_words too small for n_bits");
+  if (n_rows <= 0) return AR_OK;
+  bits_from_csr_kernel<<<(unsigned)n_rows, 128, 0, (cudaStream_t)stream>>>(indptr, idx, n_rows, stride_words, n_bits, out);
   AR_LAUNCH_CHECK();
   return AR_OK;
 }

@@ -208,26 +208,41 @@ int ar_cosine_topk_query(const float* W, int64_t n_rows, int32_t dim, int64_t q,
 int ar_topk_merge(const int32_t* idx, const float* score, int32_t n_lists, int64_t n_queries,
                   int32_t k_in, int32_t k_out, int32_t* out_idx, float* out_score, void* stream);
 
-/* Exact fp32 re-rank: for each query row, score the n_cand candidate rows (cand[query][n_cand],
- * -1 = empty) with fp32 cosine and keep the best k.  Q rows come from Wq[q0 + i], candidates from Wc. */
+/* Exact fp32 re-rank.  Candidates: n_lists lists of list_k row ids per query, layout
+ * [list][query][list_k], -1 = empty (the output layout of ar_cosine_topk_allpairs / the input layout of
+ * ar_topk_merge).  Query rows are Wq[q0 + i], candidate rows index Wc.  Keeps the best k by fp32 cosine
+ * (duplicates collapse).  Optional certification: with the candidates' selection scores `cand_score`
+ * (same layout) and the bound `eps` on |selection score - fp32 score|, certified[i] = 1 iff the fp32
+ * top-k of query i is provably the true top-k over ALL rows the lists were drawn from. */
 int ar_cosine_rerank(const float* Wq, int64_t q0, int64_t n_queries, const float* Wc, int32_t dim,
-                     const int32_t* cand, int32_t n_cand, int32_t k, int32_t* out_idx,
-                     float* out_score, void* stream);
+                     const int32_t* cand, const float* cand_score, int32_t n_lists, int32_t list_k,
+                     int32_t k, float eps, int32_t* out_idx, float* out_score, uint8_t* certified,
+                     void* stream);
 
-/* All-pairs / many-query cosine candidates on the tensor cores (tcgen05, bf16 operands, fp32
- * accumulation in TMEM): for query rows [q0, q0+n_q) of Qn and candidate rows [c0, c0+n_c) of Cn
- * (both ROW-NORMALISED bf16, produced by ar_rownorm_bf16), keep per query the kprime best
- * candidates by bf16 score.  exclude_self: drop candidate == query row id (same-table case).
- * watched (optional): bit matrix [n_q][ (n_c_total+31)/32 ] words, bit set = drop.  sign: +1/-1,
- * ranks by sign*score (model_recs with a negative Dense kernel).
- * out_idx/out_score: [n_q][kprime].  workspace from ar_allpairs_workspace(). */
+/* Many-query cosine candidates on the tensor cores (tcgen05.mma, bf16 operands, fp32 accumulation in
+ * TMEM, TMA-fed): for query rows [q0, q0+n_q) of Qn and candidate rows [c0, c0+n_c) of Cn -- both
+ * ROW-NORMALISED bf16 (q_rows_total|c_rows_total, dim) tables made by ar_rownorm_bf16, dim == 128 --
+ * keep per query and candidate chunk the kprime (16 or 32) best candidates by bf16-operand score.
+ *   exclude_self     drop candidate id == query id (Qn and Cn are the same table)
+ *   watched          optional bit rows [n_q][watched_stride] over candidate ids, set bit = drop
+ *                    (model_recs.py:144-155: anime the user already rated)
+ *   n_chunks         from ar_allpairs_chunks(n_q, n_c): the candidate range is split so every SM has work
+ *   out_idx/out_score [n_chunks][n_q][kprime], unsorted, -1 / -inf = empty
+ *   dump_scores      optional [n_q][n_c] raw scores (tests only)
+ * Replaces the reference's np.dot + np.argsort per query (similar_anime.py:404-409, similar_users.py:
+ * 293-296) looped over all rows, and model.predict over (user x all anime) (model_recs.py:394-396). */
 int ar_rownorm_bf16(const float* W, int64_t n_rows, int32_t dim, void* out_bf16, void* stream);
-int64_t ar_allpairs_workspace(int64_t n_q, int32_t kprime);
-int ar_cosine_topk_allpairs(const void* Qn_bf16, int64_t q0, int64_t n_q, const void* Cn_bf16,
-                            int64_t c0, int64_t n_c, int64_t c_total, int32_t dim, int32_t kprime,
-                            int32_t exclude_self, const uint32_t* watched, int64_t watched_stride,
-                            float sign, int32_t* out_idx, float* out_score, void* workspace,
-                            void* stream);
+int32_t ar_allpairs_chunks(int64_t n_q, int64_t n_c);
+int ar_cosine_topk_allpairs(const void* Qn_bf16, int64_t q_rows_total, int64_t q0, int64_t n_q,
+                            const void* Cn_bf16, int64_t c_rows_total, int64_t c0, int64_t n_c,
+                            int32_t dim, int32_t kprime, int32_t exclude_self, const uint32_t* watched,
+                            int64_t watched_stride, int32_t n_chunks, int32_t* out_idx, float* out_score,
+                            float* dump_scores, void* stream);
+
+/* OR the CSR (indptr int64[n_rows+1], idx int32) into bit rows out[n_rows][stride_words] (caller
+ * initialises `out`): the "already watched" mask of model_recs.py:144-155 for ar_cosine_topk_allpairs. */
+int ar_bits_from_csr(const int64_t* indptr, const int32_t* idx, int64_t n_rows, int64_t stride_words,
+                     int64_t n_bits, uint32_t* out, void* stream);
 
 #ifdef __cplusplus
 }

@@ -120,7 +120,7 @@ def test_merge_and_rerank():
     cand[:, 15] = -1
     cand[np.arange(64), 12] = np.arange(100, 164)             # the query itself sneaks in: caller filters
     Wd = sim.as_table(W)
-    gi, gs = sim.rerank(Wd, 100, 64, Wd, dev(cand), k + 1)
+    gi, gs, _ = sim.rerank(Wd, 100, 64, Wd, dev(cand), k + 1)
     gi, gs = gi.cpu().numpy(), gs.cpu().numpy()
     for r in range(64):
         keep = gi[r] != 100 + r
