@@ -22,6 +22,8 @@
 #include <cuda_bf16.h>
 #include <math_constants.h>
 
+#include <stdlib.h>
+
 #include <algorithm>
 
 #include "common.cuh"
@@ -50,11 +52,16 @@ struct ApParams {
   int64_t c0, n_c;          // candidate rows [c0, c0+n_c) of the C table
   int n_qtiles, n_chunks, tiles_per_chunk, n_tiles;
   int exclude_self;
+  const int32_t* self_ids;  // optional [n_q]: candidate id to drop per query row (overrides q0 + row)
   const uint32_t* watched;  // optional [n_q][watched_stride] bit rows over candidate ids; set bit = drop
   int64_t watched_stride;
-  int32_t* out_idx;         // [n_chunks][n_q][KP]
-  float* out_score;
+  const float* thr_init;    // optional [n_q]: only candidates with score > thr_init[row] are listed
+  int32_t* out_idx;         // [n_chunks][n_q][CAP]
+  float* out_score;         // [n_chunks][n_q][CAP]
+  int32_t* out_cnt;         // [n_chunks][n_q] entries kept
+  float* out_thr;           // [n_chunks][n_q] every unlisted candidate of the chunk has score <= this
   float* dump;              // optional raw scores [n_q][n_c] (tests)
+  int dbg;                  // perf attribution (AR_AP_DEBUG): 0 full, 1 no slow path, 2 TMEM loads only, 3 no TMEM loads
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -118,35 +125,113 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
       : "memory");
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+// 3-input maximum: one FMNMX3 (sm_100a) absorbs two new values per ALU slot
+__device__ __forceinline__ float fmax3(float a, float b, float c) {
+  float r;
+  asm("max.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c));
+  return r;
+}
 
-template <int KP>
+// Shared-memory plan: KP = entries a compaction keeps (16 or 24), list capacity 32 entries per query row.
+constexpr int CAP = 32;
 struct ApSmem {
-  static constexpr int kStages = (KP <= 16) ? 4 : 3;
-  static constexpr uint32_t kListBytes = KP * QT * 8;
+  static constexpr int kStages = 3;
+  static constexpr uint32_t kListBytes = CAP * QT * 8;
   static constexpr uint32_t kOffB = kABytes;
   static constexpr uint32_t kOffList = kOffB + kStages * kBStageBytes;
   static constexpr uint32_t kOffBar = kOffList + kListBytes;
-  static constexpr uint32_t kNumBars = 2 * kStages + 2 + 4;
+  static constexpr uint32_t kNumBars = 2 * kStages + 2 + 8;
   static constexpr uint32_t kBytes = kOffBar + kNumBars * 8 + 16;
 };
 
+__device__ __forceinline__ float lds_f32(uint32_t a) {
+  float v;
+  asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(a));
+  return v;
+}
+__device__ __forceinline__ int lds_s32(uint32_t a) {
+  int v;
+  asm volatile("ld.shared.s32 %0, [%1];" : "=r"(v) : "r"(a));
+  return v;
+}
+__device__ __forceinline__ void sts_f32(uint32_t a, float v) { asm volatile("st.shared.f32 [%0], %1;" ::"r"(a), "f"(v) : "memory"); }
+__device__ __forceinline__ void sts_s32(uint32_t a, int v) { asm volatile("st.shared.s32 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
+
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t (&v)[8]) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
+               : "r"(taddr)
+               : "memory");
+}
+
+// Row-private candidate list in shared memory (entry j of a row at byte offset j*QT*4 from the row's base:
+// bank = thread, conflict-free).  Invariant: every admissible candidate seen so far with score > thr is in
+// the list.  list_compact() pulls the held scores into registers, sorts them with a 32-key bitonic network
+// (240 compare-exchanges = 480 FMNMX, no memory traffic), raises thr to the (KP+1)-th best held score and
+// squeezes the list down to the entries above it (exactly KP unless scores tie at the cut).
+// Everything on the slow path is written ONCE, behind a rolled loop, with no calls: an earlier version that
+// inlined the scan into the unrolled fast path was 120 KB of code and stalled on instruction fetch (ncu: icc
+// hit rate 60 %, `no_instruction` the top stall), and out-of-line functions cost stack spills that go to L2
+// here (this kernel leaves the SM ~2 KB of L1).
 template <int KP>
+__device__ __forceinline__ void list_compact(uint32_t sa, uint32_t ia, int& cnt, float& thr) {
+  float s[CAP];
+#pragma unroll
+  for (int j = 0; j < CAP; ++j) s[j] = (j < cnt) ? lds_f32(sa + j * QT * 4) : -CUDART_INF_F;
+  // bitonic sort, descending
+#pragma unroll
+  for (int k = 2; k <= CAP; k <<= 1) {
+#pragma unroll
+    for (int j = k >> 1; j > 0; j >>= 1) {
+#pragma unroll
+      for (int i = 0; i < CAP; ++i) {
+        const int l = i ^ j;
+        if (l > i) {
+          const float a = s[i], b = s[l];
+          const bool desc = ((i & k) == 0);
+          s[i] = desc ? fmaxf(a, b) : fminf(a, b);
+          s[l] = desc ? fminf(a, b) : fmaxf(a, b);
+        }
+      }
+    }
+  }
+  const float nt = fmaxf(s[KP], thr);  // (KP+1)-th best: at most KP entries lie strictly above it
+  int w = 0;
+#pragma unroll 4
+  for (int j = 0; j < CAP; ++j) {
+    if (j < cnt) {
+      const float x = lds_f32(sa + j * QT * 4);
+      if (x > nt) {
+        const int id = lds_s32(ia + j * QT * 4);
+        sts_f32(sa + w * QT * 4, x);
+        sts_s32(ia + w * QT * 4, id);
+        ++w;
+      }
+    }
+  }
+  cnt = w;
+  thr = nt;
+}
+
+template <int KP, bool DUMP>
 __global__ void __launch_bounds__(kApThreads, 1)
 allpairs_topk_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmC, ApParams p) {
-  using L = ApSmem<KP>;
+  using L = ApSmem;
   constexpr int S = L::kStages;
   extern __shared__ uint8_t smem_raw[];
   // SWIZZLE_128B operand tiles need 1024-byte alignment; the launch reserves 1 KB of slack for this
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   const uint32_t sbase = smem_u32(smem);
-  float* list_s = reinterpret_cast<float*>(smem + L::kOffList);           // [KP][QT]
-  int* list_i = reinterpret_cast<int*>(smem + L::kOffList + KP * QT * 4);  // [KP][QT]
+  float* list_s = reinterpret_cast<float*>(smem + L::kOffList);            // [CAP][QT]
+  int* list_i = reinterpret_cast<int*>(smem + L::kOffList + CAP * QT * 4);  // [CAP][QT]
   const uint32_t bar0 = sbase + L::kOffBar;
   auto full_b = [&](int s) { return bar0 + 8u * s; };
   auto empty_b = [&](int s) { return bar0 + 8u * (S + s); };
   const uint32_t a_full = bar0 + 8u * (2 * S), a_empty = bar0 + 8u * (2 * S + 1);
-  auto tmem_full = [&](int s) { return bar0 + 8u * (2 * S + 2 + s); };
-  auto tmem_empty = [&](int s) { return bar0 + 8u * (2 * S + 4 + s); };
+  // four accumulator buffers of 128 TMEM columns, buffer = 2*(tile parity) + m-tile, each with its own
+  // full/empty barrier: a slow epilogue warp only holds back the MMAs of its own m-tile
+  auto tmem_full = [&](int b) { return bar0 + 8u * (2 * S + 2 + b); };
+  auto tmem_empty = [&](int b) { return bar0 + 8u * (2 * S + 6 + b); };
   uint32_t* tmem_ptr_s = reinterpret_cast<uint32_t*>(smem + L::kOffBar + L::kNumBars * 8);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -157,9 +242,9 @@ allpairs_topk_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
     }
     mbar_init(a_full, 1);
     mbar_init(a_empty, 1);
-    for (int s = 0; s < 2; ++s) {
-      mbar_init(tmem_full(s), 1);
-      mbar_init(tmem_empty(s), kEpiWarps);
+    for (int b = 0; b < 2 * MT; ++b) {
+      mbar_init(tmem_full(b), 1);
+      mbar_init(tmem_empty(b), kEpiWarps / MT);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -215,10 +300,10 @@ allpairs_topk_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
         for (int t = t0; t < t1; ++t, ++bj, ++it) {
           const int s = bj % S, as = it & 1;
           mbar_wait(full_b(s), (bj / S) & 1);
-          mbar_wait(tmem_empty(as), ((it >> 1) & 1) ^ 1);
-          tc_fence_after();
 #pragma unroll
           for (int mt = 0; mt < MT; ++mt) {
+            mbar_wait(tmem_empty(as * MT + mt), ((it >> 1) & 1) ^ 1);
+            tc_fence_after();
             const uint32_t d = tmem_base + (uint32_t)((as * MT + mt) * BN);
 #pragma unroll
             for (int k = 0; k < KBLK * (BK / UMMA_K); ++k) {
@@ -227,9 +312,9 @@ allpairs_topk_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
               const uint64_t bd = smem_desc(sbase + L::kOffB + s * kBStageBytes + kb * kSubTileBytes + kk * UMMA_K * 2);
               tc_mma(d, ad, bd, kInstrDesc, k > 0 ? 1u : 0u);
             }
+            tc_commit(tmem_full(as * MT + mt));  // this m-tile's accumulators are ready for its epilogue warps
           }
-          tc_commit(empty_b(s));     // B stage reusable once these MMAs retire
-          tc_commit(tmem_full(as));  // accumulators ready for the epilogue
+          tc_commit(empty_b(s));                 // B stage reusable once these MMAs retire
         }
         tc_commit(a_empty);
       }
@@ -239,84 +324,133 @@ allpairs_topk_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
     const int quarter = warp & 3;               // TMEM lane quarter this warp may touch
     const int mt = (warp - 2) >> 2;
     const int row_in_cta = mt * BM + quarter * 32 + lane;
-    float* my_s = list_s + row_in_cta;          // stride QT between entries: bank = thread
-    int* my_i = list_i + row_in_cta;
+    const uint32_t my_s = smem_u32(list_s + row_in_cta);  // stride QT between entries: bank = thread
+    const uint32_t my_i = smem_u32(list_i + row_in_cta);
+    const int dbg = p.dbg;
     uint32_t it = 0;
     for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
       const int qt = item / p.n_chunks, ch = item - qt * p.n_chunks;
       const int64_t qlocal = (int64_t)qt * QT + row_in_cta;  // row within [0, n_q)
       const bool row_ok = qlocal < p.n_q;
-      const int self_id = p.exclude_self ? (int)(p.q0 + qlocal) : -1;
+      int self_id = -1;
+      if (p.exclude_self && row_ok) self_id = p.self_ids ? p.self_ids[qlocal] : (int)(p.q0 + qlocal);
       const uint32_t* wrow = (p.watched && row_ok) ? p.watched + qlocal * p.watched_stride : nullptr;
-#pragma unroll
-      for (int j = 0; j < KP; ++j) {
-        my_s[j * QT] = -CUDART_INF_F;
-        my_i[j * QT] = -1;
-      }
-      float thr = -CUDART_INF_F;
-      int minpos = 0;
+      float thr = CUDART_INF_F;  // rows past n_q list nothing
+      if (row_ok) thr = p.thr_init ? p.thr_init[qlocal] : -CUDART_INF_F;
+      if (dbg == 1) thr = CUDART_INF_F;
+      int cnt = 0;
       const int t0 = ch * p.tiles_per_chunk, t1 = min(p.n_tiles, t0 + p.tiles_per_chunk);
       const int c_end = (int)(p.c0 + p.n_c);
+
+      // fast path over one 32-column chunk held in registers: FMNMX3 tree (18 ALU ops) against the row's
+      // threshold; a chunk that beats it is only FLAGGED here and rescanned from TMEM below
+      auto chunk_max = [&](const uint32_t (&v)[32], int cb) -> float {
+        if (DUMP && row_ok) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            const int cid = cb + i;
+            if (cid < c_end) p.dump[qlocal * p.n_c + (cid - p.c0)] = __uint_as_float(v[i]);
+          }
+        }
+        float g[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float r1 = fmax3(__uint_as_float(v[8 * j]), __uint_as_float(v[8 * j + 1]), __uint_as_float(v[8 * j + 2]));
+          const float r2 = fmax3(__uint_as_float(v[8 * j + 3]), __uint_as_float(v[8 * j + 4]), __uint_as_float(v[8 * j + 5]));
+          g[j] = fmax3(__uint_as_float(v[8 * j + 6]), __uint_as_float(v[8 * j + 7]), fmaxf(r1, r2));
+        }
+        return fmaxf(fmax3(g[0], g[1], g[2]), g[3]);
+      };
+
       for (int t = t0; t < t1; ++t, ++it) {
         const int as = it & 1;
-        mbar_wait(tmem_full(as), (it >> 1) & 1);
+        mbar_wait(tmem_full(as * MT + mt), (it >> 1) & 1);
         tc_fence_after();
         const uint32_t tbase = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)((as * MT + mt) * BN);
         const int cbase = (int)(p.c0 + (int64_t)t * BN);
-#pragma unroll 1
-        for (int cc = 0; cc < BN / 32; ++cc) {
-          uint32_t v[32];
-          __syncwarp();  // tcgen05.ld is .sync.aligned: reconverge after the divergent insert path
-          tmem_ld32(tbase + cc * 32, v);
+        if (dbg >= 3) {  // attribution: MMA + TMA only
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(tmem_empty(as * MT + mt));
+          continue;
+        }
+        // software pipeline over the four 32-column chunks: the next tcgen05.ld is in flight while the
+        // current chunk is reduced
+        uint32_t va[32], vb[32];
+        uint32_t flags = 0;
+        __syncwarp();
+        tmem_ld32(tbase, va);
+        tmem_ld_wait();
+        __syncwarp();
+        tmem_ld32(tbase + 32, vb);
+        if (dbg < 2) flags |= (chunk_max(va, cbase) > thr) ? 1u : 0u;
+        tmem_ld_wait();
+        __syncwarp();
+        tmem_ld32(tbase + 64, va);
+        if (dbg < 2) flags |= (chunk_max(vb, cbase + 32) > thr) ? 2u : 0u;
+        tmem_ld_wait();
+        __syncwarp();
+        tmem_ld32(tbase + 96, vb);
+        if (dbg < 2) flags |= (chunk_max(va, cbase + 64) > thr) ? 4u : 0u;
+        tmem_ld_wait();
+        if (dbg < 2) flags |= (chunk_max(vb, cbase + 96) > thr) ? 8u : 0u;
+        // slow path (warp-uniform entry): rescan the flagged chunks from TMEM, eight columns at a time
+        uint32_t todo = __reduce_or_sync(0xffffffffu, flags);
+        while (todo) {
+          const int c = __ffs(todo) - 1;
+          todo &= todo - 1;
+          const bool mine = (flags >> c) & 1u;
+          __syncwarp();
+          tmem_ld32(tbase + 32 * c, va);
           tmem_ld_wait();
-          if (cc == BN / 32 - 1) {  // every column of this accumulator stage is now in registers
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(tmem_empty(as));
-          }
-          if (p.dump && row_ok) {
+#pragma unroll 1
+          for (int gq = 0; gq < 4; ++gq) {
+            float x[8];
 #pragma unroll
-            for (int i = 0; i < 32; ++i) {
-              const int cid = cbase + cc * 32 + i;
-              if (cid < c_end) p.dump[qlocal * p.n_c + (cid - p.c0)] = __uint_as_float(v[i]);
+            for (int e = 0; e < 8; ++e) {  // group gq of the chunk, selected without dynamic register indexing
+              const uint32_t lo = (gq & 1) ? va[8 + e] : va[e], hi = (gq & 1) ? va[24 + e] : va[16 + e];
+              x[e] = __uint_as_float((gq & 2) ? hi : lo);
             }
-          }
-          float m = __uint_as_float(v[0]);
+            const float gm = fmaxf(fmax3(x[0], x[1], x[2]), fmax3(x[3], x[4], fmax3(x[5], x[6], x[7])));
+            const bool hot = mine && (gm > thr);
+            // a row that needs room for eight more makes the WHOLE warp compact (same instruction stream, so the
+            // other rows' squeezes are free and their thresholds tighten early)
+            if (__any_sync(0xffffffffu, hot && cnt > CAP - 8)) {
+              if (cnt > KP) list_compact<KP>(my_s, my_i, cnt, thr);
+            }
+            if (!hot) continue;
+            const int cid0 = cbase + 32 * c + 8 * gq;
 #pragma unroll
-          for (int i = 1; i < 32; ++i) m = fmaxf(m, __uint_as_float(v[i]));
-          if (m > thr) {
-#pragma unroll
-            for (int i = 0; i < 32; ++i) {
-              const float x = __uint_as_float(v[i]);
-              if (x > thr) {
-                const int cid = cbase + cc * 32 + i;
+            for (int e = 0; e < 8; ++e) {
+              if (x[e] > thr) {
+                const int cid = cid0 + e;
                 bool ok = (cid < c_end) && (cid != self_id);
                 if (ok && wrow) ok = !((wrow[cid >> 5] >> (cid & 31)) & 1u);
                 if (ok) {
-                  my_s[minpos * QT] = x;
-                  my_i[minpos * QT] = cid;
-                  thr = CUDART_INF_F;
-#pragma unroll
-                  for (int j = 0; j < KP; ++j) {
-                    const float sj = my_s[j * QT];
-                    if (sj < thr) {
-                      thr = sj;
-                      minpos = j;
-                    }
-                  }
+                  sts_f32(my_s + cnt * QT * 4, x[e]);
+                  sts_s32(my_i + cnt * QT * 4, cid);
+                  ++cnt;
                 }
               }
             }
           }
         }
+        // this accumulator stage is fully consumed: hand it back to the MMA warp
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(tmem_empty(as * MT + mt));
       }
       if (row_ok) {
-        const int64_t o = ((int64_t)ch * p.n_q + qlocal) * KP;
-#pragma unroll
-        for (int j = 0; j < KP; ++j) {
-          p.out_idx[o + j] = my_i[j * QT];
-          p.out_score[o + j] = my_s[j * QT];
+        const int64_t r = (int64_t)ch * p.n_q + qlocal;
+        const int64_t o = r * CAP;
+#pragma unroll 4
+        for (int j = 0; j < CAP; ++j) {
+          const bool in = j < cnt;
+          p.out_idx[o + j] = in ? lds_s32(my_i + j * QT * 4) : -1;
+          p.out_score[o + j] = in ? lds_f32(my_s + j * QT * 4) : -CUDART_INF_F;
         }
+        p.out_cnt[r] = cnt;
+        p.out_thr[r] = thr;
       }
     }
   }
@@ -375,17 +509,17 @@ static int ap_sm_count() {
   return n;
 }
 
-template <int KP>
+template <int KP, bool DUMP>
 static int launch_allpairs(const CUtensorMap& tq, const CUtensorMap& tc, const ApParams& p, cudaStream_t st) {
-  using L = ApSmem<KP>;
+  using L = ApSmem;
   static bool attr = false;
   if (!attr) {
-    AR_CUDA(cudaFuncSetAttribute(allpairs_topk_kernel<KP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L::kBytes + 1024));
+    AR_CUDA(cudaFuncSetAttribute(allpairs_topk_kernel<KP, DUMP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L::kBytes + 1024));
     attr = true;
   }
   const int items = p.n_qtiles * p.n_chunks;
   const int grid = std::max(1, std::min(items, ap_sm_count()));
-  allpairs_topk_kernel<KP><<<grid, kApThreads, L::kBytes + 1024, st>>>(tq, tc, p);
+  allpairs_topk_kernel<KP, DUMP><<<grid, kApThreads, L::kBytes + 1024, st>>>(tq, tc, p);
   AR_LAUNCH_CHECK();
   return AR_OK;
 }
@@ -395,7 +529,7 @@ static int launch_allpairs(const CUtensorMap& tq, const CUtensorMap& tc, const A
 using namespace ar;
 
 // Candidate chunks that keep every SM busy: one chunk when there are enough 256-query tiles, otherwise split
-// the candidate range so that items ~ 2 x SMs (each chunk keeps its own k' list; the re-rank sees them all).
+// the candidate range so that items ~ 2 x SMs (each chunk keeps its own list; the re-rank sees them all).
 extern "C" int32_t ar_allpairs_chunks(int64_t n_q, int64_t n_c) {
   if (n_q <= 0 || n_c <= 0) return 1;
   const int64_t qtiles = (n_q + QT - 1) / QT, tiles = (n_c + BN - 1) / BN;
@@ -408,44 +542,56 @@ extern "C" int32_t ar_allpairs_chunks(int64_t n_q, int64_t n_c) {
   return (int32_t)((tiles + per - 1) / per);                        // the count the kernel will actually use
 }
 
+extern "C" int32_t ar_allpairs_list_cap(int32_t kprime) {
+  return (kprime == 16 || kprime == 24) ? CAP : 0;
+}
+
 extern "C" int ar_cosine_topk_allpairs(const void* Qn_bf16, int64_t q_rows_total, int64_t q0, int64_t n_q,
                                        const void* Cn_bf16, int64_t c_rows_total, int64_t c0, int64_t n_c,
-                                       int32_t dim, int32_t kprime, int32_t exclude_self, const uint32_t* watched,
-                                       int64_t watched_stride, int32_t n_chunks, int32_t* out_idx, float* out_score,
-                                       float* dump_scores, void* stream) {
-  AR_REQUIRE(Qn_bf16 && Cn_bf16 && out_idx && out_score, "ar_cosine_topk_allpairs: null pointer");
+                                       int32_t dim, int32_t kprime, int32_t exclude_self, const int32_t* self_ids,
+                                       const uint32_t* watched, int64_t watched_stride, const float* thr_init,
+                                       int32_t n_chunks, int32_t* out_idx, float* out_score, int32_t* out_cnt,
+                                       float* out_thr, float* dump_scores, void* stream) {
+  const char* who = "ar_cosine_topk_allpairs";
+  AR_REQUIRE(out_idx && out_score && out_cnt && out_thr, "%s: null output", who);
+  AR_REQUIRE(kprime == 16 || kprime == 24, "%s: kprime must be 16 or 24 (got %d)", who, kprime);
+  AR_REQUIRE(Qn_bf16 && Cn_bf16, "%s: null table", who);
   if (dim != KBLK * BK) {
-    set_error("ar_cosine_topk_allpairs: the tcgen05 path is built for dim %d (got %d)", KBLK * BK, dim);
+    set_error("%s: the tcgen05 path is built for dim %d (got %d)", who, KBLK * BK, dim);
     return AR_ERR_UNSUPPORTED;
   }
-  AR_REQUIRE(kprime == 16 || kprime == 32, "ar_cosine_topk_allpairs: kprime must be 16 or 32 (got %d)", kprime);
-  AR_REQUIRE(q0 >= 0 && n_q >= 0 && q0 + n_q <= q_rows_total, "ar_cosine_topk_allpairs: query range outside the table");
-  AR_REQUIRE(c0 >= 0 && n_c >= 0 && c0 + n_c <= c_rows_total, "ar_cosine_topk_allpairs: candidate range outside the table");
-  AR_REQUIRE(q_rows_total < (1ll << 31) && c_rows_total < (1ll << 31), "ar_cosine_topk_allpairs: table too large");
-  AR_REQUIRE(n_chunks >= 1, "ar_cosine_topk_allpairs: n_chunks must be >= 1");
-  AR_REQUIRE(((uintptr_t)Qn_bf16 & 15) == 0 && ((uintptr_t)Cn_bf16 & 15) == 0, "ar_cosine_topk_allpairs: tables must be 16-byte aligned");
+  AR_REQUIRE(q0 >= 0 && n_q >= 0 && q0 + n_q <= q_rows_total, "%s: query range outside the table", who);
+  AR_REQUIRE(c0 >= 0 && n_c >= 0 && c0 + n_c <= c_rows_total, "%s: candidate range outside the table", who);
+  AR_REQUIRE(q_rows_total < (1ll << 31) && c_rows_total < (1ll << 31), "%s: table too large", who);
+  AR_REQUIRE(n_chunks >= 1, "%s: bad n_chunks", who);
+  AR_REQUIRE(((uintptr_t)Qn_bf16 & 15) == 0 && ((uintptr_t)Cn_bf16 & 15) == 0, "%s: tables must be 16-byte aligned", who);
   if (n_q == 0 || n_c == 0) return AR_OK;
-  CUtensorMap tq, tc;
-  int rc = make_map(&tq, Qn_bf16, q_rows_total, dim);
-  if (rc) return rc;
-  if ((rc = make_map(&tc, Cn_bf16, c_rows_total, dim))) return rc;
   ApParams p{};
   p.q0 = q0; p.n_q = n_q; p.c0 = c0; p.n_c = n_c;
   p.n_qtiles = (int)((n_q + QT - 1) / QT);
   p.n_tiles = (int)((n_c + BN - 1) / BN);
-  p.n_chunks = std::min<int>(n_chunks, p.n_tiles);
-  p.tiles_per_chunk = (p.n_tiles + p.n_chunks - 1) / p.n_chunks;
+  const int want = std::min<int>(n_chunks, p.n_tiles);
+  p.tiles_per_chunk = (p.n_tiles + want - 1) / want;
   p.n_chunks = (p.n_tiles + p.tiles_per_chunk - 1) / p.tiles_per_chunk;
-  if (p.n_chunks != n_chunks) {
-    set_error("ar_cosine_topk_allpairs: n_chunks %d does not tile %d candidate tiles evenly; use %d", n_chunks, p.n_tiles, p.n_chunks);
-    return AR_ERR_INVALID;
-  }
+  AR_REQUIRE(p.n_chunks == n_chunks, "%s: n_chunks %d does not tile %d candidate tiles; use %d", who, n_chunks,
+             p.n_tiles, p.n_chunks);
   p.exclude_self = exclude_self;
+  p.self_ids = self_ids;
   p.watched = watched;
   p.watched_stride = watched_stride;
+  p.thr_init = thr_init;
   p.out_idx = out_idx;
   p.out_score = out_score;
+  p.out_cnt = out_cnt;
+  p.out_thr = out_thr;
   p.dump = dump_scores;
+  static const int dbg = [] { const char* e = getenv("AR_AP_DEBUG"); return e ? atoi(e) : 0; }();
+  p.dbg = dbg;
+  CUtensorMap tq, tc;
+  int rc;
+  if ((rc = make_map(&tq, Qn_bf16, q_rows_total, dim))) return rc;
+  if ((rc = make_map(&tc, Cn_bf16, c_rows_total, dim))) return rc;
   cudaStream_t st = (cudaStream_t)stream;
-  return kprime == 16 ? launch_allpairs<16>(tq, tc, p, st) : launch_allpairs<32>(tq, tc, p, st);
+  if (dump_scores) return kprime == 16 ? launch_allpairs<16, true>(tq, tc, p, st) : launch_allpairs<24, true>(tq, tc, p, st);
+  return kprime == 16 ? launch_allpairs<16, false>(tq, tc, p, st) : launch_allpairs<24, false>(tq, tc, p, st);
 }

@@ -79,8 +79,11 @@ __device__ __forceinline__ void cta_merge(WarpList& wl, float* sm_s, int* sm_i, 
 }
 
 // ---------------------------------------------------------------------------------------------
+// resid (optional, with out_bf): ||w_hat - bf16(w_hat)||_2 per row, the rounding residual that bounds the
+// bf16-operand score error of the tensor-core pass (|q~.c~ - q^.c^| <= resid_q + resid_c + resid_q*resid_c).
 __global__ void __launch_bounds__(256) rownorm_kernel(const float* __restrict__ W, int64_t n, int dim,
-                                                      float* __restrict__ out, __nv_bfloat16* __restrict__ out_bf) {
+                                                      float* __restrict__ out, __nv_bfloat16* __restrict__ out_bf,
+                                                      float* __restrict__ resid) {
   const int lane = threadIdx.x & 31;
   const int d4 = dim >> 2;
   for (int64_t row = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5); row < n; row += (int64_t)gridDim.x * 8) {
@@ -92,6 +95,7 @@ __global__ void __launch_bounds__(256) rownorm_kernel(const float* __restrict__ 
     }
     ss = warp_sum(ss);
     const float nrm = sqrtf(ss);
+    float rs = 0.f;
     for (int j = lane; j < d4; j += 32) {
       float4 x = ld4(src + 4 * j);
       x.x /= nrm; x.y /= nrm; x.z /= nrm; x.w /= nrm;
@@ -103,7 +107,14 @@ __global__ void __launch_bounds__(256) rownorm_kernel(const float* __restrict__ 
         pk.x = *reinterpret_cast<uint32_t*>(&lo);
         pk.y = *reinterpret_cast<uint32_t*>(&hi);
         *reinterpret_cast<uint2*>(out_bf + row * dim + 4 * j) = pk;
+        const float2 fl = __bfloat1622float2(lo), fh = __bfloat1622float2(hi);
+        const float e0 = x.x - fl.x, e1 = x.y - fl.y, e2 = x.z - fh.x, e3 = x.w - fh.y;
+        rs += e0 * e0 + e1 * e1 + e2 * e2 + e3 * e3;
       }
+    }
+    if (resid) {
+      rs = warp_sum(rs);
+      if (lane == 0) resid[row] = sqrtf(rs) * 1.0000005f;  // rounded up: used as an upper bound
     }
   }
 }
@@ -210,16 +221,19 @@ topk_merge_kernel(const int* __restrict__ idx, const float* __restrict__ score, 
   }
 }
 
-// Exact fp32 re-rank: warp per query row.  Candidates come as n_lists lists of list_k entries per query
-// (layout [list][query][list_k], -1 = empty), e.g. the per-chunk bf16 lists of the tensor-core pass.
-// Certification (optional): a list that is full may have cut candidates off at its smallest bf16 score;
-// any row left out therefore has fp32 score <= that score + eps.  The fp32 top-k is provably exact when
-// the k-th re-ranked score clears max_l(min score of full list l) + eps; flag = 1 then, else 0.
+// Exact fp32 re-rank: warp per query row.  Candidates come as n_lists lists per query (layout
+// [list][query][list_cap]; cand_cnt[list][query] entries are valid, or every non-negative entry when cand_cnt
+// is null), e.g. the per-chunk lists of the tensor-core pass.
+// Certification (optional): list l left out only candidates whose selection (bf16-operand) score is
+// <= cand_thr[l][query]; such a row has fp32 score <= that + eps.  The fp32 top-k is therefore provably the
+// exact top-k over ALL rows the lists were drawn from when the k-th re-ranked score clears
+// max_l cand_thr[l] + eps (+ q_eps[query]); flag = 1 then, else 0.
 template <int NV>
 __global__ void __launch_bounds__(kTopkThreads)
 rerank_kernel(const float* __restrict__ Wq, int64_t q0, int64_t n_queries, const float* __restrict__ Wc,
-              int dim, const int* __restrict__ cand, const float* __restrict__ cand_score, int n_lists,
-              int list_k, int k, float eps, int* __restrict__ out_idx, float* __restrict__ out_score,
+              int dim, const int* __restrict__ cand, const int* __restrict__ cand_cnt,
+              const float* __restrict__ cand_thr, int n_lists, int list_cap, int k, float eps,
+              const float* __restrict__ q_eps, int* __restrict__ out_idx, float* __restrict__ out_score,
               unsigned char* __restrict__ certified) {
   const int lane = threadIdx.x & 31;
   const int d4 = dim >> 2;
@@ -242,41 +256,42 @@ rerank_kernel(const float* __restrict__ Wq, int64_t q0, int64_t n_queries, const
   wl.init();
   float bound = -CUDART_INF_F;
   for (int l = 0; l < n_lists; ++l) {
-    const int64_t lo = ((int64_t)l * n_queries + qi) * list_k;
-    bool full = true;
-    float lmin = CUDART_INF_F;
-    for (int j0 = 0; j0 < list_k; j0 += 32) {
-      const bool in = j0 + lane < list_k;
-      const int mine = in ? cand[lo + j0 + lane] : -1;
-      if (cand_score) {
-        const float ms = (in && mine >= 0) ? cand_score[lo + j0 + lane] : CUDART_INF_F;
-        float mm = ms;
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) mm = fminf(mm, __shfl_xor_sync(0xffffffffu, mm, o));
-        lmin = fminf(lmin, mm);
-        full = full && !__any_sync(0xffffffffu, in && mine < 0);
-      }
-      const int cnt = min(32, list_k - j0);
-      for (int j = 0; j < cnt; ++j) {
-        const int r = __shfl_sync(0xffffffffu, mine, j);
-        if (r < 0) continue;
-        float dot = 0.f, ss = 0.f;
+    const int64_t lq = (int64_t)l * n_queries + qi;
+    const int* cl = cand + lq * list_cap;
+    const int cnt = cand_cnt ? min(cand_cnt[lq], list_cap) : list_cap;
+    if (cand_thr) bound = fmaxf(bound, cand_thr[lq]);
+    for (int j0 = 0; j0 < cnt; j0 += 32) {
+      const int mine = (j0 + lane < cnt) ? cl[j0 + lane] : -1;
+      const int m = min(32, cnt - j0);
+      for (int j = 0; j < m; j += 2) {  // two candidate rows in flight
+        const int r0 = __shfl_sync(0xffffffffu, mine, j);
+        const int r1 = (j + 1 < m) ? __shfl_sync(0xffffffffu, mine, j + 1) : -1;
+        float d0 = 0.f, s0 = 0.f, d1 = 0.f, s1 = 0.f;
 #pragma unroll
         for (int i = 0; i < NV; ++i) {
           const int jj = lane + 32 * i;
           if (jj < d4) {
-            float4 x = ld4_nc(Wc + (int64_t)r * dim + 4 * jj);
-            dot += dot4(x, qv[i]);
-            ss += dot4(x, x);
+            const float4 x0 = (r0 >= 0) ? ld4_nc(Wc + (int64_t)r0 * dim + 4 * jj) : make_float4(0.f, 0.f, 0.f, 0.f);
+            const float4 x1 = (r1 >= 0) ? ld4_nc(Wc + (int64_t)r1 * dim + 4 * jj) : make_float4(0.f, 0.f, 0.f, 0.f);
+            d0 += dot4(x0, qv[i]); s0 += dot4(x0, x0);
+            d1 += dot4(x1, qv[i]); s1 += dot4(x1, x1);
           }
         }
-        dot = warp_sum(dot);
-        ss = warp_sum(ss);
-        const float sc = dot / sqrtf(ss);
-        if (sc == sc) wl.insert(sc, r, lane, true);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+          d0 += __shfl_xor_sync(0xffffffffu, d0, o); s0 += __shfl_xor_sync(0xffffffffu, s0, o);
+          d1 += __shfl_xor_sync(0xffffffffu, d1, o); s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+        }
+        if (r0 >= 0) {
+          const float sc0 = d0 / sqrtf(s0);
+          if (sc0 == sc0) wl.insert(sc0, r0, lane, true);
+        }
+        if (r1 >= 0) {
+          const float sc1 = d1 / sqrtf(s1);
+          if (sc1 == sc1) wl.insert(sc1, r1, lane, true);
+        }
       }
     }
-    if (cand_score && full) bound = fmaxf(bound, lmin);
   }
   if (lane < k) {
     out_idx[qi * k + lane] = (wl.i == 0x7fffffff) ? -1 : wl.i;
@@ -284,7 +299,8 @@ rerank_kernel(const float* __restrict__ Wq, int64_t q0, int64_t n_queries, const
   }
   if (certified) {
     const float kth = __shfl_sync(0xffffffffu, wl.s, k - 1);  // -inf when fewer than k candidates exist
-    if (lane == 0) certified[qi] = (bound == -CUDART_INF_F || kth >= bound + eps) ? 1 : 0;
+    const float e = eps + (q_eps ? q_eps[qi] : 0.f);
+    if (lane == 0) certified[qi] = (bound == -CUDART_INF_F || kth >= bound + e) ? 1 : 0;
   }
 }
 
@@ -325,17 +341,18 @@ extern "C" int ar_rownorm(const float* W, int64_t n_rows, int32_t dim, float* ou
   AR_REQUIRE(dim_ok(dim), "ar_rownorm: dim %d unsupported", dim);
   if (n_rows <= 0) return AR_OK;
   int blocks = (int)std::min<int64_t>((n_rows + 7) / 8, (int64_t)sm_count() * 8);
-  rownorm_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(W, n_rows, dim, out, nullptr);
+  rownorm_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(W, n_rows, dim, out, nullptr, nullptr);
   AR_LAUNCH_CHECK();
   return AR_OK;
 }
 
-extern "C" int ar_rownorm_bf16(const float* W, int64_t n_rows, int32_t dim, void* out_bf16, void* stream) {
+extern "C" int ar_rownorm_bf16(const float* W, int64_t n_rows, int32_t dim, void* out_bf16, float* resid,
+                               void* stream) {
   AR_REQUIRE(W && out_bf16, "ar_rownorm_bf16: null pointer");
   AR_REQUIRE(dim_ok(dim), "ar_rownorm_bf16: dim %d unsupported", dim);
   if (n_rows <= 0) return AR_OK;
   int blocks = (int)std::min<int64_t>((n_rows + 7) / 8, (int64_t)sm_count() * 8);
-  rownorm_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(W, n_rows, dim, nullptr, (__nv_bfloat16*)out_bf16);
+  rownorm_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(W, n_rows, dim, nullptr, (__nv_bfloat16*)out_bf16, resid);
   AR_LAUNCH_CHECK();
   return AR_OK;
 }
@@ -377,18 +394,18 @@ extern "C" int ar_topk_merge(const int32_t* idx, const float* score, int32_t n_l
 }
 
 extern "C" int ar_cosine_rerank(const float* Wq, int64_t q0, int64_t n_queries, const float* Wc, int32_t dim,
-                                const int32_t* cand, const float* cand_score, int32_t n_lists, int32_t list_k,
-                                int32_t k, float eps, int32_t* out_idx, float* out_score, uint8_t* certified,
-                                void* stream) {
+                                const int32_t* cand, const int32_t* cand_cnt, const float* cand_thr,
+                                int32_t n_lists, int32_t list_cap, int32_t k, float eps, const float* q_eps,
+                                int32_t* out_idx, float* out_score, uint8_t* certified, void* stream) {
   AR_REQUIRE(Wq && Wc && cand && out_idx && out_score, "ar_cosine_rerank: null pointer");
   AR_REQUIRE(dim_ok(dim), "ar_cosine_rerank: dim %d unsupported", dim);
-  AR_REQUIRE(k > 0 && k <= kMaxK && n_lists > 0 && list_k > 0, "ar_cosine_rerank: bad k/n_lists/list_k");
-  AR_REQUIRE(!certified || cand_score, "ar_cosine_rerank: certification needs the candidates' bf16 scores");
+  AR_REQUIRE(k > 0 && k <= kMaxK && n_lists > 0 && list_cap > 0, "ar_cosine_rerank: bad k/n_lists/list_cap");
+  AR_REQUIRE(!certified || cand_thr, "ar_cosine_rerank: certification needs the lists' admission thresholds");
   if (n_queries <= 0) return AR_OK;
   const int blocks = (int)((n_queries + kTopkWarps - 1) / kTopkWarps);
   cudaStream_t st = (cudaStream_t)stream;
-#define AR_RERANK(NVV) rerank_kernel<NVV><<<blocks, kTopkThreads, 0, st>>>(Wq, q0, n_queries, Wc, dim, cand, cand_score, \
-                                                                            n_lists, list_k, k, eps, out_idx, out_score, certified)
+#define AR_RERANK(NVV) rerank_kernel<NVV><<<blocks, kTopkThreads, 0, st>>>(Wq, q0, n_queries, Wc, dim, cand, cand_cnt, cand_thr, \
+                                                                            n_lists, list_cap, k, eps, q_eps, out_idx, out_score, certified)
   switch ((dim + 127) / 128) {
     case 1: AR_RERANK(1); break;
     case 2: AR_RERANK(2); break;

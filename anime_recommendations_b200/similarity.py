@@ -98,68 +98,216 @@ def similar_anime(W_anime, q, count, mask=None):
     return cosine_topk_query(W_anime, q, count, mask=mask, exclude=q)
 
 
-BF16_SCORE_EPS = 0.004   # |bf16-operand score - fp32 score| <= 2^-8 for unit vectors (+ accumulation slack)
+# |bf16-operand score - fp32 cosine| <= resid_q + resid_c + resid_q*resid_c (rounding residual norms of the two
+# unit rows, ar_rownorm_bf16) + the tensor core's fp32 accumulation error over dim terms of magnitude <= 1.
+ACCUM_EPS = 3e-5
+BF16_SCORE_EPS = 0.004   # blanket bound when no residuals are at hand: 2 * 2^-9 (+ accumulation slack)
 
 
-def normalize_rows_bf16(W):
-    """Row-normalised bf16 copy of a table: the operand format of the tensor-core pass."""
+def normalize_rows_bf16(W, with_resid=False):
+    """Row-normalised bf16 copy of a table: the operand format of the tensor-core pass.
+    with_resid -> (table, resid [n] float32 rounding-residual norms)."""
     W = as_table(W)
     out = torch.empty(W.shape, dtype=torch.bfloat16, device=W.device)
-    check(lib().ar_rownorm_bf16(ptr(W), W.shape[0], W.shape[1], ptr(out), stream_ptr()), "ar_rownorm_bf16")
-    return out
+    res = torch.empty(W.shape[0], dtype=torch.float32, device=W.device) if with_resid else None
+    check(lib().ar_rownorm_bf16(ptr(W), W.shape[0], W.shape[1], ptr(out), ptr(res), stream_ptr()), "ar_rownorm_bf16")
+    return (out, res) if with_resid else out
 
 
-def allpairs_candidates(Qn, q0, nq, Cn, c0, nc, kprime=16, exclude_self=False, watched=None, dump=False):
-    """Tensor-core candidate pass: per query row and candidate chunk the kprime best rows by bf16 score.
-    -> (idx [n_chunks, nq, kprime] int32, score same float32, dump [nq, nc] or None), device tensors."""
+class CandidateLists:
+    """Output of the tensor-core pass: idx/score [n_chunks, nq, cap], cnt/thr [n_chunks, nq] (device)."""
+    __slots__ = ("idx", "score", "cnt", "thr", "dump")
+
+    def __init__(self, idx, score, cnt, thr, dump=None):
+        self.idx, self.score, self.cnt, self.thr, self.dump = idx, score, cnt, thr, dump
+
+
+def allpairs_candidates(Qn, q0, nq, Cn, c0, nc, kprime=16, exclude_self=False, watched=None, dump=False,
+                        self_ids=None, thr_init=None, n_chunks=None):
+    """Tensor-core candidate pass (ar_cosine_topk_allpairs): per query row and candidate chunk every
+    candidate whose bf16 score beats a running threshold that rises to the kprime-th best seen."""
     L = lib()
-    n_chunks = int(L.ar_allpairs_chunks(nq, nc))
+    n_chunks = int(L.ar_allpairs_chunks(nq, nc)) if n_chunks is None else int(n_chunks)
+    cap = int(L.ar_allpairs_list_cap(kprime))
+    if cap <= 0:
+        raise ValueError("kprime must be 16 or 24")
     dev = Qn.device
-    oi = torch.empty((n_chunks, nq, kprime), dtype=torch.int32, device=dev)
-    os_ = torch.empty((n_chunks, nq, kprime), dtype=torch.float32, device=dev)
+    oi = torch.empty((n_chunks, nq, cap), dtype=torch.int32, device=dev)
+    os_ = torch.empty((n_chunks, nq, cap), dtype=torch.float32, device=dev)
+    oc = torch.zeros((n_chunks, nq), dtype=torch.int32, device=dev)
+    ot = torch.full((n_chunks, nq), float("-inf"), dtype=torch.float32, device=dev)
     dm = torch.zeros((nq, nc), dtype=torch.float32, device=dev) if dump else None
     stride = 0 if watched is None else watched.shape[1]
     check(L.ar_cosine_topk_allpairs(ptr(Qn), Qn.shape[0], q0, nq, ptr(Cn), Cn.shape[0], c0, nc, Qn.shape[1], kprime,
-                                    1 if exclude_self else 0, ptr(watched), stride, n_chunks, ptr(oi), ptr(os_),
-                                    ptr(dm), stream_ptr()), "ar_cosine_topk_allpairs")
-    return oi, os_, dm
+                                    1 if exclude_self else 0, ptr(self_ids), ptr(watched), stride, ptr(thr_init),
+                                    n_chunks, ptr(oi), ptr(os_), ptr(oc), ptr(ot), ptr(dm), stream_ptr()),
+          "ar_cosine_topk_allpairs")
+    return CandidateLists(oi, os_, oc, ot, dm)
 
 
-def rerank(Wq, q0, nq, Wc, cand, k, cand_score=None, eps=BF16_SCORE_EPS):
-    """Exact fp32 cosine re-rank of candidate lists cand [n_lists, nq, list_k] (or [nq, list_k]).
+def rerank(Wq, q0, nq, Wc, cand, k, cand_cnt=None, cand_thr=None, eps=BF16_SCORE_EPS, q_eps=None):
+    """Exact fp32 cosine re-rank of candidate lists cand [n_lists, nq, cap] (or [nq, cap]).
     -> (idx [nq,k], score [nq,k], certified [nq] uint8 or None), device tensors."""
     if cand.dim() == 2:
         cand = cand.unsqueeze(0)
-        cand_score = None if cand_score is None else cand_score.unsqueeze(0)
-    nl, _, lk = cand.shape
+    nl, _, cap = cand.shape
     oi = torch.empty((nq, k), dtype=torch.int32, device=Wq.device)
     os_ = torch.empty((nq, k), dtype=torch.float32, device=Wq.device)
-    cert = torch.empty(nq, dtype=torch.uint8, device=Wq.device) if cand_score is not None else None
+    cert = torch.empty(nq, dtype=torch.uint8, device=Wq.device) if cand_thr is not None else None
     check(lib().ar_cosine_rerank(ptr(Wq), q0, nq, ptr(Wc), Wq.shape[1], ptr(cand.contiguous()),
-                                 ptr(None if cand_score is None else cand_score.contiguous()), nl, lk, k, eps,
-                                 ptr(oi), ptr(os_), ptr(cert), stream_ptr()), "ar_cosine_rerank")
+                                 ptr(None if cand_cnt is None else cand_cnt.contiguous()),
+                                 ptr(None if cand_thr is None else cand_thr.contiguous()), nl, cap, k, float(eps),
+                                 ptr(q_eps), ptr(oi), ptr(os_), ptr(cert), stream_ptr()), "ar_cosine_rerank")
     return oi, os_, cert
 
 
-def allpairs_topk(W, k=10, kprime=16, q0=0, nq=None, Wn_bf16=None, stats=None):
+N_SMS = 148                 # B200
+QTILE = 256                 # query rows per work item of the tensor-core kernel
+SAMPLE_FRACTION = 16        # the threshold-seeding pass scans 1/16 of the candidates
+SAMPLE_MIN_ROWS = 65536     # ... and is skipped for candidate sets smaller than this
+
+
+class _Timer:
+    """CUDA-event stage timer, active only when the caller passes stats={'time': True}."""
+
+    def __init__(self, on):
+        self.on, self.ev = on, []
+
+    def mark(self, name):
+        if self.on:
+            e = torch.cuda.Event(enable_timing=True)
+            e.record()
+            self.ev.append((name, e))
+
+    def result(self):
+        if not self.on or len(self.ev) < 2:
+            return {}
+        torch.cuda.synchronize()
+        out = {}
+        for (_, a), (nb, b) in zip(self.ev[:-1], self.ev[1:]):
+            out[nb] = out.get(nb, 0.0) + a.elapsed_time(b)
+        return out
+
+
+def _sl(t, lo, hi):
+    return None if t is None else t[lo:hi]
+
+
+def _candidate_lists(Qn, nq, Cn, kprime, exclude_self, self_ids, watched, thr_init, seed=True, tm=None):
+    """Tensor-core candidate pass over query rows [0, nq) of Qn against all of Cn, scheduled for the machine:
+      1. threshold seeding: a first pass over 1/16 of the candidates yields per row a valid lower bound on
+         its (kprime+1)-th best score; started from it the full pass appends ~4x fewer candidates (the list
+         kernel's slow path) -- any subset's (k+1)-th best is a lower bound, so exactness is unaffected;
+      2. the query range is cut into a part whose 256-row tiles fill the 148 SMs an integral number of rounds
+         (one candidate chunk) and a remainder whose candidate range is split so it also fills the machine.
+    -> [(row_lo, row_hi, CandidateLists)]"""
+    nc = Cn.shape[0]
+    if seed and thr_init is None and nc >= SAMPLE_MIN_ROWS:
+        ns = ((nc // SAMPLE_FRACTION + 127) // 128) * 128
+        cl0 = allpairs_candidates(Qn, 0, nq, Cn, 0, ns, kprime, exclude_self=exclude_self, self_ids=self_ids,
+                                  watched=watched, n_chunks=1)
+        thr_init = cl0.thr[0]
+        if tm:
+            tm.mark("seed_pass")
+    qtiles = (nq + QTILE - 1) // QTILE
+    rounds = qtiles // N_SMS
+    cuts = [0, nq]
+    if rounds >= 2 and qtiles % N_SMS:
+        cuts = [0, rounds * N_SMS * QTILE, nq]
+    parts = []
+    for lo, hi in zip(cuts[:-1], cuts[1:]):
+        cl = allpairs_candidates(Qn, lo, hi - lo, Cn, 0, nc, kprime, exclude_self=exclude_self,
+                                 self_ids=_sl(self_ids, lo, hi), watched=_sl(watched, lo, hi),
+                                 thr_init=_sl(thr_init, lo, hi))
+        parts.append((lo, hi, cl))
+    if tm:
+        tm.mark("candidate_pass")
+    return parts
+
+
+def _rerank_parts(parts, Wq_f32, Wc_f32, k, q_eps, tm=None):
+    nq = Wq_f32.shape[0]
+    oi = torch.empty((nq, k), dtype=torch.int32, device=Wq_f32.device)
+    os_ = torch.empty((nq, k), dtype=torch.float32, device=Wq_f32.device)
+    cert = torch.empty(nq, dtype=torch.uint8, device=Wq_f32.device)
+    L = lib()
+    for lo, hi, cl in parts:
+        nl, _, cap = cl.idx.shape
+        check(L.ar_cosine_rerank(ptr(Wq_f32), lo, hi - lo, ptr(Wc_f32), Wq_f32.shape[1], ptr(cl.idx), ptr(cl.cnt),
+                                 ptr(cl.thr), nl, cap, k, float(ACCUM_EPS), ptr(q_eps[lo:hi]), ptr(oi[lo:hi]),
+                                 ptr(os_[lo:hi]), ptr(cert[lo:hi]), stream_ptr()), "ar_cosine_rerank")
+    if tm:
+        tm.mark("rerank")
+    return oi, os_, cert
+
+
+def _certified_topk(Wq_f32, Qn, q_res, Wc_f32, Cn, c_res_max, k, kprime, exclude_self, self_ids, watched, stats,
+                    exact_row):
+    """Tensor-core pass + fp32 re-rank + certification, with two recovery levels for the rows the first
+    pass cannot certify: (1) the same kernel over just those rows with the provably sufficient fixed
+    threshold (k-th fp32 score found so far - eps); (2) `exact_row(i)`, the fp32 single-query kernel.
+    Qn may hold more rows than Wq_f32 (the whole table); the queries are its first Wq_f32.shape[0] rows
+    unless self_ids says otherwise."""
+    nq = Wq_f32.shape[0]
+    if kprime <= k:
+        raise ValueError("kprime (%d) must exceed k (%d)" % (kprime, k))
+    tm = _Timer(bool(stats is not None and stats.get("time")))
+    tm.mark("start")
+    q_eps = (q_res + c_res_max + q_res * c_res_max).contiguous()
+    parts = _candidate_lists(Qn, nq, Cn, kprime, exclude_self, self_ids, watched, None, tm=tm)
+    oi, os_, cert = _rerank_parts(parts, Wq_f32, Wc_f32, k, q_eps, tm)
+    bad = torch.nonzero(cert == 0).reshape(-1)
+    n_bad1 = int(bad.numel())
+    n_bad2 = 0
+    if n_bad1:
+        # every true top-k member has fp32 score >= the k-th fp32 score found so far, hence bf16 score above
+        # that minus eps: list EVERYTHING above this fixed threshold (no compaction unless > cap such rows)
+        kth = os_[bad, k - 1]
+        thr0 = torch.where(torch.isfinite(kth), kth - (q_eps[bad] + ACCUM_EPS) * 1.0001 - 1e-6,
+                           torch.full_like(kth, float("-inf"))).contiguous()
+        Qb = Qn[bad].contiguous()
+        Wb = Wq_f32[bad].contiguous()
+        ids_b = None
+        if exclude_self:
+            ids_b = (self_ids[bad] if self_ids is not None else bad.to(torch.int32)).contiguous()
+        wb = watched[bad].contiguous() if watched is not None else None
+        parts2 = _candidate_lists(Qb, n_bad1, Cn, kprime, exclude_self, ids_b, wb, thr0, tm=None)
+        oi2, os2, cert2 = _rerank_parts(parts2, Wb, Wc_f32, k, q_eps[bad].contiguous())
+        oi[bad], os_[bad] = oi2, os2
+        still = bad[cert2 == 0]
+        n_bad2 = int(still.numel())
+        for r in still.cpu().tolist():                 # exact fp32 path for the (near-)tied few
+            fi, fs = exact_row(r)
+            oi[r], os_[r] = fi, fs
+        tm.mark("recovery")
+    if stats is not None:
+        cl = parts[0][2]
+        stats.update(uncertified=n_bad1, uncertified_after_retry=n_bad2, n_chunks=[p[2].idx.shape[0] for p in parts],
+                     kprime=kprime, mean_list=float(cl.cnt.float().mean().item()), ms=tm.result())
+    return oi, os_
+
+
+def allpairs_topk(W, k=10, kprime=16, q0=0, nq=None, stats=None):
     """BASELINE cfg3: for every query row in [q0, q0+nq) the k most cosine-similar OTHER rows of W.
 
-    bf16 tensor-core pass selects kprime candidates per row (per candidate chunk), the fp32 re-rank orders
-    them exactly, and rows whose result cannot be certified exact (bf16 error bound) fall back to the fp32
+    The bf16 tensor-core pass lists the candidates, the fp32 re-rank orders them exactly, and rows whose
+    result cannot be certified exact (rigorous bf16 error bound) are retried / fall back to the fp32
     single-query kernel.  -> (idx [nq,k] int32, score [nq,k] float32) device tensors."""
     W = as_table(W)
     n = W.shape[0]
     nq = n - q0 if nq is None else nq
-    Wn = normalize_rows_bf16(W) if Wn_bf16 is None else Wn_bf16
-    ci, cs, _ = allpairs_candidates(Wn, q0, nq, Wn, 0, n, kprime, exclude_self=True)
-    oi, os_, cert = rerank(W, q0, nq, W, ci, k, cand_score=cs)
-    bad = torch.nonzero(cert == 0).reshape(-1).cpu().tolist()
-    for r in bad:                                      # exact fp32 path for the uncertified few
-        fi, fs = cosine_topk_query_device(W, q0 + r, k, exclude=q0 + r)
-        oi[r], os_[r] = fi, fs
-    if stats is not None:
-        stats.update(uncertified=len(bad), n_chunks=ci.shape[0], kprime=kprime)
-    return oi, os_
+    Wn, res = normalize_rows_bf16(W, with_resid=True)
+    res = torch.nan_to_num(res, nan=1.0)
+    whole = q0 == 0                                      # queries are the leading rows: identity self ids
+    Qn = Wn if whole else Wn[q0:q0 + nq].contiguous()
+    Wq = W[:nq] if whole else W[q0:q0 + nq].contiguous()
+    ids = None if whole else torch.arange(q0, q0 + nq, dtype=torch.int32, device=W.device)
+
+    def exact_row(r):
+        return cosine_topk_query_device(W, q0 + r, k, exclude=q0 + r)
+
+    return _certified_topk(Wq, Qn, res[q0:q0 + nq], W, Wn, float(res.max().item()), k, kprime, True, ids, None,
+                           stats, exact_row)
 
 
 def watched_bits(indptr, idx, n_rows, n_cols, device, cand_mask=None):
@@ -176,7 +324,7 @@ def watched_bits(indptr, idx, n_rows, n_cols, device, cand_mask=None):
     return out
 
 
-def score_topk(model, users, watched_indptr, watched_idx, k, cand_mask=None, kprime=32, stats=None):
+def score_topk(model, users, watched_indptr, watched_idx, k, cand_mask=None, kprime=24, stats=None):
     """model_recs over many users (BASELINE cfg4): predicted rating of every anime the user has NOT rated,
     top-k by Prediction (model_recs.py:132-192,373-456).  Prediction is a monotone map of cos(u, a)
     (Dense(1) -> BatchNorm(inference) -> sigmoid), so candidates are ranked by sign(w*gamma)*cos on the
@@ -189,14 +337,15 @@ def score_topk(model, users, watched_indptr, watched_idx, k, cand_mask=None, kpr
     head = model.head.cpu().numpy()
     sign = -1.0 if float(head[0]) * float(head[2]) < 0 else 1.0
     Uq = (model.U[users_t] * sign).contiguous()               # query rows (negated when the map decreases)
-    Qn, Cn = normalize_rows_bf16(Uq), normalize_rows_bf16(model.A)
+    (Qn, qres), (Cn, cres) = normalize_rows_bf16(Uq, True), normalize_rows_bf16(model.A, True)
+    qres, cres = torch.nan_to_num(qres, nan=1.0), torch.nan_to_num(cres, nan=1.0)
     wb = watched_bits(watched_indptr, watched_idx, nq, na, dev, cand_mask)
-    ci, cs, _ = allpairs_candidates(Qn, 0, nq, Cn, 0, na, kprime, exclude_self=False, watched=wb)
-    oi, os_, cert = rerank(Uq, 0, nq, model.A, ci, k, cand_score=cs)
-    bad = torch.nonzero(cert == 0).reshape(-1).cpu().tolist()
-    for r in bad:
-        fi, fs = _query_vs_table(Uq[r], model.A, k, wb[r])
-        oi[r], os_[r] = fi, fs
+
+    def exact_row(r):
+        return _query_vs_table(Uq[r], model.A, k, wb[r])
+
+    oi, os_ = _certified_topk(Uq, Qn, qres, model.A, Cn, float(cres.max().item()), k, kprime, False, None, wb,
+                              stats, exact_row)
     valid = oi >= 0
     iu = users_t.to(torch.int32).reshape(-1, 1).expand(-1, k)[valid].contiguous()
     ia = oi[valid].contiguous()
@@ -207,7 +356,7 @@ def score_topk(model, users, watched_indptr, watched_idx, k, cand_mask=None, kpr
                                ptr(ia), iu.numel(), ptr(out), stream_ptr()), "ar_predict")
         pred[valid] = out
     if stats is not None:
-        stats.update(uncertified=len(bad), n_chunks=ci.shape[0], kprime=kprime, sign=sign)
+        stats["sign"] = sign
     return oi.cpu().numpy(), pred.cpu().numpy()
 
 

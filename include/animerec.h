@@ -208,36 +208,47 @@ int ar_cosine_topk_query(const float* W, int64_t n_rows, int32_t dim, int64_t q,
 int ar_topk_merge(const int32_t* idx, const float* score, int32_t n_lists, int64_t n_queries,
                   int32_t k_in, int32_t k_out, int32_t* out_idx, float* out_score, void* stream);
 
-/* Exact fp32 re-rank.  Candidates: n_lists lists of list_k row ids per query, layout
- * [list][query][list_k], -1 = empty (the output layout of ar_cosine_topk_allpairs / the input layout of
- * ar_topk_merge).  Query rows are Wq[q0 + i], candidate rows index Wc.  Keeps the best k by fp32 cosine
- * (duplicates collapse).  Optional certification: with the candidates' selection scores `cand_score`
- * (same layout) and the bound `eps` on |selection score - fp32 score|, certified[i] = 1 iff the fp32
- * top-k of query i is provably the true top-k over ALL rows the lists were drawn from. */
+/* Exact fp32 re-rank.  Candidates: n_lists lists of up to list_cap row ids per query, layout
+ * [list][query][list_cap] (the output layout of ar_cosine_topk_allpairs / the input layout of ar_topk_merge);
+ * cand_cnt[list][query] = number of valid entries (null: every entry >= 0 is valid).  Query rows are
+ * Wq[q0 + i], candidate rows index Wc.  Keeps the best k by fp32 cosine (duplicates collapse).
+ * Optional certification: cand_thr[list][query] = the selection-score bound of everything list `list` left
+ * out (ar_cosine_topk_allpairs' out_thr); with eps (+ q_eps[i], optional per query) bounding
+ * |selection score - fp32 score|, certified[i] = 1 iff the fp32 top-k of query i is provably the true top-k
+ * over ALL rows the lists were drawn from (k-th score >= max_list thr + eps), else 0. */
 int ar_cosine_rerank(const float* Wq, int64_t q0, int64_t n_queries, const float* Wc, int32_t dim,
-                     const int32_t* cand, const float* cand_score, int32_t n_lists, int32_t list_k,
-                     int32_t k, float eps, int32_t* out_idx, float* out_score, uint8_t* certified,
-                     void* stream);
+                     const int32_t* cand, const int32_t* cand_cnt, const float* cand_thr, int32_t n_lists,
+                     int32_t list_cap, int32_t k, float eps, const float* q_eps, int32_t* out_idx,
+                     float* out_score, uint8_t* certified, void* stream);
 
 /* Many-query cosine candidates on the tensor cores (tcgen05.mma, bf16 operands, fp32 accumulation in
  * TMEM, TMA-fed): for query rows [q0, q0+n_q) of Qn and candidate rows [c0, c0+n_c) of Cn -- both
  * ROW-NORMALISED bf16 (q_rows_total|c_rows_total, dim) tables made by ar_rownorm_bf16, dim == 128 --
- * keep per query and candidate chunk the kprime (16 or 32) best candidates by bf16-operand score.
- *   exclude_self     drop candidate id == query id (Qn and Cn are the same table)
+ * list per query row and candidate chunk every admissible candidate whose bf16-operand score exceeds a
+ * running threshold that rises to the (kprime+1)-th (kprime = 16 or 24) best score seen.
+ *   exclude_self     drop candidate id == query id (Qn and Cn are the same table); self_ids (optional,
+ *                    [n_q]) gives the id to drop per query row when the query table is a gathered subset
  *   watched          optional bit rows [n_q][watched_stride] over candidate ids, set bit = drop
  *                    (model_recs.py:144-155: anime the user already rated)
+ *   thr_init         optional [n_q] starting threshold (only scores above it are ever listed)
  *   n_chunks         from ar_allpairs_chunks(n_q, n_c): the candidate range is split so every SM has work
- *   out_idx/out_score [n_chunks][n_q][kprime], unsorted, -1 / -inf = empty
+ *   out_idx/out_score [n_chunks][n_q][cap], cap = ar_allpairs_list_cap(kprime); unsorted, -1 / -inf = empty
+ *   out_cnt          [n_chunks][n_q] valid entries (kprime <= cnt <= cap once kprime candidates were seen)
+ *   out_thr          [n_chunks][n_q] every admissible candidate of the chunk NOT listed scored <= this
  *   dump_scores      optional [n_q][n_c] raw scores (tests only)
  * Replaces the reference's np.dot + np.argsort per query (similar_anime.py:404-409, similar_users.py:
  * 293-296) looped over all rows, and model.predict over (user x all anime) (model_recs.py:394-396). */
-int ar_rownorm_bf16(const float* W, int64_t n_rows, int32_t dim, void* out_bf16, void* stream);
+/* resid (optional, [n_rows]): ||w_hat - bf16(w_hat)||_2 per row; |bf16 score - fp32 cosine| of a pair is
+ * bounded by resid_q + resid_c + resid_q*resid_c (+ fp32 accumulation error). */
+int ar_rownorm_bf16(const float* W, int64_t n_rows, int32_t dim, void* out_bf16, float* resid, void* stream);
 int32_t ar_allpairs_chunks(int64_t n_q, int64_t n_c);
+int32_t ar_allpairs_list_cap(int32_t kprime);
 int ar_cosine_topk_allpairs(const void* Qn_bf16, int64_t q_rows_total, int64_t q0, int64_t n_q,
                             const void* Cn_bf16, int64_t c_rows_total, int64_t c0, int64_t n_c,
-                            int32_t dim, int32_t kprime, int32_t exclude_self, const uint32_t* watched,
-                            int64_t watched_stride, int32_t n_chunks, int32_t* out_idx, float* out_score,
-                            float* dump_scores, void* stream);
+                            int32_t dim, int32_t kprime, int32_t exclude_self, const int32_t* self_ids,
+                            const uint32_t* watched, int64_t watched_stride, const float* thr_init,
+                            int32_t n_chunks, int32_t* out_idx, float* out_score, int32_t* out_cnt,
+                            float* out_thr, float* dump_scores, void* stream);
 
 /* OR the CSR (indptr int64[n_rows+1], idx int32) into bit rows out[n_rows][stride_words] (caller
  * initialises `out`): the "already watched" mask of model_recs.py:144-155 for ar_cosine_topk_allpairs. */

@@ -28,29 +28,57 @@ def test_tcgen05_scores_match_matmul_of_same_bf16_operands(nq, nc, q0, c0):
     Q = rng.standard_normal((nq + q0 + 5, 128)).astype(np.float32)
     C = rng.standard_normal((nc + c0 + 3, 128)).astype(np.float32)
     Qn, Cn = sim.normalize_rows_bf16(Q), sim.normalize_rows_bf16(C)
-    np.testing.assert_array_equal(Qn.float().cpu().numpy(), _bf16_round(osim.get_weights(Q)))
-    ci, cs, dump = sim.allpairs_candidates(Qn, q0, nq, Cn, c0, nc, kprime=16, dump=True)
+    got, want = Qn.float().cpu().numpy(), _bf16_round(osim.get_weights(Q))
+    np.testing.assert_allclose(got, want, rtol=2 ** -7, atol=0)      # a 1-ulp fp32 difference can flip a bf16 rounding
+    assert (got != want).mean() < 1e-3
+    cl = sim.allpairs_candidates(Qn, q0, nq, Cn, c0, nc, kprime=16, dump=True)
     ref = Qn.float().cpu().numpy()[q0:q0 + nq] @ Cn.float().cpu().numpy()[c0:c0 + nc].T
-    np.testing.assert_allclose(dump.cpu().numpy(), ref, rtol=0, atol=2e-6)
-    # the kept candidates are exactly the kprime largest bf16 scores of each chunk
-    ci, cs = ci.cpu().numpy(), cs.cpu().numpy()
-    n_chunks = ci.shape[0]
+    d = cl.dump.cpu().numpy()
+    np.testing.assert_allclose(d, ref, rtol=0, atol=2e-6)
+    # list invariant per (chunk, row): the list is EXACTLY the set of chunk candidates scoring above the final
+    # threshold, it holds the 16 best of the chunk, and it never exceeds the capacity
+    ci, cs, cc, ct = (x.cpu().numpy() for x in (cl.idx, cl.score, cl.cnt, cl.thr))
+    n_chunks, _, cap = ci.shape
     tiles = (nc + 127) // 128
     per = (tiles + n_chunks - 1) // n_chunks
-    d = dump.cpu().numpy()
     for ch in range(n_chunks):
         lo, hi = ch * per * 128, min(nc, (ch + 1) * per * 128)
         for r in range(0, nq, max(1, nq // 50)):
-            want = np.sort(d[r, lo:hi])[::-1][:16]
-            got = np.sort(cs[ch, r][ci[ch, r] >= 0])[::-1]
-            assert len(got) == min(16, hi - lo)
-            np.testing.assert_array_equal(got, want[:len(got)])
-            sel = ci[ch, r][ci[ch, r] >= 0]
-            assert ((sel >= c0 + lo) & (sel < c0 + hi)).all()
-            np.testing.assert_array_equal(np.sort(d[r, sel - c0])[::-1], got)
+            cnt, thr = int(cc[ch, r]), float(ct[ch, r])
+            assert min(16, hi - lo) <= cnt <= cap
+            sel = ci[ch, r, :cnt]
+            assert (ci[ch, r, cnt:] == -1).all() and (sel >= c0 + lo).all() and (sel < c0 + hi).all()
+            np.testing.assert_array_equal(cs[ch, r, :cnt], d[r, sel - c0])
+            above = np.nonzero(d[r, lo:hi] > thr)[0] + lo + c0
+            np.testing.assert_array_equal(np.sort(sel), above)
+            top = np.argsort(-d[r, lo:hi], kind="stable")[:16] + lo + c0
+            assert set(top) <= set(sel)
 
 
-@pytest.mark.parametrize("n,kprime", [(3000, 16), (18000, 16), (5000, 32)])
+def test_candidate_lists_honour_thr_init_self_ids_and_watched():
+    rng = np.random.RandomState(5)
+    W = rng.standard_normal((1500, 128)).astype(np.float32)
+    Wn = sim.normalize_rows_bf16(W)
+    rows = torch.tensor([7, 300, 1499, 42], dtype=torch.int64, device=DEV)
+    Qb = Wn[rows].contiguous()
+    thr0 = torch.tensor([0.15, -1.0, 0.3, 0.2], dtype=torch.float32, device=DEV)
+    watched = torch.zeros((4, (1500 + 31) // 32), dtype=torch.int32, device=DEV)
+    watched[3, 0] = 0x7fffffff                                        # query 3 has "watched" rows 0..30
+    cl = sim.allpairs_candidates(Qb, 0, 4, Wn, 0, 1500, kprime=16, exclude_self=True,
+                                 self_ids=rows.to(torch.int32), watched=watched, thr_init=thr0, dump=True, n_chunks=1)
+    d = cl.dump.cpu().numpy()
+    for i in range(4):
+        cnt, thr = int(cl.cnt[0, i]), float(cl.thr[0, i])
+        assert thr >= float(thr0[i])
+        ok = np.ones(1500, bool)
+        ok[int(rows[i])] = False
+        if i == 3:
+            ok[:31] = False
+        want = np.nonzero((d[i] > thr) & ok)[0]
+        np.testing.assert_array_equal(np.sort(cl.idx[0, i, :cnt].cpu().numpy()), want)
+
+
+@pytest.mark.parametrize("n,kprime", [(3000, 16), (18000, 16), (5000, 24)])
 def test_allpairs_topk_matches_oracle(n, kprime):
     rng = np.random.RandomState(n)
     W = rng.standard_normal((n, 128)).astype(np.float32)
@@ -121,7 +149,7 @@ def test_allpairs_full_user_table_sampled_against_oracle():
     st = {}
     gi, gs = sim.allpairs_topk(W, k=10, kprime=16, stats=st)
     gi, gs = gi.cpu().numpy(), gs.cpu().numpy()
-    assert st["uncertified"] < 100
+    assert st["uncertified"] < n // 20 and st["uncertified_after_retry"] < 50
     Wn = osim.get_weights(W)
     for r in range(0, n, 5000):
         full = Wn @ Wn[r]
