@@ -157,56 +157,44 @@ __device__ __forceinline__ int lds_s32(uint32_t a) {
 __device__ __forceinline__ void sts_f32(uint32_t a, float v) { asm volatile("st.shared.f32 [%0], %1;" ::"r"(a), "f"(v) : "memory"); }
 __device__ __forceinline__ void sts_s32(uint32_t a, int v) { asm volatile("st.shared.s32 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
 
-__device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t (&v)[8]) {
-  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
-               : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
-               : "r"(taddr)
-               : "memory");
-}
-
 // Row-private candidate list in shared memory (entry j of a row at byte offset j*QT*4 from the row's base:
 // bank = thread, conflict-free).  Invariant: every admissible candidate seen so far with score > thr is in
-// the list.  list_compact() pulls the held scores into registers, sorts them with a 32-key bitonic network
-// (240 compare-exchanges = 480 FMNMX, no memory traffic), raises thr to the (KP+1)-th best held score and
-// squeezes the list down to the entries above it (exactly KP unless scores tie at the cut).
-// Everything on the slow path is written ONCE, behind a rolled loop, with no calls: an earlier version that
-// inlined the scan into the unrolled fast path was 120 KB of code and stalled on instruction fetch (ncu: icc
-// hit rate 60 %, `no_instruction` the top stall), and out-of-line functions cost stack spills that go to L2
-// here (this kernel leaves the SM ~2 KB of L1).
+// the list.  list_compact() pulls the held scores into registers, bisects (10 rolled steps of 32 compares)
+// for the lowest cut with at most KP scores above it (within (hi-lo)/1024), raises thr to the cut and
+// squeezes the list.  Scores tied at the cut are dropped together (list under-full: the re-rank cannot
+// certify such a row and the caller's exact path takes it).
+// Code size matters as much as instruction count here: an earlier version that inlined an unrolled scan at
+// every use was 120 KB of code and stalled on instruction fetch (ncu: icc hit rate 60 %, `no_instruction`
+// the top stall); out-of-line functions cost stack spills that go to L2 (this kernel leaves ~2 KB of L1).
 template <int KP>
 __device__ __forceinline__ void list_compact(uint32_t sa, uint32_t ia, int& cnt, float& thr) {
   float s[CAP];
+  float hi = -CUDART_INF_F;
 #pragma unroll
-  for (int j = 0; j < CAP; ++j) s[j] = (j < cnt) ? lds_f32(sa + j * QT * 4) : -CUDART_INF_F;
-  // bitonic sort, descending
-#pragma unroll
-  for (int k = 2; k <= CAP; k <<= 1) {
-#pragma unroll
-    for (int j = k >> 1; j > 0; j >>= 1) {
-#pragma unroll
-      for (int i = 0; i < CAP; ++i) {
-        const int l = i ^ j;
-        if (l > i) {
-          const float a = s[i], b = s[l];
-          const bool desc = ((i & k) == 0);
-          s[i] = desc ? fmaxf(a, b) : fminf(a, b);
-          s[l] = desc ? fminf(a, b) : fmaxf(a, b);
-        }
-      }
-    }
-  }
-  const float nt = fmaxf(s[KP], thr);  // (KP+1)-th best: at most KP entries lie strictly above it
-  int w = 0;
-#pragma unroll 4
   for (int j = 0; j < CAP; ++j) {
-    if (j < cnt) {
-      const float x = lds_f32(sa + j * QT * 4);
-      if (x > nt) {
-        const int id = lds_s32(ia + j * QT * 4);
-        sts_f32(sa + w * QT * 4, x);
-        sts_s32(ia + w * QT * 4, id);
-        ++w;
-      }
+    s[j] = (j < cnt) ? lds_f32(sa + j * QT * 4) : -CUDART_INF_F;
+    hi = fmaxf(hi, s[j]);
+  }
+  // bisect for the LOWEST cut that leaves at most KP scores above it (a lower thr certifies more rows):
+  // invariant count(s > lo) > KP (true for lo = thr: cnt > KP entries, all above thr) and count(s > hi) <= KP
+  float lo = fmaxf(thr, -1.01f);
+#pragma unroll 1
+  for (int it = 0; it < 10; ++it) {
+    const float mid = 0.5f * (lo + hi);
+    int c = 0;
+#pragma unroll
+    for (int j = 0; j < CAP; ++j) c += (s[j] > mid) ? 1 : 0;
+    if (c > KP) lo = mid; else hi = mid;
+  }
+  const float nt = hi;  // <= KP entries survive, whatever the ties
+  int w = 0;
+#pragma unroll
+  for (int j = 0; j < CAP; ++j) {
+    if (s[j] > nt) {  // padding entries are -inf: never kept
+      const int id = lds_s32(ia + j * QT * 4);
+      sts_f32(sa + w * QT * 4, s[j]);
+      sts_s32(ia + w * QT * 4, id);
+      ++w;
     }
   }
   cnt = w;
@@ -342,9 +330,12 @@ allpairs_topk_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
       const int t0 = ch * p.tiles_per_chunk, t1 = min(p.n_tiles, t0 + p.tiles_per_chunk);
       const int c_end = (int)(p.c0 + p.n_c);
 
-      // fast path over one 32-column chunk held in registers: FMNMX3 tree (18 ALU ops) against the row's
-      // threshold; a chunk that beats it is only FLAGGED here and rescanned from TMEM below
-      auto chunk_max = [&](const uint32_t (&v)[32], int cb) -> float {
+      // One 32-column chunk held in registers.  Fast path: FMNMX3 tree (18 ALU ops) against the row's
+      // threshold and one vote.  Slow path (some row of the warp beat its threshold; warp-uniform entry):
+      // vote per group of eight, then per hot group select its eight scores (no dynamic register indexing),
+      // make room if a row needs it -- the WHOLE warp compacts, same instruction stream, so the other rows'
+      // squeezes are free and their thresholds tighten early -- and append the admissible hits.
+      auto consume = [&](const uint32_t (&v)[32], int cb) {
         if (DUMP && row_ok) {
 #pragma unroll
           for (int i = 0; i < 32; ++i) {
@@ -359,67 +350,28 @@ allpairs_topk_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
           const float r2 = fmax3(__uint_as_float(v[8 * j + 3]), __uint_as_float(v[8 * j + 4]), __uint_as_float(v[8 * j + 5]));
           g[j] = fmax3(__uint_as_float(v[8 * j + 6]), __uint_as_float(v[8 * j + 7]), fmaxf(r1, r2));
         }
-        return fmaxf(fmax3(g[0], g[1], g[2]), g[3]);
-      };
-
-      for (int t = t0; t < t1; ++t, ++it) {
-        const int as = it & 1;
-        mbar_wait(tmem_full(as * MT + mt), (it >> 1) & 1);
-        tc_fence_after();
-        const uint32_t tbase = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)((as * MT + mt) * BN);
-        const int cbase = (int)(p.c0 + (int64_t)t * BN);
-        if (dbg >= 3) {  // attribution: MMA + TMA only
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(tmem_empty(as * MT + mt));
-          continue;
-        }
-        // software pipeline over the four 32-column chunks: the next tcgen05.ld is in flight while the
-        // current chunk is reduced
-        uint32_t va[32], vb[32];
-        uint32_t flags = 0;
-        __syncwarp();
-        tmem_ld32(tbase, va);
-        tmem_ld_wait();
-        __syncwarp();
-        tmem_ld32(tbase + 32, vb);
-        if (dbg < 2) flags |= (chunk_max(va, cbase) > thr) ? 1u : 0u;
-        tmem_ld_wait();
-        __syncwarp();
-        tmem_ld32(tbase + 64, va);
-        if (dbg < 2) flags |= (chunk_max(vb, cbase + 32) > thr) ? 2u : 0u;
-        tmem_ld_wait();
-        __syncwarp();
-        tmem_ld32(tbase + 96, vb);
-        if (dbg < 2) flags |= (chunk_max(va, cbase + 64) > thr) ? 4u : 0u;
-        tmem_ld_wait();
-        if (dbg < 2) flags |= (chunk_max(vb, cbase + 96) > thr) ? 8u : 0u;
-        // slow path (warp-uniform entry): rescan the flagged chunks from TMEM, eight columns at a time
-        uint32_t todo = __reduce_or_sync(0xffffffffu, flags);
-        while (todo) {
-          const int c = __ffs(todo) - 1;
-          todo &= todo - 1;
-          const bool mine = (flags >> c) & 1u;
-          __syncwarp();
-          tmem_ld32(tbase + 32 * c, va);
-          tmem_ld_wait();
-#pragma unroll 1
-          for (int gq = 0; gq < 4; ++gq) {
-            float x[8];
+        const float m = fmaxf(fmax3(g[0], g[1], g[2]), g[3]);
+        if (!__any_sync(0xffffffffu, m > thr)) return;
+        uint32_t gmask = 0;
 #pragma unroll
-            for (int e = 0; e < 8; ++e) {  // group gq of the chunk, selected without dynamic register indexing
-              const uint32_t lo = (gq & 1) ? va[8 + e] : va[e], hi = (gq & 1) ? va[24 + e] : va[16 + e];
-              x[e] = __uint_as_float((gq & 2) ? hi : lo);
-            }
-            const float gm = fmaxf(fmax3(x[0], x[1], x[2]), fmax3(x[3], x[4], fmax3(x[5], x[6], x[7])));
-            const bool hot = mine && (gm > thr);
-            // a row that needs room for eight more makes the WHOLE warp compact (same instruction stream, so the
-            // other rows' squeezes are free and their thresholds tighten early)
-            if (__any_sync(0xffffffffu, hot && cnt > CAP - 8)) {
-              if (cnt > KP) list_compact<KP>(my_s, my_i, cnt, thr);
-            }
-            if (!hot) continue;
-            const int cid0 = cbase + 32 * c + 8 * gq;
+        for (int j = 0; j < 4; ++j) gmask |= __any_sync(0xffffffffu, g[j] > thr) ? (1u << j) : 0u;
+#pragma unroll 1
+        while (gmask) {
+          const int gq = __ffs(gmask) - 1;
+          gmask &= gmask - 1;
+          float x[8];
+#pragma unroll
+          for (int e = 0; e < 8; ++e) {
+            const uint32_t lo = (gq & 1) ? v[8 + e] : v[e], hi = (gq & 1) ? v[24 + e] : v[16 + e];
+            x[e] = __uint_as_float((gq & 2) ? hi : lo);
+          }
+          const float glo = (gq & 1) ? g[1] : g[0], ghi = (gq & 1) ? g[3] : g[2];
+          const bool hot = ((gq & 2) ? ghi : glo) > thr;
+          if (__any_sync(0xffffffffu, hot && cnt > CAP - 8)) {
+            if (cnt > KP) list_compact<KP>(my_s, my_i, cnt, thr);
+          }
+          if (hot) {
+            const int cid0 = cb + 8 * gq;
 #pragma unroll
             for (int e = 0; e < 8; ++e) {
               if (x[e] > thr) {
@@ -435,10 +387,43 @@ allpairs_topk_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
             }
           }
         }
-        // this accumulator stage is fully consumed: hand it back to the MMA warp
-        tc_fence_before();
+      };
+
+      for (int t = t0; t < t1; ++t, ++it) {
+        const int as = it & 1;
+        mbar_wait(tmem_full(as * MT + mt), (it >> 1) & 1);
+        tc_fence_after();
+        const uint32_t tbase = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)((as * MT + mt) * BN);
+        const int cbase = (int)(p.c0 + (int64_t)t * BN);
+        if (dbg >= 3) {  // attribution: MMA + TMA only
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(tmem_empty(as * MT + mt));
+          continue;
+        }
+        // software pipeline over the four 32-column chunks (two per trip of a rolled loop, so that the slow
+        // path exists twice, not four times): the next tcgen05.ld is in flight while the current chunk is scanned
+        uint32_t va[32], vb[32];
         __syncwarp();
-        if (lane == 0) mbar_arrive(tmem_empty(as * MT + mt));
+        tmem_ld32(tbase, va);
+#pragma unroll 1
+        for (int h = 0; h < 2; ++h) {
+          tmem_ld_wait();
+          __syncwarp();
+          tmem_ld32(tbase + 64 * h + 32, vb);
+          if (dbg < 2) consume(va, cbase + 64 * h);
+          tmem_ld_wait();
+          if (h == 0) {
+            __syncwarp();
+            tmem_ld32(tbase + 64, va);
+          } else {
+            // every column of this accumulator buffer is now in registers: hand it back to the MMA warp
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(tmem_empty(as * MT + mt));
+          }
+          if (dbg < 2) consume(vb, cbase + 64 * h + 32);
+        }
       }
       if (row_ok) {
         const int64_t r = (int64_t)ch * p.n_q + qlocal;

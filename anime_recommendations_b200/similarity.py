@@ -161,6 +161,7 @@ def rerank(Wq, q0, nq, Wc, cand, k, cand_cnt=None, cand_thr=None, eps=BF16_SCORE
     return oi, os_, cert
 
 
+TENSOR_DIM = 128            # embedding size the tcgen05 candidate kernel is built for (config.yaml:63 default)
 N_SMS = 148                 # B200
 QTILE = 256                 # query rows per work item of the tensor-core kernel
 SAMPLE_FRACTION = 16        # the threshold-seeding pass scans 1/16 of the candidates
@@ -193,18 +194,21 @@ def _sl(t, lo, hi):
     return None if t is None else t[lo:hi]
 
 
-def _candidate_lists(Qn, nq, Cn, kprime, exclude_self, self_ids, watched, thr_init, seed=True, tm=None):
+def _candidate_lists(Qn, nq, Cn, kprime, exclude_self, self_ids, watched, thr_init, seed=False, tm=None,
+                     c_range=None):
     """Tensor-core candidate pass over query rows [0, nq) of Qn against all of Cn, scheduled for the machine:
-      1. threshold seeding: a first pass over 1/16 of the candidates yields per row a valid lower bound on
-         its (kprime+1)-th best score; started from it the full pass appends ~4x fewer candidates (the list
-         kernel's slow path) -- any subset's (k+1)-th best is a lower bound, so exactness is unaffected;
+      1. (seed=True, off by default) threshold seeding: a first pass over 1/16 of the candidates yields per row
+         a valid lower bound on its (kprime+1)-th best score.  Measured on 350k x 350k it does not pay: the
+         slow-path events are dominated by the steady-state rate 1024*kprime/m per warp-chunk, not by the
+         warm-up, and the seeding pass itself runs entirely in warm-up mode (8.4 ms to save 5 ms);
       2. the query range is cut into a part whose 256-row tiles fill the 148 SMs an integral number of rounds
          (one candidate chunk) and a remainder whose candidate range is split so it also fills the machine.
     -> [(row_lo, row_hi, CandidateLists)]"""
-    nc = Cn.shape[0]
+    c0, c1 = c_range or (0, Cn.shape[0])
+    nc = c1 - c0
     if seed and thr_init is None and nc >= SAMPLE_MIN_ROWS:
         ns = ((nc // SAMPLE_FRACTION + 127) // 128) * 128
-        cl0 = allpairs_candidates(Qn, 0, nq, Cn, 0, ns, kprime, exclude_self=exclude_self, self_ids=self_ids,
+        cl0 = allpairs_candidates(Qn, 0, nq, Cn, c0, ns, kprime, exclude_self=exclude_self, self_ids=self_ids,
                                   watched=watched, n_chunks=1)
         thr_init = cl0.thr[0]
         if tm:
@@ -216,7 +220,7 @@ def _candidate_lists(Qn, nq, Cn, kprime, exclude_self, self_ids, watched, thr_in
         cuts = [0, rounds * N_SMS * QTILE, nq]
     parts = []
     for lo, hi in zip(cuts[:-1], cuts[1:]):
-        cl = allpairs_candidates(Qn, lo, hi - lo, Cn, 0, nc, kprime, exclude_self=exclude_self,
+        cl = allpairs_candidates(Qn, lo, hi - lo, Cn, c0, nc, kprime, exclude_self=exclude_self,
                                  self_ids=_sl(self_ids, lo, hi), watched=_sl(watched, lo, hi),
                                  thr_init=_sl(thr_init, lo, hi))
         parts.append((lo, hi, cl))
@@ -242,7 +246,7 @@ def _rerank_parts(parts, Wq_f32, Wc_f32, k, q_eps, tm=None):
 
 
 def _certified_topk(Wq_f32, Qn, q_res, Wc_f32, Cn, c_res_max, k, kprime, exclude_self, self_ids, watched, stats,
-                    exact_row):
+                    exact_row, c_range=None):
     """Tensor-core pass + fp32 re-rank + certification, with two recovery levels for the rows the first
     pass cannot certify: (1) the same kernel over just those rows with the provably sufficient fixed
     threshold (k-th fp32 score found so far - eps); (2) `exact_row(i)`, the fp32 single-query kernel.
@@ -254,7 +258,7 @@ def _certified_topk(Wq_f32, Qn, q_res, Wc_f32, Cn, c_res_max, k, kprime, exclude
     tm = _Timer(bool(stats is not None and stats.get("time")))
     tm.mark("start")
     q_eps = (q_res + c_res_max + q_res * c_res_max).contiguous()
-    parts = _candidate_lists(Qn, nq, Cn, kprime, exclude_self, self_ids, watched, None, tm=tm)
+    parts = _candidate_lists(Qn, nq, Cn, kprime, exclude_self, self_ids, watched, None, tm=tm, c_range=c_range)
     oi, os_, cert = _rerank_parts(parts, Wq_f32, Wc_f32, k, q_eps, tm)
     bad = torch.nonzero(cert == 0).reshape(-1)
     n_bad1 = int(bad.numel())
@@ -271,7 +275,7 @@ def _certified_topk(Wq_f32, Qn, q_res, Wc_f32, Cn, c_res_max, k, kprime, exclude
         if exclude_self:
             ids_b = (self_ids[bad] if self_ids is not None else bad.to(torch.int32)).contiguous()
         wb = watched[bad].contiguous() if watched is not None else None
-        parts2 = _candidate_lists(Qb, n_bad1, Cn, kprime, exclude_self, ids_b, wb, thr0, tm=None)
+        parts2 = _candidate_lists(Qb, n_bad1, Cn, kprime, exclude_self, ids_b, wb, thr0, tm=None, c_range=c_range)
         oi2, os2, cert2 = _rerank_parts(parts2, Wb, Wc_f32, k, q_eps[bad].contiguous())
         oi[bad], os_[bad] = oi2, os2
         still = bad[cert2 == 0]
@@ -296,6 +300,12 @@ def allpairs_topk(W, k=10, kprime=16, q0=0, nq=None, stats=None):
     W = as_table(W)
     n = W.shape[0]
     nq = n - q0 if nq is None else nq
+    if W.shape[1] != TENSOR_DIM:                              # other embedding sizes: the fp32 single-query kernel per row
+        oi = torch.empty((nq, k), dtype=torch.int32, device=W.device)
+        os_ = torch.empty((nq, k), dtype=torch.float32, device=W.device)
+        for r in range(nq):
+            oi[r], os_[r] = cosine_topk_query_device(W, q0 + r, k, exclude=q0 + r)
+        return oi, os_
     Wn, res = normalize_rows_bf16(W, with_resid=True)
     res = torch.nan_to_num(res, nan=1.0)
     whole = q0 == 0                                      # queries are the leading rows: identity self ids
@@ -337,15 +347,21 @@ def score_topk(model, users, watched_indptr, watched_idx, k, cand_mask=None, kpr
     head = model.head.cpu().numpy()
     sign = -1.0 if float(head[0]) * float(head[2]) < 0 else 1.0
     Uq = (model.U[users_t] * sign).contiguous()               # query rows (negated when the map decreases)
-    (Qn, qres), (Cn, cres) = normalize_rows_bf16(Uq, True), normalize_rows_bf16(model.A, True)
-    qres, cres = torch.nan_to_num(qres, nan=1.0), torch.nan_to_num(cres, nan=1.0)
     wb = watched_bits(watched_indptr, watched_idx, nq, na, dev, cand_mask)
 
     def exact_row(r):
         return _query_vs_table(Uq[r], model.A, k, wb[r])
 
-    oi, os_ = _certified_topk(Uq, Qn, qres, model.A, Cn, float(cres.max().item()), k, kprime, False, None, wb,
-                              stats, exact_row)
+    if model.dim == TENSOR_DIM:
+        (Qn, qres), (Cn, cres) = normalize_rows_bf16(Uq, True), normalize_rows_bf16(model.A, True)
+        qres, cres = torch.nan_to_num(qres, nan=1.0), torch.nan_to_num(cres, nan=1.0)
+        oi, os_ = _certified_topk(Uq, Qn, qres, model.A, Cn, float(cres.max().item()), k, kprime, False, None, wb,
+                                  stats, exact_row)
+    else:                                                     # other embedding sizes: fp32 GEMV + top-k per user
+        oi = torch.empty((nq, k), dtype=torch.int32, device=dev)
+        os_ = torch.empty((nq, k), dtype=torch.float32, device=dev)
+        for r in range(nq):
+            oi[r], os_[r] = exact_row(r)
     valid = oi >= 0
     iu = users_t.to(torch.int32).reshape(-1, 1).expand(-1, k)[valid].contiguous()
     ia = oi[valid].contiguous()

@@ -39,6 +39,16 @@ def peaks():
     return dict(hbm_gbs=6650.0, bf16_tflops=1590.0, bf16_tflops_sustained=1400.0, source="fallback")
 
 
+def ncu_traffic(kernel, mode):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of `kernel` from the committed `ncu --set full`
+    capture (profiles/ncu_traffic.json, written by tools/ncu_summary.py); None if that kernel was not captured."""
+    p = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    if not os.path.exists(p):
+        return None
+    d = json.load(open(p))
+    return d.get(mode, {}).get(kernel, d.get("any", {}).get(kernel))
+
+
 class ClockSampler(threading.Thread):
     """SM clock + throttle reasons while the timed region runs, read in-process through NVML (pynvml);
     an external `nvidia-smi -lms` would contend for the driver lock and perturb a 15 ms timed region."""
@@ -110,14 +120,6 @@ def synth(n_samples, seed, device, zipf=False):
         ia = torch.randint(0, N_ANIME, (n_samples,), generator=g, device=device, dtype=torch.int32)
     y = torch.randint(0, 11, (n_samples,), generator=g, device=device).float() / 10.0
     return iu, ia, y
-
-
-def unique_rows_per_step(idx, steps):
-    import torch
-    tot = 0
-    for s in range(steps):
-        tot += int(torch.unique(idx[s * BATCH:(s + 1) * BATCH]).numel())
-    return tot / max(1, steps)
 
 
 # ------------------------------------------------------------------------------------------ CPU arm
@@ -234,8 +236,10 @@ def gpu_main(args):
         prof = [0.0] * 5
         iu2, ia2, y2 = synth(K * BATCH, 4242, dev, zipf=args.zipf)
         sess.run(iu2, ia2, y2, LR, profile=prof)
-        uu = unique_rows_per_step(iu2, min(K, 16))
-        ua = unique_rows_per_step(ia2, min(K, 16))
+        # distinct rows per step, from the library's own dedup plans of the steps just run (meta[slot][0])
+        nslot = min(K, sess.n_slots) if K <= sess.n_slots else (K % sess.n_slots or sess.n_slots)
+        uu = float(sess._keep_u["meta"][:nslot, 0].float().mean().item())
+        ua = float(sess._keep_a["meta"][:nslot, 0].float().mean().item())
         names = ["rows_catchup", "embed_fwd", "head_step", "rows_update", "dense_flush"]
         row_b = DIM * 4
         alg = dict(rows_catchup=(uu + ua) * row_b * 6,
@@ -252,7 +256,8 @@ def gpu_main(args):
         else:
             step_bytes = BATCH * row_b * 2 + (uu + ua) * row_b * 6 + BATCH * 12
         line["roofline"] = dict(bound="hbm", kernel=dom, achieved=stage[dom]["gbs"], peak=pk["hbm_gbs"], unit="GB/s",
-                                frac=stage[dom]["gbs"] / pk["hbm_gbs"], traffic=None, peak_source=pk["source"],
+                                frac=stage[dom]["gbs"] / pk["hbm_gbs"], traffic=ncu_traffic(dom, mode),
+                                peak_source=pk["source"],
                                 accounting="dense" if mode == "dense" else "touched-rows",
                                 step=dict(alg_bytes=step_bytes, gbs=step_bytes / (ms / K * 1e-3) / 1e9,
                                           frac=step_bytes / (ms / K * 1e-3) / 1e9 / pk["hbm_gbs"],
@@ -260,20 +265,7 @@ def gpu_main(args):
                                 stages=stage)
 
         # ---- e2e: the public API (Model.fit) fed from pinned HOST buffers, copies inside the timed region
-        m2 = ar.EmbeddingDotModel(N_USERS, N_ANIME, DIM, l2_reg_factor=L2, seed=1, adam_mode=mode, dense_kernel=1.0)
-        m2.lr = LR
-        hu, ha, hy = (t.cpu().pin_memory() for t in synth(K * BATCH, 77, dev, zipf=args.zipf))
-        wu, wa, wy = (t.cpu().pin_memory() for t in synth(W * BATCH, 78, dev, zipf=args.zipf))
-        m2.fit([wu, wa], wy, batch_size=BATCH, epochs=1, shuffle=False)         # warm-up epoch
-        torch.cuda.synchronize()
-        t0 = time.perf_counter()
-        h = m2.fit([hu, ha], hy, batch_size=BATCH, epochs=1, shuffle=False)
-        torch.cuda.synchronize()
-        dt = time.perf_counter() - t0
-        line["e2e"] = dict(value=K * BATCH / dt, unit=UNIT, h2d_bytes_per_step=BATCH * 12, d2h_bytes_per_step=16,
-                           seconds=dt, loss=h.history["loss"][0],
-                           what="Model.fit([users, animes], ratings) from pinned host arrays: H2D of the step inputs, "
-                                "plan build, K steps, end-of-epoch flush + L2 term, D2H of per-step metrics")
+        line["e2e"] = e2e_fit(ar, dev, mode, K, args.zipf)
 
         # ---- CPU baseline (bounded sample) beside the GPU number
         if not args.skip_cpu:
@@ -283,7 +275,11 @@ def gpu_main(args):
                                                "restatement of the TF step" % (r["steps"], BATCH),
                                         ms_per_step=r["ms_per_step"])
         if not args.skip_extras:
+            del sess, model, iu, ia, y
+            torch.cuda.empty_cache()
             line["extras"] = extras(dev, pk)
+            line["extras"]["train_modes"] = {m: mode_run(ar, dev, m, min(K, 100), W) for m in ("dense", "touched")
+                                             if m != mode}
     elif rank == 0:
         line["e2e"] = None
     if rank == 0:
@@ -291,6 +287,53 @@ def gpu_main(args):
     if world > 1:
         dist.destroy_process_group()
     return 0
+
+
+def mode_run(ar, dev, mode, K, W):
+    """Device-resident throughput of the other Adam modes (same kernels, same workload), for context:
+    `dense` = the reference-literal update of every row every step (HBM-bound, dense accounting);
+    `touched` = the north-star-literal update of the batch's rows only (not the reference's arithmetic)."""
+    import torch
+    from anime_recommendations_b200.model import TrainSession
+    m = ar.EmbeddingDotModel(N_USERS, N_ANIME, DIM, l2_reg_factor=L2, seed=1, adam_mode=mode, dense_kernel=1.0)
+    iu, ia, y = synth((W + K) * BATCH, 4242, dev)
+    sess = TrainSession(m, BATCH, total_steps=W + K + 8)
+    sess.run(iu[:W * BATCH], ia[:W * BATCH], y[:W * BATCH], LR)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    e0.record()
+    sess.run(iu[W * BATCH:], ia[W * BATCH:], y[W * BATCH:], LR)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    row_b = DIM * 4
+    by = (N_USERS + N_ANIME) * row_b * 6 + BATCH * row_b * 2 + BATCH * 12 if mode == "dense" else None
+    out = dict(samples_per_s=K * BATCH / (ms / 1e3), ms_per_step=ms / K, steps=K)
+    if by:
+        out.update(accounting="dense", step_gbs=by / (ms / K * 1e-3) / 1e9,
+                   step_frac_hbm=by / (ms / K * 1e-3) / 1e9 / peaks()["hbm_gbs"])
+    return out
+
+
+def e2e_fit(ar, dev, mode, K, zipf):
+    """`Model.fit([users, animes], ratings)` on pinned host arrays: every step's inputs cross PCIe inside the
+    timed region, the per-step metrics come back, and the epoch ends with the table flush + L2 term exactly
+    as a user's epoch does.  One untimed epoch of the same shape first (allocator and plan buffers warm)."""
+    import torch
+    m2 = ar.EmbeddingDotModel(N_USERS, N_ANIME, DIM, l2_reg_factor=L2, seed=1, adam_mode=mode, dense_kernel=1.0)
+    m2.lr = LR
+    hu, ha, hy = (t.cpu().pin_memory() for t in synth(K * BATCH, 77, dev, zipf=zipf))
+    wu, wa, wy = (t.cpu().pin_memory() for t in synth(K * BATCH, 78, dev, zipf=zipf))
+    m2.fit([wu, wa], wy, batch_size=BATCH, epochs=1, shuffle=False)         # warm-up epoch
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    h = m2.fit([hu, ha], hy, batch_size=BATCH, epochs=1, shuffle=False)
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    return dict(value=K * BATCH / dt, unit=UNIT, h2d_bytes_per_step=BATCH * 12, d2h_bytes_per_step=16,
+                seconds=dt, loss=h.history["loss"][0],
+                what="Model.fit([users, animes], ratings) from pinned host arrays: H2D of the step inputs, "
+                     "plan build, K steps, end-of-epoch flush + L2 term, D2H of per-step metrics")
 
 
 def extras(dev, pk):
@@ -317,7 +360,35 @@ def extras(dev, pk):
     by = N_USERS * DIM * 4
     out["query_topk_users"] = dict(rows=N_USERS, dim=DIM, k=11, ms=ms, rows_per_s=N_USERS / (ms / 1e3),
                                    gbs=by / (ms / 1e3) / 1e9, frac_hbm=by / (ms / 1e3) / 1e9 / pk["hbm_gbs"],
-                                   l2_flush="256 MB write between iterations")
+                                   bound="hbm", l2_flush="256 MB write between iterations")
+    del flush
+    # ---- all-pairs cosine top-10 (BASELINE cfg3): tensor-core candidate pass + fp32 re-rank + recovery
+    for name, n in (("allpairs_users", N_USERS), ("allpairs_anime", N_ANIME)):
+        Wn = Wt[:n].contiguous()
+        sim.allpairs_topk(Wn[:4096].contiguous(), k=10)                       # warm-up
+        best, st_best = None, None
+        for _ in range(3):
+            st = {"time": True}
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            sim.allpairs_topk(Wn, k=10, stats=st)
+            e1.record()
+            torch.cuda.synchronize()
+            t = e0.elapsed_time(e1)
+            if best is None or t < best:
+                best, st_best = t, st
+        fl = 2.0 * n * n * DIM
+        cand_ms = st_best["ms"].get("candidate_pass", best)
+        out[name] = dict(rows=n, dim=DIM, k=10, ms=best, rows_per_s=n / (best / 1e3), bound="tensor",
+                         tflops=fl / (best / 1e3) / 1e12, frac_tensor=fl / (best / 1e3) / 1e12 / pk["bf16_tflops"],
+                         frac_tensor_sustained=fl / (best / 1e3) / 1e12 / pk["bf16_tflops_sustained"],
+                         candidate_kernel=dict(ms=cand_ms, tflops=fl / (cand_ms / 1e3) / 1e12,
+                                               frac_tensor=fl / (cand_ms / 1e3) / 1e12 / pk["bf16_tflops"]),
+                         stages_ms=st_best["ms"], uncertified=st_best["uncertified"],
+                         uncertified_after_retry=st_best["uncertified_after_retry"],
+                         what="exact fp32 top-10 of every row: rownorm -> bf16 tcgen05 candidate pass -> fp32 re-rank "
+                              "-> certified or retried; flops counted as 2*n*n*dim, inputs (n x 128 fp32) resident in HBM, "
+                              "table re-read per call (bf16 copy 90 MB << work per call)")
     return out
 
 

@@ -10,11 +10,42 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 
 
+def sim_main(shard, dev, rank, world):
+    """Sharded all-pairs top-k == the single-process oracle (every rank must hold the full, identical result)."""
+    from anime_recommendations_b200 import similarity_dist as sd
+    from anime_recommendations_b200.dist import Comm
+    from oracle import similarity as osim
+    from gpu_util import assert_topk_close
+    n, k = 3001, 10
+    W = np.random.RandomState(11).standard_normal((n, 128)).astype(np.float32)
+    comm = Comm()
+    gi, gs = sd.allpairs_topk_sharded(W, k, comm, shard=shard)
+    gi, gs = gi.cpu().numpy(), gs.cpu().numpy()
+    oi, os_ = osim.allpairs_topk_fast(W, k)
+    np.testing.assert_allclose(gs, os_, rtol=0, atol=3e-6)
+    Wn = osim.get_weights(W)
+    for r in np.nonzero((gi != oi).any(axis=1))[0]:
+        assert_topk_close(gi[r], gs[r], oi[r], os_[r], Wn @ Wn[r])
+    t = torch.from_numpy(gi).to(dev)
+    g = [torch.empty_like(t) for _ in range(world)]
+    dist.all_gather(g, t)
+    assert all(torch.equal(g[0], o) for o in g[1:]), "ranks disagree"
+    comm.close()
+    if rank == 0:
+        print("DIST_OK", shard)
+
+
 def main(mode):
     rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
     torch.cuda.set_device(int(os.environ["LOCAL_RANK"]))
     dev = torch.device("cuda", int(os.environ["LOCAL_RANK"]))
     dist.init_process_group("nccl", device_id=dev)
+    if mode.startswith("sim_"):
+        sys.path.insert(0, os.path.join(ROOT, "tests"))
+        sim_main(mode[4:], dev, rank, world)
+        dist.barrier()
+        dist.destroy_process_group()
+        return
     import anime_recommendations_b200 as ar
     from anime_recommendations_b200.dist import DistTrainSession
     from anime_recommendations_b200.model import TrainSession
