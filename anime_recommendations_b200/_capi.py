@@ -10,7 +10,7 @@ import os
 
 PKG = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(PKG, "lib", "libanimerec.so")
-ABI_VERSION = 5
+ABI_VERSION = 6
 
 AR_MAX_BATCH = 16384
 AR_HEAVY_LEN = 64
@@ -43,7 +43,7 @@ class ArTrainCtx(C.Structure):
                 ("uh", C.c_void_p), ("ah", C.c_void_p), ("c", C.c_void_p), ("ru", C.c_void_p),
                 ("ra", C.c_void_p), ("dy", C.c_void_p), ("fwd_part", C.c_void_p), ("head_part", C.c_void_p),
                 ("stepc", C.c_void_p), ("ticket", C.c_void_p),
-                ("metrics", C.c_void_p), ("reg_sumsq", C.c_void_p)]
+                ("metrics", C.c_void_p), ("reg_sumsq", C.c_void_p), ("sched_ws", C.c_void_p)]
 
 
 class ArDistCtx(C.Structure):

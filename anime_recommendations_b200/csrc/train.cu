@@ -16,6 +16,7 @@
 //
 // Arithmetic follows oracle/train.py (the restatement of neural_network.py:66-106 under
 // Keras-2.12 semantics); citations there.
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -67,10 +68,13 @@ template <int NV>
 __device__ __forceinline__ void replay_l2(RowTile<NV>& w, RowTile<NV>& m, RowTile<NV>& v,
                                           const float* __restrict__ alpha, int64_t from, int64_t to,
                                           float l2x2, int lane) {
+  // both loops stay ROLLED: unrolled by the compiler the body was 20 KB of code per instantiation for no gain
+#pragma unroll 1
   for (int64_t t0 = from + 1; t0 <= to; t0 += 32) {
     int64_t tl = t0 + lane;
     float a_l = (tl <= to) ? __ldg(alpha + tl) : 0.f;
     int cnt = (int)min((int64_t)32, to - t0 + 1);
+#pragma unroll 1
     for (int s = 0; s < cnt; ++s) {
       float a = __shfl_sync(0xffffffffu, a_l, s);
 #pragma unroll
@@ -90,27 +94,109 @@ struct CatchupArgs {
   const int32_t* uniq[2];
   const int32_t* meta[2];
   int blocks0;  // CTAs assigned to table 0
+  // look-ahead catch-up: rows that are ALSO in this (earlier) step's sorted distinct-row list are skipped --
+  // that step's own update brings them up to date, and may be running concurrently
+  const int32_t* skip_uniq[2];
+  const int32_t* skip_meta[2];
+  // longest-first schedule (ar_train_ctx.sched_ws): three buckets of (table << 31 | row) by replay length,
+  // bucket b at sched + b*cap, their fill counts at sched + 3*cap
+  int32_t* sched;
+  int cap;
 };
+constexpr int kLongReplay = 128, kMidReplay = 32;
 
-// One warp per CTA: replay lengths are geometric (mean n_rows/unique-per-step, max ~10x that), and a CTA
-// only frees its SM slot when its slowest warp ends -- with 8 rows per CTA the SFU sat idle ~60% of the
-// time (measured 57 us vs a 20 us MUFU floor); single-warp CTAs let every finished row make room at once.
-constexpr int kCatchThreads = 32;
+// Replay lengths are geometric (mean n_rows/unique-per-step, max ~10x that), and a CTA only frees its SM slot
+// when its slowest warp ends -- with 8 rows of unrelated length per CTA the SFU sat idle ~60% of the time
+// (measured 57 us vs a 20 us MUFU floor).  One-warp CTAs fixed that but cap the SM at 32 resident warps;
+// with the longest-first bucket order neighbours have similar lengths and kCatchThreads/32 rows share a CTA.
+#ifndef AR_CATCH_THREADS
+#define AR_CATCH_THREADS 64
+#endif
+constexpr int kCatchThreads = AR_CATCH_THREADS;
+// Which rows need how much replay?  Thread per distinct row of the step: rows the skip list covers or that
+// are already current drop out, the rest go to the long / mid / short bucket (warp-aggregated append).
+// Replay lengths are geometric (mean n_rows / distinct-per-step, tail ~10x that); launching the catch-up in
+// bucket order starts the long rows first, so they no longer form the kernel's tail.
+__global__ void __launch_bounds__(256)
+rows_classify_kernel(CatchupArgs a, int64_t t_target, int n0_cap, int n1_cap) {
+  const int g = blockIdx.x * blockDim.x + threadIdx.x;
+  const bool second = g >= n0_cap;
+  const int seg = second ? g - n0_cap : g;
+  int bucket = -1, row = 0;
+  if (seg < (second ? n1_cap : n0_cap) && seg < (second ? a.meta[1] : a.meta[0])[0]) {
+    row = (second ? a.uniq[1] : a.uniq[0])[seg];
+    bool skip_it = false;
+    const int32_t* __restrict__ skip = second ? a.skip_uniq[1] : a.skip_uniq[0];
+    if (skip) {
+      const int n_skip = (second ? a.skip_meta[1] : a.skip_meta[0])[0];
+      int lo = 0, hi = n_skip;
+      while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        if (__ldg(skip + mid) < row) lo = mid + 1; else hi = mid;
+      }
+      skip_it = lo < n_skip && __ldg(skip + lo) == row;
+    }
+    if (!skip_it) {
+      const int64_t len = t_target - (int64_t)(second ? a.tab[1].last_step : a.tab[0].last_step)[row];
+      if (len > 0) bucket = len > kLongReplay ? 0 : (len > kMidReplay ? 1 : 2);
+    }
+  }
+  int32_t* counts = a.sched + 3 * (size_t)a.cap;
+  const int lane = threadIdx.x & 31;
+#pragma unroll
+  for (int b = 0; b < 3; ++b) {
+    const unsigned m = __ballot_sync(0xffffffffu, bucket == b);
+    if (!m) continue;
+    int base = 0;
+    if (lane == __ffs(m) - 1) base = atomicAdd(counts + b, __popc(m));
+    base = __shfl_sync(0xffffffffu, base, __ffs(m) - 1);
+    if (bucket == b) a.sched[(size_t)b * a.cap + base + __popc(m & ((1u << lane) - 1))] = row | (second ? (int)0x80000000 : 0);
+  }
+}
+
+// kCatchWarps rows per CTA.  In plan order that would pair rows of unrelated replay lengths (a CTA frees its
+// SM slot only when its slowest warp ends); in bucket order neighbours have similar lengths, so several warps
+// per CTA lift the 32-CTA-per-SM cap on resident warps without re-creating that tail.
 template <int NV>
 __global__ void __launch_bounds__(kCatchThreads)
 rows_catchup_kernel(CatchupArgs a, const float* __restrict__ alpha, float l2x2, int64_t t_target) {
-  const bool second = blockIdx.x >= a.blocks0;
-  const int seg = second ? blockIdx.x - a.blocks0 : blockIdx.x;
   const int lane = threadIdx.x & 31;
-  const int32_t* meta = second ? a.meta[1] : a.meta[0];
-  if (seg >= meta[0]) return;
+  const int unit = blockIdx.x * (kCatchThreads / 32) + (threadIdx.x >> 5);
+  bool second;
+  int row;
+  if (a.sched) {  // bucket order: long rows first
+    const int32_t* counts = a.sched + 3 * (size_t)a.cap;
+    const int n0 = counts[0], n1 = counts[1], n2 = counts[2];
+    int b = unit, code;
+    if (b < n0) code = a.sched[b];
+    else if ((b -= n0) < n1) code = a.sched[(size_t)a.cap + b];
+    else if ((b -= n1) < n2) code = a.sched[2 * (size_t)a.cap + b];
+    else return;
+    second = code < 0;
+    row = code & 0x7fffffff;
+  } else {
+    second = unit >= a.blocks0;
+    const int seg = second ? unit - a.blocks0 : unit;
+    const int32_t* meta = second ? a.meta[1] : a.meta[0];
+    if (seg >= (second ? a.cap - a.blocks0 : a.blocks0) || seg >= meta[0]) return;
+    row = (second ? a.uniq[1] : a.uniq[0])[seg];
+    const int32_t* __restrict__ skip = second ? a.skip_uniq[1] : a.skip_uniq[0];
+    if (skip) {  // warp-uniform binary search in the other step's ascending distinct rows
+      const int n_skip = (second ? a.skip_meta[1] : a.skip_meta[0])[0];
+      int lo = 0, hi = n_skip;
+      while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        if (__ldg(skip + mid) < row) lo = mid + 1; else hi = mid;
+      }
+      if (lo < n_skip && __ldg(skip + lo) == row) return;
+    }
+  }
   ar_table tb;
   tb.dim = a.tab[0].dim;
   tb.W = second ? a.tab[1].W : a.tab[0].W;
   tb.m = second ? a.tab[1].m : a.tab[0].m;
   tb.v = second ? a.tab[1].v : a.tab[0].v;
   tb.last_step = second ? a.tab[1].last_step : a.tab[0].last_step;
-  const int row = (second ? a.uniq[1] : a.uniq[0])[seg];
   const int64_t last = tb.last_step[row];
   if (last >= t_target) return;
   const int d4 = tb.dim >> 2;
@@ -665,21 +751,36 @@ static int num_sms() {
 
 static int launch_catchup(const ar_table* t0, const ar_plan* p0, int slot0, const ar_table* t1,
                           const ar_plan* p1, int slot1, const float* alpha, float l2, int64_t t_target,
-                          cudaStream_t st) {
+                          cudaStream_t st, int skip_slot = -1, int32_t* sched_ws = nullptr) {
   CatchupArgs a{};
+  if (skip_slot >= 0) {
+    a.skip_uniq[0] = p0->uniq + (int64_t)skip_slot * p0->batch_cap;
+    a.skip_meta[0] = p0->meta + (int64_t)skip_slot * 4;
+    if (t1) {
+      a.skip_uniq[1] = p1->uniq + (int64_t)skip_slot * p1->batch_cap;
+      a.skip_meta[1] = p1->meta + (int64_t)skip_slot * 4;
+    }
+  }
   a.tab[0] = *t0;
   a.uniq[0] = p0->uniq + (int64_t)slot0 * p0->batch_cap;
   a.meta[0] = p0->meta + (int64_t)slot0 * 4;
   a.blocks0 = p0->batch_cap;
-  int blocks = a.blocks0;
+  int units = a.blocks0;
   if (t1) {
     a.tab[1] = *t1;
     a.uniq[1] = p1->uniq + (int64_t)slot1 * p1->batch_cap;
     a.meta[1] = p1->meta + (int64_t)slot1 * 4;
-    blocks += p1->batch_cap;
+    units += p1->batch_cap;
   }
+  a.cap = units;
   const float l2x2 = (float)(2.0 * (double)l2);
-  AR_DISPATCH_NV(t0->dim, rows_catchup_kernel<NV><<<blocks, kCatchThreads, 0, st>>>(a, alpha, l2x2, t_target));
+  if (sched_ws) {  // longest-first: classify into buckets, then replay in bucket order
+    a.sched = sched_ws;
+    AR_CUDA(cudaMemsetAsync(sched_ws + 3 * (size_t)units, 0, 4 * sizeof(int32_t), st));
+    rows_classify_kernel<<<ceil_div(units, 256), 256, 0, st>>>(a, t_target, a.blocks0, t1 ? p1->batch_cap : 0);
+    AR_LAUNCH_CHECK();
+  }
+  AR_DISPATCH_NV(t0->dim, rows_catchup_kernel<NV><<<ceil_div(units, kCatchThreads / 32), kCatchThreads, 0, st>>>(a, alpha, l2x2, t_target));
   AR_LAUNCH_CHECK();
   return AR_OK;
 }
@@ -809,9 +910,41 @@ struct StageTimer {
     if (rc__) return rc__;                  \
   }
 
+// Side stream + events of the look-ahead catch-up (one set per device, created on first use).
+struct Lookahead {
+  cudaStream_t st2 = nullptr;
+  cudaEvent_t ev_upd[2] = {nullptr, nullptr};  // "row update of step s is complete" (recorded on the main stream)
+  cudaEvent_t ev_ahead = nullptr;              // "look-ahead catch-up for the next step is complete" (side stream)
+  bool ok = false;
+};
+static Lookahead* lookahead() {
+  static Lookahead la[64];
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
+  Lookahead& l = la[dev];
+  if (!l.ok) {
+    if (cudaStreamCreateWithFlags(&l.st2, cudaStreamNonBlocking) != cudaSuccess) return nullptr;
+    for (int i = 0; i < 2; ++i)
+      if (cudaEventCreateWithFlags(&l.ev_upd[i], cudaEventDisableTiming) != cudaSuccess) return nullptr;
+    if (cudaEventCreateWithFlags(&l.ev_ahead, cudaEventDisableTiming) != cudaSuccess) return nullptr;
+    l.ok = true;
+  }
+  return &l;
+}
+
+// AR_ADAM_REPLAY overlaps the SFU-bound replay with the memory-bound rest of the step: while step s runs its
+// forward / head / row update on the main stream, the rows of step s+1 that step s does not touch are brought
+// to optimizer step t(s) on a side stream (for them step s is a pure-L2 step too, and alpha[t] is known in
+// advance).  The two row sets are disjoint, so nothing races; rows in BOTH steps need no replay at all after
+// update(s).  Only the first step of a call pays an exposed catch-up.
 static int run_steps(const ar_train_ctx& x, int64_t epoch_step0, int32_t slot0, int64_t t0, int32_t n_steps,
                      cudaStream_t st, StageTimer* timer) {
   const int dim = x.users.dim;
+  static const bool no_overlap = getenv("AR_NO_LOOKAHEAD") != nullptr;
+  Lookahead* la = (x.mode == AR_ADAM_REPLAY && !timer && !no_overlap) ? lookahead() : nullptr;
+  if (la) {
+    AR_CUDA(cudaEventRecord(la->ev_upd[1], st));  // everything queued before this call (stands in for "update(-1)")
+  }
   for (int s = 0; s < n_steps; ++s) {
     const int64_t e = epoch_step0 + s;
     const int64_t base = e * (int64_t)x.batch;
@@ -820,10 +953,20 @@ static int run_steps(const ar_train_ctx& x, int64_t epoch_step0, int32_t slot0, 
     const int slot = slot0 + s;
     const int64_t t = t0 + s + 1;
     const int32_t* meta_u = x.plan_u.meta + (int64_t)slot * 4;
+    const bool has_next = (s + 1 < n_steps) && ((e + 1) * (int64_t)x.batch < x.n_samples);
     AR_TICK(0);
-    if (x.mode == AR_ADAM_REPLAY) {
-      int rc = launch_catchup(&x.users, &x.plan_u, slot, &x.anime, &x.plan_a, slot, x.alpha, x.l2, t - 1, st);
+    if (x.mode == AR_ADAM_REPLAY && (!la || s == 0)) {
+      int rc = launch_catchup(&x.users, &x.plan_u, slot, &x.anime, &x.plan_a, slot, x.alpha, x.l2, t - 1, st, -1, x.sched_ws);
       if (rc) return rc;
+    }
+    bool ahead = false;
+    if (la && has_next) {  // queue the look-ahead BEFORE this step's kernels so the GPU can start it at once
+      AR_CUDA(cudaStreamWaitEvent(la->st2, la->ev_upd[(s + 1) & 1], 0));  // update(s-1) done
+      int rc = launch_catchup(&x.users, &x.plan_u, slot + 1, &x.anime, &x.plan_a, slot + 1, x.alpha, x.l2, t, la->st2, slot,
+                              x.sched_ws);
+      if (rc) return rc;
+      AR_CUDA(cudaEventRecord(la->ev_ahead, la->st2));
+      ahead = true;
     }
     AR_TICK(1);
     AR_DISPATCH_NV(dim, embed_fwd_kernel<NV><<<ceil_div(n, kRowWarps), kRowThreads, 0, st>>>(
@@ -841,6 +984,10 @@ static int run_steps(const ar_train_ctx& x, int64_t epoch_step0, int32_t slot0, 
     double* ss = (x.mode == AR_ADAM_DENSE && x.reg_sumsq) ? x.reg_sumsq + t * 32 : nullptr;
     int rc = launch_update(a, true, x.c, x.dy, x.stepc, x.alpha, x.l2, t, 0, ss, st);
     if (rc) return rc;
+    if (la) {
+      AR_CUDA(cudaEventRecord(la->ev_upd[s & 1], st));
+      if (ahead) AR_CUDA(cudaStreamWaitEvent(st, la->ev_ahead, 0));  // the next forward needs the look-ahead rows
+    }
     AR_TICK(4);
     if (x.mode == AR_ADAM_DENSE) {
       // every row the batch did not touch takes the same Adam step with the pure L2 gradient

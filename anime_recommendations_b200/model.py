@@ -390,6 +390,7 @@ class TrainSession:
         self.head_part = torch.zeros(8 * ((B + 255) // 256), dtype=torch.float64, device=dev)
         self.stepc = torch.zeros(8, **f)
         self.ticket = torch.zeros(1, dtype=torch.int32, device=dev)
+        self.sched_ws = torch.zeros(3 * 2 * B + 4, dtype=torch.int32, device=dev)
         self.t_cap = model.iterations + int(total_steps)
         model._ensure_alpha(self.t_cap)
         self.metrics = torch.zeros((self.t_cap + 1, 4), **f)
@@ -427,6 +428,7 @@ class TrainSession:
         ctx.stepc, ctx.ticket = self.stepc.data_ptr(), self.ticket.data_ptr()
         ctx.metrics = self.metrics.data_ptr()
         ctx.reg_sumsq = self.reg_ss.data_ptr() if self.reg_ss is not None else None
+        ctx.sched_ws = self.sched_ws.data_ptr() if os.environ.get("AR_NO_LPT") is None else None
         return ctx
 
     def run(self, iu, ia, y, lr, profile=None):
@@ -443,7 +445,7 @@ class TrainSession:
         m._set_alpha(lr, t0 + 1, steps)
         ctx = self._ctx(iu, ia, y)
         st, L = stream_ptr(), lib()
-        per_step = {"replay": 4, "dense": 5, "touched": 3}[m.adam_mode]
+        per_step = {"replay": 5 if ctx.sched_ws else 4, "dense": 5, "touched": 3}[m.adam_mode]
         for s0 in range(0, steps, self.n_slots):
             ns = min(self.n_slots, steps - s0)
             check(L.ar_plan_build(ptr(iu), N, B, s0, ns, C.byref(self.plan_u), st), "ar_plan_build(users)")

@@ -115,6 +115,9 @@ typedef struct {
    * (written in AR_ADAM_DENSE only; may be null) */
   float* metrics;
   double* reg_sumsq;
+  /* optional (AR_ADAM_REPLAY): (3 * (plan_u.batch_cap + plan_a.batch_cap) + 4) int32 of scratch for the
+   * longest-first schedule of the catch-up kernel; null = plan order */
+  int32_t* sched_ws;
 } ar_train_ctx;
 
 /* Run `n_steps` consecutive training steps.  Epoch-local step e = epoch_step0 + s reads samples
