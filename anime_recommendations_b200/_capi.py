@@ -9,8 +9,8 @@ import ctypes as C
 import os
 
 PKG = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(PKG, "lib", "libanimerec.so")
-ABI_VERSION = 6
+LIB_PATH = os.environ.get("ANIMEREC_LIB") or os.path.join(PKG, "lib", "libanimerec.so")   # override: A/B builds
+ABI_VERSION = 7
 
 AR_MAX_BATCH = 16384
 AR_HEAVY_LEN = 64
@@ -53,6 +53,16 @@ class ArDistCtx(C.Structure):
                 ("send", C.c_void_p), ("recv", C.c_void_p)]
 
 
+class ArShardCtx(C.Structure):
+    _fields_ = [("comm", C.c_void_p), ("n_ranks", C.c_int32), ("rank", C.c_int32),
+                ("req_send", C.c_void_p * 2), ("req_recv", C.c_void_p * 2), ("emit_map", C.c_void_p * 2),
+                ("cache_idx", C.c_void_p * 2), ("max_count", C.c_void_p),
+                ("rows_out", C.c_void_p * 2), ("rows_in", C.c_void_p * 2),
+                ("grad_send", C.c_void_p * 2), ("grad_recv", C.c_void_p * 2),
+                ("c_all", C.c_void_p), ("label_all", C.c_void_p), ("dy_all", C.c_void_p),
+                ("fwd_part_all", C.c_void_p), ("head_part_all", C.c_void_p)]
+
+
 class AnimerecError(RuntimeError):
     pass
 
@@ -73,6 +83,8 @@ SIGNATURES = {
     "ar_comm_destroy": (C.c_int, [_P]),
     "ar_train_steps_dist": (C.c_int, [C.POINTER(ArTrainCtx), C.POINTER(ArDistCtx), _I64, _I32, _I64, _I32, _P]),
     "ar_allgather_bytes": (C.c_int, [_P, _P, _P, _I64, _P]),
+    "ar_shard_plan": (C.c_int, [C.POINTER(ArPlan), C.POINTER(ArPlan), _I32, C.POINTER(ArShardCtx), _P]),
+    "ar_train_steps_sharded": (C.c_int, [C.POINTER(ArTrainCtx), C.POINTER(ArShardCtx), _I64, _I32, _I64, _I32, _I32, _P]),
     "ar_table_flush": (C.c_int, [C.POINTER(ArTable), _P, _F, _I64, _P]),
     "ar_embed_fwd": (C.c_int, [_P, _P, _I32, _P, _P, _I32, _P, _P, _P, _P, _P, _P]),
     "ar_head_step": (C.c_int, [_P, _P, _I32, _P, _P, _P, _P, _P, _I64, _P, _P, _P]),

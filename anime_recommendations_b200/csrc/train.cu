@@ -492,6 +492,10 @@ struct UpdateArgs {
   float* emit_q[2];
   float* emit_P[2];
   int emit_cap;           // entries per table in the emit buffers; ids beyond n_uniq are set to INT_MAX
+  // row-sharded tables: segment s goes to row emit_map[s] of emit_P, rows are emit_stride (> dim) floats
+  // apart and carry q in column `dim`; ids are not emitted (the owners already hold the request lists)
+  const int32_t* emit_map[2];
+  int emit_stride;
 };
 
 template <int NV>
@@ -561,6 +565,7 @@ rows_update_kernel(UpdateArgs a, const float* __restrict__ c, const float* __res
   int32_t* __restrict__ emit_ids = which ? a.emit_ids[1] : a.emit_ids[0];
   float* __restrict__ emit_q = which ? a.emit_q[1] : a.emit_q[0];
   float* __restrict__ emit_P = which ? a.emit_P[1] : a.emit_P[0];
+  const int32_t* __restrict__ emit_map = which ? a.emit_map[1] : a.emit_map[0];
   float kk[K_STEPC];
 #pragma unroll
   for (int i = 0; i < K_STEPC; ++i) kk[i] = stepc[i];
@@ -601,6 +606,12 @@ rows_update_kernel(UpdateArgs a, const float* __restrict__ c, const float* __res
       q = fmaf(d0, c0, q);
 #pragma unroll
       for (int k = 0; k < NV; ++k) acc.x[k] = fma4(d0, o0.x[k], acc.x[k]);
+    }
+    if (emit_map) {
+      float* dst = emit_P + (size_t)emit_map[seg] * a.emit_stride;
+      acc.store(dst, d4, lane);
+      if (lane == 0) dst[dim] = q;
+      return;
     }
     if (emit_ids) {
       acc.store(emit_P + (size_t)seg * dim, d4, lane);
@@ -646,6 +657,12 @@ rows_update_kernel(UpdateArgs a, const float* __restrict__ c, const float* __res
       acc.x[k].x += p.x[k].x; acc.x[k].y += p.x[k].y; acc.x[k].z += p.x[k].z; acc.x[k].w += p.x[k].w;
     }
     q += qred[w8];
+  }
+  if (emit_map) {
+    float* dst = emit_P + (size_t)emit_map[seg] * a.emit_stride;
+    acc.store(dst, d4, lane);
+    if (lane == 0) dst[dim] = q;
+    return;
   }
   if (emit_ids) {
     acc.store(emit_P + (size_t)seg * dim, d4, lane);
@@ -962,8 +979,9 @@ static int run_steps(const ar_train_ctx& x, int64_t epoch_step0, int32_t slot0, 
     bool ahead = false;
     if (la && has_next) {  // queue the look-ahead BEFORE this step's kernels so the GPU can start it at once
       AR_CUDA(cudaStreamWaitEvent(la->st2, la->ev_upd[(s + 1) & 1], 0));  // update(s-1) done
-      int rc = launch_catchup(&x.users, &x.plan_u, slot + 1, &x.anime, &x.plan_a, slot + 1, x.alpha, x.l2, t, la->st2, slot,
-                              x.sched_ws);
+      // the look-ahead owns the SECOND half of sched_ws: at s == 0 it runs concurrently with the main-stream catch-up
+      int32_t* ws2 = x.sched_ws ? x.sched_ws + 3 * ((size_t)x.plan_u.batch_cap + x.plan_a.batch_cap) + 4 : nullptr;
+      int rc = launch_catchup(&x.users, &x.plan_u, slot + 1, &x.anime, &x.plan_a, slot + 1, x.alpha, x.l2, t, la->st2, slot, ws2);
       if (rc) return rc;
       AR_CUDA(cudaEventRecord(la->ev_ahead, la->st2));
       ahead = true;
@@ -1048,6 +1066,7 @@ extern "C" int ar_train_steps_profile(const ar_train_ctx* ctx, int64_t epoch_ste
 }
 
 #include "dist.inl"
+#include "shard.inl"
 
 extern "C" int ar_predict(const float* U, const float* A, int32_t dim, const float* head, const float* bn_moving,
                           const int32_t* iu, const int32_t* ia, int64_t n, float* out, void* stream) {

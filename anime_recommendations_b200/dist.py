@@ -91,3 +91,76 @@ class DistTrainSession(TrainSession):
             self.launches += 2 + ns * per_step
         m.iterations = t0 + steps
         return steps
+
+
+def shard_rows(full, rank, world):
+    """Rows of `full` owned by `rank` under the row % world rule, in local-index order (row // world)."""
+    return full[rank::world]
+
+
+class ShardedTrainSession(TrainSession):
+    """Row-sharded data-parallel training (BASELINE cfg5): `model` holds THIS rank's shards -- an
+    EmbeddingDotModel built with n_users = ceil(n_users_global / world) (same for anime) whose table row i is
+    global row i * world + rank -- while the index arrays passed to run() hold GLOBAL row ids.  `batch` is
+    the per-rank batch; BatchNorm statistics and the head update are global."""
+
+    def __init__(self, model, batch, total_steps, comm=None):
+        super().__init__(model, batch, total_steps)
+        from ._capi import ArShardCtx
+        self.comm = comm or Comm()
+        G, B, D, dev, S = self.comm.world, self.B, model.dim, model.device, self.n_slots
+        if G > 8:
+            raise _capi.AnimerecError("row-sharded training supports up to 8 ranks")
+        f = dict(dtype=torch.float32, device=dev)
+        i32 = dict(dtype=torch.int32, device=dev)
+        self._sh = dict(
+            req_send=[torch.empty((G, S, B), **i32) for _ in range(2)],
+            req_recv=[torch.empty((G, S, B), **i32) for _ in range(2)],
+            emit_map=[torch.zeros((S, B), **i32) for _ in range(2)],
+            cache_idx=[torch.zeros((S, B), **i32) for _ in range(2)],
+            rows_out=[torch.zeros((G, B, D), **f) for _ in range(2)],
+            rows_in=[torch.zeros((G, B, D), **f) for _ in range(2)],
+            grad_send=[torch.zeros((G, B, D + 4), **f) for _ in range(2)],
+            grad_recv=[torch.zeros((G, B, D + 4), **f) for _ in range(2)])
+        self.max_count = torch.zeros(2, **i32)
+        self.c_all, self.label_all, self.dy_all = (torch.empty(G * B, **f) for _ in range(3))
+        self.fwd_part_all = torch.zeros(2 * ((G * B + 7) // 8), dtype=torch.float64, device=dev)
+        self.head_part_all = torch.zeros(8 * ((G * B + 255) // 256), dtype=torch.float64, device=dev)
+        h = ArShardCtx()
+        h.comm, h.n_ranks, h.rank = self.comm.handle, G, self.comm.rank
+        for name, bufs in self._sh.items():
+            arr = getattr(h, name)
+            for k in range(2):
+                arr[k] = bufs[k].data_ptr()
+        h.max_count = self.max_count.data_ptr()
+        h.c_all, h.label_all, h.dy_all = self.c_all.data_ptr(), self.label_all.data_ptr(), self.dy_all.data_ptr()
+        h.fwd_part_all, h.head_part_all = self.fwd_part_all.data_ptr(), self.head_part_all.data_ptr()
+        self.hctx = h
+        self.caps = []
+
+    def run(self, iu, ia, y, lr, profile=None):
+        m, B = self.model, self.B
+        N = iu.numel()
+        steps = (N + B - 1) // B
+        t0 = m.iterations
+        if t0 + steps > self.t_cap:
+            raise _capi.AnimerecError("ShardedTrainSession sized for %d optimizer steps, %d requested" % (self.t_cap, t0 + steps))
+        m._set_alpha(lr, t0 + 1, steps)
+        ctx = self._ctx(iu, ia, y)
+        ctx.sched_ws = None
+        st, L = stream_ptr(), lib()
+        for s0 in range(0, steps, self.n_slots):
+            ns = min(self.n_slots, steps - s0)
+            check(L.ar_plan_build(ptr(iu), N, B, s0, ns, C.byref(self.plan_u), st), "ar_plan_build(users)")
+            check(L.ar_plan_build(ptr(ia), N, B, s0, ns, C.byref(self.plan_a), st), "ar_plan_build(anime)")
+            check(L.ar_shard_plan(C.byref(self.plan_u), C.byref(self.plan_a), ns, C.byref(self.hctx), st), "ar_shard_plan")
+            # one host read per chunk of steps: the exchange size every rank uses for the chunk (max over ranks)
+            mc = self.max_count.max().reshape(1).to(torch.int64)
+            dist.all_reduce(mc, op=dist.ReduceOp.MAX)
+            cap = min(B, (int(mc.item()) + 3) // 4 * 4)
+            self.caps.append(cap)
+            check(L.ar_train_steps_sharded(C.byref(ctx), C.byref(self.hctx), s0, 0, t0 + s0, ns, max(cap, 4), st),
+                  "ar_train_steps_sharded")
+            self.launches += 4 + ns * (11 if m.adam_mode == "replay" else 9)
+        m.iterations = t0 + steps
+        return steps

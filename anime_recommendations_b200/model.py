@@ -390,7 +390,7 @@ class TrainSession:
         self.head_part = torch.zeros(8 * ((B + 255) // 256), dtype=torch.float64, device=dev)
         self.stepc = torch.zeros(8, **f)
         self.ticket = torch.zeros(1, dtype=torch.int32, device=dev)
-        self.sched_ws = torch.zeros(3 * 2 * B + 4, dtype=torch.int32, device=dev)
+        self.sched_ws = torch.zeros(2 * (3 * 2 * B + 4), dtype=torch.int32, device=dev)
         self.t_cap = model.iterations + int(total_steps)
         model._ensure_alpha(self.t_cap)
         self.metrics = torch.zeros((self.t_cap + 1, 4), **f)

@@ -115,8 +115,9 @@ typedef struct {
    * (written in AR_ADAM_DENSE only; may be null) */
   float* metrics;
   double* reg_sumsq;
-  /* optional (AR_ADAM_REPLAY): (3 * (plan_u.batch_cap + plan_a.batch_cap) + 4) int32 of scratch for the
-   * longest-first schedule of the catch-up kernel; null = plan order */
+  /* optional (AR_ADAM_REPLAY): 2 * (3 * (plan_u.batch_cap + plan_a.batch_cap) + 4) int32 of scratch for the
+   * longest-first schedule of the catch-up kernel (one half per stream: the look-ahead catch-up of the
+   * next step runs concurrently with the current one); null = plan order */
   int32_t* sched_ws;
 } ar_train_ctx;
 
@@ -160,6 +161,40 @@ typedef struct {
  * replicas stay bit-identical and equal to a single-GPU run on the concatenated batch. */
 int ar_train_steps_dist(const ar_train_ctx* ctx, const ar_dist_ctx* d, int64_t epoch_step0,
                         int32_t slot0, int64_t t0, int32_t n_steps, void* stream);
+/* ---- multi-GPU training, ROW-SHARDED tables (BASELINE cfg5: tables too large to replicate) ----
+ * Global row g of a table lives on rank g % n_ranks at local index g / n_ranks, with its Adam slots; ctx->users /
+ * ctx->anime describe THIS rank's shards; ctx->iu / ia hold GLOBAL row ids of this rank's samples and the plans
+ * are built on them.  Per step the owners serve the requested rows (NCCL all-to-all), the requesters run the
+ * forward on that row cache, BatchNorm/head run over the global batch, and the partial row gradients travel
+ * back to the owners (all-to-all), which merge them and apply Adam.  Equal to a single-GPU run on the
+ * concatenated batch up to rounding. */
+typedef struct {
+  void* comm;            /* from ar_comm_init */
+  int32_t n_ranks;       /* <= 8 */
+  int32_t rank;
+  int32_t* req_send[2];  /* [n_ranks][n_slots][batch_cap] per table (0 users, 1 anime): ids asked of each owner */
+  int32_t* req_recv[2];  /* same shape: ids each rank asks of me */
+  int32_t* emit_map[2];  /* [n_slots][batch_cap] plan segment -> row of the step's row cache */
+  int32_t* cache_idx[2]; /* [n_slots][batch_cap] sample -> row of the step's row cache */
+  int32_t* max_count;    /* [2] largest per-owner request list of the planned chunk, per table */
+  float* rows_out[2];    /* [n_ranks][batch_cap][dim] rows served to each requester */
+  float* rows_in[2];     /* [n_ranks][batch_cap][dim] the step's row cache */
+  float* grad_send[2];   /* [n_ranks][batch_cap][dim+4] partial gradients (P[dim], q, pad) for each owner */
+  float* grad_recv[2];
+  float* c_all;          /* as in ar_dist_ctx */
+  float* label_all;
+  float* dy_all;
+  double* fwd_part_all;
+  double* head_part_all;
+} ar_shard_ctx;
+
+/* After ar_plan_build of both tables for `n_steps` slots: split every step's distinct rows by owner, build the
+ * cache maps and ship all request lists of the chunk to their owners (one all-to-all per table).  max_count is
+ * written on the device; read it back and pass a `cap` >= both values to ar_train_steps_sharded. */
+int ar_shard_plan(const ar_plan* plan_u, const ar_plan* plan_a, int32_t n_steps, const ar_shard_ctx* sh, void* stream);
+int ar_train_steps_sharded(const ar_train_ctx* ctx, const ar_shard_ctx* sh, int64_t epoch_step0, int32_t slot0,
+                           int64_t t0, int32_t n_steps, int32_t cap, void* stream);
+
 /* NCCL all-gather of equally sized byte buffers (sharded top-k lists before ar_topk_merge). */
 int ar_allgather_bytes(void* comm, const void* send, void* recv, int64_t bytes_per_rank, void* stream);
 

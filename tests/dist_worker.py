@@ -35,11 +35,78 @@ def sim_main(shard, dev, rank, world):
         print("DIST_OK", shard)
 
 
+def shard_main(mode, dev, rank, world):
+    """Row-sharded training == single-GPU training on the concatenated batch."""
+    import anime_recommendations_b200 as ar
+    from anime_recommendations_b200.dist import ShardedTrainSession, shard_rows
+    from anime_recommendations_b200.model import TrainSession
+    nu, na, D, B, steps = 5001, 703, 128, 1000, 6
+    rng = np.random.RandomState(5)
+    n_glob = world * B * steps - world * 300
+    iu = rng.randint(0, nu, n_glob).astype(np.int32)
+    ia = rng.randint(0, na, n_glob).astype(np.int32)
+    ia[rng.rand(n_glob) < 0.2] = 3                                # heavy anime row
+    y = (rng.randint(0, 11, n_glob) / 10.0).astype(np.float32)
+    per = n_glob // world
+    sl = slice(rank * per, (rank + 1) * per)
+    full = ar.EmbeddingDotModel(nu, na, D, seed=2, adam_mode=mode, dense_kernel=-1.2)    # the single-GPU twin
+    fw = full.get_weights()
+    nul, nal = (nu + world - 1) // world, (na + world - 1) // world
+    m = ar.EmbeddingDotModel(nul, nal, D, seed=0, adam_mode=mode, dense_kernel=-1.2)
+    Us, As = np.zeros((nul, D), np.float32), np.zeros((nal, D), np.float32)
+    mine_u, mine_a = shard_rows(fw[0], rank, world), shard_rows(fw[1], rank, world)
+    Us[:len(mine_u)], As[:len(mine_a)] = mine_u, mine_a
+    m.set_weights([Us, As] + fw[2:])
+    sess = ShardedTrainSession(m, B, total_steps=steps)
+    sess.run(torch.from_numpy(iu[sl]).to(dev), torch.from_numpy(ia[sl]).to(dev), torch.from_numpy(y[sl]).to(dev), 2e-3)
+    m._sync_tables()
+    # assemble the global tables on rank 0
+    parts = {}
+    for name, t in (("U", m.U), ("A", m.A), ("mU", m.mU), ("vU", m.vU), ("mA", m.mA), ("vA", m.vA)):
+        g = [torch.empty_like(t) for _ in range(world)]
+        dist.all_gather(g, t.contiguous())
+        parts[name] = [x.cpu().numpy() for x in g]
+    heads = [torch.empty_like(m.head) for _ in range(world)]
+    dist.all_gather(heads, m.head)
+    assert all(torch.equal(heads[0], h) for h in heads[1:]), "head replicas diverged"
+    if rank == 0:
+        order = []
+        for s in range(steps):
+            for r in range(world):
+                lo = r * per + s * B
+                order.append(np.arange(lo, min(lo + B, (r + 1) * per)))
+        order = np.concatenate(order)
+        s1 = TrainSession(full, world * B, total_steps=steps)
+        s1.run(torch.from_numpy(iu[order]).to(dev), torch.from_numpy(ia[order]).to(dev),
+               torch.from_numpy(y[order]).to(dev), 2e-3)
+        full._sync_tables()
+        ref = dict(U=full.U, A=full.A, mU=full.mU, vU=full.vU, mA=full.mA, vA=full.vA)
+        for name, tref in ref.items():
+            tref = tref.cpu().numpy()
+            got = np.zeros_like(tref)
+            for r in range(world):
+                rows = tref[r::world].shape[0]
+                got[r::world] = parts[name][r][:rows]
+            tol = dict(rtol=1e-4, atol=3e-6) if name[0] != "v" else dict(rtol=2e-4, atol=1e-11)
+            np.testing.assert_allclose(got, tref, err_msg=name, **tol)
+        np.testing.assert_allclose(np.delete(m.head.cpu().numpy(), 1), np.delete(full.head.cpu().numpy(), 1), rtol=1e-4, atol=3e-6)
+        mt = sess.metrics[1:steps + 1].cpu().numpy()
+        m1t = s1.metrics[1:steps + 1].cpu().numpy()
+        np.testing.assert_allclose(mt[:, :3], m1t[:, :3], rtol=2e-6, atol=2e-6)
+        assert max(sess.caps) <= B and min(sess.caps) >= 4
+        print("DIST_OK shard", mode, "cap", sess.caps)
+
+
 def main(mode):
     rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
     torch.cuda.set_device(int(os.environ["LOCAL_RANK"]))
     dev = torch.device("cuda", int(os.environ["LOCAL_RANK"]))
     dist.init_process_group("nccl", device_id=dev)
+    if mode.startswith("shard_"):
+        shard_main(mode[6:], dev, rank, world)
+        dist.barrier()
+        dist.destroy_process_group()
+        return
     if mode.startswith("sim_"):
         sys.path.insert(0, os.path.join(ROOT, "tests"))
         sim_main(mode[4:], dev, rank, world)
