@@ -10,7 +10,7 @@ import os
 
 PKG = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("ANIMEREC_LIB") or os.path.join(PKG, "lib", "libanimerec.so")   # override: A/B builds
-ABI_VERSION = 7
+ABI_VERSION = 8
 
 AR_MAX_BATCH = 16384
 AR_HEAVY_LEN = 64
@@ -50,7 +50,8 @@ class ArDistCtx(C.Structure):
     _fields_ = [("comm", C.c_void_p), ("n_ranks", C.c_int32), ("rank", C.c_int32),
                 ("c_all", C.c_void_p), ("label_all", C.c_void_p), ("dy_all", C.c_void_p),
                 ("fwd_part_all", C.c_void_p), ("head_part_all", C.c_void_p),
-                ("send", C.c_void_p), ("recv", C.c_void_p)]
+                ("send", C.c_void_p), ("recv", C.c_void_p),
+                ("uniq_all", C.c_void_p * 2), ("meta_all", C.c_void_p * 2)]
 
 
 class ArShardCtx(C.Structure):

@@ -352,6 +352,8 @@ allpairs_topk_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
         }
         const float m = fmaxf(fmax3(g[0], g[1], g[2]), g[3]);
         if (!__any_sync(0xffffffffu, m > thr)) return;
+        // (measured alternatives, 350k x 350k: four static-index copies of the scan instead of the select chain
+        // -- 70 KB of code, 91 ms; fully predicated appends -- 44 ms; this version -- 35.8 ms)
         uint32_t gmask = 0;
 #pragma unroll
         for (int j = 0; j < 4; ++j) gmask |= __any_sync(0xffffffffu, g[j] > thr) ? (1u << j) : 0u;
@@ -370,6 +372,8 @@ allpairs_topk_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
           if (__any_sync(0xffffffffu, hot && cnt > CAP - 8)) {
             if (cnt > KP) list_compact<KP>(my_s, my_i, cnt, thr);
           }
+          // (a straight-line, fully predicated version of this append loop was measured 23 % SLOWER -- 44.1 vs
+          // 35.9 ms on 350k x 350k -- the skipped instructions matter more than the reconvergence stalls)
           if (hot) {
             const int cid0 = cb + 8 * gq;
 #pragma unroll

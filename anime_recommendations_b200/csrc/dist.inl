@@ -161,6 +161,14 @@ static int run_steps_dist(const ar_train_ctx& x, const ar_dist_ctx& d, int64_t e
   const int dim = x.users.dim, G = d.n_ranks, B = x.batch;
   const size_t tw = pack_table_words(B, dim);
   const float l2x2 = (float)(2.0 * (double)x.l2);
+  static const bool no_overlap = getenv("AR_NO_LOOKAHEAD") != nullptr;
+  SkipAll all{};
+  all.uniq[0] = d.uniq_all[0]; all.uniq[1] = d.uniq_all[1];
+  all.meta[0] = d.meta_all[0]; all.meta[1] = d.meta_all[1];
+  all.n_ranks = G;
+  const bool can_ahead = d.uniq_all[0] && d.uniq_all[1] && d.meta_all[0] && d.meta_all[1];
+  Lookahead* la = (x.mode == AR_ADAM_REPLAY && can_ahead && !no_overlap) ? lookahead() : nullptr;
+  if (la) AR_CUDA(cudaEventRecord(la->ev_upd[1], st));
   for (int s = 0; s < n_steps; ++s) {
     const int64_t e = epoch_step0 + s;
     const int64_t base = e * (int64_t)B;
@@ -170,8 +178,20 @@ static int run_steps_dist(const ar_train_ctx& x, const ar_dist_ctx& d, int64_t e
     const int64_t t = t0 + s + 1;
     const int ng = n * G;
     int rc;
-    if (x.mode == AR_ADAM_REPLAY) {
-      if ((rc = launch_catchup(&x.users, &x.plan_u, slot, &x.anime, &x.plan_a, slot, x.alpha, x.l2, t - 1, st))) return rc;
+    const bool has_next = (s + 1 < n_steps) && ((e + 1) * (int64_t)B < x.n_samples);
+    if (x.mode == AR_ADAM_REPLAY && (!la || s == 0)) {
+      if ((rc = launch_catchup(&x.users, &x.plan_u, slot, &x.anime, &x.plan_a, slot, x.alpha, x.l2, t - 1, st, -1, x.sched_ws))) return rc;
+    }
+    bool ahead = false;
+    if (la && has_next) {
+      // look-ahead (see run_steps): my rows of step s+1 that NO rank touches in step s are brought to step t on
+      // the side stream while step s runs; the rest are brought up to date by this step's merge (replay = 1)
+      AR_CUDA(cudaStreamWaitEvent(la->st2, la->ev_upd[(s + 1) & 1], 0));
+      int32_t* ws2 = x.sched_ws ? x.sched_ws + 3 * ((size_t)x.plan_u.batch_cap + x.plan_a.batch_cap) + 4 : nullptr;
+      if ((rc = launch_catchup(&x.users, &x.plan_u, slot + 1, &x.anime, &x.plan_a, slot + 1, x.alpha, x.l2, t, la->st2, slot, ws2, &all)))
+        return rc;
+      AR_CUDA(cudaEventRecord(la->ev_ahead, la->st2));
+      ahead = true;
     }
     AR_DISPATCH_NV(dim, embed_fwd_kernel<NV><<<ceil_div(n, kRowWarps), kRowThreads, 0, st>>>(
                             x.users.W, x.anime.W, dim, x.iu + base, x.ia + base, n, nullptr, x.uh, x.ah, x.c, x.ru, x.ra, nullptr));
@@ -211,6 +231,10 @@ static int run_steps_dist(const ar_train_ctx& x, const ar_dist_ctx& d, int64_t e
     AR_DISPATCH_NV(dim, rows_merge_update_kernel<NV><<<2 * m.blocks_tab0, kRowThreads, 0, st>>>(
                             m, x.alpha, l2x2, t, x.mode == AR_ADAM_REPLAY ? 1 : 0, ss));
     AR_LAUNCH_CHECK();
+    if (la) {
+      AR_CUDA(cudaEventRecord(la->ev_upd[s & 1], st));
+      if (ahead) AR_CUDA(cudaStreamWaitEvent(st, la->ev_ahead, 0));
+    }
     if (x.mode == AR_ADAM_DENSE) {
       if ((rc = launch_flush(&x.users, x.alpha, x.l2, t, ss, st))) return rc;
       if ((rc = launch_flush(&x.anime, x.alpha, x.l2, t, ss, st))) return rc;

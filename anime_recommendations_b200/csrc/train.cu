@@ -96,14 +96,34 @@ struct CatchupArgs {
   int blocks0;  // CTAs assigned to table 0
   // look-ahead catch-up: rows that are ALSO in this (earlier) step's sorted distinct-row list are skipped --
   // that step's own update brings them up to date, and may be running concurrently
-  const int32_t* skip_uniq[2];
-  const int32_t* skip_meta[2];
+  const int32_t* skip_uniq[2];   // per table: skip_lists ascending lists, skip_uniq_stride apart
+  const int32_t* skip_meta[2];   // their lengths at [0] of 4-int records, skip_meta_stride apart
+  int skip_lists;                // 1 on a single GPU; n_ranks for replicated multi-GPU training (all ranks' rows)
+  int64_t skip_uniq_stride, skip_meta_stride;
   // longest-first schedule (ar_train_ctx.sched_ws): three buckets of (table << 31 | row) by replay length,
   // bucket b at sched + b*cap, their fill counts at sched + 3*cap
   int32_t* sched;
   int cap;
 };
 constexpr int kLongReplay = 128, kMidReplay = 32;
+
+// is `row` in any of the table's skip lists?  (warp-uniform when `row` is)
+__device__ __forceinline__ bool in_skip_lists(const CatchupArgs& a, bool second, int row) {
+  const int32_t* __restrict__ base = second ? a.skip_uniq[1] : a.skip_uniq[0];
+  if (!base) return false;
+  const int32_t* __restrict__ mbase = second ? a.skip_meta[1] : a.skip_meta[0];
+  for (int l = 0; l < a.skip_lists; ++l) {
+    const int32_t* __restrict__ skip = base + l * a.skip_uniq_stride;
+    const int n_skip = mbase[l * a.skip_meta_stride];
+    int lo = 0, hi = n_skip;
+    while (lo < hi) {
+      const int mid = (lo + hi) >> 1;
+      if (__ldg(skip + mid) < row) lo = mid + 1; else hi = mid;
+    }
+    if (lo < n_skip && __ldg(skip + lo) == row) return true;
+  }
+  return false;
+}
 
 // Replay lengths are geometric (mean n_rows/unique-per-step, max ~10x that), and a CTA only frees its SM slot
 // when its slowest warp ends -- with 8 rows of unrelated length per CTA the SFU sat idle ~60% of the time
@@ -125,18 +145,7 @@ rows_classify_kernel(CatchupArgs a, int64_t t_target, int n0_cap, int n1_cap) {
   int bucket = -1, row = 0;
   if (seg < (second ? n1_cap : n0_cap) && seg < (second ? a.meta[1] : a.meta[0])[0]) {
     row = (second ? a.uniq[1] : a.uniq[0])[seg];
-    bool skip_it = false;
-    const int32_t* __restrict__ skip = second ? a.skip_uniq[1] : a.skip_uniq[0];
-    if (skip) {
-      const int n_skip = (second ? a.skip_meta[1] : a.skip_meta[0])[0];
-      int lo = 0, hi = n_skip;
-      while (lo < hi) {
-        const int mid = (lo + hi) >> 1;
-        if (__ldg(skip + mid) < row) lo = mid + 1; else hi = mid;
-      }
-      skip_it = lo < n_skip && __ldg(skip + lo) == row;
-    }
-    if (!skip_it) {
+    if (!in_skip_lists(a, second, row)) {
       const int64_t len = t_target - (int64_t)(second ? a.tab[1].last_step : a.tab[0].last_step)[row];
       if (len > 0) bucket = len > kLongReplay ? 0 : (len > kMidReplay ? 1 : 2);
     }
@@ -180,16 +189,7 @@ rows_catchup_kernel(CatchupArgs a, const float* __restrict__ alpha, float l2x2, 
     const int32_t* meta = second ? a.meta[1] : a.meta[0];
     if (seg >= (second ? a.cap - a.blocks0 : a.blocks0) || seg >= meta[0]) return;
     row = (second ? a.uniq[1] : a.uniq[0])[seg];
-    const int32_t* __restrict__ skip = second ? a.skip_uniq[1] : a.skip_uniq[0];
-    if (skip) {  // warp-uniform binary search in the other step's ascending distinct rows
-      const int n_skip = (second ? a.skip_meta[1] : a.skip_meta[0])[0];
-      int lo = 0, hi = n_skip;
-      while (lo < hi) {
-        const int mid = (lo + hi) >> 1;
-        if (__ldg(skip + mid) < row) lo = mid + 1; else hi = mid;
-      }
-      if (lo < n_skip && __ldg(skip + lo) == row) return;
-    }
+    if (in_skip_lists(a, second, row)) return;
   }
   ar_table tb;
   tb.dim = a.tab[0].dim;
@@ -766,11 +766,29 @@ static int num_sms() {
     default: { constexpr int NV = 4; __VA_ARGS__; } break; \
   }
 
+// all ranks' distinct-row lists of the planned chunk (replicated multi-GPU training): [rank][slot][batch_cap]
+struct SkipAll {
+  const int32_t* uniq[2];
+  const int32_t* meta[2];
+  int n_ranks;
+};
+
 static int launch_catchup(const ar_table* t0, const ar_plan* p0, int slot0, const ar_table* t1,
                           const ar_plan* p1, int slot1, const float* alpha, float l2, int64_t t_target,
-                          cudaStream_t st, int skip_slot = -1, int32_t* sched_ws = nullptr) {
+                          cudaStream_t st, int skip_slot = -1, int32_t* sched_ws = nullptr, const SkipAll* all = nullptr) {
   CatchupArgs a{};
-  if (skip_slot >= 0) {
+  if (skip_slot >= 0 && all) {
+    a.skip_lists = all->n_ranks;
+    a.skip_uniq_stride = (int64_t)p0->n_slots * p0->batch_cap;
+    a.skip_meta_stride = (int64_t)p0->n_slots * 4;
+    a.skip_uniq[0] = all->uniq[0] + (int64_t)skip_slot * p0->batch_cap;
+    a.skip_meta[0] = all->meta[0] + (int64_t)skip_slot * 4;
+    if (t1) {
+      a.skip_uniq[1] = all->uniq[1] + (int64_t)skip_slot * p1->batch_cap;
+      a.skip_meta[1] = all->meta[1] + (int64_t)skip_slot * 4;
+    }
+  } else if (skip_slot >= 0) {
+    a.skip_lists = 1;
     a.skip_uniq[0] = p0->uniq + (int64_t)skip_slot * p0->batch_cap;
     a.skip_meta[0] = p0->meta + (int64_t)skip_slot * 4;
     if (t1) {

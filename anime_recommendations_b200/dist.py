@@ -70,6 +70,14 @@ class DistTrainSession(TrainSession):
         d.c_all, d.label_all, d.dy_all = self.c_all.data_ptr(), self.label_all.data_ptr(), self.dy_all.data_ptr()
         d.fwd_part_all, d.head_part_all = self.fwd_part_all.data_ptr(), self.head_part_all.data_ptr()
         d.send, d.recv = self.send.data_ptr(), self.recv.data_ptr()
+        # every rank's distinct-row lists of the planned chunk (look-ahead catch-up needs to know which rows
+        # the OTHER ranks touch in the current step)
+        S = self.n_slots
+        self.uniq_all = [torch.zeros((G, S, B), dtype=torch.int32, device=dev) for _ in range(2)]
+        self.meta_all = [torch.zeros((G, S, 4), dtype=torch.int32, device=dev) for _ in range(2)]
+        for k in range(2):
+            d.uniq_all[k] = self.uniq_all[k].data_ptr()
+            d.meta_all[k] = self.meta_all[k].data_ptr()
         self.dctx = d
 
     def run(self, iu, ia, y, lr, profile=None):
@@ -87,6 +95,9 @@ class DistTrainSession(TrainSession):
             ns = min(self.n_slots, steps - s0)
             check(L.ar_plan_build(ptr(iu), N, B, s0, ns, C.byref(self.plan_u), st), "ar_plan_build(users)")
             check(L.ar_plan_build(ptr(ia), N, B, s0, ns, C.byref(self.plan_a), st), "ar_plan_build(anime)")
+            for k, keep in enumerate((self._keep_u, self._keep_a)):
+                for src, dst in ((keep["uniq"], self.uniq_all[k]), (keep["meta"], self.meta_all[k])):
+                    check(L.ar_allgather_bytes(self.comm.handle, ptr(src), ptr(dst), src.numel() * 4, st), "ar_allgather_bytes")
             check(L.ar_train_steps_dist(C.byref(ctx), C.byref(self.dctx), s0, 0, t0 + s0, ns, st), "ar_train_steps_dist")
             self.launches += 2 + ns * per_step
         m.iterations = t0 + steps

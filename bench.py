@@ -195,11 +195,17 @@ def gpu_main(args):
     K, W = args.steps, args.warmup
     mode = args.mode
 
-    model = ar.EmbeddingDotModel(N_USERS, N_ANIME, DIM, l2_reg_factor=L2, seed=1, adam_mode=mode, dense_kernel=1.0)
+    sharded = world > 1 and args.dist == "sharded"
+    if sharded:   # this rank's shards of both tables (global row g lives on rank g % world), same init law
+        model = ar.EmbeddingDotModel((N_USERS + world - 1) // world, (N_ANIME + world - 1) // world, DIM,
+                                     l2_reg_factor=L2, seed=1 + rank, adam_mode=mode, dense_kernel=1.0)
+    else:
+        model = ar.EmbeddingDotModel(N_USERS, N_ANIME, DIM, l2_reg_factor=L2, seed=1, adam_mode=mode, dense_kernel=1.0)
     iu, ia, y = synth((W + K) * BATCH, 42 + rank, dev, zipf=args.zipf)
     if world > 1:
         from anime_recommendations_b200 import dist as ardist
-        sess = ardist.DistTrainSession(model, BATCH, total_steps=2 * (W + K) + 8)
+        cls = ardist.ShardedTrainSession if sharded else ardist.DistTrainSession
+        sess = cls(model, BATCH, total_steps=2 * (W + K) + 8)
     else:
         sess = TrainSession(model, BATCH, total_steps=2 * (W + K) + 8)
     # warm-up (untimed)
@@ -230,6 +236,8 @@ def gpu_main(args):
     line = dict(metric=METRIC, value=value, unit=UNIT, n_gpus=world, steps=K, warmup=W, ms_per_step=ms / K,
                 higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f32", data="synthetic",
                 config=workload_config(mode, world), gpu_launches=int(launches), clocks=clocks)
+    if world > 1:
+        line["config"]["parallelism"] = "dp%d, %s tables" % (world, args.dist)
 
     if rank == 0 and world == 1:
         # ---- roofline of the dominant kernel: per-stage device time measured live with CUDA events
@@ -280,8 +288,26 @@ def gpu_main(args):
             line["extras"] = extras(dev, pk)
             line["extras"]["train_modes"] = {m: mode_run(ar, dev, m, min(K, 100), W) for m in ("dense", "touched")
                                              if m != mode}
-    elif rank == 0:
-        line["e2e"] = None
+    if world > 1:
+        # ---- e2e at N GPUs: every rank feeds its shard of each global batch from pinned HOST memory
+        hu, ha, hy = (t.cpu().pin_memory() for t in synth(K * BATCH, 177 + rank, dev, zipf=args.zipf))
+        model._sync_tables()
+        torch.cuda.synchronize()
+        dist.barrier()
+        t0 = time.perf_counter()
+        du, da, dy = (t.to(dev, non_blocking=True) for t in (hu, ha, hy))
+        t_first = model.iterations
+        sess.run(du, da, dy, LR)
+        model._sync_tables()
+        mt = sess.metrics[t_first + 1:t_first + K + 1].cpu()              # D2H of the per-step metrics
+        torch.cuda.synchronize()
+        dt = torch.tensor([time.perf_counter() - t0], device=dev)
+        dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+        dist.barrier()
+        line["e2e"] = dict(value=world * K * BATCH / float(dt.item()), unit=UNIT, h2d_bytes_per_step=BATCH * 12,
+                           d2h_bytes_per_step=16, seconds=float(dt.item()), loss_bce_last=float(mt[-1, 0]),
+                           what="per rank: pinned host arrays -> H2D, K data-parallel steps (SyncBN + NCCL row-gradient "
+                                "exchange), table flush, D2H of the per-step metrics; max over ranks")
     if rank == 0:
         print(json.dumps(line))
     if world > 1:
@@ -442,6 +468,8 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--mode", default="replay", choices=["replay", "dense", "touched"])
     ap.add_argument("--zipf", action="store_true", help="Zipf(1) anime popularity instead of uniform")
+    ap.add_argument("--dist", default="replicated", choices=["replicated", "sharded"],
+                    help="N > 1: replicated tables + all-gathered row gradients (cfg2) or row-sharded tables + all-to-all (cfg5 scheme)")
     ap.add_argument("--skip-cpu", action="store_true")
     ap.add_argument("--skip-extras", action="store_true")
     args = ap.parse_args()

@@ -153,6 +153,10 @@ typedef struct {
   float* send;           /* (2*batch*(dim+2)) packed partial row gradients of this rank:
                             [ids_u | q_u | P_u(batch,dim) | ids_a | q_a | P_a(batch,dim)], ids int32 */
   float* recv;           /* n_ranks such blocks */
+  /* optional (AR_ADAM_REPLAY look-ahead catch-up): every rank's plan.uniq / plan.meta of the planned chunk,
+   * all-gathered: uniq_all[table] is [n_ranks][n_slots][batch_cap], meta_all[table] is [n_ranks][n_slots][4] */
+  const int32_t* uniq_all[2];
+  const int32_t* meta_all[2];
 } ar_dist_ctx;
 
 /* ar_train_steps for rank `d->rank` of `d->n_ranks`: ctx holds this rank's samples (every rank must
