@@ -10,7 +10,7 @@ import os
 
 PKG = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("ANIMEREC_LIB") or os.path.join(PKG, "lib", "libanimerec.so")   # override: A/B builds
-ABI_VERSION = 8
+ABI_VERSION = 9
 
 AR_MAX_BATCH = 16384
 AR_HEAVY_LEN = 64
@@ -98,7 +98,7 @@ SIGNATURES = {
     "ar_rownorm": (C.c_int, [_P, _I64, _I32, _P, _P]),
     "ar_topk_query_workspace": (C.c_int64, [_I64, _I32]),
     "ar_cosine_topk_query": (C.c_int, [_P, _I64, _I32, _I64, _P, _I64, _I32, _P, _P, _P, _P]),
-    "ar_topk_merge": (C.c_int, [_P, _P, _I32, _I64, _I32, _I32, _P, _P, _P]),
+    "ar_topk_merge": (C.c_int, [_P, _P, _I32, _I64, _I32, _I32, _I32, _P, _P, _P]),
     "ar_cosine_rerank": (C.c_int, [_P, _I64, _I64, _P, _I32, _P, _P, _P, _I32, _I32, _I32, _F, _P, _P, _P, _P, _P]),
     "ar_bits_from_csr": (C.c_int, [_P, _P, _I64, _I64, _I64, _P, _P]),
     "ar_rownorm_bf16": (C.c_int, [_P, _I64, _I32, _P, _P, _P]),

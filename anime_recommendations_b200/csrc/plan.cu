@@ -138,7 +138,7 @@ plan_build_kernel(const int32_t* __restrict__ idx, int64_t n_total, int batch, i
 }  // namespace ar
 
 extern "C" const char* ar_last_error(void) { return ar::g_err; }
-extern "C" int ar_abi_version(void) { return 8; }
+extern "C" int ar_abi_version(void) { return 9; }
 
 extern "C" int ar_check_device(void) {
   int dev = 0;

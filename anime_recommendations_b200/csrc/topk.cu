@@ -155,33 +155,50 @@ query_topk_kernel(const float* __restrict__ W, int64_t n, int dim, int64_t q,
   wl.init();
   const int64_t warp_global = (int64_t)blockIdx.x * kTopkWarps + wid;
   const int64_t n_warps = (int64_t)gridDim.x * kTopkWarps;
-  for (int64_t r0 = warp_global * 4; r0 < n; r0 += n_warps * 4) {
+  // software pipeline: the loads of the NEXT 4 rows are in flight while the current 4 are reduced and ranked
+  auto load_rows = [&](int64_t r0, float4 (&x)[NQ]) {
     const int64_t row = r0 + grp;
+#pragma unroll
+    for (int i = 0; i < NQ; ++i) {
+      const int j = sub + 8 * i;
+      x[i] = (row < n && j < d4) ? ld4_nc(W + row * dim + 4 * j) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+  };
+  float4 xa[NQ], xb[NQ];
+  int64_t r0 = warp_global * 4;
+  if (r0 < n) load_rows(r0, xa);
+  float thr = -CUDART_INF_F;  // k-th best held by this warp (list admission bound), refreshed after inserts
+  auto rank_rows = [&](int64_t rbase, const float4 (&x)[NQ]) {
+    const int64_t row = rbase + grp;
     float dot = 0.f, ss = 0.f;
-    if (row < n) {
-      const float* src = W + row * dim;
-      float4 x[NQ];
 #pragma unroll
-      for (int i = 0; i < NQ; ++i) {
-        const int j = sub + 8 * i;
-        x[i] = (j < d4) ? ld4_nc(src + 4 * j) : make_float4(0.f, 0.f, 0.f, 0.f);
-      }
-#pragma unroll
-      for (int i = 0; i < NQ; ++i) {
-        dot += dot4(x[i], qv[i]);
-        ss += dot4(x[i], x[i]);
-      }
+    for (int i = 0; i < NQ; ++i) {
+      dot += dot4(x[i], qv[i]);
+      ss += dot4(x[i], x[i]);
     }
 #pragma unroll
     for (int o = 1; o < 8; o <<= 1) {
       dot += __shfl_xor_sync(0xffffffffu, dot, o);
       ss += __shfl_xor_sync(0xffffffffu, ss, o);
     }
-    float sc = dot / sqrtf(ss);  // 0/0 -> NaN for zero rows, rejected below
+    const float sc = dot / sqrtf(ss);  // 0/0 -> NaN for zero rows, rejected below
     bool ok = (row < n) && (sc == sc) && (row != exclude);
     if (ok && cand_mask) ok = (cand_mask[row >> 5] >> (row & 31)) & 1u;
-    // one candidate per 8-lane group: lanes 0, 8, 16, 24 offer theirs
-    wl.insert_lanes(sc, (int)row, ok && sub == 0, k, lane);
+    // one candidate per 8-lane group: lanes 0, 8, 16, 24 offer theirs; a score below the warp's k-th best
+    // cannot enter (ties go to the lower row id, which a later row never has), so most iterations stop here
+    if (__any_sync(0xffffffffu, ok && sub == 0 && sc >= thr)) {
+      wl.insert_lanes(sc, (int)row, ok && sub == 0, k, lane);
+      thr = __shfl_sync(0xffffffffu, wl.s, k - 1);
+    }
+  };
+  for (; r0 < n; r0 += n_warps * 8) {
+    const int64_t r1 = r0 + n_warps * 4;
+    if (r1 < n) load_rows(r1, xb);
+    rank_rows(r0, xa);
+    if (r1 >= n) break;
+    const int64_t r2 = r1 + n_warps * 4;
+    if (r2 < n) load_rows(r2, xa);
+    rank_rows(r1, xb);
   }
   cta_merge(wl, sm_s, sm_i, k, kTopkWarps);
   if (wid == 0 && lane < k) {
@@ -190,15 +207,39 @@ query_topk_kernel(const float* __restrict__ W, int64_t n, int dim, int64_t q,
   }
 }
 
-// Merge n_lists partial lists per query.  idx/score layout: [list][query][k_in].  One CTA per query.
+// Merge n_lists partial lists per query.  idx/score layout: [list][query][k_in], each list sorted best first.
+// One CTA per query.  The k_out-th best of the union is at least the largest k_out-th entry of any single
+// list, so everything below that bound T is dropped before the (serial, shuffle-heavy) list insertion:
+// merging the 592 per-CTA lists of a single-query scan inserts ~k candidates instead of thousands.
 __global__ void __launch_bounds__(kTopkThreads)
 topk_merge_kernel(const int* __restrict__ idx, const float* __restrict__ score, int n_lists,
-                  int64_t n_queries, int k_in, int k_out, int* __restrict__ out_idx,
+                  int64_t n_queries, int k_in, int k_out, int lists_sorted, int* __restrict__ out_idx,
                   float* __restrict__ out_score) {
   __shared__ float sm_s[kTopkWarps * 32];
   __shared__ int sm_i[kTopkWarps * 32];
+  __shared__ float bound_s;
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   const int64_t qy = blockIdx.x;
+  float tmax = -CUDART_INF_F;
+  if (lists_sorted && k_in >= k_out) {
+    for (int l = threadIdx.x; l < n_lists; l += kTopkThreads) {
+      const int64_t o = ((int64_t)l * n_queries + qy) * k_in + (k_out - 1);
+      const float sc = score[o];
+      if (idx[o] >= 0 && sc == sc) tmax = fmaxf(tmax, sc);
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) tmax = fmaxf(tmax, __shfl_xor_sync(0xffffffffu, tmax, o));
+  if (lane == 0) sm_s[wid] = tmax;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float t = sm_s[0];
+    for (int w = 1; w < kTopkWarps; ++w) t = fmaxf(t, sm_s[w]);
+    bound_s = t;
+  }
+  __syncthreads();
+  const float bound = bound_s;
+  __syncthreads();
   WarpList wl;
   wl.init();
   const int total = n_lists * k_in;
@@ -212,7 +253,8 @@ topk_merge_kernel(const int* __restrict__ idx, const float* __restrict__ score, 
       ci = idx[o];
       cs = score[o];
     }
-    wl.insert_lanes(cs, ci, ci >= 0 && cs == cs, k_out, lane);
+    const bool valid = ci >= 0 && cs == cs && cs >= bound;
+    if (__any_sync(0xffffffffu, valid)) wl.insert_lanes(cs, ci, valid, k_out, lane);
   }
   cta_merge(wl, sm_s, sm_i, k_out, kTopkWarps);
   if (wid == 0 && lane < k_out) {
@@ -378,17 +420,18 @@ extern "C" int ar_cosine_topk_query(const float* W, int64_t n_rows, int32_t dim,
   else if (nq <= 8) query_topk_kernel<8><<<blocks, kTopkThreads, 0, st>>>(W, n_rows, dim, q, cand_mask, exclude, k, pidx, pscore);
   else query_topk_kernel<16><<<blocks, kTopkThreads, 0, st>>>(W, n_rows, dim, q, cand_mask, exclude, k, pidx, pscore);
   AR_LAUNCH_CHECK();
-  topk_merge_kernel<<<1, kTopkThreads, 0, st>>>(pidx, pscore, blocks, 1, k, k, out_idx, out_score);
+  topk_merge_kernel<<<1, kTopkThreads, 0, st>>>(pidx, pscore, blocks, 1, k, k, 1, out_idx, out_score);
   AR_LAUNCH_CHECK();
   return AR_OK;
 }
 
 extern "C" int ar_topk_merge(const int32_t* idx, const float* score, int32_t n_lists, int64_t n_queries,
-                             int32_t k_in, int32_t k_out, int32_t* out_idx, float* out_score, void* stream) {
+                             int32_t k_in, int32_t k_out, int32_t lists_sorted, int32_t* out_idx, float* out_score,
+                             void* stream) {
   AR_REQUIRE(idx && score && out_idx && out_score, "ar_topk_merge: null pointer");
   AR_REQUIRE(k_out > 0 && k_out <= kMaxK && k_in > 0 && n_lists > 0, "ar_topk_merge: bad k/n_lists");
   if (n_queries <= 0) return AR_OK;
-  topk_merge_kernel<<<(unsigned)n_queries, kTopkThreads, 0, (cudaStream_t)stream>>>(idx, score, n_lists, n_queries, k_in, k_out, out_idx, out_score);
+  topk_merge_kernel<<<(unsigned)n_queries, kTopkThreads, 0, (cudaStream_t)stream>>>(idx, score, n_lists, n_queries, k_in, k_out, lists_sorted, out_idx, out_score);
   AR_LAUNCH_CHECK();
   return AR_OK;
 }

@@ -386,11 +386,12 @@ def _query_vs_table(qrow, C, k, drop_bits):
     return cosine_topk_query_device(T, n, k, mask_bits=keep, exclude=n)
 
 
-def topk_merge(idx, score, k_out):
-    """Merge [n_lists, n_queries, k_in] partial lists (global row ids) into [n_queries, k_out]."""
+def topk_merge(idx, score, k_out, lists_sorted=True):
+    """Merge [n_lists, n_queries, k_in] partial lists (global row ids) into [n_queries, k_out].
+    lists_sorted: every list is best-first (what the top-k entry points return) -> bound pruning."""
     nl, nq, kin = idx.shape
     oi = torch.empty((nq, k_out), dtype=torch.int32, device=idx.device)
     os_ = torch.empty((nq, k_out), dtype=torch.float32, device=idx.device)
-    check(lib().ar_topk_merge(ptr(idx), ptr(score), nl, nq, kin, k_out, ptr(oi), ptr(os_), stream_ptr()),
+    check(lib().ar_topk_merge(ptr(idx), ptr(score), nl, nq, kin, k_out, 1 if lists_sorted else 0, ptr(oi), ptr(os_), stream_ptr()),
           "ar_topk_merge")
     return oi, os_

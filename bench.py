@@ -14,7 +14,6 @@ import json
 import os
 import subprocess
 import sys
-import threading
 import time
 
 import numpy as np
@@ -49,62 +48,69 @@ def ncu_traffic(kernel, mode):
     return d.get(mode, {}).get(kernel, d.get("any", {}).get(kernel))
 
 
-class ClockSampler(threading.Thread):
-    """SM clock + throttle reasons while the timed region runs, read in-process through NVML (pynvml);
-    an external `nvidia-smi -lms` would contend for the driver lock and perturb a 15 ms timed region."""
+class ClockSampler:
+    """SM clock + throttle reasons DURING the timed region, sampled by a separate `nvidia-smi -lms` process
+    (B200_PROFILING.md's clocks line).  An in-process NVML poller was measured to slow the multi-GPU timed
+    region by 20-60 % (its driver calls serialise with the launching thread while NCCL keeps the host on the
+    critical path), so the sampling lives in another process; rows are matched to the region by timestamp."""
 
-    def __init__(self, gpu_index, period_s=0.005):
-        super().__init__(daemon=True)
-        self.gpu, self.period, self.rows, self._halt = gpu_index, period_s, [], threading.Event()
-        self.nv = None
-        try:
-            import pynvml
-            pynvml.nvmlInit()
-            self.nv = pynvml
-            self.h = pynvml.nvmlDeviceGetHandleByIndex(gpu_index)
-            self.max_sm = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
-        except Exception:  # noqa: BLE001
-            self.nv = None
+    QUERY = ("timestamp,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
 
-    def _sample(self):
-        nv = self.nv
-        sm = float(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
-        try:
-            r = int(nv.nvmlDeviceGetCurrentClocksEventReasons(self.h))
-        except Exception:  # noqa: BLE001
-            r = int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h))
-        try:
-            util = int(nv.nvmlDeviceGetUtilizationRates(self.h).gpu)
-        except Exception:  # noqa: BLE001
-            util = -1
-        self.rows.append((sm, r, util))
+    def __init__(self, gpu_index, period_ms=20):
+        self.gpu, self.period_ms, self.proc, self.t0, self.t1 = gpu_index, period_ms, None, None, None
 
-    def run(self):
-        if self.nv is None:
-            return
-        while not self._halt.is_set():
-            try:
-                self._sample()
-            except Exception:  # noqa: BLE001
-                pass
-            self._halt.wait(self.period)
+    def start(self):
+        """Launch the poller and give it time to print its first rows; call mark_begin() right before timing."""
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.QUERY,
+                                          "--format=csv,noheader,nounits", "-lms", str(self.period_ms)],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            time.sleep(0.6)
+        except Exception:  # noqa: BLE001
+            self.proc = None
+
+    def mark_begin(self):
+        self.t0 = time.time()
+
+    def mark_end(self):
+        self.t1 = time.time()
 
     def stop(self):
-        self._halt.set()
-        self.join(timeout=3)
-        if self.nv is None or not self.rows:
-            return dict(sm_mhz=None, sm_max_mhz=None, reasons=[], samples=0, source="nvml unavailable")
-        nv = self.nv
-        names = dict(hw_slowdown=0x8, sw_power_cap=0x4, sw_thermal_slowdown=0x20, hw_thermal_slowdown=0x40,
-                     hw_power_brake_slowdown=0x80)
-        seen = set()
-        for _, r, _ in self.rows:
-            for k, bit in names.items():
-                if r & bit:
-                    seen.add(k)
-        sm = [x[0] for x in self.rows]
-        return dict(sm_mhz=float(np.median(sm)), sm_min_mhz=float(min(sm)), sm_max_mhz=self.max_sm,
-                    reasons=sorted(seen), samples=len(sm), source="nvml, %.0f ms period" % (self.period * 1e3))
+        if self.proc is None:
+            return dict(sm_mhz=None, sm_max_mhz=None, reasons=[], samples=0, source="nvidia-smi unavailable")
+        time.sleep(max(0.05, 2.5 * self.period_ms / 1e3))
+        self.proc.terminate()
+        try:
+            out, _ = self.proc.communicate(timeout=5)
+        except Exception:  # noqa: BLE001
+            self.proc.kill()
+            out = ""
+        import datetime
+        rows = []
+        for ln in out.splitlines():
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 8:
+                continue
+            try:
+                ts = datetime.datetime.strptime(f[0], "%Y/%m/%d %H:%M:%S.%f").timestamp()
+                rows.append((ts, float(f[1]), float(f[2]), f[3], [n for n, v in zip(
+                    ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[4:8]) if v.lower().startswith("active")]))
+            except ValueError:
+                continue
+        inside = [r for r in rows if self.t0 <= r[0] <= self.t1]
+        note = "rows inside the timed region"
+        if not inside:   # region shorter than the polling period: the rows that bracket it
+            inside = sorted(rows, key=lambda r: min(abs(r[0] - self.t0), abs(r[0] - self.t1)))[:2]
+            note = "timed region shorter than the polling period: nearest rows"
+        if not inside:
+            return dict(sm_mhz=None, sm_max_mhz=None, reasons=[], samples=0, source="nvidia-smi printed no rows")
+        sm = [r[1] for r in inside]
+        return dict(sm_mhz=float(np.median(sm)), sm_min_mhz=float(min(sm)), sm_max_mhz=float(inside[0][2]),
+                    reasons=sorted({x for r in inside for x in r[4]}), samples=len(inside),
+                    power_w=[r[3] for r in inside][:4],
+                    source="nvidia-smi -lms %d in a separate process; %s" % (self.period_ms, note))
 
 
 def synth(n_samples, seed, device, zipf=False):
@@ -213,16 +219,22 @@ def gpu_main(args):
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
-    sampler = ClockSampler(local) if rank == 0 else None
+    sampler = ClockSampler(local) if rank == 0 and os.environ.get("AR_BENCH_NO_SAMPLER") is None else None
     if sampler:
         sampler.start()
+    if world > 1:
+        dist.barrier()
     l0 = sess.launches
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     torch.cuda.synchronize()
+    if sampler:
+        sampler.mark_begin()
     e0.record()
     sess.run(iu[W * BATCH:], ia[W * BATCH:], y[W * BATCH:], LR)
     e1.record()
     torch.cuda.synchronize()
+    if sampler:
+        sampler.mark_end()
     ms = e0.elapsed_time(e1)
     launches = sess.launches - l0
     if world > 1:
@@ -463,8 +475,8 @@ def scoring_extra(dev, pk, n_query=65_000, k=20):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=200)
-    ap.add_argument("--warmup", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=1000)
+    ap.add_argument("--warmup", type=int, default=50)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--mode", default="replay", choices=["replay", "dense", "touched"])
     ap.add_argument("--zipf", action="store_true", help="Zipf(1) anime popularity instead of uniform")

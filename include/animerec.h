@@ -246,9 +246,12 @@ int ar_cosine_topk_query(const float* W, int64_t n_rows, int32_t dim, int64_t q,
                          const uint32_t* cand_mask, int64_t exclude, int32_t k, int32_t* out_idx,
                          float* out_score, void* workspace, void* stream);
 
-/* Merge `n_lists` partial top-k lists per query (lists[l][query][k], global row ids) into one. */
+/* Merge `n_lists` partial top-k lists per query (lists[l][query][k], global row ids) into one.
+ * lists_sorted != 0: every list is sorted best first (the output order of the top-k entry points), which lets
+ * the kernel drop everything below the largest k_out-th entry of any list before merging. */
 int ar_topk_merge(const int32_t* idx, const float* score, int32_t n_lists, int64_t n_queries,
-                  int32_t k_in, int32_t k_out, int32_t* out_idx, float* out_score, void* stream);
+                  int32_t k_in, int32_t k_out, int32_t lists_sorted, int32_t* out_idx, float* out_score,
+                  void* stream);
 
 /* Exact fp32 re-rank.  Candidates: n_lists lists of up to list_cap row ids per query, layout
  * [list][query][list_cap] (the output layout of ar_cosine_topk_allpairs / the input layout of ar_topk_merge);

@@ -105,13 +105,17 @@ def test_merge_and_rerank():
     score = rng.standard_normal((nl, nq, kin)).astype(np.float32)
     idx = rng.permutation(nl * nq * kin).reshape(nl, nq, kin).astype(np.int32)
     idx[0, :, -1] = -1                                        # empty slots are skipped
-    oi, os_ = sim.topk_merge(dev(idx), dev(score), k)
-    oi, os_ = oi.cpu().numpy(), os_.cpu().numpy()
-    for qy in range(nq):
-        s = np.where(idx[:, qy].ravel() >= 0, score[:, qy].ravel(), -np.inf)
-        ri, rs = osim.rank_desc(s, k)
-        np.testing.assert_array_equal(oi[qy], idx[:, qy].ravel()[ri])
-        np.testing.assert_array_equal(os_[qy], rs)
+    for sorted_lists in (False, True):
+        if sorted_lists:                                      # best-first lists: the bound-pruned merge
+            score = -np.sort(-score, axis=2)
+            idx[0, :, -1], score[0, :, -1] = -1, -np.inf
+        oi, os_ = sim.topk_merge(dev(idx), dev(score), k, lists_sorted=sorted_lists)
+        oi, os_ = oi.cpu().numpy(), os_.cpu().numpy()
+        for qy in range(nq):
+            s = np.where(idx[:, qy].ravel() >= 0, score[:, qy].ravel(), -np.inf)
+            ri, rs = osim.rank_desc(s, k)
+            np.testing.assert_array_equal(oi[qy], idx[:, qy].ravel()[ri])
+            np.testing.assert_array_equal(os_[qy], rs)
     # rerank: candidates = a superset of the true top-k -> exact fp32 top-k back
     W = rng.standard_normal((3000, 128)).astype(np.float32)
     Wn = osim.get_weights(W)
