@@ -10,7 +10,7 @@ import os
 
 PKG = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("ANIMEREC_LIB") or os.path.join(PKG, "lib", "libanimerec.so")   # override: A/B builds
-ABI_VERSION = 9
+ABI_VERSION = 10
 
 AR_MAX_BATCH = 16384
 AR_HEAVY_LEN = 64
@@ -30,7 +30,7 @@ class ArTable(C.Structure):
 class ArPlan(C.Structure):
     _fields_ = [("batch_cap", C.c_int32), ("heavy_cap", C.c_int32), ("n_slots", C.c_int32),
                 ("order", C.c_void_p), ("uniq", C.c_void_p), ("off", C.c_void_p), ("meta", C.c_void_p),
-                ("heavy", C.c_void_p)]
+                ("heavy", C.c_void_p), ("in_prev", C.c_void_p)]
 
 
 class ArTrainCtx(C.Structure):
@@ -50,8 +50,7 @@ class ArDistCtx(C.Structure):
     _fields_ = [("comm", C.c_void_p), ("n_ranks", C.c_int32), ("rank", C.c_int32),
                 ("c_all", C.c_void_p), ("label_all", C.c_void_p), ("dy_all", C.c_void_p),
                 ("fwd_part_all", C.c_void_p), ("head_part_all", C.c_void_p),
-                ("send", C.c_void_p), ("recv", C.c_void_p),
-                ("uniq_all", C.c_void_p * 2), ("meta_all", C.c_void_p * 2)]
+                ("send", C.c_void_p), ("recv", C.c_void_p)]
 
 
 class ArShardCtx(C.Structure):
@@ -77,6 +76,7 @@ SIGNATURES = {
     "ar_abi_version": (C.c_int, []),
     "ar_check_device": (C.c_int, []),
     "ar_plan_build": (C.c_int, [_P, _I64, _I32, _I64, _I32, C.POINTER(ArPlan), _P]),
+    "ar_plan_link": (C.c_int, [C.POINTER(ArPlan), _I32, _P, _P, _I32, _P]),
     "ar_train_steps": (C.c_int, [C.POINTER(ArTrainCtx), _I64, _I32, _I64, _I32, _P]),
     "ar_train_steps_profile": (C.c_int, [C.POINTER(ArTrainCtx), _I64, _I32, _I64, _I32, C.POINTER(C.c_float), _P]),
     "ar_nccl_unique_id": (C.c_int, [_P]),

@@ -162,11 +162,7 @@ static int run_steps_dist(const ar_train_ctx& x, const ar_dist_ctx& d, int64_t e
   const size_t tw = pack_table_words(B, dim);
   const float l2x2 = (float)(2.0 * (double)x.l2);
   static const bool no_overlap = getenv("AR_NO_LOOKAHEAD") != nullptr;
-  SkipAll all{};
-  all.uniq[0] = d.uniq_all[0]; all.uniq[1] = d.uniq_all[1];
-  all.meta[0] = d.meta_all[0]; all.meta[1] = d.meta_all[1];
-  all.n_ranks = G;
-  const bool can_ahead = d.uniq_all[0] && d.uniq_all[1] && d.meta_all[0] && d.meta_all[1];
+  const bool can_ahead = x.plan_u.in_prev && x.plan_a.in_prev;  // flags built from ALL ranks' lists (ar_plan_link)
   Lookahead* la = (x.mode == AR_ADAM_REPLAY && can_ahead && !no_overlap) ? lookahead() : nullptr;
   if (la) AR_CUDA(cudaEventRecord(la->ev_upd[1], st));
   for (int s = 0; s < n_steps; ++s) {
@@ -180,7 +176,7 @@ static int run_steps_dist(const ar_train_ctx& x, const ar_dist_ctx& d, int64_t e
     int rc;
     const bool has_next = (s + 1 < n_steps) && ((e + 1) * (int64_t)B < x.n_samples);
     if (x.mode == AR_ADAM_REPLAY && (!la || s == 0)) {
-      if ((rc = launch_catchup(&x.users, &x.plan_u, slot, &x.anime, &x.plan_a, slot, x.alpha, x.l2, t - 1, st, -1, x.sched_ws))) return rc;
+      if ((rc = launch_catchup(&x.users, &x.plan_u, slot, &x.anime, &x.plan_a, slot, x.alpha, x.l2, t - 1, st, false, x.sched_ws))) return rc;
     }
     bool ahead = false;
     if (la && has_next) {
@@ -188,7 +184,7 @@ static int run_steps_dist(const ar_train_ctx& x, const ar_dist_ctx& d, int64_t e
       // the side stream while step s runs; the rest are brought up to date by this step's merge (replay = 1)
       AR_CUDA(cudaStreamWaitEvent(la->st2, la->ev_upd[(s + 1) & 1], 0));
       int32_t* ws2 = x.sched_ws ? x.sched_ws + 3 * ((size_t)x.plan_u.batch_cap + x.plan_a.batch_cap) + 4 : nullptr;
-      if ((rc = launch_catchup(&x.users, &x.plan_u, slot + 1, &x.anime, &x.plan_a, slot + 1, x.alpha, x.l2, t, la->st2, slot, ws2, &all)))
+      if ((rc = launch_catchup(&x.users, &x.plan_u, slot + 1, &x.anime, &x.plan_a, slot + 1, x.alpha, x.l2, t, la->st2, true, ws2)))
         return rc;
       AR_CUDA(cudaEventRecord(la->ev_ahead, la->st2));
       ahead = true;

@@ -135,10 +135,53 @@ plan_build_kernel(const int32_t* __restrict__ idx, int64_t n_total, int batch, i
   }
 }
 
+// in_prev[slot][seg] = 1 iff distinct row `seg` of step `slot` is also a distinct row of step slot-1 in any of
+// the n_lists lists (this rank's own plan, or every rank's all-gathered plans).  One CTA per slot >= 1.
+__global__ void __launch_bounds__(256)
+plan_link_kernel(ar_plan plan, const int32_t* __restrict__ uniq_lists, const int32_t* __restrict__ meta_lists,
+                 int n_lists, int64_t uniq_stride, int64_t meta_stride) {
+  const int slot = blockIdx.x + 1;
+  const int B = plan.batch_cap;
+  const int32_t* uniq = plan.uniq + (int64_t)slot * B;
+  const int n = plan.meta[(int64_t)slot * 4];
+  uint8_t* out = plan.in_prev + (int64_t)slot * B;
+  for (int s = threadIdx.x; s < n; s += blockDim.x) {
+    const int row = uniq[s];
+    bool hit = false;
+    for (int l = 0; l < n_lists && !hit; ++l) {
+      const int32_t* prev = uniq_lists + l * uniq_stride + (int64_t)(slot - 1) * B;
+      const int np = meta_lists[l * meta_stride + (int64_t)(slot - 1) * 4];
+      int lo = 0, hi = np;
+      while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        if (prev[mid] < row) lo = mid + 1; else hi = mid;
+      }
+      hit = lo < np && prev[lo] == row;
+    }
+    out[s] = hit ? 1 : 0;
+  }
+}
+
 }  // namespace ar
 
+extern "C" int ar_plan_link(const ar_plan* plan, int32_t n_steps, const int32_t* uniq_all, const int32_t* meta_all,
+                            int32_t n_ranks, void* stream) {
+  AR_REQUIRE(plan && plan->in_prev, "ar_plan_link: plan without in_prev");
+  AR_REQUIRE(n_steps >= 0 && n_steps <= plan->n_slots, "ar_plan_link: n_steps %d > plan.n_slots %d", n_steps, plan->n_slots);
+  AR_REQUIRE((uniq_all == nullptr) == (meta_all == nullptr) && n_ranks >= 1, "ar_plan_link: bad list arguments");
+  AR_CUDA(cudaMemsetAsync(plan->in_prev, 0, (size_t)plan->batch_cap, (cudaStream_t)stream));  // slot 0: nothing known
+  if (n_steps <= 1) return AR_OK;
+  const int32_t* ul = uniq_all ? uniq_all : plan->uniq;
+  const int32_t* ml = meta_all ? meta_all : plan->meta;
+  const int nl = uniq_all ? n_ranks : 1;
+  ar::plan_link_kernel<<<n_steps - 1, 256, 0, (cudaStream_t)stream>>>(*plan, ul, ml, nl, (int64_t)plan->n_slots * plan->batch_cap,
+                                                                       (int64_t)plan->n_slots * 4);
+  AR_LAUNCH_CHECK();
+  return AR_OK;
+}
+
 extern "C" const char* ar_last_error(void) { return ar::g_err; }
-extern "C" int ar_abi_version(void) { return 9; }
+extern "C" int ar_abi_version(void) { return 10; }
 
 extern "C" int ar_check_device(void) {
   int dev = 0;

@@ -15,6 +15,8 @@ namespace ar {
 constexpr int kTopkThreads = 256;
 constexpr int kTopkWarps = kTopkThreads / 32;
 constexpr int kMaxK = 32;
+constexpr int kMergeThreads = 1024;
+constexpr int kMergeWarps = kMergeThreads / 32;
 
 __device__ __forceinline__ bool better(float as, int ai, float bs, int bi) {
   return (as > bs) || (as == bs && ai < bi);
@@ -211,18 +213,18 @@ query_topk_kernel(const float* __restrict__ W, int64_t n, int dim, int64_t q,
 // One CTA per query.  The k_out-th best of the union is at least the largest k_out-th entry of any single
 // list, so everything below that bound T is dropped before the (serial, shuffle-heavy) list insertion:
 // merging the 592 per-CTA lists of a single-query scan inserts ~k candidates instead of thousands.
-__global__ void __launch_bounds__(kTopkThreads)
+__global__ void __launch_bounds__(kMergeThreads)
 topk_merge_kernel(const int* __restrict__ idx, const float* __restrict__ score, int n_lists,
                   int64_t n_queries, int k_in, int k_out, int lists_sorted, int* __restrict__ out_idx,
                   float* __restrict__ out_score) {
-  __shared__ float sm_s[kTopkWarps * 32];
-  __shared__ int sm_i[kTopkWarps * 32];
+  __shared__ float sm_s[kMergeWarps * 32];
+  __shared__ int sm_i[kMergeWarps * 32];
   __shared__ float bound_s;
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   const int64_t qy = blockIdx.x;
   float tmax = -CUDART_INF_F;
   if (lists_sorted && k_in >= k_out) {
-    for (int l = threadIdx.x; l < n_lists; l += kTopkThreads) {
+    for (int l = threadIdx.x; l < n_lists; l += kMergeThreads) {
       const int64_t o = ((int64_t)l * n_queries + qy) * k_in + (k_out - 1);
       const float sc = score[o];
       if (idx[o] >= 0 && sc == sc) tmax = fmaxf(tmax, sc);
@@ -234,7 +236,7 @@ topk_merge_kernel(const int* __restrict__ idx, const float* __restrict__ score, 
   __syncthreads();
   if (threadIdx.x == 0) {
     float t = sm_s[0];
-    for (int w = 1; w < kTopkWarps; ++w) t = fmaxf(t, sm_s[w]);
+    for (int w = 1; w < kMergeWarps; ++w) t = fmaxf(t, sm_s[w]);
     bound_s = t;
   }
   __syncthreads();
@@ -243,20 +245,31 @@ topk_merge_kernel(const int* __restrict__ idx, const float* __restrict__ score, 
   WarpList wl;
   wl.init();
   const int total = n_lists * k_in;
-  for (int e0 = wid * 32; e0 < total; e0 += kTopkWarps * 32) {
-    const int e = e0 + lane;
-    float cs = -CUDART_INF_F;
-    int ci = -1;
-    if (e < total) {
-      const int l = e / k_in, j = e - l * k_in;
-      const int64_t o = ((int64_t)l * n_queries + qy) * k_in + j;
-      ci = idx[o];
-      cs = score[o];
+  // every thread fetches its (up to 8) entries of a pass BEFORE any is ranked: one exposed load latency per
+  // pass instead of one per entry (the 592 x 11 lists of a single-query scan are one pass of 1024 threads)
+  constexpr int kPer = 8;
+  for (int p0 = 0; p0 < total; p0 += kMergeThreads * kPer) {
+    float cs[kPer];
+    int ci[kPer];
+#pragma unroll
+    for (int u = 0; u < kPer; ++u) {
+      const int e = p0 + (u * kMergeWarps + wid) * 32 + lane;
+      cs[u] = -CUDART_INF_F;
+      ci[u] = -1;
+      if (e < total) {
+        const int l = e / k_in, j = e - l * k_in;
+        const int64_t o = ((int64_t)l * n_queries + qy) * k_in + j;
+        ci[u] = idx[o];
+        cs[u] = score[o];
+      }
     }
-    const bool valid = ci >= 0 && cs == cs && cs >= bound;
-    if (__any_sync(0xffffffffu, valid)) wl.insert_lanes(cs, ci, valid, k_out, lane);
+#pragma unroll
+    for (int u = 0; u < kPer; ++u) {
+      const bool valid = ci[u] >= 0 && cs[u] == cs[u] && cs[u] >= bound;
+      if (__any_sync(0xffffffffu, valid)) wl.insert_lanes(cs[u], ci[u], valid, k_out, lane);
+    }
   }
-  cta_merge(wl, sm_s, sm_i, k_out, kTopkWarps);
+  cta_merge(wl, sm_s, sm_i, k_out, kMergeWarps);
   if (wid == 0 && lane < k_out) {
     out_idx[qy * k_out + lane] = (wl.i == 0x7fffffff) ? -1 : wl.i;
     out_score[qy * k_out + lane] = wl.s;
@@ -369,9 +382,21 @@ static int sm_count() {
   return n;
 }
 static bool dim_ok(int dim) { return dim > 0 && dim <= 512 && (dim % 4) == 0; }
-static int query_blocks(int64_t n_rows) {
+// Grid of the single-query scan: exactly one wave (SMs x resident CTAs of the instantiation) -- with 80
+// registers per thread only 3 CTAs fit an SM, and a 4-per-SM grid ran as 1.33 waves (ncu: warps active 30 %).
+constexpr int kMaxQueryCtasPerSm = 8;
+template <int NQ>
+static int query_occupancy() {
+  static int occ = 0;
+  if (!occ) {
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, query_topk_kernel<NQ>, kTopkThreads, 0) != cudaSuccess || occ <= 0) occ = 2;
+    occ = std::min(occ, kMaxQueryCtasPerSm);
+  }
+  return occ;
+}
+static int query_blocks(int64_t n_rows, int occ) {
   int64_t need = (n_rows + kTopkWarps * 4 - 1) / (kTopkWarps * 4);
-  return (int)std::max<int64_t>(1, std::min<int64_t>(need, (int64_t)sm_count() * 4));
+  return (int)std::max<int64_t>(1, std::min<int64_t>(need, (int64_t)sm_count() * occ));
 }
 
 }  // namespace ar
@@ -401,7 +426,7 @@ extern "C" int ar_rownorm_bf16(const float* W, int64_t n_rows, int32_t dim, void
 
 extern "C" int64_t ar_topk_query_workspace(int64_t n_rows, int32_t k) {
   if (k <= 0 || k > kMaxK || n_rows <= 0) return 0;
-  return (int64_t)query_blocks(n_rows) * k * 8;
+  return (int64_t)query_blocks(n_rows, kMaxQueryCtasPerSm) * k * 8;
 }
 
 extern "C" int ar_cosine_topk_query(const float* W, int64_t n_rows, int32_t dim, int64_t q,
@@ -411,16 +436,17 @@ extern "C" int ar_cosine_topk_query(const float* W, int64_t n_rows, int32_t dim,
   AR_REQUIRE(dim_ok(dim), "ar_cosine_topk_query: dim %d unsupported", dim);
   AR_REQUIRE(k > 0 && k <= kMaxK, "ar_cosine_topk_query: k %d outside [1,%d]", k, kMaxK);
   AR_REQUIRE(n_rows > 0 && q >= 0 && q < n_rows, "ar_cosine_topk_query: query row %lld outside [0,%lld)", (long long)q, (long long)n_rows);
-  const int blocks = query_blocks(n_rows);
-  int* pidx = (int*)workspace;
-  float* pscore = (float*)workspace + (int64_t)blocks * k;
   cudaStream_t st = (cudaStream_t)stream;
   const int nq = ((dim >> 2) + 7) / 8;
+  const int occ = nq <= 4 ? query_occupancy<4>() : (nq <= 8 ? query_occupancy<8>() : query_occupancy<16>());
+  const int blocks = query_blocks(n_rows, occ);
+  int* pidx = (int*)workspace;
+  float* pscore = (float*)workspace + (int64_t)blocks * k;
   if (nq <= 4) query_topk_kernel<4><<<blocks, kTopkThreads, 0, st>>>(W, n_rows, dim, q, cand_mask, exclude, k, pidx, pscore);
   else if (nq <= 8) query_topk_kernel<8><<<blocks, kTopkThreads, 0, st>>>(W, n_rows, dim, q, cand_mask, exclude, k, pidx, pscore);
   else query_topk_kernel<16><<<blocks, kTopkThreads, 0, st>>>(W, n_rows, dim, q, cand_mask, exclude, k, pidx, pscore);
   AR_LAUNCH_CHECK();
-  topk_merge_kernel<<<1, kTopkThreads, 0, st>>>(pidx, pscore, blocks, 1, k, k, 1, out_idx, out_score);
+  topk_merge_kernel<<<1, kMergeThreads, 0, st>>>(pidx, pscore, blocks, 1, k, k, 1, out_idx, out_score);
   AR_LAUNCH_CHECK();
   return AR_OK;
 }
@@ -431,7 +457,7 @@ extern "C" int ar_topk_merge(const int32_t* idx, const float* score, int32_t n_l
   AR_REQUIRE(idx && score && out_idx && out_score, "ar_topk_merge: null pointer");
   AR_REQUIRE(k_out > 0 && k_out <= kMaxK && k_in > 0 && n_lists > 0, "ar_topk_merge: bad k/n_lists");
   if (n_queries <= 0) return AR_OK;
-  topk_merge_kernel<<<(unsigned)n_queries, kTopkThreads, 0, (cudaStream_t)stream>>>(idx, score, n_lists, n_queries, k_in, k_out, lists_sorted, out_idx, out_score);
+  topk_merge_kernel<<<(unsigned)n_queries, kMergeThreads, 0, (cudaStream_t)stream>>>(idx, score, n_lists, n_queries, k_in, k_out, lists_sorted, out_idx, out_score);
   AR_LAUNCH_CHECK();
   return AR_OK;
 }

@@ -94,36 +94,16 @@ struct CatchupArgs {
   const int32_t* uniq[2];
   const int32_t* meta[2];
   int blocks0;  // CTAs assigned to table 0
-  // look-ahead catch-up: rows that are ALSO in this (earlier) step's sorted distinct-row list are skipped --
-  // that step's own update brings them up to date, and may be running concurrently
-  const int32_t* skip_uniq[2];   // per table: skip_lists ascending lists, skip_uniq_stride apart
-  const int32_t* skip_meta[2];   // their lengths at [0] of 4-int records, skip_meta_stride apart
-  int skip_lists;                // 1 on a single GPU; n_ranks for replicated multi-GPU training (all ranks' rows)
-  int64_t skip_uniq_stride, skip_meta_stride;
+  // look-ahead catch-up: distinct rows flagged here are ALSO touched by the previous step (of any rank) and
+  // are skipped -- that step's own update brings them up to date, and may be running concurrently.  The
+  // flags come from ar_plan_link (per chunk, off the critical path), so the check is one byte load
+  const uint8_t* skip_flag[2];
   // longest-first schedule (ar_train_ctx.sched_ws): three buckets of (table << 31 | row) by replay length,
   // bucket b at sched + b*cap, their fill counts at sched + 3*cap
   int32_t* sched;
   int cap;
 };
 constexpr int kLongReplay = 128, kMidReplay = 32;
-
-// is `row` in any of the table's skip lists?  (warp-uniform when `row` is)
-__device__ __forceinline__ bool in_skip_lists(const CatchupArgs& a, bool second, int row) {
-  const int32_t* __restrict__ base = second ? a.skip_uniq[1] : a.skip_uniq[0];
-  if (!base) return false;
-  const int32_t* __restrict__ mbase = second ? a.skip_meta[1] : a.skip_meta[0];
-  for (int l = 0; l < a.skip_lists; ++l) {
-    const int32_t* __restrict__ skip = base + l * a.skip_uniq_stride;
-    const int n_skip = mbase[l * a.skip_meta_stride];
-    int lo = 0, hi = n_skip;
-    while (lo < hi) {
-      const int mid = (lo + hi) >> 1;
-      if (__ldg(skip + mid) < row) lo = mid + 1; else hi = mid;
-    }
-    if (lo < n_skip && __ldg(skip + lo) == row) return true;
-  }
-  return false;
-}
 
 // Replay lengths are geometric (mean n_rows/unique-per-step, max ~10x that), and a CTA only frees its SM slot
 // when its slowest warp ends -- with 8 rows of unrelated length per CTA the SFU sat idle ~60% of the time
@@ -133,6 +113,7 @@ __device__ __forceinline__ bool in_skip_lists(const CatchupArgs& a, bool second,
 #define AR_CATCH_THREADS 64
 #endif
 constexpr int kCatchThreads = AR_CATCH_THREADS;
+
 // Which rows need how much replay?  Thread per distinct row of the step: rows the skip list covers or that
 // are already current drop out, the rest go to the long / mid / short bucket (warp-aggregated append).
 // Replay lengths are geometric (mean n_rows / distinct-per-step, tail ~10x that); launching the catch-up in
@@ -145,7 +126,8 @@ rows_classify_kernel(CatchupArgs a, int64_t t_target, int n0_cap, int n1_cap) {
   int bucket = -1, row = 0;
   if (seg < (second ? n1_cap : n0_cap) && seg < (second ? a.meta[1] : a.meta[0])[0]) {
     row = (second ? a.uniq[1] : a.uniq[0])[seg];
-    if (!in_skip_lists(a, second, row)) {
+    const uint8_t* __restrict__ flag = second ? a.skip_flag[1] : a.skip_flag[0];
+    if (!(flag && flag[seg])) {
       const int64_t len = t_target - (int64_t)(second ? a.tab[1].last_step : a.tab[0].last_step)[row];
       if (len > 0) bucket = len > kLongReplay ? 0 : (len > kMidReplay ? 1 : 2);
     }
@@ -189,7 +171,8 @@ rows_catchup_kernel(CatchupArgs a, const float* __restrict__ alpha, float l2x2, 
     const int32_t* meta = second ? a.meta[1] : a.meta[0];
     if (seg >= (second ? a.cap - a.blocks0 : a.blocks0) || seg >= meta[0]) return;
     row = (second ? a.uniq[1] : a.uniq[0])[seg];
-    if (in_skip_lists(a, second, row)) return;
+    const uint8_t* __restrict__ flag = second ? a.skip_flag[1] : a.skip_flag[0];
+    if (flag && flag[seg]) return;
   }
   ar_table tb;
   tb.dim = a.tab[0].dim;
@@ -766,35 +749,13 @@ static int num_sms() {
     default: { constexpr int NV = 4; __VA_ARGS__; } break; \
   }
 
-// all ranks' distinct-row lists of the planned chunk (replicated multi-GPU training): [rank][slot][batch_cap]
-struct SkipAll {
-  const int32_t* uniq[2];
-  const int32_t* meta[2];
-  int n_ranks;
-};
-
 static int launch_catchup(const ar_table* t0, const ar_plan* p0, int slot0, const ar_table* t1,
                           const ar_plan* p1, int slot1, const float* alpha, float l2, int64_t t_target,
-                          cudaStream_t st, int skip_slot = -1, int32_t* sched_ws = nullptr, const SkipAll* all = nullptr) {
+                          cudaStream_t st, bool skip_prev = false, int32_t* sched_ws = nullptr) {
   CatchupArgs a{};
-  if (skip_slot >= 0 && all) {
-    a.skip_lists = all->n_ranks;
-    a.skip_uniq_stride = (int64_t)p0->n_slots * p0->batch_cap;
-    a.skip_meta_stride = (int64_t)p0->n_slots * 4;
-    a.skip_uniq[0] = all->uniq[0] + (int64_t)skip_slot * p0->batch_cap;
-    a.skip_meta[0] = all->meta[0] + (int64_t)skip_slot * 4;
-    if (t1) {
-      a.skip_uniq[1] = all->uniq[1] + (int64_t)skip_slot * p1->batch_cap;
-      a.skip_meta[1] = all->meta[1] + (int64_t)skip_slot * 4;
-    }
-  } else if (skip_slot >= 0) {
-    a.skip_lists = 1;
-    a.skip_uniq[0] = p0->uniq + (int64_t)skip_slot * p0->batch_cap;
-    a.skip_meta[0] = p0->meta + (int64_t)skip_slot * 4;
-    if (t1) {
-      a.skip_uniq[1] = p1->uniq + (int64_t)skip_slot * p1->batch_cap;
-      a.skip_meta[1] = p1->meta + (int64_t)skip_slot * 4;
-    }
+  if (skip_prev) {  // look-ahead: leave the rows the previous step also touches to that step's update
+    a.skip_flag[0] = p0->in_prev + (int64_t)slot0 * p0->batch_cap;
+    if (t1) a.skip_flag[1] = p1->in_prev + (int64_t)slot1 * p1->batch_cap;
   }
   a.tab[0] = *t0;
   a.uniq[0] = p0->uniq + (int64_t)slot0 * p0->batch_cap;
@@ -958,7 +919,11 @@ static Lookahead* lookahead() {
   if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
   Lookahead& l = la[dev];
   if (!l.ok) {
-    if (cudaStreamCreateWithFlags(&l.st2, cudaStreamNonBlocking) != cudaSuccess) return nullptr;
+    // lowest priority: when SM slots free up, the step's own (latency-bound) kernels get them first and the
+    // SFU-bound replay of the NEXT step fills the gaps
+    int least = 0, greatest = 0;
+    cudaDeviceGetStreamPriorityRange(&least, &greatest);
+    if (cudaStreamCreateWithPriority(&l.st2, cudaStreamNonBlocking, least) != cudaSuccess) return nullptr;
     for (int i = 0; i < 2; ++i)
       if (cudaEventCreateWithFlags(&l.ev_upd[i], cudaEventDisableTiming) != cudaSuccess) return nullptr;
     if (cudaEventCreateWithFlags(&l.ev_ahead, cudaEventDisableTiming) != cudaSuccess) return nullptr;
@@ -976,7 +941,7 @@ static int run_steps(const ar_train_ctx& x, int64_t epoch_step0, int32_t slot0, 
                      cudaStream_t st, StageTimer* timer) {
   const int dim = x.users.dim;
   static const bool no_overlap = getenv("AR_NO_LOOKAHEAD") != nullptr;
-  Lookahead* la = (x.mode == AR_ADAM_REPLAY && !timer && !no_overlap) ? lookahead() : nullptr;
+  Lookahead* la = (x.mode == AR_ADAM_REPLAY && !timer && !no_overlap && x.plan_u.in_prev && x.plan_a.in_prev) ? lookahead() : nullptr;
   if (la) {
     AR_CUDA(cudaEventRecord(la->ev_upd[1], st));  // everything queued before this call (stands in for "update(-1)")
   }
@@ -991,7 +956,7 @@ static int run_steps(const ar_train_ctx& x, int64_t epoch_step0, int32_t slot0, 
     const bool has_next = (s + 1 < n_steps) && ((e + 1) * (int64_t)x.batch < x.n_samples);
     AR_TICK(0);
     if (x.mode == AR_ADAM_REPLAY && (!la || s == 0)) {
-      int rc = launch_catchup(&x.users, &x.plan_u, slot, &x.anime, &x.plan_a, slot, x.alpha, x.l2, t - 1, st, -1, x.sched_ws);
+      int rc = launch_catchup(&x.users, &x.plan_u, slot, &x.anime, &x.plan_a, slot, x.alpha, x.l2, t - 1, st, false, x.sched_ws);
       if (rc) return rc;
     }
     bool ahead = false;
@@ -999,7 +964,7 @@ static int run_steps(const ar_train_ctx& x, int64_t epoch_step0, int32_t slot0, 
       AR_CUDA(cudaStreamWaitEvent(la->st2, la->ev_upd[(s + 1) & 1], 0));  // update(s-1) done
       // the look-ahead owns the SECOND half of sched_ws: at s == 0 it runs concurrently with the main-stream catch-up
       int32_t* ws2 = x.sched_ws ? x.sched_ws + 3 * ((size_t)x.plan_u.batch_cap + x.plan_a.batch_cap) + 4 : nullptr;
-      int rc = launch_catchup(&x.users, &x.plan_u, slot + 1, &x.anime, &x.plan_a, slot + 1, x.alpha, x.l2, t, la->st2, slot, ws2);
+      int rc = launch_catchup(&x.users, &x.plan_u, slot + 1, &x.anime, &x.plan_a, slot + 1, x.alpha, x.l2, t, la->st2, true, ws2);
       if (rc) return rc;
       AR_CUDA(cudaEventRecord(la->ev_ahead, la->st2));
       ahead = true;

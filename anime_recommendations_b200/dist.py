@@ -75,9 +75,6 @@ class DistTrainSession(TrainSession):
         S = self.n_slots
         self.uniq_all = [torch.zeros((G, S, B), dtype=torch.int32, device=dev) for _ in range(2)]
         self.meta_all = [torch.zeros((G, S, 4), dtype=torch.int32, device=dev) for _ in range(2)]
-        for k in range(2):
-            d.uniq_all[k] = self.uniq_all[k].data_ptr()
-            d.meta_all[k] = self.meta_all[k].data_ptr()
         self.dctx = d
 
     def run(self, iu, ia, y, lr, profile=None):
@@ -98,6 +95,10 @@ class DistTrainSession(TrainSession):
             for k, keep in enumerate((self._keep_u, self._keep_a)):
                 for src, dst in ((keep["uniq"], self.uniq_all[k]), (keep["meta"], self.meta_all[k])):
                     check(L.ar_allgather_bytes(self.comm.handle, ptr(src), ptr(dst), src.numel() * 4, st), "ar_allgather_bytes")
+            if m.adam_mode == "replay":
+                for k, pl in enumerate((self.plan_u, self.plan_a)):
+                    check(L.ar_plan_link(C.byref(pl), ns, ptr(self.uniq_all[k]), ptr(self.meta_all[k]), self.comm.world, st),
+                          "ar_plan_link")
             check(L.ar_train_steps_dist(C.byref(ctx), C.byref(self.dctx), s0, 0, t0 + s0, ns, st), "ar_train_steps_dist")
             self.launches += 2 + ns * per_step
         m.iterations = t0 + steps

@@ -74,7 +74,7 @@ class EmbeddingDotModel:
     def __init__(self, n_users, n_anime, embedding_size=128, l2_reg_factor=1e-4,
                  kernel_initializer="he_normal", ID_emb_name="user_embedding",
                  anime_emb_name="anime_embedding", merged_name="dot_product", seed=None,
-                 device=None, adam_mode="replay", dense_kernel=None):
+                 device=None, adam_mode="replay", dense_kernel=None, device_init=False):
         if not torch.cuda.is_available():
             raise _capi.AnimerecError("EmbeddingDotModel needs a CUDA device (sm_100a); there is no CPU fallback")
         lib()
@@ -92,9 +92,15 @@ class EmbeddingDotModel:
         rng = np.random.RandomState(seed)
         if kernel_initializer != "he_normal" and dense_kernel is None:
             raise ValueError("only kernel_initializer='he_normal' (config.yaml:56) or an explicit dense_kernel")
-        U = rng.uniform(-0.05, 0.05, size=(self.n_users, D)).astype(np.float32)
-        A = rng.uniform(-0.05, 0.05, size=(self.n_anime, D)).astype(np.float32)
         w = he_normal_scalar(rng) if dense_kernel is None else np.float32(dense_kernel)
+        if device_init:    # very large tables (cfg5: 10 M x 256): draw U(-0.05, 0.05) on the device
+            g = torch.Generator(device=self.device)
+            g.manual_seed(0 if seed is None else int(seed))
+            U = torch.rand((self.n_users, D), generator=g, device=self.device) * 0.1 - 0.05
+            A = torch.rand((self.n_anime, D), generator=g, device=self.device) * 0.1 - 0.05
+        else:
+            U = rng.uniform(-0.05, 0.05, size=(self.n_users, D)).astype(np.float32)
+            A = rng.uniform(-0.05, 0.05, size=(self.n_anime, D)).astype(np.float32)
         self._alloc(U, A, np.array([w, 0.0, 1.0, 0.0], np.float32), np.array([0.0, 1.0], np.float32))
         self.iterations = 0
         self.lr = 1e-3                      # Keras Adam default until a LearningRateScheduler sets it
@@ -108,8 +114,9 @@ class EmbeddingDotModel:
     def _alloc(self, U, A, head, bn):
         dev = self.device
         f = dict(dtype=torch.float32, device=dev)
-        self.U = torch.from_numpy(np.ascontiguousarray(U, np.float32)).to(dev)
-        self.A = torch.from_numpy(np.ascontiguousarray(A, np.float32)).to(dev)
+        as_dev = lambda t: t.to(dev).contiguous() if isinstance(t, torch.Tensor) else \
+            torch.from_numpy(np.ascontiguousarray(t, np.float32)).to(dev)  # noqa: E731
+        self.U, self.A = as_dev(U), as_dev(A)
         self.mU, self.vU = torch.zeros_like(self.U), torch.zeros_like(self.U)
         self.mA, self.vA = torch.zeros_like(self.A), torch.zeros_like(self.A)
         self.lastU = torch.zeros(self.n_users, dtype=torch.int32, device=dev)
@@ -405,7 +412,8 @@ class TrainSession:
                     uniq=torch.empty((n_slots, batch), dtype=torch.int32, device=dev),
                     off=torch.empty((n_slots, batch + 1), dtype=torch.int32, device=dev),
                     meta=torch.zeros((n_slots, 4), dtype=torch.int32, device=dev),
-                    heavy=torch.empty((n_slots, hc), dtype=torch.int32, device=dev))
+                    heavy=torch.empty((n_slots, hc), dtype=torch.int32, device=dev),
+                    in_prev=torch.zeros((n_slots, batch), dtype=torch.uint8, device=dev))
         p = ArPlan()
         p.batch_cap, p.heavy_cap, p.n_slots = batch, hc, n_slots
         for k, v in bufs.items():
@@ -450,6 +458,9 @@ class TrainSession:
             ns = min(self.n_slots, steps - s0)
             check(L.ar_plan_build(ptr(iu), N, B, s0, ns, C.byref(self.plan_u), st), "ar_plan_build(users)")
             check(L.ar_plan_build(ptr(ia), N, B, s0, ns, C.byref(self.plan_a), st), "ar_plan_build(anime)")
+            if m.adam_mode == "replay":
+                for pl in (self.plan_u, self.plan_a):
+                    check(L.ar_plan_link(C.byref(pl), ns, None, None, 1, st), "ar_plan_link")
             if profile is None:
                 check(L.ar_train_steps(C.byref(ctx), s0, 0, t0 + s0, ns, st), "ar_train_steps")
             else:
@@ -457,7 +468,7 @@ class TrainSession:
                 check(L.ar_train_steps_profile(C.byref(ctx), s0, 0, t0 + s0, ns, ms, st), "ar_train_steps_profile")
                 for i in range(5):
                     profile[i] += ms[i]
-            self.launches += 2 + ns * per_step
+            self.launches += (4 if m.adam_mode == "replay" else 2) + ns * per_step
         m.iterations = t0 + steps
         return steps
 

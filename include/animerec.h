@@ -66,6 +66,8 @@ typedef struct {
   int32_t* off;       /* [slot][batch_cap+1] segment starts into order; off[n_uniq] = n */
   int32_t* meta;      /* [slot][4]  n_uniq, n_heavy, n (samples in the step), 0 */
   int32_t* heavy;     /* [slot][heavy_cap] segment ids longer than AR_HEAVY_LEN */
+  uint8_t* in_prev;   /* optional [slot][batch_cap]: 1 = the distinct row is also touched by step slot-1 (of any
+                         rank); written by ar_plan_link, enables the look-ahead catch-up of AR_ADAM_REPLAY */
 } ar_plan;
 
 /* Build the plan of `n_steps` consecutive steps of one table.  Step s (0-based within the
@@ -74,6 +76,12 @@ typedef struct {
  * Replaces TF's IndexedSlices -> UnsortedSegmentSum aggregation. */
 int ar_plan_build(const int32_t* idx, int64_t n_total, int32_t batch, int64_t step0,
                   int32_t n_steps, const ar_plan* plan, void* stream);
+
+/* After ar_plan_build of `n_steps` slots: fill plan->in_prev.  uniq_all / meta_all: every rank's plan.uniq
+ * ([n_ranks][n_slots][batch_cap]) and plan.meta ([n_ranks][n_slots][4]) of the same chunk, all-gathered, for
+ * replicated multi-GPU training; null = this plan's own lists (single GPU). */
+int ar_plan_link(const ar_plan* plan, int32_t n_steps, const int32_t* uniq_all, const int32_t* meta_all,
+                 int32_t n_ranks, void* stream);
 
 typedef enum {
   AR_ADAM_REPLAY = 0,  /* reference-equivalent: missed dense steps of a row are replayed when it is next touched */
@@ -153,10 +161,6 @@ typedef struct {
   float* send;           /* (2*batch*(dim+2)) packed partial row gradients of this rank:
                             [ids_u | q_u | P_u(batch,dim) | ids_a | q_a | P_a(batch,dim)], ids int32 */
   float* recv;           /* n_ranks such blocks */
-  /* optional (AR_ADAM_REPLAY look-ahead catch-up): every rank's plan.uniq / plan.meta of the planned chunk,
-   * all-gathered: uniq_all[table] is [n_ranks][n_slots][batch_cap], meta_all[table] is [n_ranks][n_slots][4] */
-  const int32_t* uniq_all[2];
-  const int32_t* meta_all[2];
 } ar_dist_ctx;
 
 /* ar_train_steps for rank `d->rank` of `d->n_ranks`: ctx holds this rank's samples (every rank must
