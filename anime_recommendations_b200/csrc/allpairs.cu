@@ -353,7 +353,9 @@ allpairs_topk_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
         const float m = fmaxf(fmax3(g[0], g[1], g[2]), g[3]);
         if (!__any_sync(0xffffffffu, m > thr)) return;
         // (measured alternatives, 350k x 350k: four static-index copies of the scan instead of the select chain
-        // -- 70 KB of code, 91 ms; fully predicated appends -- 44 ms; this version -- 35.8 ms)
+        // -- 70 KB of code, 91 ms; static copies with compaction hoisted to one site per chunk pair and a
+        // drop-and-remember overflow rule -- 56 KB, 46.6 ms; fully predicated appends -- 44 ms; this version
+        // -- 35.8 ms.  Every variant that grew the code lost more to instruction fetch than it saved.)
         uint32_t gmask = 0;
 #pragma unroll
         for (int j = 0; j < 4; ++j) gmask |= __any_sync(0xffffffffu, g[j] > thr) ? (1u << j) : 0u;

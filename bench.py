@@ -38,6 +38,19 @@ def peaks():
     return dict(hbm_gbs=6650.0, bf16_tflops=1590.0, bf16_tflops_sustained=1400.0, source="fallback")
 
 
+def sfu_roofline(stage, mode):
+    """rows_catchup against the SFU peak: in steady state the rows touched per step pay off exactly the replay
+    debt all rows accrue per step, i.e. (n_users + n_anime) * dim element-steps of 2 MUFU ops (sqrt, reciprocal)
+    each; the SFU retires 16 lanes/clk/SM.  The stage time includes the classify launch and the launch gaps."""
+    if mode != "replay" or stage["rows_catchup"]["ms_per_step"] <= 0:
+        return None
+    mufu = 2.0 * (N_USERS + N_ANIME) * DIM
+    peak = 16 * 148 * 1.965e9
+    ach = mufu / (stage["rows_catchup"]["ms_per_step"] * 1e-3)
+    return dict(bound="sfu", mufu_per_launch=mufu, achieved_mufu_per_s=ach, peak_mufu_per_s=peak, frac=ach / peak,
+                peak_source="16 MUFU lanes/clk/SM x 148 SMs x 1.965 GHz (nominal)")
+
+
 def ncu_traffic(kernel, mode):
     """dram__bytes_read.sum + dram__bytes_write.sum per launch of `kernel` from the committed `ncu --set full`
     capture (profiles/ncu_traffic.json, written by tools/ncu_summary.py); None if that kernel was not captured."""
@@ -279,6 +292,10 @@ def gpu_main(args):
                                 frac=stage[dom]["gbs"] / pk["hbm_gbs"], traffic=ncu_traffic(dom, mode),
                                 peak_source=pk["source"],
                                 accounting="dense" if mode == "dense" else "touched-rows",
+                                note=("replay mode: the dominant kernel replays every row's missed dense-L2 Adam steps in "
+                                      "registers and is SFU-bound, not HBM-bound (see `sfu`); extras.train_modes.dense "
+                                      "runs the same arithmetic HBM-bound") if mode == "replay" else None,
+                                sfu=sfu_roofline(stage, mode),
                                 step=dict(alg_bytes=step_bytes, gbs=step_bytes / (ms / K * 1e-3) / 1e9,
                                           frac=step_bytes / (ms / K * 1e-3) / 1e9 / pk["hbm_gbs"],
                                           unique_user_rows=uu, unique_anime_rows=ua),
