@@ -355,7 +355,11 @@ allpairs_topk_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
         // (measured alternatives, 350k x 350k: four static-index copies of the scan instead of the select chain
         // -- 70 KB of code, 91 ms; static copies with compaction hoisted to one site per chunk pair and a
         // drop-and-remember overflow rule -- 56 KB, 46.6 ms; fully predicated appends -- 44 ms; this version
-        // -- 35.8 ms.  Every variant that grew the code lost more to instruction fetch than it saved.)
+        // -- 35.8 ms.  Every variant that grew the code lost more to instruction fetch than it saved.  Also tried:
+        // moving ALL of this to dedicated scanner warps fed through shared-memory descriptor rings by
+        // never-diverging filter warps (scanner re-reads the chunk from TMEM): 62 ms with 4 scanners, 40 ms
+        // with 8, 49 ms with descriptors pushed per chunk -- the rescans hold the accumulator buffer longer
+        // than the two-tile slack allows.)
         uint32_t gmask = 0;
 #pragma unroll
         for (int j = 0; j < 4; ++j) gmask |= __any_sync(0xffffffffu, g[j] > thr) ? (1u << j) : 0u;
