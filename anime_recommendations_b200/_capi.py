@@ -10,7 +10,7 @@ import os
 
 PKG = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("ANIMEREC_LIB") or os.path.join(PKG, "lib", "libanimerec.so")   # override: A/B builds
-ABI_VERSION = 10
+ABI_VERSION = 11
 
 AR_MAX_BATCH = 16384
 AR_HEAVY_LEN = 64
@@ -63,6 +63,18 @@ class ArShardCtx(C.Structure):
                 ("fwd_part_all", C.c_void_p), ("head_part_all", C.c_void_p)]
 
 
+PEER_MAX_RANKS, PEER_HANDLE_BYTES, PEER_FLAG_WORDS = 8, 64, 64
+
+
+class ArPeerCtx(C.Structure):
+    _fields_ = [("n_ranks", C.c_int32), ("rank", C.c_int32),
+                ("W_peer", (C.c_void_p * PEER_MAX_RANKS) * 2), ("c_all_peer", C.c_void_p * PEER_MAX_RANKS),
+                ("flags_peer", C.c_void_p * PEER_MAX_RANKS), ("sel_cap", C.c_int32),
+                ("sel_key", C.c_void_p * 2), ("sel_samp", C.c_void_p * 2), ("sel_oth", C.c_void_p * 2),
+                ("sel_cnt", C.c_void_p * 2), ("max_count", C.c_void_p), ("label_step", C.c_void_p),
+                ("dy_all", C.c_void_p), ("fwd_part_all", C.c_void_p), ("head_part_all", C.c_void_p)]
+
+
 class AnimerecError(RuntimeError):
     pass
 
@@ -76,6 +88,7 @@ SIGNATURES = {
     "ar_abi_version": (C.c_int, []),
     "ar_check_device": (C.c_int, []),
     "ar_plan_build": (C.c_int, [_P, _I64, _I32, _I64, _I32, C.POINTER(ArPlan), _P]),
+    "ar_plan_build_lists": (C.c_int, [_P, _I32, _P, _I32, C.POINTER(ArPlan), _P]),
     "ar_plan_link": (C.c_int, [C.POINTER(ArPlan), _I32, _P, _P, _I32, _P]),
     "ar_train_steps": (C.c_int, [C.POINTER(ArTrainCtx), _I64, _I32, _I64, _I32, _P]),
     "ar_train_steps_profile": (C.c_int, [C.POINTER(ArTrainCtx), _I64, _I32, _I64, _I32, C.POINTER(C.c_float), _P]),
@@ -86,6 +99,13 @@ SIGNATURES = {
     "ar_allgather_bytes": (C.c_int, [_P, _P, _P, _I64, _P]),
     "ar_shard_plan": (C.c_int, [C.POINTER(ArPlan), C.POINTER(ArPlan), _I32, C.POINTER(ArShardCtx), _P]),
     "ar_train_steps_sharded": (C.c_int, [C.POINTER(ArTrainCtx), C.POINTER(ArShardCtx), _I64, _I32, _I64, _I32, _I32, _P]),
+    "ar_peer_export": (C.c_int, [_P, _P, C.POINTER(C.c_int64)]),
+    "ar_peer_open": (C.c_int, [_P, _I64, C.POINTER(C.c_void_p)]),
+    "ar_peer_close_all": (C.c_int, []),
+    "ar_peer_plan": (C.c_int, [_P, _P, _P, _I64, _I64, _I32, _I32, C.POINTER(ArPlan), C.POINTER(ArPlan),
+                               C.POINTER(ArPeerCtx), _P]),
+    "ar_train_steps_peer": (C.c_int, [C.POINTER(ArTrainCtx), C.POINTER(ArPeerCtx), _I64, _I32, _I64, _I32, _I32, _P]),
+    "ar_peer_barrier": (C.c_int, [C.POINTER(ArPeerCtx), _I32, _P]),
     "ar_table_flush": (C.c_int, [C.POINTER(ArTable), _P, _F, _I64, _P]),
     "ar_embed_fwd": (C.c_int, [_P, _P, _I32, _P, _P, _I32, _P, _P, _P, _P, _P, _P]),
     "ar_head_step": (C.c_int, [_P, _P, _I32, _P, _P, _P, _P, _P, _I64, _P, _P, _P]),

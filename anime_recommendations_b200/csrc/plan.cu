@@ -23,15 +23,20 @@ constexpr int kPlanThreads = 1024;
 
 __global__ void __launch_bounds__(kPlanThreads, 1)
 plan_build_kernel(const int32_t* __restrict__ idx, int64_t n_total, int batch, int64_t step0,
-                  ar_plan plan, int pow2) {
+                  ar_plan plan, int pow2, const int32_t* __restrict__ counts) {
   extern __shared__ unsigned long long keys[];  // pow2 entries
   __shared__ int warp_tot[kPlanThreads / 32];
   __shared__ int n_heavy_s;
   const int slot = blockIdx.x;
   const int tid = threadIdx.x;
-  const int64_t base = (step0 + slot) * (int64_t)batch;
+  int64_t base = (step0 + slot) * (int64_t)batch;
   int n = 0;
-  if (base < n_total) n = (int)min((int64_t)batch, n_total - base);
+  if (counts) {  // list form (ar_plan_build_lists): slot's keys at idx[slot*batch ...], counts[slot] of them
+    base = (int64_t)slot * batch;
+    n = min(batch, counts[slot]);
+  } else if (base < n_total) {
+    n = (int)min((int64_t)batch, n_total - base);
+  }
 
   for (int i = tid; i < pow2; i += kPlanThreads) {
     unsigned long long k = ~0ull;
@@ -181,7 +186,7 @@ extern "C" int ar_plan_link(const ar_plan* plan, int32_t n_steps, const int32_t*
 }
 
 extern "C" const char* ar_last_error(void) { return ar::g_err; }
-extern "C" int ar_abi_version(void) { return 10; }
+extern "C" int ar_abi_version(void) { return 11; }
 
 extern "C" int ar_check_device(void) {
   int dev = 0;
@@ -195,8 +200,22 @@ extern "C" int ar_check_device(void) {
   return AR_OK;
 }
 
+static int plan_build_impl(const int32_t* idx, int64_t n_total, int32_t batch, int64_t step0, int32_t n_steps,
+                           const ar_plan* plan, const int32_t* counts, void* stream);
+
 extern "C" int ar_plan_build(const int32_t* idx, int64_t n_total, int32_t batch, int64_t step0,
                              int32_t n_steps, const ar_plan* plan, void* stream) {
+  return plan_build_impl(idx, n_total, batch, step0, n_steps, plan, nullptr, stream);
+}
+
+extern "C" int ar_plan_build_lists(const int32_t* keys, int32_t stride, const int32_t* counts, int32_t n_steps,
+                                   const ar_plan* plan, void* stream) {
+  AR_REQUIRE(counts, "ar_plan_build_lists: null counts");
+  return plan_build_impl(keys, 0, stride, 0, n_steps, plan, counts, stream);
+}
+
+static int plan_build_impl(const int32_t* idx, int64_t n_total, int32_t batch, int64_t step0, int32_t n_steps,
+                           const ar_plan* plan, const int32_t* counts, void* stream) {
   AR_REQUIRE(idx && plan, "ar_plan_build: null pointer");
   AR_REQUIRE(batch > 0 && batch <= AR_MAX_BATCH, "ar_plan_build: batch %d outside (0, %d]", batch, AR_MAX_BATCH);
   AR_REQUIRE(plan->batch_cap >= batch, "ar_plan_build: plan.batch_cap %d < batch %d", plan->batch_cap, batch);
@@ -211,7 +230,7 @@ extern "C" int ar_plan_build(const int32_t* idx, int64_t n_total, int32_t batch,
     AR_CUDA(cudaFuncSetAttribute(ar::plan_build_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, AR_MAX_BATCH * 8));
     attr_set = true;
   }
-  ar::plan_build_kernel<<<n_steps, ar::kPlanThreads, smem, (cudaStream_t)stream>>>(idx, n_total, batch, step0, *plan, pow2);
+  ar::plan_build_kernel<<<n_steps, ar::kPlanThreads, smem, (cudaStream_t)stream>>>(idx, n_total, batch, step0, *plan, pow2, counts);
   AR_LAUNCH_CHECK();
   return AR_OK;
 }

@@ -479,6 +479,9 @@ struct UpdateArgs {
   // apart and carry q in column `dim`; ids are not emitted (the owners already hold the request lists)
   const int32_t* emit_map[2];
   int emit_stride;
+  // peer mode: the plan's sample ids index this rank's selection list; samp maps them to the position in the
+  // GLOBAL batch that c / dy are indexed by (`other` and `rinv` stay indexed by the plan's own sample id)
+  const int32_t* samp[2];
 };
 
 template <int NV>
@@ -549,6 +552,7 @@ rows_update_kernel(UpdateArgs a, const float* __restrict__ c, const float* __res
   float* __restrict__ emit_q = which ? a.emit_q[1] : a.emit_q[0];
   float* __restrict__ emit_P = which ? a.emit_P[1] : a.emit_P[0];
   const int32_t* __restrict__ emit_map = which ? a.emit_map[1] : a.emit_map[0];
+  const int32_t* __restrict__ samp = which ? a.samp[1] : a.samp[0];
   float kk[K_STEPC];
 #pragma unroll
   for (int i = 0; i < K_STEPC; ++i) kk[i] = stepc[i];
@@ -570,8 +574,9 @@ rows_update_kernel(UpdateArgs a, const float* __restrict__ c, const float* __res
       RowTile<NV> o0, o1;
       o0.load(other + (size_t)s0 * dim, d4, lane);
       o1.load(other + (size_t)s1 * dim, d4, lane);
-      const float c0 = c[s0], c1 = c[s1];
-      const float d0 = dc_of(dy[s0], c0, kk), d1 = dc_of(dy[s1], c1, kk);
+      const int g0 = samp ? samp[s0] : s0, g1 = samp ? samp[s1] : s1;
+      const float c0 = c[g0], c1 = c[g1];
+      const float d0 = dc_of(dy[g0], c0, kk), d1 = dc_of(dy[g1], c1, kk);
       q = fmaf(d0, c0, q);
       q = fmaf(d1, c1, q);
 #pragma unroll
@@ -584,8 +589,9 @@ rows_update_kernel(UpdateArgs a, const float* __restrict__ c, const float* __res
       const int s0 = order[j];
       RowTile<NV> o0;
       o0.load(other + (size_t)s0 * dim, d4, lane);
-      const float c0 = c[s0];
-      const float d0 = dc_of(dy[s0], c0, kk);
+      const int g0 = samp ? samp[s0] : s0;
+      const float c0 = c[g0];
+      const float d0 = dc_of(dy[g0], c0, kk);
       q = fmaf(d0, c0, q);
 #pragma unroll
       for (int k = 0; k < NV; ++k) acc.x[k] = fma4(d0, o0.x[k], acc.x[k]);
@@ -619,8 +625,9 @@ rows_update_kernel(UpdateArgs a, const float* __restrict__ c, const float* __res
     const int s0 = order[j];
     RowTile<NV> o0;
     o0.load(other + (size_t)s0 * dim, d4, lane);
-    const float c0 = c[s0];
-    const float d0 = dc_of(dy[s0], c0, kk);
+    const int g0 = samp ? samp[s0] : s0;
+    const float c0 = c[g0];
+    const float d0 = dc_of(dy[g0], c0, kk);
     q = fmaf(d0, c0, q);
 #pragma unroll
     for (int k = 0; k < NV; ++k) acc.x[k] = fma4(d0, o0.x[k], acc.x[k]);
@@ -1050,6 +1057,7 @@ extern "C" int ar_train_steps_profile(const ar_train_ctx* ctx, int64_t epoch_ste
 
 #include "dist.inl"
 #include "shard.inl"
+#include "peer.inl"
 
 extern "C" int ar_predict(const float* U, const float* A, int32_t dim, const float* head, const float* bn_moving,
                           const int32_t* iu, const int32_t* ia, int64_t n, float* out, void* stream) {

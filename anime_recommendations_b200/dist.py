@@ -176,3 +176,141 @@ class ShardedTrainSession(TrainSession):
             self.launches += 4 + ns * (11 if m.adam_mode == "replay" else 9)
         m.iterations = t0 + steps
         return steps
+
+
+def peer_plan_cap(batch, world):
+    """Capacity of one per-step selection list in peer mode: a rank lists the samples of the GLOBAL batch that
+    touch its rows -- `batch` on average.  Small global batches get the worst case, large ones 1.5x + slack
+    (bounded by the plan sort); a chunk that overflows is refused (use the NCCL row-sharded session then)."""
+    if batch * world <= 4096:
+        return batch * world
+    return min(_capi.AR_MAX_BATCH, batch + batch // 2 + 512)
+
+
+class PeerTrainSession(TrainSession):
+    """Row-sharded data-parallel training over NVLink peer memory (csrc/peer.inl): same model / index contract
+    as ShardedTrainSession (`model` holds THIS rank's shards, index arrays hold GLOBAL row ids, `batch` is the
+    per-rank batch), but no collective on the step's critical path: every rank processes the samples of the
+    global batch that touch its rows and reads the other table's rows from the owners' HBM.  One node, up to 8
+    ranks, all-to-all peer access (NVSwitch)."""
+
+    def __init__(self, model, batch, total_steps, comm=None):
+        from ._capi import ArPeerCtx, PEER_FLAG_WORDS, PEER_HANDLE_BYTES
+        if not dist.is_initialized():
+            raise _capi.AnimerecError("torch.distributed must be initialised (torchrun) before PeerTrainSession()")
+        G, rank = dist.get_world_size(), dist.get_rank()
+        if G > _capi.PEER_MAX_RANKS:
+            raise _capi.AnimerecError("peer-memory training supports up to %d ranks" % _capi.PEER_MAX_RANKS)
+        cap = peer_plan_cap(int(batch), G)
+        super().__init__(model, batch, total_steps, plan_cap=cap)
+        self.comm = comm or Comm()
+        B, D, dev, S = self.B, model.dim, model.device, self.n_slots
+        f = dict(dtype=torch.float32, device=dev)
+        i32 = dict(dtype=torch.int32, device=dev)
+        # everything the other ranks read or write lives in ONE allocation: [U | A | c_all | flags]
+        nU, nA = model.U.numel(), model.A.numel()
+        words = nU + nA + G * B + PEER_FLAG_WORDS
+        self.arena = torch.zeros(words, **f)
+        o = 0
+        U = self.arena[o:o + nU].view_as(model.U); o += nU
+        A = self.arena[o:o + nA].view_as(model.A); o += nA
+        self.c_all = self.arena[o:o + G * B]; o += G * B
+        self.flags = self.arena[o:o + PEER_FLAG_WORDS].view(torch.int32)
+        U.copy_(model.U)
+        A.copy_(model.A)
+        model.U, model.A = U, A                # the model's tables now live in the exported arena
+        L = lib()
+        handle = (C.c_ubyte * PEER_HANDLE_BYTES)()
+        off = C.c_int64()
+        check(L.ar_peer_export(ptr(self.arena), handle, C.byref(off)), "ar_peer_export")
+        mine = torch.tensor(list(bytes(handle)) + [int(b) for b in int(off.value).to_bytes(8, "little")],
+                            dtype=torch.uint8, device=dev)
+        torch.cuda.synchronize()
+        every = self.comm.allgather(mine).cpu().numpy()
+        h = ArPeerCtx()
+        h.n_ranks, h.rank, h.sel_cap = G, rank, cap
+        self.peer_base = []
+        for r in range(G):
+            if r == rank:
+                base = self.arena.data_ptr()
+            else:
+                hb = (C.c_ubyte * PEER_HANDLE_BYTES)(*every[r, :PEER_HANDLE_BYTES].tolist())
+                roff = int.from_bytes(bytes(every[r, PEER_HANDLE_BYTES:].tolist()), "little")
+                p = C.c_void_p()
+                check(L.ar_peer_open(hb, roff, C.byref(p)), "ar_peer_open(rank %d)" % r)
+                base = p.value
+            self.peer_base.append(base)
+        # shard sizes differ by at most one row between ranks, so every rank reports its own layout
+        lay = torch.tensor([nU, nA], dtype=torch.int64, device=dev)
+        lays = self.comm.allgather(lay).cpu().tolist()
+        for r in range(G):
+            h.W_peer[0][r] = self.peer_base[r]
+            h.W_peer[1][r] = self.peer_base[r] + 4 * lays[r][0]
+            h.c_all_peer[r] = self.peer_base[r] + 4 * (lays[r][0] + lays[r][1])
+            h.flags_peer[r] = self.peer_base[r] + 4 * (lays[r][0] + lays[r][1] + G * B)
+        self._sel = dict(sel_key=[torch.zeros((S, cap), **i32) for _ in range(2)],
+                         sel_samp=[torch.zeros((S, cap), **i32) for _ in range(2)],
+                         sel_oth=[torch.zeros((S, cap), **i32) for _ in range(2)],
+                         sel_cnt=[torch.zeros(S, **i32) for _ in range(2)])
+        for name, bufs in self._sel.items():
+            arr = getattr(h, name)
+            for k in range(2):
+                arr[k] = bufs[k].data_ptr()
+        self.max_count = torch.zeros(2, **i32)
+        self.label_step = torch.zeros((S, G * B), **f)
+        self.dy_all = torch.empty(G * B, **f)
+        self.fwd_part_all = torch.zeros(2 * ((G * B + 7) // 8), dtype=torch.float64, device=dev)
+        self.head_part_all = torch.zeros(8 * ((G * B + 255) // 256), dtype=torch.float64, device=dev)
+        h.max_count, h.label_step, h.dy_all = self.max_count.data_ptr(), self.label_step.data_ptr(), self.dy_all.data_ptr()
+        h.fwd_part_all, h.head_part_all = self.fwd_part_all.data_ptr(), self.head_part_all.data_ptr()
+        self.pctx = h
+        self.gather = [torch.empty((G, S * B), **i32), torch.empty((G, S * B), **i32), torch.empty((G, S * B), **f)]
+        self.counts = []
+        # nobody may signal a flag before every rank has zeroed and mapped its arena
+        torch.cuda.synchronize()
+        dist.barrier()
+
+    def check_flags(self):
+        """Raise if a flag barrier timed out (a rank died or fell out of step)."""
+        bad = int(self.flags[32].item())
+        if bad:
+            raise _capi.AnimerecError("peer barrier %d timed out on rank %d" % (bad, self.pctx.rank))
+
+    def run(self, iu, ia, y, lr, profile=None):
+        m, B, G = self.model, self.B, self.pctx.n_ranks
+        N = iu.numel()
+        steps = (N + B - 1) // B
+        t0 = m.iterations
+        if t0 + steps > self.t_cap:
+            raise _capi.AnimerecError("PeerTrainSession sized for %d optimizer steps, %d requested" % (self.t_cap, t0 + steps))
+        m._set_alpha(lr, t0 + 1, steps)
+        ctx = self._ctx(iu, ia, y)
+        st, L = stream_ptr(), lib()
+        S = self.n_slots
+        for s0 in range(0, steps, S):
+            ns = min(S, steps - s0)
+            lo, hi = s0 * B, min(N, (s0 + ns) * B)
+            for src, dst in zip((iu, ia, y), self.gather):
+                # rank r's slice lands at dst[r, :hi-lo]: all-gather into a [G, hi-lo] view when the chunk is full
+                if hi - lo == S * B:
+                    check(L.ar_allgather_bytes(self.comm.handle, ptr(src[lo:hi]), ptr(dst), (hi - lo) * 4, st), "ar_allgather_bytes")
+                else:
+                    tmp = self.comm.allgather(src[lo:hi])
+                    dst[:, :hi - lo].copy_(tmp)
+            check(L.ar_peer_plan(ptr(self.gather[0]), ptr(self.gather[1]), ptr(self.gather[2]), S * B, hi - lo, B, ns,
+                                 C.byref(self.plan_u), C.byref(self.plan_a), C.byref(self.pctx), st), "ar_peer_plan")
+            # one host read per chunk: the longest selection list (grid size; overflow check), max over ranks so
+            # that every rank takes the same decision
+            mc = self.max_count.max().reshape(1).to(torch.int64)
+            dist.all_reduce(mc, op=dist.ReduceOp.MAX)
+            mc = int(mc.item())
+            if mc > self.P:
+                raise _capi.AnimerecError("peer mode: %d samples of one step touch one rank's rows, capacity %d; "
+                                          "use ShardedTrainSession for this data" % (mc, self.P))
+            self.counts.append(mc)
+            self.check_flags()
+            check(L.ar_train_steps_peer(C.byref(ctx), C.byref(self.pctx), s0, 0, t0 + s0, ns, max(mc, 1), st),
+                  "ar_train_steps_peer")
+            self.launches += 6 + ns * (9 if m.adam_mode == "replay" else 7)
+        m.iterations = t0 + steps
+        return steps

@@ -384,20 +384,23 @@ class TrainSession:
     """Device-side buffers of one training run: dedup plans (PLAN_CHUNK steps at a time), the per-step
     scratch, the per-step metrics and the ar_train_ctx handed to libanimerec."""
 
-    def __init__(self, model, batch, total_steps):
+    def __init__(self, model, batch, total_steps, plan_cap=None):
         self.model, self.B = model, int(batch)
         dev, D, B = model.device, model.dim, int(batch)
+        # plan_cap: per-step capacity of the plans and the per-sample scratch (peer mode lists up to plan_cap
+        # samples of the GLOBAL batch per rank and step); the per-rank batch otherwise
+        P = self.P = int(plan_cap or B)
         self.n_slots = max(1, min(int(total_steps) if total_steps else PLAN_CHUNK, PLAN_CHUNK))
-        self.plan_u, self._keep_u = self._make_plan(self.n_slots, B, dev)
-        self.plan_a, self._keep_a = self._make_plan(self.n_slots, B, dev)
+        self.plan_u, self._keep_u = self._make_plan(self.n_slots, P, dev)
+        self.plan_a, self._keep_a = self._make_plan(self.n_slots, P, dev)
         f = dict(dtype=torch.float32, device=dev)
-        self.uh, self.ah = torch.empty((B, D), **f), torch.empty((B, D), **f)
-        self.c, self.ru, self.ra, self.dy = (torch.empty(B, **f) for _ in range(4))
-        self.fwd_part = torch.zeros(2 * ((B + 7) // 8), dtype=torch.float64, device=dev)
-        self.head_part = torch.zeros(8 * ((B + 255) // 256), dtype=torch.float64, device=dev)
+        self.uh, self.ah = torch.empty((P, D), **f), torch.empty((P, D), **f)
+        self.c, self.ru, self.ra, self.dy = (torch.empty(P, **f) for _ in range(4))
+        self.fwd_part = torch.zeros(2 * ((P + 7) // 8), dtype=torch.float64, device=dev)
+        self.head_part = torch.zeros(8 * ((P + 255) // 256), dtype=torch.float64, device=dev)
         self.stepc = torch.zeros(8, **f)
         self.ticket = torch.zeros(1, dtype=torch.int32, device=dev)
-        self.sched_ws = torch.zeros(2 * (3 * 2 * B + 4), dtype=torch.int32, device=dev)
+        self.sched_ws = torch.zeros(2 * (3 * 2 * P + 4), dtype=torch.int32, device=dev)
         self.t_cap = model.iterations + int(total_steps)
         model._ensure_alpha(self.t_cap)
         self.metrics = torch.zeros((self.t_cap + 1, 4), **f)

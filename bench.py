@@ -214,7 +214,7 @@ def gpu_main(args):
     K, W = args.steps, args.warmup
     mode = args.mode
 
-    sharded = world > 1 and args.dist == "sharded"
+    sharded = world > 1 and args.dist in ("sharded", "peer")
     if sharded:   # this rank's shards of both tables (global row g lives on rank g % world), same init law
         model = ar.EmbeddingDotModel((N_USERS + world - 1) // world, (N_ANIME + world - 1) // world, DIM,
                                      l2_reg_factor=L2, seed=1 + rank, adam_mode=mode, dense_kernel=1.0)
@@ -223,7 +223,8 @@ def gpu_main(args):
     iu, ia, y = synth((W + K) * BATCH, 42 + rank, dev, zipf=args.zipf)
     if world > 1:
         from anime_recommendations_b200 import dist as ardist
-        cls = ardist.ShardedTrainSession if sharded else ardist.DistTrainSession
+        cls = {"sharded": ardist.ShardedTrainSession, "peer": ardist.PeerTrainSession,
+               "replicated": ardist.DistTrainSession}[args.dist]
         sess = cls(model, BATCH, total_steps=2 * (W + K) + 8)
     else:
         sess = TrainSession(model, BATCH, total_steps=2 * (W + K) + 8)
@@ -497,7 +498,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--mode", default="replay", choices=["replay", "dense", "touched"])
     ap.add_argument("--zipf", action="store_true", help="Zipf(1) anime popularity instead of uniform")
-    ap.add_argument("--dist", default="replicated", choices=["replicated", "sharded"],
+    ap.add_argument("--dist", default="replicated", choices=["replicated", "sharded", "peer"],
                     help="N > 1: replicated tables + all-gathered row gradients (cfg2) or row-sharded tables + all-to-all (cfg5 scheme)")
     ap.add_argument("--skip-cpu", action="store_true")
     ap.add_argument("--skip-extras", action="store_true")

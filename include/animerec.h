@@ -77,6 +77,11 @@ typedef struct {
 int ar_plan_build(const int32_t* idx, int64_t n_total, int32_t batch, int64_t step0,
                   int32_t n_steps, const ar_plan* plan, void* stream);
 
+/* List form: step s groups the `counts[s]` keys at keys[s*stride ...] (counts on the device, stride <=
+ * AR_MAX_BATCH); the plan's sample ids are positions in that list.  Used by ar_peer_plan. */
+int ar_plan_build_lists(const int32_t* keys, int32_t stride, const int32_t* counts, int32_t n_steps,
+                        const ar_plan* plan, void* stream);
+
 /* After ar_plan_build of `n_steps` slots: fill plan->in_prev.  uniq_all / meta_all: every rank's plan.uniq
  * ([n_ranks][n_slots][batch_cap]) and plan.meta ([n_ranks][n_slots][4]) of the same chunk, all-gathered, for
  * replicated multi-GPU training; null = this plan's own lists (single GPU). */
@@ -202,6 +207,56 @@ typedef struct {
 int ar_shard_plan(const ar_plan* plan_u, const ar_plan* plan_a, int32_t n_steps, const ar_shard_ctx* sh, void* stream);
 int ar_train_steps_sharded(const ar_train_ctx* ctx, const ar_shard_ctx* sh, int64_t epoch_step0, int32_t slot0,
                            int64_t t0, int32_t n_steps, int32_t cap, void* stream);
+
+/* ---- multi-GPU training over NVLink PEER MEMORY (row-sharded tables, owner computes) ----
+ * Same ownership rule as the row-sharded path, no collective on the step's critical path: every rank works on
+ * the samples of the global batch that touch ITS rows and loads the sample's row of the other table straight
+ * from the owner's HBM (cudaIpc-mapped shards, 128-bit loads over NVLink); the ranks meet at two flag barriers
+ * per step (spin on peer-written words).  One process per GPU on ONE node with all-to-all peer access. */
+#define AR_PEER_MAX_RANKS 8
+#define AR_PEER_HANDLE_BYTES 64
+#define AR_PEER_FLAG_WORDS 64
+/* handle (host, AR_PEER_HANDLE_BYTES) + byte offset naming dev_ptr inside its cudaMalloc allocation */
+int ar_peer_export(const void* dev_ptr, void* handle_out_host, int64_t* offset_out);
+/* map another process's allocation (each distinct handle is opened once per process) */
+int ar_peer_open(const void* handle_host, int64_t offset, void** ptr_out);
+int ar_peer_close_all(void);
+
+typedef struct {
+  int32_t n_ranks;                              /* <= AR_PEER_MAX_RANKS */
+  int32_t rank;
+  float* W_peer[2][AR_PEER_MAX_RANKS];          /* [0 users | 1 anime][rank]: base of that rank's shard; the own
+                                                   entry is the local pointer (= ctx->users.W / ctx->anime.W) */
+  float* c_all_peer[AR_PEER_MAX_RANKS];         /* every rank's (n_ranks*batch) cosine buffer */
+  int32_t* flags_peer[AR_PEER_MAX_RANKS];       /* every rank's AR_PEER_FLAG_WORDS int32, zero-initialised before
+                                                   any rank's first step; word 32 != 0: a barrier timed out */
+  int32_t sel_cap;                              /* capacity of one selection list = batch_cap of both plans */
+  int32_t* sel_key[2];                          /* [n_slots][sel_cap] local row of my table */
+  int32_t* sel_samp[2];                         /* [n_slots][sel_cap] position in the global batch */
+  int32_t* sel_oth[2];                          /* [n_slots][sel_cap] GLOBAL row of the other table */
+  int32_t* sel_cnt[2];                          /* [n_slots] */
+  int32_t* max_count;                           /* [2] longest list of the planned chunk per table (> sel_cap:
+                                                   overflow, the chunk must not be run) */
+  float* label_step;                            /* [n_slots][n_ranks*batch] labels in global-batch order */
+  float* dy_all;                                /* (n_ranks*batch) */
+  double* fwd_part_all;                         /* as in ar_dist_ctx */
+  double* head_part_all;
+} ar_peer_ctx;
+
+/* Plan a chunk: iu_all / ia_all / label_all hold every rank's samples of the chunk, rank r's at
+ * [r*rank_stride, r*rank_stride + n_local) (GLOBAL row ids; all-gathered by the caller); step s of the chunk
+ * is samples [s*batch, min(n_local, (s+1)*batch)) of every rank.  Builds the selection lists, label_step and
+ * both plans (+ in_prev when the plans carry it). */
+int ar_peer_plan(const int32_t* iu_all, const int32_t* ia_all, const float* label_all, int64_t rank_stride,
+                 int64_t n_local, int32_t batch, int32_t n_steps, const ar_plan* plan_u, const ar_plan* plan_a,
+                 const ar_peer_ctx* peer, void* stream);
+/* ar_train_steps for this rank.  ctx->users / anime: my shards; ctx->uh / ah: (sel_cap, dim) and ctx->c / ru /
+ * ra: (sel_cap) scratch; ctx->iu / ia / label are not read (n_samples and batch are).  count_hint >= both
+ * max_count values (grid sizing).  Equal to a single-GPU run on the concatenated batch up to rounding. */
+int ar_train_steps_peer(const ar_train_ctx* ctx, const ar_peer_ctx* peer, int64_t epoch_step0, int32_t slot0,
+                        int64_t t0, int32_t n_steps, int32_t count_hint, void* stream);
+/* one flag barrier across the ranks on `stream` (epochs must grow; the training steps use 2t and 2t+1) */
+int ar_peer_barrier(const ar_peer_ctx* peer, int32_t epoch, void* stream);
 
 /* NCCL all-gather of equally sized byte buffers (sharded top-k lists before ar_topk_merge). */
 int ar_allgather_bytes(void* comm, const void* send, void* recv, int64_t bytes_per_rank, void* stream);

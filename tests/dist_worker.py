@@ -35,10 +35,10 @@ def sim_main(shard, dev, rank, world):
         print("DIST_OK", shard)
 
 
-def shard_main(mode, dev, rank, world):
-    """Row-sharded training == single-GPU training on the concatenated batch."""
+def shard_main(mode, dev, rank, world, peer=False):
+    """Row-sharded training (NCCL all-to-all, or NVLink peer memory) == single-GPU training on the concatenated batch."""
     import anime_recommendations_b200 as ar
-    from anime_recommendations_b200.dist import ShardedTrainSession, shard_rows
+    from anime_recommendations_b200.dist import PeerTrainSession, ShardedTrainSession, shard_rows
     from anime_recommendations_b200.model import TrainSession
     nu, na, D, B, steps = 5001, 703, 128, 1000, 6
     rng = np.random.RandomState(5)
@@ -57,7 +57,7 @@ def shard_main(mode, dev, rank, world):
     mine_u, mine_a = shard_rows(fw[0], rank, world), shard_rows(fw[1], rank, world)
     Us[:len(mine_u)], As[:len(mine_a)] = mine_u, mine_a
     m.set_weights([Us, As] + fw[2:])
-    sess = ShardedTrainSession(m, B, total_steps=steps)
+    sess = (PeerTrainSession if peer else ShardedTrainSession)(m, B, total_steps=steps)
     sess.run(torch.from_numpy(iu[sl]).to(dev), torch.from_numpy(ia[sl]).to(dev), torch.from_numpy(y[sl]).to(dev), 2e-3)
     m._sync_tables()
     # assemble the global tables on rank 0
@@ -93,8 +93,14 @@ def shard_main(mode, dev, rank, world):
         mt = sess.metrics[1:steps + 1].cpu().numpy()
         m1t = s1.metrics[1:steps + 1].cpu().numpy()
         np.testing.assert_allclose(mt[:, :3], m1t[:, :3], rtol=2e-6, atol=2e-6)
-        assert max(sess.caps) <= B and min(sess.caps) >= 4
-        print("DIST_OK shard", mode, "cap", sess.caps)
+        if peer:
+            assert B // 2 <= max(sess.counts) <= world * B
+            print("DIST_OK peer", mode, "longest list", sess.counts)
+        else:
+            assert max(sess.caps) <= B and min(sess.caps) >= 4
+            print("DIST_OK shard", mode, "cap", sess.caps)
+    if peer:
+        sess.check_flags()
 
 
 def main(mode):
@@ -102,8 +108,8 @@ def main(mode):
     torch.cuda.set_device(int(os.environ["LOCAL_RANK"]))
     dev = torch.device("cuda", int(os.environ["LOCAL_RANK"]))
     dist.init_process_group("nccl", device_id=dev)
-    if mode.startswith("shard_"):
-        shard_main(mode[6:], dev, rank, world)
+    if mode.startswith("shard_") or mode.startswith("peer_"):
+        shard_main(mode.split("_", 1)[1], dev, rank, world, peer=mode.startswith("peer_"))
         dist.barrier()
         dist.destroy_process_group()
         return

@@ -42,3 +42,15 @@ def test_two_rank_row_sharded_training_equals_single_gpu(mode):
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
     assert "DIST_OK" in r.stdout
+
+
+@pytest.mark.parametrize("mode", ["replay", "dense", "touched"])
+def test_two_rank_peer_memory_training_equals_single_gpu(mode):
+    """csrc/peer.inl: owners pull the other table's rows over NVLink, flag barriers instead of collectives."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr",
+           "127.0.0.1", "--master-port", "29547", os.path.join(ROOT, "tests", "dist_worker.py"), "peer_" + mode]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
+    assert "DIST_OK" in r.stdout
