@@ -34,7 +34,7 @@ def build_lib(force=False, verbose=False):
     """Compile every .cu under csrc/ and link libanimerec.so.  Returns the library path."""
     os.makedirs(LIBDIR, exist_ok=True)
     nvcc = _nvcc()
-    headers = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cuh", ".h"))]
+    headers = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cuh", ".h", ".inl"))]
     headers.append(os.path.join(ROOT, "include", "animerec.h"))
     objs = []
     procs = []

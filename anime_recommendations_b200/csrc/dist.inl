@@ -201,7 +201,7 @@ static int run_steps_dist(const ar_train_ctx& x, const ar_dist_ctx& d, int64_t e
     AR_LAUNCH_CHECK();
     head_step_kernel<<<ceil_div(ng, kHeadThreads), kHeadThreads, 0, st>>>(
         d.c_all, d.label_all, ng, nullptr, d.fwd_part_all, x.head, x.head_m, x.head_v, x.bn_moving, x.alpha, t,
-        d.dy_all, d.head_part_all, x.stepc, x.ticket, x.metrics + t * 4);
+        d.dy_all, d.head_part_all, x.stepc, x.ticket, x.metrics + t * 4, 0);
     AR_LAUNCH_CHECK();
     // partial row gradients of the local samples -> packed send block
     UpdateArgs a{};

@@ -24,10 +24,10 @@
 // G*B cosines out.  Nothing is staged, packed or merged, and a row's gradient is summed by one warp in plan
 // order -- the result does not depend on which rank a sample came from.
 //
-// The barrier is a 32-thread kernel: lane r stores the epoch into rank r's flag word for me (st.release.sys
-// after a system fence) and spins on my flag word for rank r (ld.acquire.sys).  Epochs are derived from the
-// optimizer step, so they only grow; a rank that waits longer than kPeerTimeoutNs raises a sticky error word
-// instead of hanging the GPU.
+// Flag barriers: rank r's arrival is the epoch number stored (st.release.sys) into word r of EVERY rank's flag
+// array; a waiter spins (ld.acquire.sys) on its own array.  Epochs are derived from the optimizer step, so
+// they only grow; a rank that waits longer than kPeerTimeoutNs raises a sticky error word instead of hanging
+// the GPU.  ar_peer_barrier is the stand-alone form (one 32-thread kernel); the step uses the split form.
 namespace ar {
 
 constexpr int kPeerMaxRanks = AR_PEER_MAX_RANKS;
@@ -75,6 +75,62 @@ __global__ void __launch_bounds__(32) peer_barrier_kernel(PeerFlags f, int epoch
       st_release_sys(mine + kPeerErrWord, epoch);
       break;
     }
+  }
+}
+
+// The training step splits the barrier: arrival is signalled by a one-warp kernel (epoch 2t, "my rows are
+// current") or by the last CTA of the forward (epoch 2t+1, "my cosines are published"), and the FIRST kernel
+// that needs the other ranks' data waits in its prologue -- its CTAs are already resident when the flags land,
+// which takes a launch gap and a separate spinning kernel off the critical path.
+__global__ void __launch_bounds__(32) peer_signal_kernel(PeerFlags f, int epoch) {
+  const int r = threadIdx.x;
+  if (r < f.G) st_release_sys(f.peer[r] + f.me, epoch);
+}
+
+// called by every thread of a CTA; threads r < G wait for rank r's arrival
+__device__ __forceinline__ void peer_wait(int32_t* mine, int G, int epoch) {
+  if ((int)threadIdx.x < G && ld_acquire_sys(mine + kPeerErrWord) == 0) {
+    const unsigned long long t0 = global_ns();
+    while (ld_acquire_sys(mine + threadIdx.x) < epoch) {
+      if (global_ns() - t0 > kPeerTimeoutNs) {
+        st_release_sys(mine + kPeerErrWord, epoch);
+        break;
+      }
+    }
+  }
+  __syncthreads();
+}
+
+// (sum c, sum c^2) per kPartSamples cosines, behind the "cosines published" flags.  One partial per CTA (the
+// single-GPU forward emits one per 8 samples; at G*B samples every head CTA would re-read G times as many)
+constexpr int kPartThreads = 128, kPartSamples = kPartThreads * 8;
+__global__ void __launch_bounds__(kPartThreads)
+c_partials_wait_kernel(const float* __restrict__ c, int n, double* __restrict__ fwd_part, int32_t* flags, int G, int epoch) {
+  __shared__ double red[2][kPartThreads / 32];
+  peer_wait(flags, G, epoch);
+  const int i0 = (blockIdx.x * kPartThreads + threadIdx.x) * 8;
+  double a0 = 0.0, a1 = 0.0;
+  for (int i = i0; i < min(n, i0 + 8); ++i) {
+    const double x = (double)__ldcg(c + i);
+    a0 += x;
+    a1 += x * x;
+  }
+  a0 = warp_sum(a0);
+  a1 = warp_sum(a1);
+  if ((threadIdx.x & 31) == 0) {
+    red[0][threadIdx.x >> 5] = a0;
+    red[1][threadIdx.x >> 5] = a1;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double b0 = 0.0, b1 = 0.0;
+#pragma unroll
+    for (int w = 0; w < kPartThreads / 32; ++w) {
+      b0 += red[0][w];
+      b1 += red[1][w];
+    }
+    fwd_part[2 * blockIdx.x] = b0;
+    fwd_part[2 * blockIdx.x + 1] = b1;
   }
 }
 
@@ -165,7 +221,11 @@ struct PeerFwdArgs {
   float* stash[2];   // [cap][dim] normalised row of the OTHER table per listed sample
   float* rinv[2];    // [cap] 1/||my row||
   int G, me, dim, blocks0;
+  int32_t* flags_peer[kPeerMaxRanks];  // every rank's flag words
+  int epoch_rows;    // wait for this epoch (all owners' rows current) before touching peer rows
+  int epoch_c;       // the last CTA to finish signals this epoch (my cosines are in every c_all)
 };
+constexpr int kPeerTicketWord = 40;    // flags[40]: arrival counter of peer_fwd_kernel's CTAs (local)
 
 template <int NV>
 __global__ void __launch_bounds__(kRowThreads) peer_fwd_kernel(PeerFwdArgs a) {
@@ -174,7 +234,9 @@ __global__ void __launch_bounds__(kRowThreads) peer_fwd_kernel(PeerFwdArgs a) {
   const int lane = threadIdx.x & 31;
   const int k = blk * kRowWarps + (threadIdx.x >> 5);
   const int cnt = second ? a.cnt[1][0] : a.cnt[0][0];
-  if (k >= cnt) return;
+  int32_t* my_flags = a.flags_peer[a.me];
+  if (blk * kRowWarps < cnt) peer_wait(my_flags, a.G, a.epoch_rows);  // CTA-uniform
+  if (k < cnt) {
   const int32_t* keyp = second ? a.key[1] : a.key[0];
   const int32_t* othp = second ? a.oth[1] : a.oth[0];
   const int dim = a.dim, d4 = dim >> 2;
@@ -208,6 +270,17 @@ __global__ void __launch_bounds__(kRowThreads) peer_fwd_kernel(PeerFwdArgs a) {
     const float cs = tile_dot<NV>(w, o);
     const int j = __ldg(a.samp[0] + k);
     if (lane < a.G) a.c_peer[lane][j] = cs;
+  }
+  }
+  // arrival: once every CTA's peer stores are fenced, the last one tells every rank (threadFenceReduction pattern)
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence_system();
+    const int old = atomicAdd(my_flags + kPeerTicketWord, 1);
+    if (old == (int)gridDim.x - 1) {
+      my_flags[kPeerTicketWord] = 0;
+      for (int r = 0; r < a.G; ++r) st_release_sys(a.flags_peer[r] + a.me, a.epoch_c);
+    }
   }
 }
 
@@ -348,6 +421,13 @@ extern "C" int ar_train_steps_peer(const ar_train_ctx* ctx, const ar_peer_ctx* h
   Lookahead* la = (x.mode == AR_ADAM_REPLAY && can_ahead && !no_overlap) ? lookahead() : nullptr;
   if (la) AR_CUDA(cudaEventRecord(la->ev_upd[1], st));
   float* c_all = h->c_all_peer[h->rank];
+  // AR_PEER_PROFILE=1: events around every launch, per-stage averages to stderr (developer aid; synchronises)
+  static const bool prof = getenv("AR_PEER_PROFILE") != nullptr;
+  // AR_PEER_UNFUSED=1: stand-alone barrier kernels instead of the split form (A/B measurement)
+  static const bool unfused = getenv("AR_PEER_UNFUSED") != nullptr;
+  StageTimer tm_store;
+  tm_store.st = st;
+  StageTimer* timer = prof ? &tm_store : nullptr;
   for (int s = 0; s < n_steps; ++s) {
     const int64_t e = epoch_step0 + s;
     const int64_t base = e * (int64_t)B;
@@ -369,7 +449,18 @@ extern "C" int ar_train_steps_peer(const ar_train_ctx* ctx, const ar_peer_ctx* h
       AR_CUDA(cudaEventRecord(la->ev_ahead, la->st2));
       ahead = true;
     }
-    if ((rc = peer_barrier(*h, (int)(2 * t), st))) return rc;  // every owner's rows of this step are current
+    AR_TICK(0);
+    PeerFlags pf{};
+    for (int r = 0; r < G; ++r) pf.peer[r] = h->flags_peer[r];
+    pf.G = G;
+    pf.me = h->rank;
+    if (unfused) {
+      if ((rc = peer_barrier(*h, (int)(2 * t), st))) return rc;
+    } else {
+      peer_signal_kernel<<<1, 32, 0, st>>>(pf, (int)(2 * t));  // my rows of this step are current
+      AR_LAUNCH_CHECK();
+    }
+    AR_TICK(1);
     PeerFwdArgs f{};
     for (int r = 0; r < G; ++r) {
       f.W_peer[0][r] = h->W_peer[0][r];
@@ -385,16 +476,24 @@ extern "C" int ar_train_steps_peer(const ar_train_ctx* ctx, const ar_peer_ctx* h
     f.stash[0] = x.ah; f.stash[1] = x.uh;
     f.rinv[0] = x.ru; f.rinv[1] = x.ra;
     f.G = G; f.me = h->rank; f.dim = dim;
+    for (int r = 0; r < G; ++r) f.flags_peer[r] = h->flags_peer[r];
+    f.epoch_rows = unfused ? 0 : (int)(2 * t);
+    f.epoch_c = (int)(2 * t + 1);
     f.blocks0 = ceil_div(count_hint, kRowWarps);
     AR_DISPATCH_NV(dim, peer_fwd_kernel<NV><<<2 * f.blocks0, kRowThreads, 0, st>>>(f));
     AR_LAUNCH_CHECK();
-    if ((rc = peer_barrier(*h, (int)(2 * t + 1), st))) return rc;  // c_all complete on every rank
-    c_partials_kernel<<<ceil_div(ceil_div(ng, kRowWarps), 128), 128, 0, st>>>(c_all, ng, h->fwd_part_all);
+    AR_TICK(2);
+    if (unfused && (rc = peer_barrier(*h, (int)(2 * t + 1), st))) return rc;
+    const int nfp = ceil_div(ng, kPartSamples);
+    c_partials_wait_kernel<<<nfp, kPartThreads, 0, st>>>(c_all, ng, h->fwd_part_all, h->flags_peer[h->rank], G,
+                                                         unfused ? 0 : (int)(2 * t + 1));
     AR_LAUNCH_CHECK();
+    AR_TICK(3);
     head_step_kernel<<<ceil_div(ng, kHeadThreads), kHeadThreads, 0, st>>>(
         c_all, h->label_step + (int64_t)slot * G * B, ng, nullptr, h->fwd_part_all, x.head, x.head_m, x.head_v,
-        x.bn_moving, x.alpha, t, h->dy_all, h->head_part_all, x.stepc, x.ticket, x.metrics + t * 4);
+        x.bn_moving, x.alpha, t, h->dy_all, h->head_part_all, x.stepc, x.ticket, x.metrics + t * 4, nfp);
     AR_LAUNCH_CHECK();
+    AR_TICK(4);
     UpdateArgs a{};
     fill_update(a, 0, &x.users, &x.plan_u, slot, x.ah, x.ru, count_hint);
     fill_update(a, 1, &x.anime, &x.plan_a, slot, x.uh, x.ra, count_hint);
@@ -402,6 +501,7 @@ extern "C" int ar_train_steps_peer(const ar_train_ctx* ctx, const ar_peer_ctx* h
     a.samp[1] = f.samp[1];
     double* ss = (x.mode == AR_ADAM_DENSE && x.reg_sumsq) ? x.reg_sumsq + t * 32 : nullptr;
     if ((rc = launch_update(a, true, c_all, h->dy_all, x.stepc, x.alpha, x.l2, t, 0, ss, st))) return rc;
+    AR_TICK(5);
     if (la) {
       AR_CUDA(cudaEventRecord(la->ev_upd[s & 1], st));
       if (ahead) AR_CUDA(cudaStreamWaitEvent(st, la->ev_ahead, 0));
@@ -410,6 +510,24 @@ extern "C" int ar_train_steps_peer(const ar_train_ctx* ctx, const ar_peer_ctx* h
       if ((rc = launch_flush(&x.users, x.alpha, x.l2, t, ss, st))) return rc;
       if ((rc = launch_flush(&x.anime, x.alpha, x.l2, t, ss, st))) return rc;
     }
+  }
+  if (timer && timer->ev.size() >= 12) {
+    AR_CUDA(cudaStreamSynchronize(st));
+    const size_t ns = timer->ev.size() / 6;
+    double acc[6] = {0, 0, 0, 0, 0, 0};
+    for (size_t i = 1; i < ns; ++i) {  // skip the first step (exposed catch-up)
+      float ms = 0.f;
+      for (int k = 0; k < 5; ++k) {
+        cudaEventElapsedTime(&ms, timer->ev[i * 6 + k], timer->ev[i * 6 + k + 1]);
+        acc[k] += ms;
+      }
+      cudaEventElapsedTime(&ms, timer->ev[(i - 1) * 6 + 5], timer->ev[i * 6]);
+      acc[5] += ms;
+    }
+    fprintf(stderr, "[peer rank %d] us/step over %zu steps: signal %.1f  wait+fwd %.1f  wait+c_partials %.1f  head %.1f  update %.1f  between-steps %.1f\n",
+            h->rank, ns - 1, 1e3 * acc[0] / (ns - 1), 1e3 * acc[1] / (ns - 1), 1e3 * acc[2] / (ns - 1),
+            1e3 * acc[3] / (ns - 1), 1e3 * acc[4] / (ns - 1), 1e3 * acc[5] / (ns - 1));
+    for (cudaEvent_t ev : timer->ev) cudaEventDestroy(ev);
   }
   return AR_OK;
 }

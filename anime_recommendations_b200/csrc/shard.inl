@@ -298,7 +298,7 @@ extern "C" int ar_train_steps_sharded(const ar_train_ctx* ctx, const ar_shard_ct
     AR_LAUNCH_CHECK();
     head_step_kernel<<<ceil_div(ng, kHeadThreads), kHeadThreads, 0, st>>>(
         h->c_all, h->label_all, ng, nullptr, h->fwd_part_all, x.head, x.head_m, x.head_v, x.bn_moving, x.alpha, t,
-        h->dy_all, h->head_part_all, x.stepc, x.ticket, x.metrics + t * 4);
+        h->dy_all, h->head_part_all, x.stepc, x.ticket, x.metrics + t * 4, 0);
     AR_LAUNCH_CHECK();
     UpdateArgs a{};
     fill_update(a, 0, &x.users, &x.plan_u, slot, x.ah, x.ru, B);

@@ -334,7 +334,7 @@ head_step_kernel(const float* __restrict__ c, const float* __restrict__ label, i
                  float* __restrict__ head, float* __restrict__ head_m, float* __restrict__ head_v,
                  float* __restrict__ bn_moving, const float* __restrict__ alpha, int64_t t,
                  float* __restrict__ dy_out, double* __restrict__ head_part, float* __restrict__ stepc,
-                 unsigned int* __restrict__ ticket, float* __restrict__ metrics_row) {
+                 unsigned int* __restrict__ ticket, float* __restrict__ metrics_row, int nfp_in) {
   __shared__ double red[kHeadSums * 32];
   __shared__ int is_last;
   if (meta_n) n = min(n, meta_n[2]);
@@ -346,7 +346,7 @@ head_step_kernel(const float* __restrict__ c, const float* __restrict__ label, i
   const float fn = (float)n;
 
   // batch statistics from the forward's per-CTA partials (fixed summation order in every CTA)
-  const int nfp = (n + kRowWarps - 1) / kRowWarps;
+  const int nfp = nfp_in > 0 ? nfp_in : (n + kRowWarps - 1) / kRowWarps;  // peer mode pre-reduces per 1024 samples
   double s0[2] = {0.0, 0.0};
   for (int i = tid; i < nfp; i += kHeadThreads) {
     s0[0] += __ldcg(fwd_part + 2 * i);
@@ -783,6 +783,8 @@ static int launch_catchup(const ar_table* t0, const ar_plan* p0, int slot0, cons
     rows_classify_kernel<<<ceil_div(units, 256), 256, 0, st>>>(a, t_target, a.blocks0, t1 ? p1->batch_cap : 0);
     AR_LAUNCH_CHECK();
   }
+  // (capping the resident catch-up CTAs per SM with dynamic shared memory, to leave warp slots for the step's
+  // own kernels, was measured: 8..28 KB per CTA cost 0..10% of the step -- the replay wants the occupancy)
   AR_DISPATCH_NV(t0->dim, rows_catchup_kernel<NV><<<ceil_div(units, kCatchThreads / 32), kCatchThreads, 0, st>>>(a, alpha, l2x2, t_target));
   AR_LAUNCH_CHECK();
   return AR_OK;
@@ -866,7 +868,7 @@ extern "C" int ar_head_step(const float* c, const float* label, int32_t n, float
   c_partials_kernel<<<ceil_div(nfp, 128), 128, 0, st>>>(c, n, fwd_part);
   AR_LAUNCH_CHECK();
   head_step_kernel<<<nhb, kHeadThreads, 0, st>>>(c, label, n, nullptr, fwd_part, head, head_m, head_v, bn_moving,
-                                                  alpha, t, dy, head_part, stepc, ticket, metrics_row);
+                                                  alpha, t, dy, head_part, stepc, ticket, metrics_row, 0);
   AR_LAUNCH_CHECK();
   dc_from_dy_kernel<<<ceil_div(n, 256), 256, 0, st>>>(dy, c, n, stepc, dc);
   AR_LAUNCH_CHECK();
@@ -983,7 +985,7 @@ static int run_steps(const ar_train_ctx& x, int64_t epoch_step0, int32_t slot0, 
     AR_TICK(2);
     head_step_kernel<<<ceil_div(n, kHeadThreads), kHeadThreads, 0, st>>>(
         x.c, x.label + base, n, meta_u, x.fwd_part, x.head, x.head_m, x.head_v, x.bn_moving, x.alpha, t, x.dy,
-        x.head_part, x.stepc, x.ticket, x.metrics + t * 4);
+        x.head_part, x.stepc, x.ticket, x.metrics + t * 4, 0);
     AR_LAUNCH_CHECK();
     AR_TICK(3);
     UpdateArgs a{};

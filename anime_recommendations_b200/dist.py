@@ -180,11 +180,9 @@ class ShardedTrainSession(TrainSession):
 
 def peer_plan_cap(batch, world):
     """Capacity of one per-step selection list in peer mode: a rank lists the samples of the GLOBAL batch that
-    touch its rows -- `batch` on average.  Small global batches get the worst case, large ones 1.5x + slack
-    (bounded by the plan sort); a chunk that overflows is refused (use the NCCL row-sharded session then)."""
-    if batch * world <= 4096:
-        return batch * world
-    return min(_capi.AR_MAX_BATCH, batch + batch // 2 + 512)
+    touch its rows -- `batch` on average.  Twice that plus slack, bounded by the global batch and by what the
+    plan sort holds; a chunk that overflows is refused (use the NCCL row-sharded session then)."""
+    return min(_capi.AR_MAX_BATCH, batch * world, 2 * batch + 512)
 
 
 class PeerTrainSession(TrainSession):
