@@ -10,7 +10,7 @@ import os
 
 PKG = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("ANIMEREC_LIB") or os.path.join(PKG, "lib", "libanimerec.so")   # override: A/B builds
-ABI_VERSION = 11
+ABI_VERSION = 12
 
 AR_MAX_BATCH = 16384
 AR_HEAVY_LEN = 64
@@ -68,11 +68,11 @@ PEER_MAX_RANKS, PEER_HANDLE_BYTES, PEER_FLAG_WORDS = 8, 64, 64
 
 class ArPeerCtx(C.Structure):
     _fields_ = [("n_ranks", C.c_int32), ("rank", C.c_int32),
-                ("W_peer", (C.c_void_p * PEER_MAX_RANKS) * 2), ("c_all_peer", C.c_void_p * PEER_MAX_RANKS),
+                ("W_peer", (C.c_void_p * PEER_MAX_RANKS) * 2), ("pub_peer", C.c_void_p * PEER_MAX_RANKS),
                 ("flags_peer", C.c_void_p * PEER_MAX_RANKS), ("sel_cap", C.c_int32),
                 ("sel_key", C.c_void_p * 2), ("sel_samp", C.c_void_p * 2), ("sel_oth", C.c_void_p * 2),
                 ("sel_cnt", C.c_void_p * 2), ("max_count", C.c_void_p), ("label_step", C.c_void_p),
-                ("dy_all", C.c_void_p), ("fwd_part_all", C.c_void_p), ("head_part_all", C.c_void_p)]
+                ("c_all", C.c_void_p), ("dy_all", C.c_void_p), ("fwd_part_all", C.c_void_p), ("head_part_all", C.c_void_p)]
 
 
 class AnimerecError(RuntimeError):

@@ -12,17 +12,20 @@
 // every sum below has a fixed order), and the ordinary dedup plan is built over those lists.
 // Per step t:
 //   look-ahead catch-up of my rows (side stream, as on one GPU)
-//   [flag barrier 2t]     every owner's rows are current
-//   peer_fwd   warp per listed sample: my row (local) + the other table's row (NVLink) -> 1/||.||, cosine c;
-//              the normalised other row is stashed locally for the gradient; the user side publishes c to
-//              every rank's c_all (G 4-byte peer stores)
-//   [flag barrier 2t+1]   c_all complete everywhere
-//   head_step  over the global batch, redundantly on every rank (SyncBN; replicas of the 4 head scalars
-//              stay bit-identical)
+//   peer_fwd   first CTA: flag 2t "my rows are current"; every CTA waits for all ranks' 2t, then warp per
+//              listed sample: my row (local) + the other table's row (NVLink) -> 1/||.||, cosine c; the
+//              normalised other row is stashed locally for the gradient; the user side appends (sample, c) to
+//              my PUBLISHED list (local stores); last CTA: flag 2t+1 "my cosines are published"
+//   peer_pull  waits for all ranks' 2t+1, reads every rank's published list (coalesced 8-byte NVLink loads),
+//              scatters c into the local global-batch array and reduces (sum c, sum c^2) in list order
+//   head_step  over the global batch, redundantly on every rank (SyncBN; the 4 head scalars stay bit-identical
+//              because every rank sums the same lists in the same order)
 //   rows_update  the single-GPU kernel on my rows: segment sums over the stash, catch-up-free Adam
-// NVLink traffic per step and GPU: the pulled rows, ~2*B*dim*4 bytes (10 MB at B = 10000, dim = 128), and
-// G*B cosines out.  Nothing is staged, packed or merged, and a row's gradient is summed by one warp in plan
-// order -- the result does not depend on which rank a sample came from.
+// NVLink traffic per step and GPU: the pulled rows, ~2*B*dim*4 bytes (10 MB at B = 10000, dim = 128; measured
+// ~610 GB/s, i.e. bandwidth-bound) plus 8*G*B bytes of cosines.  All of it is READS -- the only peer stores are
+// the flag words, so no CTA needs a system-scope fence (a first version scattered c to every rank with 4-byte
+// peer stores + a __threadfence_system per CTA: ~10 us slower per step).  Nothing is staged, packed or merged,
+// and a row's gradient is summed by one warp in plan order.
 //
 // Flag barriers: rank r's arrival is the epoch number stored (st.release.sys) into word r of EVERY rank's flag
 // array; a waiter spins (ld.acquire.sys) on its own array.  Epochs are derived from the optimizer step, so
@@ -78,20 +81,28 @@ __global__ void __launch_bounds__(32) peer_barrier_kernel(PeerFlags f, int epoch
   }
 }
 
-// The training step splits the barrier: arrival is signalled by a one-warp kernel (epoch 2t, "my rows are
-// current") or by the last CTA of the forward (epoch 2t+1, "my cosines are published"), and the FIRST kernel
-// that needs the other ranks' data waits in its prologue -- its CTAs are already resident when the flags land,
-// which takes a launch gap and a separate spinning kernel off the critical path.
-__global__ void __launch_bounds__(32) peer_signal_kernel(PeerFlags f, int epoch) {
-  const int r = threadIdx.x;
-  if (r < f.G) st_release_sys(f.peer[r] + f.me, epoch);
-}
+// The training step splits the barrier and folds both halves into its kernels: the FIRST CTA of the forward to
+// start signals epoch 2t ("my rows are current" -- everything before it in the stream is complete), its LAST
+// CTA to finish signals 2t+1 ("my cosines are published"), and the first kernel that needs the other ranks'
+// data waits in its prologue -- its CTAs are already resident when the flags land.  No barrier launches, no
+// launch gaps around them (a separate signal kernel cost 5 us of gap before the forward, measured).
+// AR_PEER_LOG=1: %globaltimer stamps of one step, written by the kernels themselves (no events, no
+// perturbation): 0 fwd start, 1 fwd past its wait, 2 fwd last CTA done, 3 pull start, 4 pull past its wait,
+// 5 pull done
+constexpr int kLogStamps = 8;
 
-// called by every thread of a CTA; threads r < G wait for rank r's arrival
+__device__ __forceinline__ int ld_relaxed_sys(const int32_t* p) {
+  int v;
+  asm volatile("ld.volatile.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+// Called by every thread of a CTA; threads r < G wait for rank r's arrival.  The poll is a relaxed system-scope
+// load: everything read behind it that another rank wrote is read with system-scope (L1-bypassing) loads as
+// well, and only after the __syncthreads, so no acquire (L1 invalidation per CTA) is needed.
 __device__ __forceinline__ void peer_wait(int32_t* mine, int G, int epoch) {
-  if ((int)threadIdx.x < G && ld_acquire_sys(mine + kPeerErrWord) == 0) {
+  if ((int)threadIdx.x < G && ld_relaxed_sys(mine + kPeerErrWord) == 0) {
     const unsigned long long t0 = global_ns();
-    while (ld_acquire_sys(mine + threadIdx.x) < epoch) {
+    while (ld_relaxed_sys(mine + threadIdx.x) < epoch) {
       if (global_ns() - t0 > kPeerTimeoutNs) {
         st_release_sys(mine + kPeerErrWord, epoch);
         break;
@@ -101,19 +112,50 @@ __device__ __forceinline__ void peer_wait(int32_t* mine, int G, int epoch) {
   __syncthreads();
 }
 
-// (sum c, sum c^2) per kPartSamples cosines, behind the "cosines published" flags.  One partial per CTA (the
-// single-GPU forward emits one per 8 samples; at G*B samples every head CTA would re-read G times as many)
-constexpr int kPartThreads = 128, kPartSamples = kPartThreads * 8;
-__global__ void __launch_bounds__(kPartThreads)
-c_partials_wait_kernel(const float* __restrict__ c, int n, double* __restrict__ fwd_part, int32_t* flags, int G, int epoch) {
-  __shared__ double red[2][kPartThreads / 32];
-  peer_wait(flags, G, epoch);
-  const int i0 = (blockIdx.x * kPartThreads + threadIdx.x) * 8;
+// Gather the published (sample, cosine) lists of every rank: CTA (b, r) takes pairs [b*kPullPairs, ...) of
+// rank r's list, scatters c into the local global-batch array and writes one (sum c, sum c^2) partial -- in
+// list order, so every rank computes bit-identical batch statistics.
+constexpr int kPullThreads = 128, kPullPer = 8, kPullPairs = kPullThreads * kPullPer;
+constexpr int kPeerCountWord = 42;     // flags[42]: length of my published list of the current step
+struct PeerPullArgs {
+  const float2* pub_peer[kPeerMaxRanks];   // every rank's published list: (.x = sample position as int bits, .y = c)
+  int32_t* flags_peer[kPeerMaxRanks];
+  float* c_all;                            // local (G*B)
+  double* fwd_part;                        // [G * gridDim.x] x 2
+  int G, me, epoch, ng;
+  unsigned long long* log;
+};
+__device__ __forceinline__ float2 ld2_sys(const float2* p) {
+  float2 r;
+  asm volatile("ld.volatile.global.v2.f32 {%0,%1}, [%2];" : "=f"(r.x), "=f"(r.y) : "l"(p) : "memory");
+  return r;
+}
+__global__ void __launch_bounds__(kPullThreads) peer_pull_kernel(PeerPullArgs a) {
+  __shared__ double red[2][kPullThreads / 32];
+  const int r = blockIdx.y;
+  const bool first = blockIdx.x == 0 && r == 0 && threadIdx.x == 0;
+  if (a.log && first) a.log[3] = global_ns();
+  peer_wait(a.flags_peer[a.me], a.G, a.epoch);
+  if (a.log && first) a.log[4] = global_ns();
+  const int cnt = ld_relaxed_sys(a.flags_peer[r] + kPeerCountWord);
+  const float2* pub = a.pub_peer[r];
+  const int i0 = blockIdx.x * kPullPairs + threadIdx.x;
+  float2 v[kPullPer];
+#pragma unroll
+  for (int k = 0; k < kPullPer; ++k) {
+    const int i = i0 + k * kPullThreads;
+    v[k] = (i < cnt) ? ld2_sys(pub + i) : make_float2(__int_as_float(-1), 0.f);
+  }
   double a0 = 0.0, a1 = 0.0;
-  for (int i = i0; i < min(n, i0 + 8); ++i) {
-    const double x = (double)__ldcg(c + i);
-    a0 += x;
-    a1 += x * x;
+#pragma unroll
+  for (int k = 0; k < kPullPer; ++k) {
+    const int j = __float_as_int(v[k].x);
+    if (j >= 0 && j < a.ng) {
+      a.c_all[j] = v[k].y;
+      const double x = (double)v[k].y;
+      a0 += x;
+      a1 += x * x;
+    }
   }
   a0 = warp_sum(a0);
   a1 = warp_sum(a1);
@@ -125,12 +167,14 @@ c_partials_wait_kernel(const float* __restrict__ c, int n, double* __restrict__ 
   if (threadIdx.x == 0) {
     double b0 = 0.0, b1 = 0.0;
 #pragma unroll
-    for (int w = 0; w < kPartThreads / 32; ++w) {
+    for (int w = 0; w < kPullThreads / 32; ++w) {
       b0 += red[0][w];
       b1 += red[1][w];
     }
-    fwd_part[2 * blockIdx.x] = b0;
-    fwd_part[2 * blockIdx.x + 1] = b1;
+    const int slot = r * gridDim.x + blockIdx.x;
+    a.fwd_part[2 * slot] = b0;
+    a.fwd_part[2 * slot + 1] = b1;
+    if (a.log && blockIdx.x == gridDim.x - 1 && r == a.G - 1) a.log[5] = global_ns();
   }
 }
 
@@ -213,7 +257,7 @@ __global__ void __launch_bounds__(kSelThreads, 1) peer_select_kernel(PeerSelArgs
 // per step: forward of the listed samples
 struct PeerFwdArgs {
   const float* W_peer[2][kPeerMaxRanks];  // [table][rank] shard bases (own entry = local pointer)
-  float* c_peer[kPeerMaxRanks];           // every rank's c_all
+  float2* pub;                            // my published (sample position, c) list of this step (local, peer-read)
   const int32_t* key[2];
   const int32_t* samp[2];
   const int32_t* oth[2];
@@ -224,8 +268,12 @@ struct PeerFwdArgs {
   int32_t* flags_peer[kPeerMaxRanks];  // every rank's flag words
   int epoch_rows;    // wait for this epoch (all owners' rows current) before touching peer rows
   int epoch_c;       // the last CTA to finish signals this epoch (my cosines are in every c_all)
+  unsigned long long* log;  // AR_PEER_LOG stamps of this step, or null
+  int dbg;           // AR_PEER_DBG (timing experiments, WRONG results): 2 = read the other row from my own shard
+                     // instead of the owner's
 };
 constexpr int kPeerTicketWord = 40;    // flags[40]: arrival counter of peer_fwd_kernel's CTAs (local)
+constexpr int kPeerSignalWord = 41;    // flags[41]: last "rows current" epoch this rank has announced (local)
 
 template <int NV>
 __global__ void __launch_bounds__(kRowThreads) peer_fwd_kernel(PeerFwdArgs a) {
@@ -235,7 +283,13 @@ __global__ void __launch_bounds__(kRowThreads) peer_fwd_kernel(PeerFwdArgs a) {
   const int k = blk * kRowWarps + (threadIdx.x >> 5);
   const int cnt = second ? a.cnt[1][0] : a.cnt[0][0];
   int32_t* my_flags = a.flags_peer[a.me];
+  if (a.log && blockIdx.x == 0 && threadIdx.x == 0) a.log[0] = global_ns();
+  if (threadIdx.x == 0) {  // whichever CTA starts first announces that my rows are current
+    if (atomicMax(my_flags + kPeerSignalWord, a.epoch_rows) < a.epoch_rows)
+      for (int r = 0; r < a.G; ++r) st_release_sys(a.flags_peer[r] + a.me, a.epoch_rows);
+  }
   if (blk * kRowWarps < cnt) peer_wait(my_flags, a.G, a.epoch_rows);  // CTA-uniform
+  if (a.log && blockIdx.x == 0 && threadIdx.x == 0) a.log[1] = global_ns();
   if (k < cnt) {
   const int32_t* keyp = second ? a.key[1] : a.key[0];
   const int32_t* othp = second ? a.oth[1] : a.oth[0];
@@ -244,7 +298,7 @@ __global__ void __launch_bounds__(kRowThreads) peer_fwd_kernel(PeerFwdArgs a) {
   const int og = __ldg(othp + k);
   const int owner = og % a.G, olocal = og / a.G;
   const float* own_base = second ? a.W_peer[1][a.me] : a.W_peer[0][a.me];
-  const float* orow = (second ? a.W_peer[0][owner] : a.W_peer[1][owner]) + (size_t)olocal * dim;
+  const float* orow = (second ? a.W_peer[0][(a.dbg & 2) ? a.me : owner] : a.W_peer[1][(a.dbg & 2) ? a.me : owner]) + (size_t)olocal * dim;
   RowTile<NV> w, o;
   w.load(own_base + (size_t)row * dim, d4, lane);
 #pragma unroll
@@ -269,17 +323,19 @@ __global__ void __launch_bounds__(kRowThreads) peer_fwd_kernel(PeerFwdArgs a) {
     // identical summation on both sides is not needed for that: only this value is ever used
     const float cs = tile_dot<NV>(w, o);
     const int j = __ldg(a.samp[0] + k);
-    if (lane < a.G) a.c_peer[lane][j] = cs;
+    if (lane == 0) a.pub[k] = make_float2(__int_as_float(j), cs);
   }
   }
-  // arrival: once every CTA's peer stores are fenced, the last one tells every rank (threadFenceReduction pattern)
+  // arrival: once every CTA's stores are fenced, the last one tells every rank (threadFenceReduction pattern)
   __syncthreads();
   if (threadIdx.x == 0) {
-    __threadfence_system();
+    __threadfence();  // device scope is enough: the last CTA's release below is cumulative over the tickets
     const int old = atomicAdd(my_flags + kPeerTicketWord, 1);
     if (old == (int)gridDim.x - 1) {
       my_flags[kPeerTicketWord] = 0;
+      my_flags[kPeerCountWord] = a.cnt[0][0];
       for (int r = 0; r < a.G; ++r) st_release_sys(a.flags_peer[r] + a.me, a.epoch_c);
+      if (a.log) a.log[2] = global_ns();
     }
   }
 }
@@ -289,12 +345,12 @@ static int check_peer(const ar_peer_ctx* h) {
   AR_REQUIRE(h->n_ranks >= 1 && h->n_ranks <= kPeerMaxRanks && h->rank >= 0 && h->rank < h->n_ranks,
              "ar_train_steps_peer: rank %d / n_ranks %d unsupported (1..%d)", h->rank, h->n_ranks, kPeerMaxRanks);
   for (int r = 0; r < h->n_ranks; ++r)
-    AR_REQUIRE(h->W_peer[0][r] && h->W_peer[1][r] && h->c_all_peer[r] && h->flags_peer[r],
+    AR_REQUIRE(h->W_peer[0][r] && h->W_peer[1][r] && h->pub_peer[r] && h->flags_peer[r],
                "ar_train_steps_peer: peer pointers of rank %d missing", r);
   for (int t = 0; t < 2; ++t)
     AR_REQUIRE(h->sel_key[t] && h->sel_samp[t] && h->sel_oth[t] && h->sel_cnt[t], "ar_train_steps_peer: null selection list");
   AR_REQUIRE(h->sel_cap > 0 && h->sel_cap <= AR_MAX_BATCH, "ar_train_steps_peer: sel_cap %d outside (0, %d]", h->sel_cap, AR_MAX_BATCH);
-  AR_REQUIRE(h->max_count && h->label_step && h->dy_all && h->fwd_part_all && h->head_part_all,
+  AR_REQUIRE(h->max_count && h->label_step && h->c_all && h->dy_all && h->fwd_part_all && h->head_part_all,
              "ar_train_steps_peer: null buffer in peer ctx");
   return AR_OK;
 }
@@ -417,17 +473,22 @@ extern "C" int ar_train_steps_peer(const ar_train_ctx* ctx, const ar_peer_ctx* h
   cudaStream_t st = (cudaStream_t)stream;
   const int dim = x.users.dim, G = h->n_ranks, B = x.batch;
   static const bool no_overlap = getenv("AR_NO_LOOKAHEAD") != nullptr;
+  // where the look-ahead catch-up of step s+1 starts: behind the forward of step s (default) -- the forward is
+  // what the OTHER ranks wait for, so it gets the SMs to itself and the SFU-bound replay overlaps the head and
+  // the row update instead -- or right behind update(s-1) as on one GPU (AR_PEER_AHEAD_EARLY=1, A/B aid)
+  static const bool ahead_early = getenv("AR_PEER_AHEAD_EARLY") != nullptr;
   const bool can_ahead = x.plan_u.in_prev && x.plan_a.in_prev;
   Lookahead* la = (x.mode == AR_ADAM_REPLAY && can_ahead && !no_overlap) ? lookahead() : nullptr;
   if (la) AR_CUDA(cudaEventRecord(la->ev_upd[1], st));
-  float* c_all = h->c_all_peer[h->rank];
-  // AR_PEER_PROFILE=1: events around every launch, per-stage averages to stderr (developer aid; synchronises)
-  static const bool prof = getenv("AR_PEER_PROFILE") != nullptr;
-  // AR_PEER_UNFUSED=1: stand-alone barrier kernels instead of the split form (A/B measurement)
-  static const bool unfused = getenv("AR_PEER_UNFUSED") != nullptr;
-  StageTimer tm_store;
-  tm_store.st = st;
-  StageTimer* timer = prof ? &tm_store : nullptr;
+  float* c_all = h->c_all;
+  static const bool do_log = getenv("AR_PEER_LOG") != nullptr;
+  static const int dbg = getenv("AR_PEER_DBG") ? atoi(getenv("AR_PEER_DBG")) : 0;
+  static unsigned long long* log_dev = nullptr;
+  constexpr int kLogSteps = 1024;
+  if (do_log && !log_dev) {
+    AR_CUDA(cudaMalloc((void**)&log_dev, (size_t)kLogSteps * kLogStamps * 8));
+    AR_CUDA(cudaMemset(log_dev, 0, (size_t)kLogSteps * kLogStamps * 8));
+  }
   for (int s = 0; s < n_steps; ++s) {
     const int64_t e = epoch_step0 + s;
     const int64_t base = e * (int64_t)B;
@@ -436,36 +497,28 @@ extern "C" int ar_train_steps_peer(const ar_train_ctx* ctx, const ar_peer_ctx* h
     const int slot = slot0 + s;
     const int64_t t = t0 + s + 1;
     const int ng = n * G;
+    unsigned long long* log = (do_log && s < kLogSteps) ? log_dev + (size_t)s * kLogStamps : nullptr;
     const bool has_next = (s + 1 < n_steps) && ((e + 1) * (int64_t)B < x.n_samples);
     if (x.mode == AR_ADAM_REPLAY && (!la || s == 0)) {
       if ((rc = launch_catchup(&x.users, &x.plan_u, slot, &x.anime, &x.plan_a, slot, x.alpha, x.l2, t - 1, st, false, x.sched_ws))) return rc;
     }
     bool ahead = false;
-    if (la && has_next) {  // as in run_steps: my rows of step s+1 that step s leaves alone, on the side stream
-      AR_CUDA(cudaStreamWaitEvent(la->st2, la->ev_upd[(s + 1) & 1], 0));
+    auto launch_ahead = [&](cudaEvent_t after) -> int {
+      // as in run_steps: my rows of step s+1 that step s leaves alone are brought to step t on the side stream
+      AR_CUDA(cudaStreamWaitEvent(la->st2, after, 0));
       int32_t* ws2 = x.sched_ws ? x.sched_ws + 3 * ((size_t)x.plan_u.batch_cap + x.plan_a.batch_cap) + 4 : nullptr;
-      if ((rc = launch_catchup(&x.users, &x.plan_u, slot + 1, &x.anime, &x.plan_a, slot + 1, x.alpha, x.l2, t, la->st2, true, ws2)))
-        return rc;
+      int r2 = launch_catchup(&x.users, &x.plan_u, slot + 1, &x.anime, &x.plan_a, slot + 1, x.alpha, x.l2, t, la->st2, true, ws2);
+      if (r2) return r2;
       AR_CUDA(cudaEventRecord(la->ev_ahead, la->st2));
       ahead = true;
-    }
-    AR_TICK(0);
-    PeerFlags pf{};
-    for (int r = 0; r < G; ++r) pf.peer[r] = h->flags_peer[r];
-    pf.G = G;
-    pf.me = h->rank;
-    if (unfused) {
-      if ((rc = peer_barrier(*h, (int)(2 * t), st))) return rc;
-    } else {
-      peer_signal_kernel<<<1, 32, 0, st>>>(pf, (int)(2 * t));  // my rows of this step are current
-      AR_LAUNCH_CHECK();
-    }
-    AR_TICK(1);
+      return AR_OK;
+    };
+    if (la && has_next && ahead_early && (rc = launch_ahead(la->ev_upd[(s + 1) & 1]))) return rc;
     PeerFwdArgs f{};
     for (int r = 0; r < G; ++r) {
       f.W_peer[0][r] = h->W_peer[0][r];
       f.W_peer[1][r] = h->W_peer[1][r];
-      f.c_peer[r] = h->c_all_peer[r];
+      f.flags_peer[r] = h->flags_peer[r];
     }
     for (int k = 0; k < 2; ++k) {
       f.key[k] = h->sel_key[k] + (int64_t)slot * cap;
@@ -473,27 +526,38 @@ extern "C" int ar_train_steps_peer(const ar_train_ctx* ctx, const ar_peer_ctx* h
       f.oth[k] = h->sel_oth[k] + (int64_t)slot * cap;
       f.cnt[k] = h->sel_cnt[k] + slot;
     }
+    f.pub = reinterpret_cast<float2*>(h->pub_peer[h->rank]);
     f.stash[0] = x.ah; f.stash[1] = x.uh;
     f.rinv[0] = x.ru; f.rinv[1] = x.ra;
     f.G = G; f.me = h->rank; f.dim = dim;
-    for (int r = 0; r < G; ++r) f.flags_peer[r] = h->flags_peer[r];
-    f.epoch_rows = unfused ? 0 : (int)(2 * t);
-    f.epoch_c = (int)(2 * t + 1);
+    f.epoch_rows = (int)(2 * t);      // signalled by this kernel's first CTA: my rows of this step are current
+    f.epoch_c = (int)(2 * t + 1);     // signalled by its last CTA: my cosines are in every c_all
+    f.dbg = dbg;
+    f.log = log;
     f.blocks0 = ceil_div(count_hint, kRowWarps);
     AR_DISPATCH_NV(dim, peer_fwd_kernel<NV><<<2 * f.blocks0, kRowThreads, 0, st>>>(f));
     AR_LAUNCH_CHECK();
-    AR_TICK(2);
-    if (unfused && (rc = peer_barrier(*h, (int)(2 * t + 1), st))) return rc;
-    const int nfp = ceil_div(ng, kPartSamples);
-    c_partials_wait_kernel<<<nfp, kPartThreads, 0, st>>>(c_all, ng, h->fwd_part_all, h->flags_peer[h->rank], G,
-                                                         unfused ? 0 : (int)(2 * t + 1));
+    if (la && has_next && !ahead_early) {
+      AR_CUDA(cudaEventRecord(la->ev_mid, st));
+      if ((rc = launch_ahead(la->ev_mid))) return rc;
+    }
+    PeerPullArgs pl{};
+    for (int r = 0; r < G; ++r) {
+      pl.pub_peer[r] = reinterpret_cast<const float2*>(h->pub_peer[r]);
+      pl.flags_peer[r] = h->flags_peer[r];
+    }
+    pl.c_all = c_all;
+    pl.fwd_part = h->fwd_part_all;
+    pl.G = G; pl.me = h->rank; pl.epoch = (int)(2 * t + 1); pl.ng = ng;
+    pl.log = log;
+    const int pull_blocks = ceil_div(count_hint, kPullPairs);
+    const int nfp = G * pull_blocks;
+    peer_pull_kernel<<<dim3(pull_blocks, G), kPullThreads, 0, st>>>(pl);
     AR_LAUNCH_CHECK();
-    AR_TICK(3);
     head_step_kernel<<<ceil_div(ng, kHeadThreads), kHeadThreads, 0, st>>>(
         c_all, h->label_step + (int64_t)slot * G * B, ng, nullptr, h->fwd_part_all, x.head, x.head_m, x.head_v,
         x.bn_moving, x.alpha, t, h->dy_all, h->head_part_all, x.stepc, x.ticket, x.metrics + t * 4, nfp);
     AR_LAUNCH_CHECK();
-    AR_TICK(4);
     UpdateArgs a{};
     fill_update(a, 0, &x.users, &x.plan_u, slot, x.ah, x.ru, count_hint);
     fill_update(a, 1, &x.anime, &x.plan_a, slot, x.uh, x.ra, count_hint);
@@ -501,7 +565,6 @@ extern "C" int ar_train_steps_peer(const ar_train_ctx* ctx, const ar_peer_ctx* h
     a.samp[1] = f.samp[1];
     double* ss = (x.mode == AR_ADAM_DENSE && x.reg_sumsq) ? x.reg_sumsq + t * 32 : nullptr;
     if ((rc = launch_update(a, true, c_all, h->dy_all, x.stepc, x.alpha, x.l2, t, 0, ss, st))) return rc;
-    AR_TICK(5);
     if (la) {
       AR_CUDA(cudaEventRecord(la->ev_upd[s & 1], st));
       if (ahead) AR_CUDA(cudaStreamWaitEvent(st, la->ev_ahead, 0));
@@ -511,23 +574,25 @@ extern "C" int ar_train_steps_peer(const ar_train_ctx* ctx, const ar_peer_ctx* h
       if ((rc = launch_flush(&x.anime, x.alpha, x.l2, t, ss, st))) return rc;
     }
   }
-  if (timer && timer->ev.size() >= 12) {
+  if (do_log && n_steps >= 8) {
     AR_CUDA(cudaStreamSynchronize(st));
-    const size_t ns = timer->ev.size() / 6;
+    const int ns = std::min(n_steps, kLogSteps);
+    std::vector<unsigned long long> hl((size_t)ns * kLogStamps);
+    AR_CUDA(cudaMemcpy(hl.data(), log_dev, hl.size() * 8, cudaMemcpyDeviceToHost));
     double acc[6] = {0, 0, 0, 0, 0, 0};
-    for (size_t i = 1; i < ns; ++i) {  // skip the first step (exposed catch-up)
-      float ms = 0.f;
-      for (int k = 0; k < 5; ++k) {
-        cudaEventElapsedTime(&ms, timer->ev[i * 6 + k], timer->ev[i * 6 + k + 1]);
-        acc[k] += ms;
-      }
-      cudaEventElapsedTime(&ms, timer->ev[(i - 1) * 6 + 5], timer->ev[i * 6]);
-      acc[5] += ms;
+    int cntd = 0;
+    for (int i = 2; i + 1 < ns; ++i) {
+      const unsigned long long* a = &hl[(size_t)i * kLogStamps];
+      const unsigned long long* nx = &hl[(size_t)(i + 1) * kLogStamps];
+      if (!a[0] || !a[5] || !nx[0]) continue;
+      for (int k = 0; k < 5; ++k) acc[k] += (double)(long long)(a[k + 1] - a[k]);
+      acc[5] += (double)(long long)(nx[0] - a[5]);
+      ++cntd;
     }
-    fprintf(stderr, "[peer rank %d] us/step over %zu steps: signal %.1f  wait+fwd %.1f  wait+c_partials %.1f  head %.1f  update %.1f  between-steps %.1f\n",
-            h->rank, ns - 1, 1e3 * acc[0] / (ns - 1), 1e3 * acc[1] / (ns - 1), 1e3 * acc[2] / (ns - 1),
-            1e3 * acc[3] / (ns - 1), 1e3 * acc[4] / (ns - 1), 1e3 * acc[5] / (ns - 1));
-    for (cudaEvent_t ev : timer->ev) cudaEventDestroy(ev);
+    if (cntd)
+      fprintf(stderr, "[peer log rank %d] us over %d steps: fwd wait %.1f | fwd body %.1f | ->pull %.1f | pull wait %.1f | pull %.1f | head+update+gaps %.1f\n",
+              h->rank, cntd, acc[0] / cntd / 1e3, acc[1] / cntd / 1e3, acc[2] / cntd / 1e3, acc[3] / cntd / 1e3,
+              acc[4] / cntd / 1e3, acc[5] / cntd / 1e3);
   }
   return AR_OK;
 }

@@ -186,7 +186,7 @@ extern "C" int ar_plan_link(const ar_plan* plan, int32_t n_steps, const int32_t*
 }
 
 extern "C" const char* ar_last_error(void) { return ar::g_err; }
-extern "C" int ar_abi_version(void) { return 11; }
+extern "C" int ar_abi_version(void) { return 12; }
 
 extern "C" int ar_check_device(void) {
   int dev = 0;

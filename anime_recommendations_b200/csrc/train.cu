@@ -920,6 +920,7 @@ struct Lookahead {
   cudaStream_t st2 = nullptr;
   cudaEvent_t ev_upd[2] = {nullptr, nullptr};  // "row update of step s is complete" (recorded on the main stream)
   cudaEvent_t ev_ahead = nullptr;              // "look-ahead catch-up for the next step is complete" (side stream)
+  cudaEvent_t ev_mid = nullptr;                // peer mode: "forward of step s is queued" (main stream)
   bool ok = false;
 };
 static Lookahead* lookahead() {
@@ -936,6 +937,7 @@ static Lookahead* lookahead() {
     for (int i = 0; i < 2; ++i)
       if (cudaEventCreateWithFlags(&l.ev_upd[i], cudaEventDisableTiming) != cudaSuccess) return nullptr;
     if (cudaEventCreateWithFlags(&l.ev_ahead, cudaEventDisableTiming) != cudaSuccess) return nullptr;
+    if (cudaEventCreateWithFlags(&l.ev_mid, cudaEventDisableTiming) != cudaSuccess) return nullptr;
     l.ok = true;
   }
   return &l;

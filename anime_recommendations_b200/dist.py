@@ -9,6 +9,7 @@ issued from libanimerec on the kernels' stream.
 from __future__ import annotations
 
 import ctypes as C
+import time
 
 import numpy as np
 import torch
@@ -205,14 +206,14 @@ class PeerTrainSession(TrainSession):
         B, D, dev, S = self.B, model.dim, model.device, self.n_slots
         f = dict(dtype=torch.float32, device=dev)
         i32 = dict(dtype=torch.int32, device=dev)
-        # everything the other ranks read or write lives in ONE allocation: [U | A | c_all | flags]
+        # everything the other ranks read or write lives in ONE allocation: [U | A | published list | flags]
         nU, nA = model.U.numel(), model.A.numel()
-        words = nU + nA + G * B + PEER_FLAG_WORDS
+        words = nU + nA + 2 * cap + PEER_FLAG_WORDS
         self.arena = torch.zeros(words, **f)
         o = 0
         U = self.arena[o:o + nU].view_as(model.U); o += nU
         A = self.arena[o:o + nA].view_as(model.A); o += nA
-        self.c_all = self.arena[o:o + G * B]; o += G * B
+        self.pub = self.arena[o:o + 2 * cap]; o += 2 * cap
         self.flags = self.arena[o:o + PEER_FLAG_WORDS].view(torch.int32)
         U.copy_(model.U)
         A.copy_(model.A)
@@ -244,8 +245,8 @@ class PeerTrainSession(TrainSession):
         for r in range(G):
             h.W_peer[0][r] = self.peer_base[r]
             h.W_peer[1][r] = self.peer_base[r] + 4 * lays[r][0]
-            h.c_all_peer[r] = self.peer_base[r] + 4 * (lays[r][0] + lays[r][1])
-            h.flags_peer[r] = self.peer_base[r] + 4 * (lays[r][0] + lays[r][1] + G * B)
+            h.pub_peer[r] = self.peer_base[r] + 4 * (lays[r][0] + lays[r][1])
+            h.flags_peer[r] = self.peer_base[r] + 4 * (lays[r][0] + lays[r][1] + 2 * cap)
         self._sel = dict(sel_key=[torch.zeros((S, cap), **i32) for _ in range(2)],
                          sel_samp=[torch.zeros((S, cap), **i32) for _ in range(2)],
                          sel_oth=[torch.zeros((S, cap), **i32) for _ in range(2)],
@@ -256,14 +257,16 @@ class PeerTrainSession(TrainSession):
                 arr[k] = bufs[k].data_ptr()
         self.max_count = torch.zeros(2, **i32)
         self.label_step = torch.zeros((S, G * B), **f)
+        self.c_all = torch.zeros(G * B, **f)
         self.dy_all = torch.empty(G * B, **f)
-        self.fwd_part_all = torch.zeros(2 * ((G * B + 7) // 8), dtype=torch.float64, device=dev)
+        self.fwd_part_all = torch.zeros(2 * G * ((cap + 1023) // 1024), dtype=torch.float64, device=dev)
         self.head_part_all = torch.zeros(8 * ((G * B + 255) // 256), dtype=torch.float64, device=dev)
         h.max_count, h.label_step, h.dy_all = self.max_count.data_ptr(), self.label_step.data_ptr(), self.dy_all.data_ptr()
+        h.c_all = self.c_all.data_ptr()
         h.fwd_part_all, h.head_part_all = self.fwd_part_all.data_ptr(), self.head_part_all.data_ptr()
         self.pctx = h
         self.gather = [torch.empty((G, S * B), **i32), torch.empty((G, S * B), **i32), torch.empty((G, S * B), **f)]
-        self.counts = []
+        self.counts, self._maxima = [], []
         # nobody may signal a flag before every rank has zeroed and mapped its arena
         torch.cuda.synchronize()
         dist.barrier()
@@ -297,18 +300,28 @@ class PeerTrainSession(TrainSession):
                     dst[:, :hi - lo].copy_(tmp)
             check(L.ar_peer_plan(ptr(self.gather[0]), ptr(self.gather[1]), ptr(self.gather[2]), S * B, hi - lo, B, ns,
                                  C.byref(self.plan_u), C.byref(self.plan_a), C.byref(self.pctx), st), "ar_peer_plan")
-            # one host read per chunk: the longest selection list (grid size; overflow check), max over ranks so
-            # that every rank takes the same decision
-            mc = self.max_count.max().reshape(1).to(torch.int64)
-            dist.all_reduce(mc, op=dist.ReduceOp.MAX)
-            mc = int(mc.item())
-            if mc > self.P:
-                raise _capi.AnimerecError("peer mode: %d samples of one step touch one rank's rows, capacity %d; "
-                                          "use ShardedTrainSession for this data" % (mc, self.P))
-            self.counts.append(mc)
-            self.check_flags()
-            check(L.ar_train_steps_peer(C.byref(ctx), C.byref(self.pctx), s0, 0, t0 + s0, ns, max(mc, 1), st),
+            # no host round trip per chunk: the grids are sized for the list capacity, and the longest list of
+            # every chunk is checked once, after the last chunk is queued (an overflowing list is truncated on
+            # the device, so nothing is corrupted before the check raises)
+            self._maxima.append(self.max_count.clone())
+            tq = time.perf_counter()
+            check(L.ar_train_steps_peer(C.byref(ctx), C.byref(self.pctx), s0, 0, t0 + s0, ns, self.P, st),
                   "ar_train_steps_peer")
+            self.enqueue_s += time.perf_counter() - tq
             self.launches += 6 + ns * (9 if m.adam_mode == "replay" else 7)
         m.iterations = t0 + steps
         return steps
+
+    def verify(self):
+        """Host check of everything run() queued so far (synchronises): list overflow and barrier time-outs.
+        Called by the owner of the session at its own sync points (end of an epoch, before reading results)."""
+        if self._maxima:
+            mc = torch.stack(self._maxima).max().reshape(1).to(torch.int64)
+            self._maxima = []
+            dist.all_reduce(mc, op=dist.ReduceOp.MAX)
+            mc = int(mc.item())
+            self.counts.append(mc)
+            if mc > self.P:
+                raise _capi.AnimerecError("peer mode: %d samples of one step touch one rank's rows, capacity %d; the "
+                                          "results of this run are invalid -- use ShardedTrainSession for this data" % (mc, self.P))
+        self.check_flags()

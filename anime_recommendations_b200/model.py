@@ -407,6 +407,7 @@ class TrainSession:
         self.reg_ss = (torch.zeros((self.t_cap + 1, 32), dtype=torch.float64, device=dev)
                        if model.adam_mode == "dense" else None)
         self.launches = 0
+        self.enqueue_s = 0.0    # host time spent inside ar_train_steps* (queueing the launches)
 
     @staticmethod
     def _make_plan(n_slots, batch, dev):
@@ -465,7 +466,9 @@ class TrainSession:
                 for pl in (self.plan_u, self.plan_a):
                     check(L.ar_plan_link(C.byref(pl), ns, None, None, 1, st), "ar_plan_link")
             if profile is None:
+                tq = time.perf_counter()
                 check(L.ar_train_steps(C.byref(ctx), s0, 0, t0 + s0, ns, st), "ar_train_steps")
+                self.enqueue_s += time.perf_counter() - tq
             else:
                 ms = (C.c_float * 5)()
                 check(L.ar_train_steps_profile(C.byref(ctx), s0, 0, t0 + s0, ns, ms, st), "ar_train_steps_profile")

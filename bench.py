@@ -238,7 +238,7 @@ def gpu_main(args):
         sampler.start()
     if world > 1:
         dist.barrier()
-    l0 = sess.launches
+    l0, q0 = sess.launches, sess.enqueue_s
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     torch.cuda.synchronize()
     if sampler:
@@ -250,7 +250,10 @@ def gpu_main(args):
     if sampler:
         sampler.mark_end()
     ms = e0.elapsed_time(e1)
+    if hasattr(sess, "verify"):
+        sess.verify()          # peer mode: list-capacity and barrier checks of everything just run
     launches = sess.launches - l0
+    enqueue_us = (sess.enqueue_s - q0) / K * 1e6   # host time per step spent queueing launches (rank 0)
     if world > 1:
         t = torch.tensor([ms], device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -261,7 +264,8 @@ def gpu_main(args):
 
     line = dict(metric=METRIC, value=value, unit=UNIT, n_gpus=world, steps=K, warmup=W, ms_per_step=ms / K,
                 higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f32", data="synthetic",
-                config=workload_config(mode, world), gpu_launches=int(launches), clocks=clocks)
+                config=workload_config(mode, world), gpu_launches=int(launches), host_enqueue_us_per_step=enqueue_us,
+                clocks=clocks)
     if world > 1:
         line["config"]["parallelism"] = "dp%d, %s tables" % (world, args.dist)
 
@@ -328,6 +332,8 @@ def gpu_main(args):
         du, da, dy = (t.to(dev, non_blocking=True) for t in (hu, ha, hy))
         t_first = model.iterations
         sess.run(du, da, dy, LR)
+        if hasattr(sess, "verify"):
+            sess.verify()
         model._sync_tables()
         mt = sess.metrics[t_first + 1:t_first + K + 1].cpu()              # D2H of the per-step metrics
         torch.cuda.synchronize()

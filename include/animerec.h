@@ -211,8 +211,8 @@ int ar_train_steps_sharded(const ar_train_ctx* ctx, const ar_shard_ctx* sh, int6
 /* ---- multi-GPU training over NVLink PEER MEMORY (row-sharded tables, owner computes) ----
  * Same ownership rule as the row-sharded path, no collective on the step's critical path: every rank works on
  * the samples of the global batch that touch ITS rows and loads the sample's row of the other table straight
- * from the owner's HBM (cudaIpc-mapped shards, 128-bit loads over NVLink); the ranks meet at two flag barriers
- * per step (spin on peer-written words).  One process per GPU on ONE node with all-to-all peer access. */
+ * from the owner's HBM (cudaIpc-mapped shards, 128-bit loads over NVLink) and the cosines every rank published;
+ * the ranks meet at two flag barriers per step (spin on peer-written words) folded into the step's kernels.  One process per GPU on ONE node with all-to-all peer access. */
 #define AR_PEER_MAX_RANKS 8
 #define AR_PEER_HANDLE_BYTES 64
 #define AR_PEER_FLAG_WORDS 64
@@ -227,7 +227,8 @@ typedef struct {
   int32_t rank;
   float* W_peer[2][AR_PEER_MAX_RANKS];          /* [0 users | 1 anime][rank]: base of that rank's shard; the own
                                                    entry is the local pointer (= ctx->users.W / ctx->anime.W) */
-  float* c_all_peer[AR_PEER_MAX_RANKS];         /* every rank's (n_ranks*batch) cosine buffer */
+  float* pub_peer[AR_PEER_MAX_RANKS];           /* every rank's published (sample, cosine) list: sel_cap pairs of
+                                                   (int32 position in the global batch, float c) */
   int32_t* flags_peer[AR_PEER_MAX_RANKS];       /* every rank's AR_PEER_FLAG_WORDS int32, zero-initialised before
                                                    any rank's first step; word 32 != 0: a barrier timed out */
   int32_t sel_cap;                              /* capacity of one selection list = batch_cap of both plans */
@@ -238,8 +239,9 @@ typedef struct {
   int32_t* max_count;                           /* [2] longest list of the planned chunk per table (> sel_cap:
                                                    overflow, the chunk must not be run) */
   float* label_step;                            /* [n_slots][n_ranks*batch] labels in global-batch order */
+  float* c_all;                                 /* (n_ranks*batch) local */
   float* dy_all;                                /* (n_ranks*batch) */
-  double* fwd_part_all;                         /* as in ar_dist_ctx */
+  double* fwd_part_all;                         /* (2 * n_ranks * ceil(sel_cap/1024)) */
   double* head_part_all;
 } ar_peer_ctx;
 

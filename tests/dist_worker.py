@@ -59,6 +59,8 @@ def shard_main(mode, dev, rank, world, peer=False):
     m.set_weights([Us, As] + fw[2:])
     sess = (PeerTrainSession if peer else ShardedTrainSession)(m, B, total_steps=steps)
     sess.run(torch.from_numpy(iu[sl]).to(dev), torch.from_numpy(ia[sl]).to(dev), torch.from_numpy(y[sl]).to(dev), 2e-3)
+    if peer:
+        sess.verify()
     m._sync_tables()
     # assemble the global tables on rank 0
     parts = {}
@@ -99,8 +101,6 @@ def shard_main(mode, dev, rank, world, peer=False):
         else:
             assert max(sess.caps) <= B and min(sess.caps) >= 4
             print("DIST_OK shard", mode, "cap", sess.caps)
-    if peer:
-        sess.check_flags()
 
 
 def main(mode):
