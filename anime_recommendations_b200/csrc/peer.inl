@@ -91,6 +91,14 @@ __global__ void __launch_bounds__(32) peer_barrier_kernel(PeerFlags f, int epoch
 // 5 pull done
 constexpr int kLogStamps = 8;
 
+// my arrival at `epoch`, to every rank: ONE system-scope fence, then G relaxed system-scope stores (a
+// st.release.sys per rank repeats the fence G times -- ~1 us each, measured as 5.5 us of minimum wait at G = 4)
+__device__ __forceinline__ void peer_signal(int32_t* const* flags_peer, int G, int me, int epoch) {
+  __threadfence_system();
+  for (int r = 0; r < G; ++r)
+    asm volatile("st.volatile.global.s32 [%0], %1;" ::"l"(flags_peer[r] + me), "r"(epoch) : "memory");
+}
+
 __device__ __forceinline__ int ld_relaxed_sys(const int32_t* p) {
   int v;
   asm volatile("ld.volatile.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
@@ -286,7 +294,7 @@ __global__ void __launch_bounds__(kRowThreads) peer_fwd_kernel(PeerFwdArgs a) {
   if (a.log && blockIdx.x == 0 && threadIdx.x == 0) a.log[0] = global_ns();
   if (threadIdx.x == 0) {  // whichever CTA starts first announces that my rows are current
     if (atomicMax(my_flags + kPeerSignalWord, a.epoch_rows) < a.epoch_rows)
-      for (int r = 0; r < a.G; ++r) st_release_sys(a.flags_peer[r] + a.me, a.epoch_rows);
+      peer_signal(a.flags_peer, a.G, a.me, a.epoch_rows);
   }
   if (blk * kRowWarps < cnt) peer_wait(my_flags, a.G, a.epoch_rows);  // CTA-uniform
   if (a.log && blockIdx.x == 0 && threadIdx.x == 0) a.log[1] = global_ns();
@@ -334,7 +342,7 @@ __global__ void __launch_bounds__(kRowThreads) peer_fwd_kernel(PeerFwdArgs a) {
     if (old == (int)gridDim.x - 1) {
       my_flags[kPeerTicketWord] = 0;
       my_flags[kPeerCountWord] = a.cnt[0][0];
-      for (int r = 0; r < a.G; ++r) st_release_sys(a.flags_peer[r] + a.me, a.epoch_c);
+      peer_signal(a.flags_peer, a.G, a.me, a.epoch_c);
       if (a.log) a.log[2] = global_ns();
     }
   }
@@ -473,10 +481,11 @@ extern "C" int ar_train_steps_peer(const ar_train_ctx* ctx, const ar_peer_ctx* h
   cudaStream_t st = (cudaStream_t)stream;
   const int dim = x.users.dim, G = h->n_ranks, B = x.batch;
   static const bool no_overlap = getenv("AR_NO_LOOKAHEAD") != nullptr;
-  // where the look-ahead catch-up of step s+1 starts: behind the forward of step s (default) -- the forward is
-  // what the OTHER ranks wait for, so it gets the SMs to itself and the SFU-bound replay overlaps the head and
-  // the row update instead -- or right behind update(s-1) as on one GPU (AR_PEER_AHEAD_EARLY=1, A/B aid)
-  static const bool ahead_early = getenv("AR_PEER_AHEAD_EARLY") != nullptr;
+  // where the look-ahead catch-up of step s+1 starts: right behind update(s-1) as on one GPU (default), or
+  // behind the forward of step s (AR_PEER_AHEAD_LATE=1), which keeps the SFU-bound replay out of the kernel
+  // the other ranks wait for but leaves it less of the step to hide in.  Measured: 83 vs 86 us/step on 2 GPUs,
+  // 107 vs 101 on 8 -- the early start wins where it matters.
+  static const bool ahead_early = getenv("AR_PEER_AHEAD_LATE") == nullptr;
   const bool can_ahead = x.plan_u.in_prev && x.plan_a.in_prev;
   Lookahead* la = (x.mode == AR_ADAM_REPLAY && can_ahead && !no_overlap) ? lookahead() : nullptr;
   if (la) AR_CUDA(cudaEventRecord(la->ev_upd[1], st));
@@ -588,6 +597,14 @@ extern "C" int ar_train_steps_peer(const ar_train_ctx* ctx, const ar_peer_ctx* h
       for (int k = 0; k < 5; ++k) acc[k] += (double)(long long)(a[k + 1] - a[k]);
       acc[5] += (double)(long long)(nx[0] - a[5]);
       ++cntd;
+    }
+    if (const char* path = getenv("AR_PEER_LOG_DUMP")) {  // raw stamps of this call, one file per rank
+      char name[512];
+      snprintf(name, sizeof(name), "%s.rank%d.bin", path, h->rank);
+      if (FILE* fp = fopen(name, "wb")) {
+        fwrite(hl.data(), 8, hl.size(), fp);
+        fclose(fp);
+      }
     }
     if (cntd)
       fprintf(stderr, "[peer log rank %d] us over %d steps: fwd wait %.1f | fwd body %.1f | ->pull %.1f | pull wait %.1f | pull %.1f | head+update+gaps %.1f\n",

@@ -267,7 +267,7 @@ def gpu_main(args):
                 config=workload_config(mode, world), gpu_launches=int(launches), host_enqueue_us_per_step=enqueue_us,
                 clocks=clocks)
     if world > 1:
-        line["config"]["parallelism"] = "dp%d, %s tables" % (world, args.dist)
+        line["config"]["parallelism"] = "dp%d, %s" % (world, {"peer": "row-sharded tables, NVLink peer-memory pulls + flag barriers", "replicated": "replicated tables, NCCL all-gather", "sharded": "row-sharded tables, NCCL all-to-all"}[args.dist])
 
     if rank == 0 and world == 1:
         # ---- roofline of the dominant kernel: per-stage device time measured live with CUDA events
@@ -342,8 +342,10 @@ def gpu_main(args):
         dist.barrier()
         line["e2e"] = dict(value=world * K * BATCH / float(dt.item()), unit=UNIT, h2d_bytes_per_step=BATCH * 12,
                            d2h_bytes_per_step=16, seconds=float(dt.item()), loss_bce_last=float(mt[-1, 0]),
-                           what="per rank: pinned host arrays -> H2D, K data-parallel steps (SyncBN + NCCL row-gradient "
-                                "exchange), table flush, D2H of the per-step metrics; max over ranks")
+                           what="per rank: pinned host arrays -> H2D, K data-parallel steps (SyncBN, %s), table flush, D2H of "
+                                "the per-step metrics; max over ranks" % {"peer": "rows pulled over NVLink peer memory",
+                                                                          "replicated": "NCCL all-gather of row gradients",
+                                                                          "sharded": "NCCL all-to-all of rows and gradients"}[args.dist])
     if rank == 0:
         print(json.dumps(line))
     if world > 1:
@@ -504,8 +506,9 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--mode", default="replay", choices=["replay", "dense", "touched"])
     ap.add_argument("--zipf", action="store_true", help="Zipf(1) anime popularity instead of uniform")
-    ap.add_argument("--dist", default="replicated", choices=["replicated", "sharded", "peer"],
-                    help="N > 1: replicated tables + all-gathered row gradients (cfg2) or row-sharded tables + all-to-all (cfg5 scheme)")
+    ap.add_argument("--dist", default="peer", choices=["peer", "replicated", "sharded"],
+                    help="N > 1: row-sharded tables, owners pull rows over NVLink peer memory (default); replicated tables "
+                         "+ NCCL all-gathered row gradients; or row-sharded tables + NCCL all-to-all")
     ap.add_argument("--skip-cpu", action="store_true")
     ap.add_argument("--skip-extras", action="store_true")
     args = ap.parse_args()
