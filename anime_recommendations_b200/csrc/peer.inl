@@ -91,12 +91,16 @@ __global__ void __launch_bounds__(32) peer_barrier_kernel(PeerFlags f, int epoch
 // 5 pull done
 constexpr int kLogStamps = 8;
 
-// my arrival at `epoch`, to every rank: ONE system-scope fence, then G relaxed system-scope stores (a
-// st.release.sys per rank repeats the fence G times -- ~1 us each, measured as 5.5 us of minimum wait at G = 4)
-__device__ __forceinline__ void peer_signal(int32_t* const* flags_peer, int G, int me, int epoch) {
-  __threadfence_system();
-  for (int r = 0; r < G; ++r)
-    asm volatile("st.volatile.global.s32 [%0], %1;" ::"l"(flags_peer[r] + me), "r"(epoch) : "memory");
+// my arrival at `epoch`, to every rank: G relaxed system-scope stores behind at most ONE system-scope fence (a
+// st.release.sys per rank repeats the fence G times, ~1 us each: measured as 4.4 us of minimum wait at G = 4).
+// fence = false is for an arrival that only publishes what EARLIER kernels of the stream wrote: their stores
+// reached L2 -- where the peers read them -- when those kernels completed, and this thread has written nothing.
+__device__ __forceinline__ void st_relaxed_sys(int32_t* p, int v) {
+  asm volatile("st.volatile.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ void peer_signal(int32_t* const* flags_peer, int G, int me, int epoch, bool fence) {
+  if (fence) __threadfence_system();
+  for (int r = 0; r < G; ++r) st_relaxed_sys(flags_peer[r] + me, epoch);
 }
 
 __device__ __forceinline__ int ld_relaxed_sys(const int32_t* p) {
@@ -124,7 +128,7 @@ __device__ __forceinline__ void peer_wait(int32_t* mine, int G, int epoch) {
 // rank r's list, scatters c into the local global-batch array and writes one (sum c, sum c^2) partial -- in
 // list order, so every rank computes bit-identical batch statistics.
 constexpr int kPullThreads = 128, kPullPer = 8, kPullPairs = kPullThreads * kPullPer;
-constexpr int kPeerCountWord = 42;     // flags[42]: length of my published list of the current step
+constexpr int kPeerCountWord = 16;     // flags[16 + r]: length of rank r's published list of the current step
 struct PeerPullArgs {
   const float2* pub_peer[kPeerMaxRanks];   // every rank's published list: (.x = sample position as int bits, .y = c)
   int32_t* flags_peer[kPeerMaxRanks];
@@ -145,7 +149,7 @@ __global__ void __launch_bounds__(kPullThreads) peer_pull_kernel(PeerPullArgs a)
   if (a.log && first) a.log[3] = global_ns();
   peer_wait(a.flags_peer[a.me], a.G, a.epoch);
   if (a.log && first) a.log[4] = global_ns();
-  const int cnt = ld_relaxed_sys(a.flags_peer[r] + kPeerCountWord);
+  const int cnt = ld_relaxed_sys(a.flags_peer[a.me] + kPeerCountWord + r);
   const float2* pub = a.pub_peer[r];
   const int i0 = blockIdx.x * kPullPairs + threadIdx.x;
   float2 v[kPullPer];
@@ -294,7 +298,7 @@ __global__ void __launch_bounds__(kRowThreads) peer_fwd_kernel(PeerFwdArgs a) {
   if (a.log && blockIdx.x == 0 && threadIdx.x == 0) a.log[0] = global_ns();
   if (threadIdx.x == 0) {  // whichever CTA starts first announces that my rows are current
     if (atomicMax(my_flags + kPeerSignalWord, a.epoch_rows) < a.epoch_rows)
-      peer_signal(a.flags_peer, a.G, a.me, a.epoch_rows);
+      peer_signal(a.flags_peer, a.G, a.me, a.epoch_rows, false);
   }
   if (blk * kRowWarps < cnt) peer_wait(my_flags, a.G, a.epoch_rows);  // CTA-uniform
   if (a.log && blockIdx.x == 0 && threadIdx.x == 0) a.log[1] = global_ns();
@@ -341,8 +345,9 @@ __global__ void __launch_bounds__(kRowThreads) peer_fwd_kernel(PeerFwdArgs a) {
     const int old = atomicAdd(my_flags + kPeerTicketWord, 1);
     if (old == (int)gridDim.x - 1) {
       my_flags[kPeerTicketWord] = 0;
-      my_flags[kPeerCountWord] = a.cnt[0][0];
-      peer_signal(a.flags_peer, a.G, a.me, a.epoch_c);
+      const int n_pub = a.cnt[0][0];  // length of my published list, into every rank's array ahead of the flag
+      for (int r = 0; r < a.G; ++r) st_relaxed_sys(a.flags_peer[r] + kPeerCountWord + a.me, n_pub);
+      peer_signal(a.flags_peer, a.G, a.me, a.epoch_c, true);
       if (a.log) a.log[2] = global_ns();
     }
   }
