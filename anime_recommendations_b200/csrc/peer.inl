@@ -486,11 +486,14 @@ extern "C" int ar_train_steps_peer(const ar_train_ctx* ctx, const ar_peer_ctx* h
   cudaStream_t st = (cudaStream_t)stream;
   const int dim = x.users.dim, G = h->n_ranks, B = x.batch;
   static const bool no_overlap = getenv("AR_NO_LOOKAHEAD") != nullptr;
-  // where the look-ahead catch-up of step s+1 starts: right behind update(s-1) as on one GPU (default), or
-  // behind the forward of step s (AR_PEER_AHEAD_LATE=1), which keeps the SFU-bound replay out of the kernel
-  // the other ranks wait for but leaves it less of the step to hide in.  Measured: 83 vs 86 us/step on 2 GPUs,
-  // 107 vs 101 on 8 -- the early start wins where it matters.
-  static const bool ahead_early = getenv("AR_PEER_AHEAD_LATE") == nullptr;
+  // where the look-ahead catch-up of step s+1 starts: behind the forward of step s (default) -- the forward is
+  // what the OTHER ranks wait for, so it gets the SMs to itself and the replay overlaps the pull, the head and
+  // the row update -- or right behind update(s-1) as on one GPU (AR_PEER_AHEAD_EARLY=1).  Started early, the
+  // low-priority replay CTAs fill the SMs as the forward drains and the next kernel of the main stream waits
+  // for slots: a 13-18 us gap between forward and pull in the in-kernel timeline.  Measured on 2 GPUs with the
+  // plan-order schedule PeerTrainSession uses (no classify pass: sharded replays are short and even): late
+  // 72.0 us/step, early 80.5; with the longest-first schedule 78.5 / 78.3.
+  static const bool ahead_early = getenv("AR_PEER_AHEAD_EARLY") != nullptr;
   const bool can_ahead = x.plan_u.in_prev && x.plan_a.in_prev;
   Lookahead* la = (x.mode == AR_ADAM_REPLAY && can_ahead && !no_overlap) ? lookahead() : nullptr;
   if (la) AR_CUDA(cudaEventRecord(la->ev_upd[1], st));

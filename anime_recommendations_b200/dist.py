@@ -320,6 +320,10 @@ class PeerTrainSession(TrainSession):
             raise _capi.AnimerecError("PeerTrainSession sized for %d optimizer steps, %d requested" % (self.t_cap, t0 + steps))
         m._set_alpha(lr, t0 + 1, steps)
         ctx = self._ctx(iu, ia, y)
+        # plan-order catch-up: with the rows sharded a row's replay is ~G times shorter than on one GPU, and the
+        # longest-first schedule's two extra launches per step cost more than its balance gains (2 GPUs: 72.0 vs
+        # 78.5 us/step)
+        ctx.sched_ws = None
         main, L, S = torch.cuda.current_stream(), lib(), self.n_slots
         chunks = [(s0, min(S, steps - s0)) for s0 in range(0, steps, S)]
         self.plan_stream.wait_stream(main)                 # the inputs (H2D copies) are queued on `main`
@@ -343,8 +347,8 @@ class PeerTrainSession(TrainSession):
             self.enqueue_s += time.perf_counter() - tq
             st["consumed"].record(main)
             # per chunk: select, 2 plan sorts, 2 plan links; per step: forward, pull, head, row update and
-            # (replay) classify + catch-up or (dense) two table flushes
-            self.launches += 5 + ns * {"replay": 6, "dense": 6, "touched": 4}[m.adam_mode]
+            # (replay) catch-up or (dense) two table flushes
+            self.launches += 5 + ns * {"replay": 5, "dense": 6, "touched": 4}[m.adam_mode]
         main.wait_stream(self.plan_stream)                 # nothing of this call is left on the side stream
         m.iterations = t0 + steps
         return steps
