@@ -142,7 +142,7 @@ def synth(n_samples, seed, device, zipf=False):
 
 
 # ------------------------------------------------------------------------------------------ CPU arm
-def cpu_reference_run(steps, warmup, seed=42, budget_s=120.0):
+def cpu_reference_run(steps, warmup, seed=42, budget_s=120.0, batch=None):
     """The reference's arithmetic (dense gradient + dense Keras Adam, what TF-2.12 executes for
     neural_network.py:66-106) restated with PyTorch-CPU ops on all host cores (oracle/train_torch.py);
     TensorFlow itself is not installable in this image."""
@@ -150,15 +150,16 @@ def cpu_reference_run(steps, warmup, seed=42, budget_s=120.0):
     from oracle import train as ot, train_torch as tt
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
+    batch = int(batch or BATCH)
     st = ot.init_state(N_USERS, N_ANIME, DIM, seed=1, w=1.0)
     ts = tt.TorchState(st)
     rng = np.random.RandomState(seed)
     times = []
     t_begin = time.perf_counter()
     for s in range(warmup + steps):
-        iu = rng.randint(0, N_USERS, BATCH)
-        ia = rng.randint(0, N_ANIME, BATCH)
-        y = (rng.randint(0, 11, BATCH) / 10.0).astype(np.float32)
+        iu = rng.randint(0, N_USERS, batch)
+        ia = rng.randint(0, N_ANIME, batch)
+        y = (rng.randint(0, 11, batch) / 10.0).astype(np.float32)
         t0 = time.perf_counter()
         tt.train_step(ts, iu, ia, y, LR, L2)
         dt = time.perf_counter() - t0
@@ -167,19 +168,21 @@ def cpu_reference_run(steps, warmup, seed=42, budget_s=120.0):
         if time.perf_counter() - t_begin > budget_s and len(times) >= 2:
             break
     ms = 1e3 * float(np.mean(times))
-    return dict(value=BATCH / (ms / 1e3), ms_per_step=ms, steps=len(times), cores=cores)
+    return dict(value=batch / (ms / 1e3), ms_per_step=ms, steps=len(times), cores=cores)
 
 
 def reference_main(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
-    r = cpu_reference_run(args.steps, args.warmup)
-    sample = "%d dense steps of batch %d at cfg2 table shapes (after %d warm-up)" % (r["steps"], BATCH, args.warmup)
+    # the same workload as the GPU arm at this N: one optimizer step over the GLOBAL batch of N x 10000 samples
+    gb = BATCH * max(1, args.gpus)
+    r = cpu_reference_run(args.steps, args.warmup, batch=gb)
+    sample = "%d dense steps of batch %d at cfg2 table shapes (after %d warm-up)" % (r["steps"], gb, args.warmup)
     line = dict(impl="reference", metric=METRIC, value=r["value"], unit=UNIT, n_gpus=args.gpus, steps=r["steps"],
                 warmup=args.warmup, ms_per_step=r["ms_per_step"], higher_is_better=True, scaling="weak",
                 vs_baseline=None, dtype="f32", data="synthetic",
-                config=workload_config("dense (reference arithmetic)", 1),
+                config=workload_config("dense (reference arithmetic)", max(1, args.gpus)),
                 cpu_baseline=dict(value=r["value"], unit=UNIT, cores=r["cores"], kind="port", sample=sample),
                 e2e=dict(value=r["value"], unit=UNIT, h2d_bytes_per_step=0, d2h_bytes_per_step=0),
                 note="CPU restatement of the reference's TF-2.12 train step (oracle/train_torch.py); "
