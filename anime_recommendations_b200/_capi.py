@@ -105,7 +105,6 @@ SIGNATURES = {
     "ar_peer_plan": (C.c_int, [_P, _P, _P, _I64, _I64, _I32, _I32, C.POINTER(ArPlan), C.POINTER(ArPlan),
                                C.POINTER(ArPeerCtx), _P]),
     "ar_train_steps_peer": (C.c_int, [C.POINTER(ArTrainCtx), C.POINTER(ArPeerCtx), _I64, _I32, _I64, _I32, _I32, _P]),
-    "ar_peer_barrier": (C.c_int, [C.POINTER(ArPeerCtx), _I32, _P]),
     "ar_table_flush": (C.c_int, [C.POINTER(ArTable), _P, _F, _I64, _P]),
     "ar_embed_fwd": (C.c_int, [_P, _P, _I32, _P, _P, _I32, _P, _P, _P, _P, _P, _P]),
     "ar_head_step": (C.c_int, [_P, _P, _I32, _P, _P, _P, _P, _P, _I64, _P, _P, _P]),

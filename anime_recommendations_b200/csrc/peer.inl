@@ -27,10 +27,12 @@
 // peer stores + a __threadfence_system per CTA: ~10 us slower per step).  Nothing is staged, packed or merged,
 // and a row's gradient is summed by one warp in plan order.
 //
-// Flag barriers: rank r's arrival is the epoch number stored (st.release.sys) into word r of EVERY rank's flag
-// array; a waiter spins (ld.acquire.sys) on its own array.  Epochs are derived from the optimizer step, so
-// they only grow; a rank that waits longer than kPeerTimeoutNs raises a sticky error word instead of hanging
-// the GPU.  ar_peer_barrier is the stand-alone form (one 32-thread kernel); the step uses the split form.
+// Flag barriers: rank r's arrival is the epoch number stored into word r of EVERY rank's flag array (relaxed
+// system-scope stores behind at most one system fence); a waiter spins on its own array with relaxed
+// system-scope loads and reads peer data only with L1-bypassing loads.  Epochs are derived from the optimizer
+// step, so they only grow; a rank that waits longer than kPeerTimeoutNs raises a sticky error word instead of
+// hanging the GPU.  Flag words: [0, 8) arrivals, [16, 24) published-list lengths, 32 error, 40/41 local
+// ticket / last announced epoch.
 namespace ar {
 
 constexpr int kPeerMaxRanks = AR_PEER_MAX_RANKS;
@@ -39,11 +41,6 @@ constexpr unsigned long long kPeerTimeoutNs = 20ull * 1000 * 1000 * 1000;
 
 __device__ __forceinline__ void st_release_sys(int32_t* p, int v) {
   asm volatile("st.release.sys.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
-}
-__device__ __forceinline__ int ld_acquire_sys(const int32_t* p) {
-  int v;
-  asm volatile("ld.acquire.sys.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-  return v;
 }
 __device__ __forceinline__ unsigned long long global_ns() {
   unsigned long long t;
@@ -58,27 +55,6 @@ __device__ __forceinline__ float4 ld4_sys(const float* p) {
                : "l"(p)
                : "memory");
   return r;
-}
-
-struct PeerFlags {
-  int32_t* peer[kPeerMaxRanks];
-  int G, me;
-};
-
-__global__ void __launch_bounds__(32) peer_barrier_kernel(PeerFlags f, int epoch) {
-  const int r = threadIdx.x;
-  if (r >= f.G) return;
-  int32_t* mine = f.peer[f.me];
-  if (ld_acquire_sys(mine + kPeerErrWord) != 0) return;  // a barrier already timed out: do not stall again
-  __threadfence_system();
-  st_release_sys(f.peer[r] + f.me, epoch);
-  const unsigned long long t0 = global_ns();
-  while (ld_acquire_sys(mine + r) < epoch) {
-    if (global_ns() - t0 > kPeerTimeoutNs) {
-      st_release_sys(mine + kPeerErrWord, epoch);
-      break;
-    }
-  }
 }
 
 // The training step splits the barrier and folds both halves into its kernels: the FIRST CTA of the forward to
@@ -368,16 +344,6 @@ static int check_peer(const ar_peer_ctx* h) {
   return AR_OK;
 }
 
-static int peer_barrier(const ar_peer_ctx& h, int epoch, cudaStream_t st) {
-  PeerFlags f{};
-  for (int r = 0; r < h.n_ranks; ++r) f.peer[r] = h.flags_peer[r];
-  f.G = h.n_ranks;
-  f.me = h.rank;
-  peer_barrier_kernel<<<1, 32, 0, st>>>(f, epoch);
-  AR_LAUNCH_CHECK();
-  return AR_OK;
-}
-
 // cudaIpc handles opened by this process (opening one twice is an error): handle bytes -> mapped base
 struct PeerMapping {
   cudaIpcMemHandle_t h;
@@ -431,13 +397,6 @@ extern "C" int ar_peer_close_all(void) {
   for (const ar::PeerMapping& m : ar::peer_mappings()) cudaIpcCloseMemHandle(m.base);
   ar::peer_mappings().clear();
   return AR_OK;
-}
-
-extern "C" int ar_peer_barrier(const ar_peer_ctx* h, int32_t epoch, void* stream) {
-  using namespace ar;
-  AR_REQUIRE(h, "ar_peer_barrier: null peer ctx");
-  for (int r = 0; r < h->n_ranks; ++r) AR_REQUIRE(h->flags_peer[r], "ar_peer_barrier: flags of rank %d missing", r);
-  return peer_barrier(*h, epoch, (cudaStream_t)stream);
 }
 
 extern "C" int ar_peer_plan(const int32_t* iu_all, const int32_t* ia_all, const float* label_all, int64_t rank_stride,

@@ -257,8 +257,6 @@ int ar_peer_plan(const int32_t* iu_all, const int32_t* ia_all, const float* labe
  * max_count values (grid sizing).  Equal to a single-GPU run on the concatenated batch up to rounding. */
 int ar_train_steps_peer(const ar_train_ctx* ctx, const ar_peer_ctx* peer, int64_t epoch_step0, int32_t slot0,
                         int64_t t0, int32_t n_steps, int32_t count_hint, void* stream);
-/* one flag barrier across the ranks on `stream` (epochs must grow; the training steps use 2t and 2t+1) */
-int ar_peer_barrier(const ar_peer_ctx* peer, int32_t epoch, void* stream);
 
 /* NCCL all-gather of equally sized byte buffers (sharded top-k lists before ar_topk_merge). */
 int ar_allgather_bytes(void* comm, const void* send, void* recv, int64_t bytes_per_rank, void* stream);
