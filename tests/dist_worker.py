@@ -57,6 +57,9 @@ def shard_main(mode, dev, rank, world, peer=False):
     mine_u, mine_a = shard_rows(fw[0], rank, world), shard_rows(fw[1], rank, world)
     Us[:len(mine_u)], As[:len(mine_a)] = mine_u, mine_a
     m.set_weights([Us, As] + fw[2:])
+    if peer:   # 3 chunks of 2 steps: the double-buffered chunk planning is part of what is checked
+        import anime_recommendations_b200.model as arm
+        arm.PLAN_CHUNK = 2
     sess = (PeerTrainSession if peer else ShardedTrainSession)(m, B, total_steps=steps)
     sess.run(torch.from_numpy(iu[sl]).to(dev), torch.from_numpy(ia[sl]).to(dev), torch.from_numpy(y[sl]).to(dev), 2e-3)
     if peer:
