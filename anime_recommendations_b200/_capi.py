@@ -64,6 +64,7 @@ class ArShardCtx(C.Structure):
 
 
 PEER_MAX_RANKS, PEER_HANDLE_BYTES, PEER_FLAG_WORDS = 8, 64, 64
+PEER_ERR_WORD = 32   # flag word a timed-out barrier sets (csrc/peer.inl kPeerErrWord)
 
 
 class ArPeerCtx(C.Structure):

@@ -289,9 +289,15 @@ class PeerTrainSession(TrainSession):
 
     def check_flags(self):
         """Raise if a flag barrier timed out (a rank died or fell out of step)."""
-        bad = int(self.flags[32].item())
+        bad = int(self.flags[_capi.PEER_ERR_WORD].item())
         if bad:
             raise _capi.AnimerecError("peer barrier %d timed out on rank %d" % (bad, self.pctx.rank))
+
+    def close(self):
+        """Unmap the other ranks' arenas (collective: every rank must have finished with them)."""
+        torch.cuda.synchronize()
+        dist.barrier()
+        check(lib().ar_peer_close_all(), "ar_peer_close_all")
 
     def _plan_chunk(self, st, iu, ia, y, s0, ns):
         """Queue the planning of steps [s0, s0+ns) into set `st` on the CURRENT stream."""
