@@ -54,3 +54,13 @@ def test_two_rank_peer_memory_training_equals_single_gpu(mode):
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
     assert "DIST_OK" in r.stdout
+
+
+def test_one_rank_peer_memory_training_equals_single_gpu():
+    """The peer-memory path with a world of ONE rank (every pull is local): runs on a single-GPU box, so the
+    peer_select / peer_fwd / peer_pull kernels and the chunked planning are covered there too."""
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "1", "--master-addr",
+           "127.0.0.1", "--master-port", "29549", os.path.join(ROOT, "tests", "dist_worker.py"), "peer_replay"]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
+    assert "DIST_OK" in r.stdout
