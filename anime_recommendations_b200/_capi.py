@@ -10,10 +10,12 @@ import os
 
 PKG = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("ANIMEREC_LIB") or os.path.join(PKG, "lib", "libanimerec.so")   # override: A/B builds
-ABI_VERSION = 12
+ABI_VERSION = 13
 
 AR_MAX_BATCH = 16384
 AR_HEAVY_LEN = 64
+AR_SCHED_MAX_DEPTH = 8
+AR_SCHED_PARTS = 296
 ADAM_REPLAY, ADAM_DENSE, ADAM_TOUCHED = 0, 1, 2
 ADAM_MODES = {"replay": ADAM_REPLAY, "dense": ADAM_DENSE, "touched": ADAM_TOUCHED}
 MAX_K = 32
@@ -33,6 +35,11 @@ class ArPlan(C.Structure):
                 ("heavy", C.c_void_p), ("in_prev", C.c_void_p)]
 
 
+class ArSched(C.Structure):
+    _fields_ = [("cap", C.c_int32), ("n_slots", C.c_int32), ("codes", C.c_void_p), ("counts", C.c_void_p),
+                ("gap_u", C.c_void_p), ("gap_a", C.c_void_p), ("bounds", C.c_void_p)]
+
+
 class ArTrainCtx(C.Structure):
     _fields_ = [("users", ArTable), ("anime", ArTable),
                 ("head", C.c_void_p), ("head_m", C.c_void_p), ("head_v", C.c_void_p),
@@ -43,7 +50,9 @@ class ArTrainCtx(C.Structure):
                 ("uh", C.c_void_p), ("ah", C.c_void_p), ("c", C.c_void_p), ("ru", C.c_void_p),
                 ("ra", C.c_void_p), ("dy", C.c_void_p), ("fwd_part", C.c_void_p), ("head_part", C.c_void_p),
                 ("stepc", C.c_void_p), ("ticket", C.c_void_p),
-                ("metrics", C.c_void_p), ("reg_sumsq", C.c_void_p), ("sched_ws", C.c_void_p)]
+                ("metrics", C.c_void_p), ("reg_acc", C.c_void_p), ("stepw", C.c_void_p), ("reg_scale", C.c_float),
+                ("sched_ws", C.c_void_p), ("sched", ArSched), ("depth", C.c_int32), ("chunk_params", C.c_void_p),
+                ("health", C.c_void_p)]
 
 
 class ArDistCtx(C.Structure):
@@ -91,6 +100,8 @@ SIGNATURES = {
     "ar_plan_build": (C.c_int, [_P, _I64, _I32, _I64, _I32, C.POINTER(ArPlan), _P]),
     "ar_plan_build_lists": (C.c_int, [_P, _I32, _P, _I32, C.POINTER(ArPlan), _P]),
     "ar_plan_link": (C.c_int, [C.POINTER(ArPlan), _I32, _P, _P, _I32, _P]),
+    "ar_plan_sched": (C.c_int, [C.POINTER(ArPlan), C.POINTER(ArPlan), _I32, _I64, _I64, _P, _I32, _P, _I32, _I32,
+                                C.POINTER(ArSched), _P]),
     "ar_train_steps": (C.c_int, [C.POINTER(ArTrainCtx), _I64, _I32, _I64, _I32, _P]),
     "ar_train_steps_profile": (C.c_int, [C.POINTER(ArTrainCtx), _I64, _I32, _I64, _I32, C.POINTER(C.c_float), _P]),
     "ar_nccl_unique_id": (C.c_int, [_P]),
@@ -106,15 +117,16 @@ SIGNATURES = {
     "ar_peer_plan": (C.c_int, [_P, _P, _P, _I64, _I64, _I32, _I32, C.POINTER(ArPlan), C.POINTER(ArPlan),
                                C.POINTER(ArPeerCtx), _P]),
     "ar_train_steps_peer": (C.c_int, [C.POINTER(ArTrainCtx), C.POINTER(ArPeerCtx), _I64, _I32, _I64, _I32, _I32, _P]),
-    "ar_table_flush": (C.c_int, [C.POINTER(ArTable), _P, _F, _I64, _P]),
+    "ar_table_flush": (C.c_int, [C.POINTER(ArTable), _P, _F, _I64, _P, _P, _F, _P]),
     "ar_embed_fwd": (C.c_int, [_P, _P, _I32, _P, _P, _I32, _P, _P, _P, _P, _P, _P]),
     "ar_head_step": (C.c_int, [_P, _P, _I32, _P, _P, _P, _P, _P, _I64, _P, _P, _P]),
     "ar_rows_catchup": (C.c_int, [C.POINTER(ArTable), C.POINTER(ArPlan), _I32, _P, _F, _I64, _P]),
     "ar_rows_update": (C.c_int, [C.POINTER(ArTable), C.POINTER(ArPlan), _I32, _P, _P, _P, _P, _P, _P, _F,
-                                 _I64, _I32, _P, _P]),
+                                 _I64, _I32, _P]),
     "ar_predict": (C.c_int, [_P, _P, _I32, _P, _P, _P, _P, _I64, _P, _P]),
     "ar_eval_sums": (C.c_int, [_P, _P, _I32, _P, _P, _P, _P, _P, _I64, _P, _P]),
     "ar_sumsq": (C.c_int, [_P, _I64, _P, _P]),
+    "ar_bench_sfu": (C.c_int, [_P, _I32, _I32, _I32, _P]),
     "ar_rownorm": (C.c_int, [_P, _I64, _I32, _P, _P]),
     "ar_topk_query_workspace": (C.c_int64, [_I64, _I32]),
     "ar_cosine_topk_query": (C.c_int, [_P, _I64, _I32, _I64, _P, _I64, _I32, _P, _P, _P, _P]),

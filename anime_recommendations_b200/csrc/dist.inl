@@ -96,7 +96,7 @@ __device__ __forceinline__ int find_id(const int32_t* __restrict__ ids, int n, i
 template <int NV>
 __global__ void __launch_bounds__(kRowThreads)
 rows_merge_update_kernel(MergeArgs a, const float* __restrict__ alpha, float l2x2, int64_t t, int replay,
-                         double* sumsq_out) {
+                         RegAcc reg) {
   const bool second = (int)blockIdx.x >= a.blocks_tab0;
   const int blk = second ? blockIdx.x - a.blocks_tab0 : blockIdx.x;
   const int lane = threadIdx.x & 31;
@@ -140,7 +140,7 @@ rows_merge_update_kernel(MergeArgs a, const float* __restrict__ alpha, float l2x
     }
     q += __ldg(base + B + pos);
   }
-  finish_row<NV>(tb, id, acc, q, -1.0f, alpha, l2x2, t, replay, sumsq_out, lane);
+  finish_row<NV>(tb, id, acc, q, -1.0f, alpha, l2x2, t, replay, reg, nullptr, lane);
 }
 
 static int check_dist(const ar_train_ctx* ctx, const ar_dist_ctx* d) {
@@ -176,7 +176,7 @@ static int run_steps_dist(const ar_train_ctx& x, const ar_dist_ctx& d, int64_t e
     int rc;
     const bool has_next = (s + 1 < n_steps) && ((e + 1) * (int64_t)B < x.n_samples);
     if (x.mode == AR_ADAM_REPLAY && (!la || s == 0)) {
-      if ((rc = launch_catchup(&x.users, &x.plan_u, slot, &x.anime, &x.plan_a, slot, x.alpha, x.l2, t - 1, st, false, x.sched_ws))) return rc;
+      if ((rc = launch_catchup(&x.users, &x.plan_u, slot, &x.anime, &x.plan_a, slot, x.alpha, x.l2, t - 1, st, false, x.sched_ws, reg_of(x)))) return rc;
     }
     bool ahead = false;
     if (la && has_next) {
@@ -184,7 +184,7 @@ static int run_steps_dist(const ar_train_ctx& x, const ar_dist_ctx& d, int64_t e
       // the side stream while step s runs; the rest are brought up to date by this step's merge (replay = 1)
       AR_CUDA(cudaStreamWaitEvent(la->st2, la->ev_upd[(s + 1) & 1], 0));
       int32_t* ws2 = x.sched_ws ? x.sched_ws + 3 * ((size_t)x.plan_u.batch_cap + x.plan_a.batch_cap) + 4 : nullptr;
-      if ((rc = launch_catchup(&x.users, &x.plan_u, slot + 1, &x.anime, &x.plan_a, slot + 1, x.alpha, x.l2, t, la->st2, true, ws2)))
+      if ((rc = launch_catchup(&x.users, &x.plan_u, slot + 1, &x.anime, &x.plan_a, slot + 1, x.alpha, x.l2, t, la->st2, true, ws2, reg_of(x))))
         return rc;
       AR_CUDA(cudaEventRecord(la->ev_ahead, la->st2));
       ahead = true;
@@ -200,8 +200,8 @@ static int run_steps_dist(const ar_train_ctx& x, const ar_dist_ctx& d, int64_t e
     c_partials_kernel<<<ceil_div(ceil_div(ng, kRowWarps), 128), 128, 0, st>>>(d.c_all, ng, d.fwd_part_all);
     AR_LAUNCH_CHECK();
     head_step_kernel<<<ceil_div(ng, kHeadThreads), kHeadThreads, 0, st>>>(
-        d.c_all, d.label_all, ng, nullptr, d.fwd_part_all, x.head, x.head_m, x.head_v, x.bn_moving, x.alpha, t,
-        d.dy_all, d.head_part_all, x.stepc, x.ticket, x.metrics + t * 4, 0);
+        d.c_all, d.label_all, ng, nullptr, d.fwd_part_all,
+        HeadIO{x.head, x.head_m, x.head_v, x.bn_moving, x.alpha, d.dy_all, x.stepc, x.ticket, x.metrics}, t, d.head_part_all, 0);
     AR_LAUNCH_CHECK();
     // partial row gradients of the local samples -> packed send block
     UpdateArgs a{};
@@ -214,7 +214,7 @@ static int run_steps_dist(const ar_train_ctx& x, const ar_dist_ctx& d, int64_t e
     a.emit_ids[1] = reinterpret_cast<int32_t*>(d.send + tw);
     a.emit_q[1] = d.send + tw + B;
     a.emit_P[1] = d.send + tw + 2 * (size_t)B;
-    if ((rc = launch_update(a, true, x.c, d.dy_all + (size_t)d.rank * n, x.stepc, x.alpha, x.l2, t, 0, nullptr, st))) return rc;
+    if ((rc = launch_update(a, true, x.c, d.dy_all + (size_t)d.rank * n, x.stepc, x.alpha, x.l2, t, 0, RegAcc{}, st))) return rc;
     AR_NCCL(nc->AllGather(d.send, d.recv, 2 * tw, ncclFloat32, comm, st));
     MergeArgs m{};
     m.tab[0] = x.users;
@@ -223,7 +223,7 @@ static int run_steps_dist(const ar_train_ctx& x, const ar_dist_ctx& d, int64_t e
     m.n_ranks = G;
     m.B = B;
     m.blocks_tab0 = ceil_div((int64_t)G * B, kRowWarps);
-    double* ss = (x.mode == AR_ADAM_DENSE && x.reg_sumsq) ? x.reg_sumsq + t * 32 : nullptr;
+    const RegAcc ss = reg_of(x);
     AR_DISPATCH_NV(dim, rows_merge_update_kernel<NV><<<2 * m.blocks_tab0, kRowThreads, 0, st>>>(
                             m, x.alpha, l2x2, t, x.mode == AR_ADAM_REPLAY ? 1 : 0, ss));
     AR_LAUNCH_CHECK();

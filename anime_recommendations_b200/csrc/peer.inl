@@ -476,14 +476,14 @@ extern "C" int ar_train_steps_peer(const ar_train_ctx* ctx, const ar_peer_ctx* h
     unsigned long long* log = (do_log && s < kLogSteps) ? log_dev + (size_t)s * kLogStamps : nullptr;
     const bool has_next = (s + 1 < n_steps) && ((e + 1) * (int64_t)B < x.n_samples);
     if (x.mode == AR_ADAM_REPLAY && (!la || s == 0)) {
-      if ((rc = launch_catchup(&x.users, &x.plan_u, slot, &x.anime, &x.plan_a, slot, x.alpha, x.l2, t - 1, st, false, x.sched_ws))) return rc;
+      if ((rc = launch_catchup(&x.users, &x.plan_u, slot, &x.anime, &x.plan_a, slot, x.alpha, x.l2, t - 1, st, false, x.sched_ws, reg_of(x)))) return rc;
     }
     bool ahead = false;
     auto launch_ahead = [&](cudaEvent_t after) -> int {
       // as in run_steps: my rows of step s+1 that step s leaves alone are brought to step t on the side stream
       AR_CUDA(cudaStreamWaitEvent(la->st2, after, 0));
       int32_t* ws2 = x.sched_ws ? x.sched_ws + 3 * ((size_t)x.plan_u.batch_cap + x.plan_a.batch_cap) + 4 : nullptr;
-      int r2 = launch_catchup(&x.users, &x.plan_u, slot + 1, &x.anime, &x.plan_a, slot + 1, x.alpha, x.l2, t, la->st2, true, ws2);
+      int r2 = launch_catchup(&x.users, &x.plan_u, slot + 1, &x.anime, &x.plan_a, slot + 1, x.alpha, x.l2, t, la->st2, true, ws2, reg_of(x));
       if (r2) return r2;
       AR_CUDA(cudaEventRecord(la->ev_ahead, la->st2));
       ahead = true;
@@ -531,15 +531,15 @@ extern "C" int ar_train_steps_peer(const ar_train_ctx* ctx, const ar_peer_ctx* h
     peer_pull_kernel<<<dim3(pull_blocks, G), kPullThreads, 0, st>>>(pl);
     AR_LAUNCH_CHECK();
     head_step_kernel<<<ceil_div(ng, kHeadThreads), kHeadThreads, 0, st>>>(
-        c_all, h->label_step + (int64_t)slot * G * B, ng, nullptr, h->fwd_part_all, x.head, x.head_m, x.head_v,
-        x.bn_moving, x.alpha, t, h->dy_all, h->head_part_all, x.stepc, x.ticket, x.metrics + t * 4, nfp);
+        c_all, h->label_step + (int64_t)slot * G * B, ng, nullptr, h->fwd_part_all,
+        HeadIO{x.head, x.head_m, x.head_v, x.bn_moving, x.alpha, h->dy_all, x.stepc, x.ticket, x.metrics}, t, h->head_part_all, nfp);
     AR_LAUNCH_CHECK();
     UpdateArgs a{};
     fill_update(a, 0, &x.users, &x.plan_u, slot, x.ah, x.ru, count_hint);
     fill_update(a, 1, &x.anime, &x.plan_a, slot, x.uh, x.ra, count_hint);
     a.samp[0] = f.samp[0];
     a.samp[1] = f.samp[1];
-    double* ss = (x.mode == AR_ADAM_DENSE && x.reg_sumsq) ? x.reg_sumsq + t * 32 : nullptr;
+    const RegAcc ss = reg_of(x);
     if ((rc = launch_update(a, true, c_all, h->dy_all, x.stepc, x.alpha, x.l2, t, 0, ss, st))) return rc;
     if (la) {
       AR_CUDA(cudaEventRecord(la->ev_upd[s & 1], st));

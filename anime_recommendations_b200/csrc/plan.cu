@@ -7,6 +7,8 @@
 // the cost is amortised off the per-step critical path.
 #include <stdarg.h>
 
+#include <algorithm>
+
 #include "common.cuh"
 
 namespace ar {
@@ -167,6 +169,103 @@ plan_link_kernel(ar_plan plan, const int32_t* __restrict__ uniq_lists, const int
   }
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// Replay schedule (AR_ADAM_REPLAY): how long ago was every distinct row of every planned step last touched?
+// The answer depends only on the index stream, so it is computed here, at plan time and off the step's critical
+// path, instead of by a per-step classify launch.  `seen[row]` = global step (1-based) of the row's latest
+// PLANNED touch; it is carried from chunk to chunk by the caller.
+//
+// plan_bounds_kernel: the walk below splits the row range into gridDim.x contiguous parts; bounds[s][j] = first
+// segment of step s whose row is >= part j's first row (lower bound in the step's ascending distinct-row list).
+__global__ void __launch_bounds__(256)
+plan_bounds_kernel(ar_plan plan, int n_parts, int rows_per_part, int32_t* __restrict__ bounds) {
+  const int slot = blockIdx.x;
+  const int32_t* uniq = plan.uniq + (int64_t)slot * plan.batch_cap;
+  const int n = plan.meta[(int64_t)slot * 4];
+  for (int j = threadIdx.x; j <= n_parts; j += blockDim.x) {
+    const int64_t first = (int64_t)j * rows_per_part;
+    int lo = 0, hi = n;
+    while (lo < hi) {
+      const int mid = (lo + hi) >> 1;
+      if ((int64_t)uniq[mid] < first) lo = mid + 1; else hi = mid;
+    }
+    bounds[(int64_t)slot * (n_parts + 1) + j] = lo;
+  }
+}
+
+// plan_gap_kernel: CTA j owns rows [j*rows_per_part, (j+1)*rows_per_part) and walks the steps in order with its
+// slice of `seen` in shared memory: gap[s][seg] = t(s) - max(seen[row], t_flush), then seen[row] = t(s).
+__global__ void __launch_bounds__(128)
+plan_gap_kernel(ar_plan plan, int n_steps, int64_t t0, int64_t t_flush, int32_t* __restrict__ seen, int n_rows,
+                int rows_per_part, const int32_t* __restrict__ bounds, int32_t* __restrict__ gap) {
+  extern __shared__ int32_t seen_s[];
+  const int part = blockIdx.x, n_parts = gridDim.x;
+  const int64_t first = (int64_t)part * rows_per_part;
+  const int mine = (int)max((int64_t)0, min((int64_t)rows_per_part, (int64_t)n_rows - first));
+  for (int i = threadIdx.x; i < mine; i += blockDim.x) seen_s[i] = seen[first + i];
+  __syncthreads();
+  const int32_t tf = (int32_t)t_flush;
+  for (int s = 0; s < n_steps; ++s) {
+    const int lo = bounds[(int64_t)s * (n_parts + 1) + part], hi = bounds[(int64_t)s * (n_parts + 1) + part + 1];
+    const int32_t t = (int32_t)(t0 + s + 1);
+    const int32_t* uniq = plan.uniq + (int64_t)s * plan.batch_cap;
+    int32_t* g = gap + (int64_t)s * plan.batch_cap;
+    for (int i = lo + threadIdx.x; i < hi; i += blockDim.x) {   // rows of one step are distinct: no conflicts
+      const int r = uniq[i] - (int)first;
+      g[i] = t - max(seen_s[r], tf);
+      seen_s[r] = t;
+    }
+    __syncthreads();
+  }
+  for (int i = threadIdx.x; i < mine; i += blockDim.x) seen[first + i] = seen_s[i];
+}
+
+// plan_sched_kernel: one CTA per step.  Rows with gap 1 are brought up to date by the previous step's own update;
+// rows with 2 <= gap <= depth go to the B list (replayed by the previous step's update kernel, they need at most
+// depth-1 steps); rows with gap > depth go to the A list, longest replay first (log2 buckets), which a catch-up
+// launch may start as soon as step s-depth-1 has finished.  Slot 0 has no predecessor inside the chunk: all its
+// rows with gap >= 2 go to A.  codes: (table << 31) | row; A from the front of codes[slot], B from the back.
+constexpr int kSchedBuckets = 32;
+__global__ void __launch_bounds__(1024)
+plan_sched_kernel(ar_plan pu, ar_plan pa, const int32_t* __restrict__ gap_u, const int32_t* __restrict__ gap_a,
+                  int depth, ar_sched sc) {
+  __shared__ int cnt[kSchedBuckets + 1], base[kSchedBuckets + 1];
+  const int slot = blockIdx.x;
+  const int nu = pu.meta[(int64_t)slot * 4], na = pa.meta[(int64_t)slot * 4];
+  const int bdepth = slot == 0 ? 1 : depth;
+  if (threadIdx.x <= kSchedBuckets) cnt[threadIdx.x] = 0;
+  __syncthreads();
+  // bucket kSchedBuckets = B list; bucket b < kSchedBuckets: floor(log2(gap)) == 31 - b  (descending gap)
+  auto bucket_of = [&](int g) { return g <= 1 ? -1 : (g <= bdepth ? kSchedBuckets : __clz(g)); };
+  for (int i = threadIdx.x; i < nu + na; i += blockDim.x) {
+    const int g = i < nu ? gap_u[(int64_t)slot * pu.batch_cap + i] : gap_a[(int64_t)slot * pa.batch_cap + (i - nu)];
+    const int b = bucket_of(g);
+    if (b >= 0) atomicAdd(&cnt[b], 1);
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int acc = 0;
+    for (int b = 0; b < kSchedBuckets; ++b) { base[b] = acc; acc += cnt[b]; }
+    base[kSchedBuckets] = sc.cap - cnt[kSchedBuckets];
+    int32_t* c = sc.counts + (int64_t)slot * 4;
+    c[0] = acc;
+    c[1] = cnt[kSchedBuckets];
+    c[2] = 0;
+    c[3] = 0;
+  }
+  __syncthreads();
+  int32_t* codes = sc.codes + (int64_t)slot * sc.cap;
+  for (int i = threadIdx.x; i < nu + na; i += blockDim.x) {
+    const bool second = i >= nu;
+    const int g = second ? gap_a[(int64_t)slot * pa.batch_cap + (i - nu)] : gap_u[(int64_t)slot * pu.batch_cap + i];
+    const int b = bucket_of(g);
+    if (b < 0) continue;
+    const int row = second ? pa.uniq[(int64_t)slot * pa.batch_cap + (i - nu)] : pu.uniq[(int64_t)slot * pu.batch_cap + i];
+    codes[base[b] + atomicAdd(&cnt[b], -1) - 1] = row | (second ? (int)0x80000000 : 0);
+  }
+}
+
 }  // namespace ar
 
 extern "C" int ar_plan_link(const ar_plan* plan, int32_t n_steps, const int32_t* uniq_all, const int32_t* meta_all,
@@ -185,8 +284,46 @@ extern "C" int ar_plan_link(const ar_plan* plan, int32_t n_steps, const int32_t*
   return AR_OK;
 }
 
+
+extern "C" int ar_plan_sched(const ar_plan* plan_u, const ar_plan* plan_a, int32_t n_steps, int64_t t0, int64_t t_flush,
+                             int32_t* seen_u, int32_t n_rows_u, int32_t* seen_a, int32_t n_rows_a, int32_t depth,
+                             const ar_sched* sched, void* stream) {
+  AR_REQUIRE(plan_u && plan_a && sched && seen_u && seen_a, "ar_plan_sched: null pointer");
+  AR_REQUIRE(sched->codes && sched->counts && sched->gap_u && sched->gap_a && sched->bounds, "ar_plan_sched: null buffer in sched");
+  AR_REQUIRE(n_steps >= 0 && n_steps <= plan_u->n_slots && n_steps <= plan_a->n_slots && n_steps <= sched->n_slots,
+             "ar_plan_sched: n_steps %d exceeds the plans / schedule", n_steps);
+  AR_REQUIRE(sched->cap >= plan_u->batch_cap + plan_a->batch_cap, "ar_plan_sched: sched.cap too small");
+  AR_REQUIRE(depth >= 1 && depth <= AR_SCHED_MAX_DEPTH, "ar_plan_sched: depth %d outside [1, %d]", depth, AR_SCHED_MAX_DEPTH);
+  AR_REQUIRE(t0 + n_steps < 0x7fffffffLL, "ar_plan_sched: step counter exceeds int32");
+  if (n_steps == 0) return AR_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  static bool attr_set = false;
+  if (!attr_set) {
+    AR_CUDA(cudaFuncSetAttribute(ar::plan_gap_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    attr_set = true;
+  }
+  const ar_plan* plans[2] = {plan_u, plan_a};
+  int32_t* seen[2] = {seen_u, seen_a};
+  const int n_rows[2] = {n_rows_u, n_rows_a};
+  int32_t* gaps[2] = {sched->gap_u, sched->gap_a};
+  for (int w = 0; w < 2; ++w) {
+    // parts: enough CTAs to fill the GPU, slices that fit shared memory
+    int n_parts = AR_SCHED_PARTS;
+    int rows_per_part = ar::ceil_div(std::max(1, n_rows[w]), n_parts);
+    AR_REQUIRE((size_t)rows_per_part * 4 <= 200 * 1024, "ar_plan_sched: table of %d rows too large for %d parts", n_rows[w], n_parts);
+    ar::plan_bounds_kernel<<<n_steps, 256, 0, st>>>(*plans[w], n_parts, rows_per_part, sched->bounds);
+    AR_LAUNCH_CHECK();
+    ar::plan_gap_kernel<<<n_parts, 128, (size_t)rows_per_part * 4, st>>>(*plans[w], n_steps, t0, t_flush, seen[w], n_rows[w],
+                                                                        rows_per_part, sched->bounds, gaps[w]);
+    AR_LAUNCH_CHECK();
+  }
+  ar::plan_sched_kernel<<<n_steps, 1024, 0, st>>>(*plan_u, *plan_a, sched->gap_u, sched->gap_a, depth, *sched);
+  AR_LAUNCH_CHECK();
+  return AR_OK;
+}
+
 extern "C" const char* ar_last_error(void) { return ar::g_err; }
-extern "C" int ar_abi_version(void) { return 12; }
+extern "C" int ar_abi_version(void) { return 13; }
 
 extern "C" int ar_check_device(void) {
   int dev = 0;

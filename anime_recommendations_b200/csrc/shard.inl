@@ -111,7 +111,7 @@ __device__ __forceinline__ bool shard_leads(const ShardServeArgs& a, int p, int 
 
 template <int NV>
 __global__ void __launch_bounds__(kRowThreads)
-shard_catchup_kernel(ShardServeArgs a, const float* __restrict__ alpha, float l2x2, int64_t t_target) {
+shard_catchup_kernel(ShardServeArgs a, const float* __restrict__ alpha, float l2x2, int64_t t_target, RegAcc reg) {
   const int lane = threadIdx.x & 31;
   const int e = blockIdx.x * kRowWarps + (threadIdx.x >> 5);
   if (e >= a.G * a.cap) return;
@@ -127,11 +127,13 @@ shard_catchup_kernel(ShardServeArgs a, const float* __restrict__ alpha, float l2
   w.load(a.tab.W + o, d4, lane);
   m.load(a.tab.m + o, d4, lane);
   v.load(a.tab.v + o, d4, lane);
-  replay_l2<NV>(w, m, v, alpha, last, t_target, l2x2, lane);
+  double regd = 0.0;
+  replay_l2<NV>(w, m, v, alpha, reg.stepw, last, t_target, l2x2, lane, regd);
   w.store(a.tab.W + o, d4, lane);
   m.store(a.tab.m + o, d4, lane);
   v.store(a.tab.v + o, d4, lane);
   if (lane == 0) a.tab.last_step[row] = (int32_t)t_target;
+  reg_commit(regd, reg, lane);
 }
 
 template <int NV>
@@ -151,7 +153,7 @@ __global__ void __launch_bounds__(kRowThreads) shard_gather_kernel(ShardServeArg
 template <int NV>
 __global__ void __launch_bounds__(kRowThreads)
 shard_merge_update_kernel(ShardServeArgs a, const float* __restrict__ alpha, float l2x2, int64_t t,
-                          double* sumsq_out) {
+                          RegAcc reg) {
   const int lane = threadIdx.x & 31;
   const int e = blockIdx.x * kRowWarps + (threadIdx.x >> 5);
   if (e >= a.G * a.cap) return;
@@ -178,7 +180,7 @@ shard_merge_update_kernel(ShardServeArgs a, const float* __restrict__ alpha, flo
     }
     q += __ldg(g + dim);
   }
-  finish_row<NV>(a.tab, id / a.G, acc, q, -1.0f, alpha, l2x2, t, 0, sumsq_out, lane);
+  finish_row<NV>(a.tab, id / a.G, acc, q, -1.0f, alpha, l2x2, t, 0, reg, nullptr, lane);
 }
 
 static int shard_alltoall(NcclApi* nc, ncclComm_t comm, int G, const void* send, void* recv, size_t stride_bytes,
@@ -275,7 +277,7 @@ extern "C" int ar_train_steps_sharded(const ar_train_ctx* ctx, const ar_shard_ct
       sv[k].grad = h->grad_recv[k];
       const int blocks = ceil_div((int64_t)G * cap, kRowWarps);
       if (x.mode == AR_ADAM_REPLAY) {
-        AR_DISPATCH_NV(dim, shard_catchup_kernel<NV><<<blocks, kRowThreads, 0, st>>>(sv[k], x.alpha, l2x2, t - 1));
+        AR_DISPATCH_NV(dim, shard_catchup_kernel<NV><<<blocks, kRowThreads, 0, st>>>(sv[k], x.alpha, l2x2, t - 1, reg_of(x)));
         AR_LAUNCH_CHECK();
       }
       AR_DISPATCH_NV(dim, shard_gather_kernel<NV><<<blocks, kRowThreads, 0, st>>>(sv[k]));
@@ -297,8 +299,8 @@ extern "C" int ar_train_steps_sharded(const ar_train_ctx* ctx, const ar_shard_ct
     c_partials_kernel<<<ceil_div(ceil_div(ng, kRowWarps), 128), 128, 0, st>>>(h->c_all, ng, h->fwd_part_all);
     AR_LAUNCH_CHECK();
     head_step_kernel<<<ceil_div(ng, kHeadThreads), kHeadThreads, 0, st>>>(
-        h->c_all, h->label_all, ng, nullptr, h->fwd_part_all, x.head, x.head_m, x.head_v, x.bn_moving, x.alpha, t,
-        h->dy_all, h->head_part_all, x.stepc, x.ticket, x.metrics + t * 4, 0);
+        h->c_all, h->label_all, ng, nullptr, h->fwd_part_all,
+        HeadIO{x.head, x.head_m, x.head_v, x.bn_moving, x.alpha, h->dy_all, x.stepc, x.ticket, x.metrics}, t, h->head_part_all, 0);
     AR_LAUNCH_CHECK();
     UpdateArgs a{};
     fill_update(a, 0, &x.users, &x.plan_u, slot, x.ah, x.ru, B);
@@ -309,12 +311,12 @@ extern "C" int ar_train_steps_sharded(const ar_train_ctx* ctx, const ar_shard_ct
     }
     a.emit_cap = B;
     a.emit_stride = gs;
-    if ((rc = launch_update(a, true, x.c, h->dy_all + (size_t)h->rank * n, x.stepc, x.alpha, x.l2, t, 0, nullptr, st))) return rc;
+    if ((rc = launch_update(a, true, x.c, h->dy_all + (size_t)h->rank * n, x.stepc, x.alpha, x.l2, t, 0, RegAcc{}, st))) return rc;
     for (int k = 0; k < 2; ++k)
       if ((rc = shard_alltoall(nc, comm, G, h->grad_send[k], h->grad_recv[k], (size_t)plans[k]->batch_cap * gs * 4,
                                (size_t)cap * gs * 4, st)))
         return rc;
-    double* ss = (x.mode == AR_ADAM_DENSE && x.reg_sumsq) ? x.reg_sumsq + t * 32 : nullptr;
+    const RegAcc ss = reg_of(x);
     for (int k = 0; k < 2; ++k) {
       const int blocks = ceil_div((int64_t)G * cap, kRowWarps);
       AR_DISPATCH_NV(dim, shard_merge_update_kernel<NV><<<blocks, kRowThreads, 0, st>>>(sv[k], x.alpha, l2x2, t, ss));

@@ -1,18 +1,21 @@
 // Half A: the training step of the neural_network.py embedding model on sm_100a.
 //
-// Step t (global, 1-based) runs four launches on one stream:
-//   1. rows_catchup   (AR_ADAM_REPLAY only) bring the step's distinct rows to optimizer step t-1
-//                     by replaying their missed pure-L2 Adam steps in registers
-//   2. embed_fwd      warp per sample: gather both rows (128-bit loads), l2-normalise, dot
-//   3. head_step      thread per sample over ceil(n/256) CTAs: Dense(1) + BatchNorm(train) + sigmoid +
-//                     BCE and dLoss/dy; the batch statistics come from the forward's per-CTA partial
-//                     sums, the backward's from this kernel's own partials; the last CTA to finish
-//                     (ticket) reduces them in a fixed order and applies Adam to the 4 head scalars,
-//                     the moving statistics and the per-step metrics.  No atomics on data => the step
-//                     is bit-reproducible.
-//   4. rows_update    warp per distinct row: atomic-free segment reduction of the row gradient
-//                     over the plan's sorted samples + L2 term + Adam, one RMW of (W, m, v)
+// Step s of a chunk (global optimizer step t, 1-based) is three launches (single GPU):
+//   A(s) rows_catchup  (AR_ADAM_REPLAY only, side streams) bring the step's distinct rows whose previous touch
+//                      lies more than `depth` steps back to optimizer step t-1 by replaying their missed pure-L2
+//                      Adam steps in registers, longest replay first (plan-time schedule, ar_plan_sched); it
+//                      may start as soon as step s-depth-1 is done, i.e. it has `depth` step periods to finish
+//   F(s) fwd_head      warp per sample: gather both rows (128-bit loads), l2-normalise, dot; the LAST CTA to
+//                      finish (ticket) runs the head over the whole batch: Dense(1) + BatchNorm(train) +
+//                      sigmoid + BCE, dLoss/dy per sample, Adam on the 4 head scalars, moving statistics,
+//                      metrics -- fixed summation order, no atomics on data => bit-reproducible
+//   U(s) rows_update   warp per distinct row: atomic-free segment reduction of the row gradient over the
+//                      plan's sorted samples + L2 term + Adam, one RMW of (W, m, v); extra warps replay the
+//                      B list of step s+1 (rows last touched 2..depth steps ago)
+// Dependencies: A(s) -> F(s) -> U(s) -> F(s+1), U(s-depth-1) -> A(s).  The kernels read the chunk's step counter
+// and sample pointers from device memory, so a full chunk is captured once as a CUDA graph and replayed.
 // AR_ADAM_DENSE appends a flush of every other row to step t (the reference-literal dense Adam).
+// The multi-GPU paths (dist.inl, shard.inl, peer.inl) keep the separate embed_fwd / head_step launches.
 //
 // Arithmetic follows oracle/train.py (the restatement of neural_network.py:66-106 under
 // Keras-2.12 semantics); citations there.
@@ -63,27 +66,69 @@ __device__ __forceinline__ float tile_dot(const RowTile<NV>& a, const RowTile<NV
   return warp_sum(s);
 }
 
-// Replay pure-L2 Adam steps (from, to] of one row held in registers.
+// L2-regulariser accumulator of the reported loss (animerec.h: ar_train_ctx.reg_acc).
+struct RegAcc {
+  unsigned long long* acc;
+  const float* stepw;
+  float scale;
+};
+// One fixed-point add per row visit: integer addition is associative, so the total does not depend on the order
+// in which warps arrive.
+__device__ __forceinline__ void reg_commit(double regd, const RegAcc& reg, int lane) {
+  if (!reg.acc) return;
+  regd = warp_sum(regd);
+  if (lane == 0 && regd != 0.0) atomicAdd(reg.acc, (unsigned long long)__double2ll_rn(regd * (double)reg.scale));
+}
+
+// Per-chunk parameters in device memory (ar_train_ctx.chunk_params): step `slot` of the chunk is global step
+// t0 + slot + 1 and reads its samples at iu/ia/label + slot*batch.
+struct DevChunk {
+  int64_t t0;
+  const int32_t* iu;
+  const int32_t* ia;
+  const float* label;
+  int64_t pad[12];
+};
+static_assert(sizeof(DevChunk) == 128, "DevChunk is 16 x int64");
+__global__ void set_chunk_kernel(DevChunk* dc, int64_t t0, const int32_t* iu, const int32_t* ia, const float* label) {
+  dc->t0 = t0;
+  dc->iu = iu;
+  dc->ia = ia;
+  dc->label = label;
+}
+
+// Replay pure-L2 Adam steps (from, to] of one row held in registers.  regd += sum over the replayed
+// steps t of stepw[t] * (this lane's share of ||w before step t||^2).
 template <int NV>
 __device__ __forceinline__ void replay_l2(RowTile<NV>& w, RowTile<NV>& m, RowTile<NV>& v,
-                                          const float* __restrict__ alpha, int64_t from, int64_t to,
-                                          float l2x2, int lane) {
+                                          const float* __restrict__ alpha, const float* __restrict__ stepw,
+                                          int64_t from, int64_t to, float l2x2, int lane, double& regd) {
   // both loops stay ROLLED: unrolled by the compiler the body was 20 KB of code per instantiation for no gain
 #pragma unroll 1
   for (int64_t t0 = from + 1; t0 <= to; t0 += 32) {
     int64_t tl = t0 + lane;
     float a_l = (tl <= to) ? __ldg(alpha + tl) : 0.f;
+    float w_l = (stepw && tl <= to) ? __ldg(stepw + tl) : 0.f;
     int cnt = (int)min((int64_t)32, to - t0 + 1);
+    float accf = 0.f;
 #pragma unroll 1
     for (int s = 0; s < cnt; ++s) {
       float a = __shfl_sync(0xffffffffu, a_l, s);
+      float sw = __shfl_sync(0xffffffffu, w_l, s);
+      float p = 0.f;
 #pragma unroll
       for (int k = 0; k < NV; ++k) {
+        p = fmaf(w.x[k].x, w.x[k].x, p);
+        p = fmaf(w.x[k].y, w.x[k].y, p);
+        p = fmaf(w.x[k].z, w.x[k].z, p);
+        p = fmaf(w.x[k].w, w.x[k].w, p);
         float4 g = make_float4(__fmul_rn(l2x2, w.x[k].x), __fmul_rn(l2x2, w.x[k].y),
                                __fmul_rn(l2x2, w.x[k].z), __fmul_rn(l2x2, w.x[k].w));
         adam4(w.x[k], m.x[k], v.x[k], g, a);
       }
+      accf = fmaf(sw, p, accf);
     }
+    regd += (double)accf;
   }
 }
 
@@ -102,17 +147,15 @@ struct CatchupArgs {
   // bucket b at sched + b*cap, their fill counts at sched + 3*cap
   int32_t* sched;
   int cap;
+  // plan-time schedule (single GPU): rows (table << 31 | row) at list[0 .. *list_count), already longest first;
+  // the target step comes from the chunk parameters: t_target = dc->t0 + t_off
+  const int32_t* list;
+  const int32_t* list_count;
+  const DevChunk* dc;
+  int t_off;
+  RegAcc reg;
 };
 constexpr int kLongReplay = 128, kMidReplay = 32;
-
-// Replay lengths are geometric (mean n_rows/unique-per-step, max ~10x that), and a CTA only frees its SM slot
-// when its slowest warp ends -- with 8 rows of unrelated length per CTA the SFU sat idle ~60% of the time
-// (measured 57 us vs a 20 us MUFU floor).  One-warp CTAs fixed that but cap the SM at 32 resident warps;
-// with the longest-first bucket order neighbours have similar lengths and kCatchThreads/32 rows share a CTA.
-#ifndef AR_CATCH_THREADS
-#define AR_CATCH_THREADS 64
-#endif
-constexpr int kCatchThreads = AR_CATCH_THREADS;
 
 // Which rows need how much replay?  Thread per distinct row of the step: rows the skip list covers or that
 // are already current drop out, the rest go to the long / mid / short bucket (warp-aggregated append).
@@ -145,17 +188,56 @@ rows_classify_kernel(CatchupArgs a, int64_t t_target, int n0_cap, int n1_cap) {
   }
 }
 
-// kCatchWarps rows per CTA.  In plan order that would pair rows of unrelated replay lengths (a CTA frees its
-// SM slot only when its slowest warp ends); in bucket order neighbours have similar lengths, so several warps
-// per CTA lift the 32-CTA-per-SM cap on resident warps without re-creating that tail.
-template <int NV>
-__global__ void __launch_bounds__(kCatchThreads)
+// One row per CTA, ONE ELEMENT PER LANE (ceil(dim/32) warps).  A row's replay is a serial chain per element
+// (sqrt -> add -> rcp -> fma, ~65 cycles a step) and the longest row of a step (gap ~ 10x the mean) sets the
+// kernel's tail: with four elements per lane ptxas issues the four chains back to back (4x the latency per
+// step: 62 us per launch measured, the tail of one 350-step row), whatever the source order.  One element per
+// lane leaves no intra-warp ILP to lose; the SFU is kept busy by the ~50 resident warps of other rows instead.
+// Per element-step: 1 SHFL (alpha) + 1 FFMA (regulariser term) + 8 FP32 + 2 MUFU.
+__device__ __forceinline__ void replay_l2_lane(float& w, float& m, float& v, const float* __restrict__ alpha,
+                                               const float* __restrict__ stepw, int64_t from, int64_t to,
+                                               float l2x2, int lane, double& regd) {
+#pragma unroll 1
+  for (int64_t t0 = from + 1; t0 <= to; t0 += 32) {
+    const int64_t tl = t0 + lane;
+    const float a_l = (tl <= to) ? __ldg(alpha + tl) : 0.f;
+    const float w_l = (stepw && tl <= to) ? __ldg(stepw + tl) : 1.f;
+    const int cnt = (int)min((int64_t)32, to - t0 + 1);
+    float accf = 0.f;
+    if (__all_sync(0xffffffffu, w_l == 1.f)) {  // every step of the block has full weight (all but an epoch's last)
+#pragma unroll 4
+      for (int s = 0; s < cnt; ++s) {
+        const float a = __shfl_sync(0xffffffffu, a_l, s);
+        accf = fmaf(w, w, accf);
+        adam1(w, m, v, __fmul_rn(l2x2, w), a);
+      }
+    } else {
+#pragma unroll 1
+      for (int s = 0; s < cnt; ++s) {
+        const float a = __shfl_sync(0xffffffffu, a_l, s);
+        const float sw = __shfl_sync(0xffffffffu, w_l, s);
+        accf = fmaf(sw * w, w, accf);
+        adam1(w, m, v, __fmul_rn(l2x2, w), a);
+      }
+    }
+    regd += (double)accf;
+  }
+}
+
+__global__ void __launch_bounds__(512)
 rows_catchup_kernel(CatchupArgs a, const float* __restrict__ alpha, float l2x2, int64_t t_target) {
-  const int lane = threadIdx.x & 31;
-  const int unit = blockIdx.x * (kCatchThreads / 32) + (threadIdx.x >> 5);
+  __shared__ double red[16];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const int unit = blockIdx.x;
   bool second;
   int row;
-  if (a.sched) {  // bucket order: long rows first
+  if (a.list) {  // plan-time schedule
+    if (unit >= a.list_count[0]) return;
+    const int code = a.list[unit];
+    second = code < 0;
+    row = code & 0x7fffffff;
+    t_target = a.dc->t0 + a.t_off;
+  } else if (a.sched) {  // bucket order: long rows first
     const int32_t* counts = a.sched + 3 * (size_t)a.cap;
     const int n0 = counts[0], n1 = counts[1], n2 = counts[2];
     int b = unit, code;
@@ -174,36 +256,51 @@ rows_catchup_kernel(CatchupArgs a, const float* __restrict__ alpha, float l2x2, 
     const uint8_t* __restrict__ flag = second ? a.skip_flag[1] : a.skip_flag[0];
     if (flag && flag[seg]) return;
   }
-  ar_table tb;
-  tb.dim = a.tab[0].dim;
-  tb.W = second ? a.tab[1].W : a.tab[0].W;
-  tb.m = second ? a.tab[1].m : a.tab[0].m;
-  tb.v = second ? a.tab[1].v : a.tab[0].v;
-  tb.last_step = second ? a.tab[1].last_step : a.tab[0].last_step;
-  const int64_t last = tb.last_step[row];
-  if (last >= t_target) return;
-  const int d4 = tb.dim >> 2;
-  const size_t o = (size_t)row * tb.dim;
-  RowTile<NV> w, m, v;
-  w.load(tb.W + o, d4, lane);
-  m.load(tb.m + o, d4, lane);
-  v.load(tb.v + o, d4, lane);
-  replay_l2<NV>(w, m, v, alpha, last, t_target, l2x2, lane);
-  w.store(tb.W + o, d4, lane);
-  m.store(tb.m + o, d4, lane);
-  v.store(tb.v + o, d4, lane);
-  if (lane == 0) tb.last_step[row] = (int32_t)t_target;
+  const int dim = a.tab[0].dim;
+  float* __restrict__ W = second ? a.tab[1].W : a.tab[0].W;
+  float* __restrict__ M = second ? a.tab[1].m : a.tab[0].m;
+  float* __restrict__ V = second ? a.tab[1].v : a.tab[0].v;
+  int32_t* __restrict__ last_step = second ? a.tab[1].last_step : a.tab[0].last_step;
+  const int64_t last = last_step[row];
+  if (last >= t_target) return;  // uniform over the CTA
+  const int e = threadIdx.x;
+  const bool live = e < dim;
+  const size_t o = (size_t)row * dim + e;
+  float w = 0.f, m = 0.f, v = 0.f;
+  if (live) {
+    w = W[o];
+    m = M[o];
+    v = V[o];
+  }
+  double regd = 0.0;
+  replay_l2_lane(w, m, v, alpha, a.reg.stepw, last, t_target, l2x2, lane, regd);
+  if (live) {
+    W[o] = w;
+    M[o] = m;
+    V[o] = v;
+  }
+  if (a.reg.acc) {
+    regd = warp_sum(regd);
+    if (lane == 0) red[wid] = regd;
+  }
+  __syncthreads();  // every warp of the row has read last_step[row]
+  if (threadIdx.x == 0) {
+    last_step[row] = (int32_t)t_target;
+    if (a.reg.acc) {
+      double tot = 0.0;
+      for (int i = 0; i < (int)(blockDim.x >> 5); ++i) tot += red[i];
+      if (tot != 0.0) atomicAdd(a.reg.acc, (unsigned long long)__double2ll_rn(tot * (double)a.reg.scale));
+    }
+  }
 }
 
 // whole-table flush: every row to t_target
 template <int NV>
 __global__ void __launch_bounds__(kRowThreads)
-table_flush_kernel(ar_table tb, const float* __restrict__ alpha, float l2x2, int64_t t_target,
-                   double* sumsq_out) {
-  __shared__ double ss_red[kRowWarps];
+table_flush_kernel(ar_table tb, const float* __restrict__ alpha, float l2x2, int64_t t_target, RegAcc reg) {
   const int lane = threadIdx.x & 31;
   const int d4 = tb.dim >> 2;
-  double ss = 0.0;
+  double regd = 0.0;
   for (int64_t row = (int64_t)blockIdx.x * kRowWarps + (threadIdx.x >> 5); row < tb.n_rows;
        row += (int64_t)gridDim.x * kRowWarps) {
     const int64_t last = tb.last_step[row];
@@ -213,22 +310,13 @@ table_flush_kernel(ar_table tb, const float* __restrict__ alpha, float l2x2, int
     w.load(tb.W + o, d4, lane);
     m.load(tb.m + o, d4, lane);
     v.load(tb.v + o, d4, lane);
-    if (sumsq_out) ss += (double)tile_dot<NV>(w, w);
-    replay_l2<NV>(w, m, v, alpha, last, t_target, l2x2, lane);
+    replay_l2<NV>(w, m, v, alpha, reg.stepw, last, t_target, l2x2, lane, regd);
     w.store(tb.W + o, d4, lane);
     m.store(tb.m + o, d4, lane);
     v.store(tb.v + o, d4, lane);
     if (lane == 0) tb.last_step[row] = (int32_t)t_target;
   }
-  if (sumsq_out) {
-    if (lane == 0) ss_red[threadIdx.x >> 5] = ss;
-    __syncthreads();
-    if (threadIdx.x == 0) {
-      double a = 0.0;
-      for (int i = 0; i < kRowWarps; ++i) a += ss_red[i];
-      atomicAdd(sumsq_out + (blockIdx.x & 31), a);
-    }
-  }
+  reg_commit(regd, reg, lane);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -320,21 +408,115 @@ __device__ __forceinline__ float bce_logits(float y, float t) {
 
 // Per-step scalars the head hands to the row-update kernel: dc_s = K_COEF*(dy_s - K_S1N - zh_s*K_S2N),
 // zh_s = ((w*c_s + b) - mu)*inv   (oracle head_backward(): dz, dc)
-enum { K_COEF = 0, K_S1N, K_S2N, K_MU, K_INV, K_W, K_B, K_PAD, K_STEPC };
+enum { K_COEF = 0, K_S1N, K_S2N, K_MU, K_INV, K_W, K_B, K_GAMMA, K_BETA, K_FN, K_STEPC };  // 16 floats reserved
 constexpr int kHeadSums = 7;  // sum bce, sq err, dy, dy*zh, zh, dy*c, zh*c
 
 __device__ __forceinline__ float dc_of(float dy, float c, const float* __restrict__ k) {
   const float zh = ((k[K_W] * c + k[K_B]) - k[K_MU]) * k[K_INV];
   return k[K_COEF] * (dy - k[K_S1N] - zh * k[K_S2N]);
 }
+// dLoss/dy of one sample from its cosine and label: the SAME expression sequence wherever it is evaluated (the
+// head's sums and the row update's per-sample factor must see identical bits)
+__device__ __forceinline__ float dy_of(float c, float tg, float w, float b, float mu, float inv, float gamma,
+                                       float beta, float fn, float* zh_out) {
+  const float zh = ((w * c + b) - mu) * inv;
+  const float y = gamma * zh + beta;
+  *zh_out = zh;
+  return (sigmoidf_(y) - tg) / fn;
+}
+__device__ __forceinline__ float dc_of_label(float c, float tg, const float* __restrict__ k) {
+  float zh;
+  const float dy = dy_of(c, tg, k[K_W], k[K_B], k[K_MU], k[K_INV], k[K_GAMMA], k[K_BETA], k[K_FN], &zh);
+  return k[K_COEF] * (dy - k[K_S1N] - zh * k[K_S2N]);
+}
+
+// The head's state and outputs (device pointers), shared by head_step_kernel and the fused forward.
+struct HeadIO {
+  float* head;
+  float* head_m;
+  float* head_v;
+  float* bn_moving;
+  const float* alpha;
+  float* dy;
+  float* stepc;
+  unsigned int* ticket;
+  float* metrics;   // base of the per-step metrics table (row t is written), or null
+};
+struct HeadScalars {
+  float w, b, gamma, beta, mu, var, inv, fn;
+};
+// batch statistics of z = w*c + b from (sum c, sum c^2)
+__device__ __forceinline__ HeadScalars head_scalars(const float* __restrict__ head, double sum_c, double sum_c2, int n) {
+  HeadScalars h;
+  h.w = head[0]; h.b = head[1]; h.gamma = head[2]; h.beta = head[3];
+  h.fn = (float)n;
+  const double mean_c = sum_c / n;
+  const double var_c = fmax(sum_c2 / n - mean_c * mean_c, 0.0);
+  h.mu = (float)((double)h.w * mean_c + (double)h.b);
+  h.var = (float)((double)h.w * (double)h.w * var_c);
+  h.inv = 1.0f / sqrtf(h.var + kBnEps);
+  return h;
+}
+// one sample: Dense(1) -> BN(train) -> sigmoid -> BCE; returns dLoss/dy and adds the 7 head sums
+__device__ __forceinline__ float head_sample(float ci, float tg, const HeadScalars& h, double (&s1)[kHeadSums]) {
+  const float zh = ((h.w * ci + h.b) - h.mu) * h.inv;
+  const float y = h.gamma * zh + h.beta;
+  const float p = sigmoidf_(y);
+  const float dy = (p - tg) / h.fn;
+  s1[0] += (double)bce_logits(y, tg);
+  s1[1] += (double)((tg - p) * (tg - p));
+  s1[2] += (double)dy;
+  s1[3] += (double)dy * (double)zh;
+  s1[4] += (double)zh;
+  s1[5] += (double)dy * (double)ci;
+  s1[6] += (double)zh * (double)ci;
+  return dy;
+}
+// one thread: Adam on (w, b, gamma, beta), moving statistics, the scalars of the row update, metrics
+__device__ __forceinline__ void head_finalize(const HeadScalars& h, const double (&s2)[kHeadSums], double sum_c, int n,
+                                              const HeadIO& io, int64_t t) {
+  const double S1 = s2[2], S2 = s2[3], Szh = s2[4], Sdyc = s2[5], Szhc = s2[6], Sc = sum_c;
+  const double ig = (double)h.inv * (double)h.gamma;
+  // oracle head_backward(): dgamma = sum dy*zh, dbeta = sum dy, dz_i = inv*gamma*(dy_i - S1/n - zh_i*S2/n)
+  const float g[4] = {(float)(ig * (Sdyc - S1 / n * Sc - S2 / n * Szhc)),  // dw = sum dz*c
+                      (float)(-ig * (S2 / n) * Szh),                       // db = sum dz (0 up to rounding)
+                      (float)S2, (float)S1};
+  const float a = io.alpha[t];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    float th = io.head[k], m = io.head_m[k], v = io.head_v[k];
+    adam1(th, m, v, g[k], a);
+    io.head[k] = th;
+    io.head_m[k] = m;
+    io.head_v[k] = v;
+  }
+  const float mm = io.bn_moving[0], mv = io.bn_moving[1];
+  io.bn_moving[0] = mm - (mm - h.mu) * kBnOneMinusMomentum;
+  io.bn_moving[1] = mv - (mv - h.var) * kBnOneMinusMomentum;
+  io.stepc[K_COEF] = (float)((double)h.w * ig);
+  io.stepc[K_S1N] = (float)(S1 / n);
+  io.stepc[K_S2N] = (float)(S2 / n);
+  io.stepc[K_MU] = h.mu;
+  io.stepc[K_INV] = h.inv;
+  io.stepc[K_W] = h.w;
+  io.stepc[K_B] = h.b;
+  io.stepc[K_GAMMA] = h.gamma;
+  io.stepc[K_BETA] = h.beta;
+  io.stepc[K_FN] = h.fn;
+  if (io.metrics) {
+    float* row = io.metrics + t * 4;
+    row[0] = (float)(s2[0] / n);
+    row[1] = (float)(s2[1] / n);
+    row[2] = h.fn;
+    row[3] = h.mu;
+  }
+  *io.ticket = 0u;  // ready for the next step
+}
 
 __global__ void __launch_bounds__(kHeadThreads)
 head_step_kernel(const float* __restrict__ c, const float* __restrict__ label, int n,
-                 const int32_t* __restrict__ meta_n, const double* __restrict__ fwd_part,
-                 float* __restrict__ head, float* __restrict__ head_m, float* __restrict__ head_v,
-                 float* __restrict__ bn_moving, const float* __restrict__ alpha, int64_t t,
-                 float* __restrict__ dy_out, double* __restrict__ head_part, float* __restrict__ stepc,
-                 unsigned int* __restrict__ ticket, float* __restrict__ metrics_row, int nfp_in) {
+                 const int32_t* __restrict__ meta_n, const double* __restrict__ fwd_part, HeadIO io, int64_t t,
+                 double* __restrict__ head_part, int nfp_in) {
   __shared__ double red[kHeadSums * 32];
   __shared__ int is_last;
   if (meta_n) n = min(n, meta_n[2]);
@@ -342,8 +524,6 @@ head_step_kernel(const float* __restrict__ c, const float* __restrict__ label, i
   const int nblk = (n + kHeadThreads - 1) / kHeadThreads;
   if ((int)blockIdx.x >= nblk) return;
   const int tid = threadIdx.x;
-  const float w = head[0], b = head[1], gamma = head[2], beta = head[3];
-  const float fn = (float)n;
 
   // batch statistics from the forward's per-CTA partials (fixed summation order in every CTA)
   const int nfp = nfp_in > 0 ? nfp_in : (n + kRowWarps - 1) / kRowWarps;  // peer mode pre-reduces per 1024 samples
@@ -353,38 +533,19 @@ head_step_kernel(const float* __restrict__ c, const float* __restrict__ label, i
     s0[1] += __ldcg(fwd_part + 2 * i + 1);
   }
   block_sum<2>(s0, red);
-  const double mean_c = s0[0] / n;
-  const double var_c = fmax(s0[1] / n - mean_c * mean_c, 0.0);
-  const float mu = (float)((double)w * mean_c + (double)b);
-  const float var = (float)((double)w * (double)w * var_c);
-  const float inv = 1.0f / sqrtf(var + kBnEps);
+  const HeadScalars h = head_scalars(io.head, s0[0], s0[1], n);
 
   double s1[kHeadSums];
 #pragma unroll
   for (int i = 0; i < kHeadSums; ++i) s1[i] = 0.0;
   const int i = blockIdx.x * kHeadThreads + tid;
-  if (i < n) {
-    const float ci = c[i];
-    const float zh = ((w * ci + b) - mu) * inv;
-    const float y = gamma * zh + beta;
-    const float p = sigmoidf_(y);
-    const float tg = label[i];
-    const float dy = (p - tg) / fn;
-    dy_out[i] = dy;
-    s1[0] = (double)bce_logits(y, tg);
-    s1[1] = (double)((tg - p) * (tg - p));
-    s1[2] = (double)dy;
-    s1[3] = (double)dy * (double)zh;
-    s1[4] = (double)zh;
-    s1[5] = (double)dy * (double)ci;
-    s1[6] = (double)zh * (double)ci;
-  }
+  if (i < n) io.dy[i] = head_sample(c[i], label[i], h, s1);
   block_sum<kHeadSums>(s1, red);
   if (tid == 0) {
 #pragma unroll
     for (int k = 0; k < kHeadSums; ++k) head_part[blockIdx.x * 8 + k] = s1[k];
     __threadfence();
-    const unsigned int old = atomicAdd(ticket, 1u);
+    const unsigned int old = atomicAdd(io.ticket, 1u);
     is_last = (old == (unsigned int)(nblk - 1));
   }
   __syncthreads();
@@ -398,40 +559,184 @@ head_step_kernel(const float* __restrict__ c, const float* __restrict__ label, i
     for (int k = 0; k < kHeadSums; ++k) s2[k] += __ldcg(head_part + j * 8 + k);
   }
   block_sum<kHeadSums>(s2, red);
-  if (tid == 0) {
-    const double S1 = s2[2], S2 = s2[3], Szh = s2[4], Sdyc = s2[5], Szhc = s2[6], Sc = s0[0];
-    const double ig = (double)inv * (double)gamma;
-    // oracle head_backward(): dgamma = sum dy*zh, dbeta = sum dy, dz_i = inv*gamma*(dy_i - S1/n - zh_i*S2/n)
-    const float g[4] = {(float)(ig * (Sdyc - S1 / n * Sc - S2 / n * Szhc)),  // dw = sum dz*c
-                        (float)(-ig * (S2 / n) * Szh),                       // db = sum dz (0 up to rounding)
-                        (float)S2, (float)S1};
-    const float a = alpha[t];
+  if (tid == 0) head_finalize(h, s2, s0[0], n, io, t);
+}
+
+// F(s): the forward with the head's batch reductions folded into the last CTA to finish (ticket).  The tail only
+// does what the row update needs: batch statistics, the five backward sums, Adam on the 4 head scalars, moving
+// statistics and the step scalars; dLoss/dy per sample is recomputed by the row update from (c, label) and the
+// reported BCE / MSE by one extra CTA of the row-update launch -- both off this kernel's critical path.
+constexpr int kFwdThreads = 256;
+constexpr int kFwdWarps = kFwdThreads / 32;
+constexpr int kHeadUnroll = 16;     // samples per thread whose loads are in flight together in the tail
+constexpr int kTailSums = 5;        // sum dy, dy*zh, zh, dy*c, zh*c
+template <int NV>
+__global__ void __launch_bounds__(kFwdThreads)
+fwd_head_kernel(const float* __restrict__ U, const float* __restrict__ A, int dim, const DevChunk* __restrict__ dc,
+                int slot, int batch, const int32_t* __restrict__ meta_n, float* __restrict__ uh,
+                float* __restrict__ ah, float* __restrict__ c, float* __restrict__ ru, float* __restrict__ ra,
+                double* __restrict__ fwd_part, HeadIO io) {
+  __shared__ double red[kHeadSums * 32];
+  __shared__ float cs_s[kFwdWarps];
+  __shared__ int is_last;
+  const int n = min(batch, meta_n[2]);
+  if (n <= 0) return;
+  const int nblk = (n + kFwdWarps - 1) / kFwdWarps;
+  if ((int)blockIdx.x >= nblk) return;
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  const int s = blockIdx.x * kFwdWarps + wid;
+  float cs = 0.f;
+  if (s < n) {
+    const int32_t* __restrict__ iu = dc->iu + (size_t)slot * batch;
+    const int32_t* __restrict__ ia = dc->ia + (size_t)slot * batch;
+    const int d4 = dim >> 2;
+    RowTile<NV> u, a;
+    u.load(U + (size_t)iu[s] * dim, d4, lane);
+    a.load(A + (size_t)ia[s] * dim, d4, lane);
+    const float su = tile_dot<NV>(u, u);
+    const float sa = tile_dot<NV>(a, a);
+    const float r_u = 1.0f / sqrtf(fmaxf(su, kL2NormEps));
+    const float r_a = 1.0f / sqrtf(fmaxf(sa, kL2NormEps));
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      float th = head[k], m = head_m[k], v = head_v[k];
-      adam1(th, m, v, g[k], a);
-      head[k] = th;
-      head_m[k] = m;
-      head_v[k] = v;
+    for (int k = 0; k < NV; ++k) {
+      u.x[k] = scale4(u.x[k], r_u);
+      a.x[k] = scale4(a.x[k], r_a);
     }
-    const float mm = bn_moving[0], mv = bn_moving[1];
-    bn_moving[0] = mm - (mm - mu) * kBnOneMinusMomentum;
-    bn_moving[1] = mv - (mv - var) * kBnOneMinusMomentum;
-    stepc[K_COEF] = (float)((double)w * ig);
-    stepc[K_S1N] = (float)(S1 / n);
-    stepc[K_S2N] = (float)(S2 / n);
-    stepc[K_MU] = mu;
-    stepc[K_INV] = inv;
-    stepc[K_W] = w;
-    stepc[K_B] = b;
-    stepc[K_PAD] = 0.f;
-    if (metrics_row) {
-      metrics_row[0] = (float)(s2[0] / n);
-      metrics_row[1] = (float)(s2[1] / n);
-      metrics_row[2] = fn;
-      metrics_row[3] = mu;
+    cs = tile_dot<NV>(u, a);
+    u.store(uh + (size_t)s * dim, d4, lane);
+    a.store(ah + (size_t)s * dim, d4, lane);
+    if (lane == 0) {
+      c[s] = cs;
+      ru[s] = r_u;
+      ra[s] = r_a;
     }
-    *ticket = 0u;  // ready for the next step
+  }
+  if (lane == 0) cs_s[wid] = cs;
+  __syncthreads();
+  if (tid == 0) {  // (sum c, sum c^2) of this CTA's samples in a fixed order; padding samples contribute 0
+    double a0 = 0.0, a1 = 0.0;
+#pragma unroll
+    for (int i = 0; i < kFwdWarps; ++i) {
+      const double x = (double)cs_s[i];
+      a0 += x;
+      a1 += x * x;
+    }
+    fwd_part[2 * blockIdx.x] = a0;
+    fwd_part[2 * blockIdx.x + 1] = a1;
+    __threadfence();  // cumulative: also orders the c[] stores of the other warps (observed through the barrier)
+    const unsigned int old = atomicAdd(io.ticket, 1u);
+    is_last = (old == (unsigned int)(nblk - 1));
+  }
+  __syncthreads();
+  if (!is_last) return;
+  __threadfence();
+
+  // ---- tail, this CTA alone, every sum in a fixed order.  All loads that do not depend on the statistics are
+  // issued first: the forward partials, the first samples, the head state.
+  const float* __restrict__ label = dc->label + (size_t)slot * batch;
+  const int64_t t = dc->t0 + slot + 1;
+  float hst[3] = {0.f, 0.f, 0.f};   // thread k < 4: head[k], head_m[k], head_v[k]
+  float alpha_t = 0.f;
+  if (tid < 4) {
+    hst[0] = io.head[tid];
+    hst[1] = io.head_m[tid];
+    hst[2] = io.head_v[tid];
+    alpha_t = io.alpha[t];
+  }
+  float cr[kHeadUnroll], tr[kHeadUnroll];
+#pragma unroll
+  for (int k = 0; k < kHeadUnroll; ++k) {
+    const int i = k * kFwdThreads + tid;
+    cr[k] = i < n ? __ldcg((const float*)c + i) : 0.f;
+    tr[k] = i < n ? __ldg(label + i) : 0.f;
+  }
+  double s0[2] = {0.0, 0.0};
+  for (int i = tid; i < nblk; i += kFwdThreads) {
+    s0[0] += __ldcg(fwd_part + 2 * i);
+    s0[1] += __ldcg(fwd_part + 2 * i + 1);
+  }
+  block_sum<2>(s0, red);
+  const HeadScalars h = head_scalars(io.head, s0[0], s0[1], n);
+  double s1[kTailSums];
+#pragma unroll
+  for (int i = 0; i < kTailSums; ++i) s1[i] = 0.0;
+  for (int base = 0; base < n; base += kHeadUnroll * kFwdThreads) {
+    if (base) {
+#pragma unroll
+      for (int k = 0; k < kHeadUnroll; ++k) {
+        const int i = base + k * kFwdThreads + tid;
+        cr[k] = i < n ? __ldcg((const float*)c + i) : 0.f;
+        tr[k] = i < n ? __ldg(label + i) : 0.f;
+      }
+    }
+    // fp32 partial sums over the chunk's <= kHeadUnroll samples, one conversion per chunk and sum
+    float f[kTailSums] = {0.f, 0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+    for (int k = 0; k < kHeadUnroll; ++k) {
+      const int i = base + k * kFwdThreads + tid;
+      if (i < n) {
+        float zh;
+        const float dy = dy_of(cr[k], tr[k], h.w, h.b, h.mu, h.inv, h.gamma, h.beta, h.fn, &zh);
+        f[0] += dy;
+        f[1] = fmaf(dy, zh, f[1]);
+        f[2] += zh;
+        f[3] = fmaf(dy, cr[k], f[3]);
+        f[4] = fmaf(zh, cr[k], f[4]);
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < kTailSums; ++i) s1[i] += (double)f[i];
+  }
+  block_sum<kTailSums>(s1, red);
+  // every thread holds the totals; threads 0..3 each own one head scalar
+  const double S1 = s1[0], S2 = s1[1], Szh = s1[2], Sdyc = s1[3], Szhc = s1[4], Sc = s0[0];
+  const double ig = (double)h.inv * (double)h.gamma;
+  if (tid < 4) {
+    // oracle head_backward(): dgamma = sum dy*zh, dbeta = sum dy, dz_i = inv*gamma*(dy_i - S1/n - zh_i*S2/n)
+    const float g = tid == 0 ? (float)(ig * (Sdyc - S1 / n * Sc - S2 / n * Szhc))   // dw = sum dz*c
+                  : tid == 1 ? (float)(-ig * (S2 / n) * Szh)                        // db = sum dz (0 up to rounding)
+                  : tid == 2 ? (float)S2 : (float)S1;
+    adam1(hst[0], hst[1], hst[2], g, alpha_t);
+    io.head[tid] = hst[0];
+    io.head_m[tid] = hst[1];
+    io.head_v[tid] = hst[2];
+  } else if (tid == 32) {
+    const float mm = io.bn_moving[0], mv = io.bn_moving[1];
+    io.bn_moving[0] = mm - (mm - h.mu) * kBnOneMinusMomentum;
+    io.bn_moving[1] = mv - (mv - h.var) * kBnOneMinusMomentum;
+  } else if (tid == 64) {
+    io.stepc[K_COEF] = (float)((double)h.w * ig);
+    io.stepc[K_S1N] = (float)(S1 / n);
+    io.stepc[K_S2N] = (float)(S2 / n);
+    io.stepc[K_MU] = h.mu;
+    io.stepc[K_INV] = h.inv;
+    io.stepc[K_W] = h.w;
+    io.stepc[K_B] = h.b;
+    io.stepc[K_GAMMA] = h.gamma;
+    io.stepc[K_BETA] = h.beta;
+    io.stepc[K_FN] = h.fn;
+    *io.ticket = 0u;  // ready for the next step
+  }
+}
+
+// Reported metrics of one step (Keras: mean BCE from logits, mean squared error), by one CTA of the row-update
+// launch: nothing on the step's critical path needs them.
+__device__ __forceinline__ void step_metrics(const float* __restrict__ c, const float* __restrict__ label, int n,
+                                             const float* __restrict__ k, float* __restrict__ metrics_row, double* red) {
+  double s[2] = {0.0, 0.0};
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    const float zh = ((k[K_W] * c[i] + k[K_B]) - k[K_MU]) * k[K_INV];
+    const float y = k[K_GAMMA] * zh + k[K_BETA];
+    const float p = sigmoidf_(y), tg = label[i];
+    s[0] += (double)bce_logits(y, tg);
+    s[1] += (double)((tg - p) * (tg - p));
+  }
+  block_sum<2>(s, red);
+  if (threadIdx.x == 0) {
+    metrics_row[0] = (float)(s[0] / n);
+    metrics_row[1] = (float)(s[1] / n);
+    metrics_row[2] = (float)n;
+    metrics_row[3] = k[K_MU];
   }
 }
 
@@ -482,27 +787,47 @@ struct UpdateArgs {
   // peer mode: the plan's sample ids index this rank's selection list; samp maps them to the position in the
   // GLOBAL batch that c / dy are indexed by (`other` and `rinv` stay indexed by the plan's own sample id)
   const int32_t* samp[2];
+  // single GPU, AR_ADAM_REPLAY: blocks_b extra CTAs replay the B list of the NEXT step (rows last touched
+  // 2..depth steps ago, not touched by this step) to this step's t; the step counter comes from dc
+  const int32_t* blist;        // end of the next slot's codes (the B list is stored back to front)
+  const int32_t* blist_count;  // &counts[next slot][1]
+  int blocks_b;
+  const DevChunk* dc;
+  int slot;
+  // single GPU: dLoss/dy is recomputed per sample from (c, label) and the step scalars instead of being read
+  // from `dy`; labels at dc->label + slot*batch.  blocks_m (0 or 1) extra CTAs write the step's reported metrics
+  int use_label;
+  int batch;
+  int blocks_m;
+  float* metrics;
+  int32_t* health;
+  RegAcc reg;
 };
 
 template <int NV>
 __device__ __forceinline__ void finish_row(const ar_table& tb, int row, RowTile<NV>& acc, float q,
                                            float rinv, const float* __restrict__ alpha, float l2x2,
-                                           int64_t t, int replay, double* sumsq_out, int lane) {
+                                           int64_t t, int replay, const RegAcc& reg, int32_t* health, int lane) {
   const int d4 = tb.dim >> 2;
   const size_t o = (size_t)row * tb.dim;
   RowTile<NV> w, m, v;
   w.load(tb.W + o, d4, lane);
   m.load(tb.m + o, d4, lane);
   v.load(tb.v + o, d4, lane);
+  double regd = 0.0;
   if (replay) {
     const int64_t last = tb.last_step[row];
-    if (last < t - 1) replay_l2<NV>(w, m, v, alpha, last, t - 1, l2x2, lane);
+    if (last < t - 1) {
+      // with a replay schedule the row must already be current (the forward has read it): count it
+      if (health && lane == 0) atomicAdd(health, 1);
+      replay_l2<NV>(w, m, v, alpha, reg.stepw, last, t - 1, l2x2, lane, regd);
+    }
   }
-  if (sumsq_out) {
-    float ss = tile_dot<NV>(w, w);
-    if (lane == 0) atomicAdd(sumsq_out + ((blockIdx.x * kRowWarps + (threadIdx.x >> 5)) & 31), (double)ss);
+  if (reg.acc || rinv < 0.f) {
+    const float ss = tile_dot<NV>(w, w);
+    if (reg.acc && lane == 0) regd += (double)(reg.stepw[t] * ss);
+    if (rinv < 0.f) rinv = 1.0f / sqrtf(fmaxf(ss, kL2NormEps));  // same formula as embed_fwd
   }
-  if (rinv < 0.f) rinv = 1.0f / sqrtf(fmaxf(tile_dot<NV>(w, w), kL2NormEps));  // same formula as embed_fwd
   const float a = alpha[t];
 #pragma unroll
   for (int k = 0; k < NV; ++k) {
@@ -517,15 +842,51 @@ __device__ __forceinline__ void finish_row(const ar_table& tb, int row, RowTile<
   m.store(tb.m + o, d4, lane);
   v.store(tb.v + o, d4, lane);
   if (lane == 0) tb.last_step[row] = (int32_t)t;
+  reg_commit(regd, reg, lane);
 }
 
 template <int NV>
 __global__ void __launch_bounds__(kRowThreads)
 rows_update_kernel(UpdateArgs a, const float* __restrict__ c, const float* __restrict__ dy,
                    const float* __restrict__ stepc, const float* __restrict__ alpha, float l2x2, int64_t t,
-                   int replay, double* sumsq_out) {
+                   int replay) {
   extern __shared__ float red[];  // heavy path: [kRowWarps][dim] + [kRowWarps]
+  if (a.dc) t = a.dc->t0 + a.slot + 1;
+  const float* __restrict__ label = a.use_label ? a.dc->label + (size_t)a.slot * a.batch : nullptr;
   int b = blockIdx.x;
+  if (b < a.blocks_m) {  // reported BCE / MSE of the step
+    __shared__ double mred[2 * 32];
+    step_metrics(c, label, min(a.batch, a.meta[0][2]), stepc, a.metrics + t * 4, mred);
+    return;
+  }
+  b -= a.blocks_m;
+  if (b < a.blocks_b) {  // B list of the next step: a short replay to t (these rows are not in this step)
+    const int lane = threadIdx.x & 31;
+    const int nb = a.blist_count[0];
+    for (int i = b * kRowWarps + (threadIdx.x >> 5); i < nb; i += a.blocks_b * kRowWarps) {
+      const int code = a.blist[-1 - i];
+      const bool second = code < 0;
+      const int row = code & 0x7fffffff;
+      const ar_table& tb = second ? a.tab[1] : a.tab[0];
+      const int64_t last = tb.last_step[row];
+      if (last >= t) continue;
+      const int d4 = tb.dim >> 2;
+      const size_t o = (size_t)row * tb.dim;
+      RowTile<NV> w, m, v;
+      w.load(tb.W + o, d4, lane);
+      m.load(tb.m + o, d4, lane);
+      v.load(tb.v + o, d4, lane);
+      double regd = 0.0;
+      replay_l2<NV>(w, m, v, alpha, a.reg.stepw, last, t, l2x2, lane, regd);
+      w.store(tb.W + o, d4, lane);
+      m.store(tb.m + o, d4, lane);
+      v.store(tb.v + o, d4, lane);
+      if (lane == 0) tb.last_step[row] = (int32_t)t;
+      reg_commit(regd, a.reg, lane);
+    }
+    return;
+  }
+  b -= a.blocks_b;
   int which, heavy_path;
   if (b < a.blocks_norm[0]) { which = 0; heavy_path = 0; }
   else if ((b -= a.blocks_norm[0]) < a.blocks_norm[1]) { which = 1; heavy_path = 0; }
@@ -576,7 +937,8 @@ rows_update_kernel(UpdateArgs a, const float* __restrict__ c, const float* __res
       o1.load(other + (size_t)s1 * dim, d4, lane);
       const int g0 = samp ? samp[s0] : s0, g1 = samp ? samp[s1] : s1;
       const float c0 = c[g0], c1 = c[g1];
-      const float d0 = dc_of(dy[g0], c0, kk), d1 = dc_of(dy[g1], c1, kk);
+      const float d0 = label ? dc_of_label(c0, label[g0], kk) : dc_of(dy[g0], c0, kk);
+      const float d1 = label ? dc_of_label(c1, label[g1], kk) : dc_of(dy[g1], c1, kk);
       q = fmaf(d0, c0, q);
       q = fmaf(d1, c1, q);
 #pragma unroll
@@ -591,7 +953,7 @@ rows_update_kernel(UpdateArgs a, const float* __restrict__ c, const float* __res
       o0.load(other + (size_t)s0 * dim, d4, lane);
       const int g0 = samp ? samp[s0] : s0;
       const float c0 = c[g0];
-      const float d0 = dc_of(dy[g0], c0, kk);
+      const float d0 = label ? dc_of_label(c0, label[g0], kk) : dc_of(dy[g0], c0, kk);
       q = fmaf(d0, c0, q);
 #pragma unroll
       for (int k = 0; k < NV; ++k) acc.x[k] = fma4(d0, o0.x[k], acc.x[k]);
@@ -610,7 +972,7 @@ rows_update_kernel(UpdateArgs a, const float* __restrict__ c, const float* __res
       }
       return;
     }
-    finish_row<NV>(tb, uniq[seg], acc, q, rinv[order[beg]], alpha, l2x2, t, replay, sumsq_out, lane);
+    finish_row<NV>(tb, uniq[seg], acc, q, rinv[order[beg]], alpha, l2x2, t, replay, a.reg, a.health, lane);
     return;
   }
 
@@ -627,7 +989,7 @@ rows_update_kernel(UpdateArgs a, const float* __restrict__ c, const float* __res
     o0.load(other + (size_t)s0 * dim, d4, lane);
     const int g0 = samp ? samp[s0] : s0;
     const float c0 = c[g0];
-    const float d0 = dc_of(dy[g0], c0, kk);
+    const float d0 = label ? dc_of_label(c0, label[g0], kk) : dc_of(dy[g0], c0, kk);
     q = fmaf(d0, c0, q);
 #pragma unroll
     for (int k = 0; k < NV; ++k) acc.x[k] = fma4(d0, o0.x[k], acc.x[k]);
@@ -662,7 +1024,7 @@ rows_update_kernel(UpdateArgs a, const float* __restrict__ c, const float* __res
     }
     return;
   }
-  finish_row<NV>(tb, uniq[seg], acc, q, rinv[order[beg]], alpha, l2x2, t, replay, sumsq_out, lane);
+  finish_row<NV>(tb, uniq[seg], acc, q, rinv[order[beg]], alpha, l2x2, t, replay, a.reg, a.health, lane);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -708,11 +1070,11 @@ predict_kernel(const float* __restrict__ U, const float* __restrict__ A, int dim
   if (EVAL) {
     if (lane == 0) { red[wid] = sb; red[kRowWarps + wid] = sm; }
     __syncthreads();
-    if (threadIdx.x == 0) {
+    if (threadIdx.x == 0) {  // per-CTA partials; reduce_partials_kernel adds them in CTA order
       double a0 = 0.0, a1 = 0.0;
       for (int i = 0; i < kRowWarps; ++i) { a0 += red[i]; a1 += red[kRowWarps + i]; }
-      atomicAdd(sums, a0);
-      atomicAdd(sums + 1, a1);
+      sums[2 * blockIdx.x] = a0;
+      sums[2 * blockIdx.x + 1] = a1;
     }
   }
 }
@@ -730,8 +1092,20 @@ __global__ void __launch_bounds__(256) sumsq_kernel(const float* __restrict__ W,
   if (threadIdx.x == 0) {
     double a = 0.0;
     for (int i = 0; i < 8; ++i) a += red[i];
-    atomicAdd(out, a);
+    out[blockIdx.x] = a;
   }
+}
+
+// out[j] += sum_i part[i*width + j] in a fixed order (one CTA): the deterministic second half of the reductions above
+__global__ void __launch_bounds__(256) reduce_partials_kernel(const double* __restrict__ part, int n, int width,
+                                                              double* __restrict__ out) {
+  __shared__ double red[2 * 32];
+  double v[2] = {0.0, 0.0};
+  for (int i = threadIdx.x; i < n; i += blockDim.x)
+    for (int j = 0; j < width; ++j) v[j] += part[(size_t)i * width + j];
+  block_sum<2>(v, red);
+  if (threadIdx.x == 0)
+    for (int j = 0; j < width; ++j) out[j] += v[j];
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -756,10 +1130,23 @@ static int num_sms() {
     default: { constexpr int NV = 4; __VA_ARGS__; } break; \
   }
 
+static int catch_threads(int dim) { return ((dim + 31) / 32) * 32; }   // one element per lane
+
+static RegAcc reg_of(const ar_train_ctx& x) {
+  RegAcc r{};
+  if (x.reg_acc && x.stepw) {
+    r.acc = x.reg_acc;
+    r.stepw = x.stepw;
+    r.scale = x.reg_scale > 0.f ? x.reg_scale : 1.f;
+  }
+  return r;
+}
+
 static int launch_catchup(const ar_table* t0, const ar_plan* p0, int slot0, const ar_table* t1,
                           const ar_plan* p1, int slot1, const float* alpha, float l2, int64_t t_target,
-                          cudaStream_t st, bool skip_prev = false, int32_t* sched_ws = nullptr) {
+                          cudaStream_t st, bool skip_prev = false, int32_t* sched_ws = nullptr, RegAcc reg = RegAcc{}) {
   CatchupArgs a{};
+  a.reg = reg;
   if (skip_prev) {  // look-ahead: leave the rows the previous step also touches to that step's update
     a.skip_flag[0] = p0->in_prev + (int64_t)slot0 * p0->batch_cap;
     if (t1) a.skip_flag[1] = p1->in_prev + (int64_t)slot1 * p1->batch_cap;
@@ -785,7 +1172,24 @@ static int launch_catchup(const ar_table* t0, const ar_plan* p0, int slot0, cons
   }
   // (capping the resident catch-up CTAs per SM with dynamic shared memory, to leave warp slots for the step's
   // own kernels, was measured: 8..28 KB per CTA cost 0..10% of the step -- the replay wants the occupancy)
-  AR_DISPATCH_NV(t0->dim, rows_catchup_kernel<NV><<<ceil_div(units, kCatchThreads / 32), kCatchThreads, 0, st>>>(a, alpha, l2x2, t_target));
+  rows_catchup_kernel<<<units, catch_threads(t0->dim), 0, st>>>(a, alpha, l2x2, t_target);
+  AR_LAUNCH_CHECK();
+  return AR_OK;
+}
+
+// A(s): catch-up from the plan-time schedule of `slot`, to global step dc->t0 + slot (= t(s) - 1).
+static int launch_catchup_list(const ar_train_ctx& x, int slot, cudaStream_t st) {
+  CatchupArgs a{};
+  a.tab[0] = x.users;
+  a.tab[1] = x.anime;
+  a.list = x.sched.codes + (int64_t)slot * x.sched.cap;
+  a.list_count = x.sched.counts + (int64_t)slot * 4;
+  a.dc = (const DevChunk*)x.chunk_params;
+  a.t_off = slot;
+  a.reg = reg_of(x);
+  const int units = x.plan_u.batch_cap + x.plan_a.batch_cap;
+  const float l2x2 = (float)(2.0 * (double)x.l2);
+  rows_catchup_kernel<<<units, catch_threads(x.users.dim), 0, st>>>(a, x.alpha, l2x2, 0);
   AR_LAUNCH_CHECK();
   return AR_OK;
 }
@@ -806,23 +1210,24 @@ static void fill_update(UpdateArgs& a, int w, const ar_table* tab, const ar_plan
 }
 
 static int launch_update(UpdateArgs& a, bool two, const float* c, const float* dy, const float* stepc,
-                         const float* alpha, float l2, int64_t t, int replay, double* sumsq_out, cudaStream_t st) {
+                         const float* alpha, float l2, int64_t t, int replay, RegAcc reg, cudaStream_t st) {
   if (!two) { a.blocks_norm[1] = 0; a.blocks_heavy[1] = 0; a.tab[1] = a.tab[0]; }
-  int blocks = a.blocks_norm[0] + a.blocks_norm[1] + a.blocks_heavy[0] + a.blocks_heavy[1];
+  a.reg = reg;
+  int blocks = a.blocks_m + a.blocks_b + a.blocks_norm[0] + a.blocks_norm[1] + a.blocks_heavy[0] + a.blocks_heavy[1];
   const int dim = a.tab[0].dim;
   size_t smem = (size_t)kRowWarps * dim * sizeof(float) + kRowWarps * sizeof(float);
   const float l2x2 = (float)(2.0 * (double)l2);
-  AR_DISPATCH_NV(dim, rows_update_kernel<NV><<<blocks, kRowThreads, smem, st>>>(a, c, dy, stepc, alpha, l2x2, t, replay, sumsq_out));
+  AR_DISPATCH_NV(dim, rows_update_kernel<NV><<<blocks, kRowThreads, smem, st>>>(a, c, dy, stepc, alpha, l2x2, t, replay));
   AR_LAUNCH_CHECK();
   return AR_OK;
 }
 
 static int launch_flush(const ar_table* tab, const float* alpha, float l2, int64_t t_target,
-                        double* sumsq_out, cudaStream_t st) {
+                        RegAcc reg, cudaStream_t st) {
   const float l2x2 = (float)(2.0 * (double)l2);
   int blocks = (int)std::min<int64_t>(ceil_div(tab->n_rows, kRowWarps), (int64_t)num_sms() * 8);
   if (blocks <= 0) return AR_OK;
-  AR_DISPATCH_NV(tab->dim, table_flush_kernel<NV><<<blocks, kRowThreads, 0, st>>>(*tab, alpha, l2x2, t_target, sumsq_out));
+  AR_DISPATCH_NV(tab->dim, table_flush_kernel<NV><<<blocks, kRowThreads, 0, st>>>(*tab, alpha, l2x2, t_target, reg));
   AR_LAUNCH_CHECK();
   return AR_OK;
 }
@@ -831,10 +1236,17 @@ static int launch_flush(const ar_table* tab, const float* alpha, float l2, int64
 
 using namespace ar;
 
-extern "C" int ar_table_flush(const ar_table* tab, const float* alpha, float l2, int64_t t_target, void* stream) {
+extern "C" int ar_table_flush(const ar_table* tab, const float* alpha, float l2, int64_t t_target,
+                              unsigned long long* reg_acc, const float* stepw, float reg_scale, void* stream) {
   AR_REQUIRE(tab && alpha, "ar_table_flush: null pointer");
   AR_REQUIRE(dim_ok(tab->dim), "ar_table_flush: dim %d unsupported", tab->dim);
-  return launch_flush(tab, alpha, l2, t_target, nullptr, (cudaStream_t)stream);
+  RegAcc reg{};
+  if (reg_acc && stepw) {
+    reg.acc = reg_acc;
+    reg.stepw = stepw;
+    reg.scale = reg_scale > 0.f ? reg_scale : 1.f;
+  }
+  return launch_flush(tab, alpha, l2, t_target, reg, (cudaStream_t)stream);
 }
 
 extern "C" int ar_embed_fwd(const float* U, const float* A, int32_t dim, const int32_t* iu, const int32_t* ia,
@@ -867,8 +1279,8 @@ extern "C" int ar_head_step(const float* c, const float* label, int32_t n, float
   AR_CUDA(cudaMemsetAsync(ticket, 0, 4, st));
   c_partials_kernel<<<ceil_div(nfp, 128), 128, 0, st>>>(c, n, fwd_part);
   AR_LAUNCH_CHECK();
-  head_step_kernel<<<nhb, kHeadThreads, 0, st>>>(c, label, n, nullptr, fwd_part, head, head_m, head_v, bn_moving,
-                                                  alpha, t, dy, head_part, stepc, ticket, metrics_row, 0);
+  HeadIO io{head, head_m, head_v, bn_moving, alpha, dy, stepc, ticket, metrics_row ? metrics_row - t * 4 : nullptr};
+  head_step_kernel<<<nhb, kHeadThreads, 0, st>>>(c, label, n, nullptr, fwd_part, io, t, head_part, 0);
   AR_LAUNCH_CHECK();
   dc_from_dy_kernel<<<ceil_div(n, 256), 256, 0, st>>>(dy, c, n, stepc, dc);
   AR_LAUNCH_CHECK();
@@ -886,14 +1298,13 @@ extern "C" int ar_rows_catchup(const ar_table* tab, const ar_plan* plan, int32_t
 
 extern "C" int ar_rows_update(const ar_table* tab, const ar_plan* plan, int32_t slot, const float* other_hat,
                               const float* c, const float* dy, const float* stepc, const float* rinv,
-                              const float* alpha, float l2, int64_t t, int32_t replay, double* sumsq_out,
-                              void* stream) {
+                              const float* alpha, float l2, int64_t t, int32_t replay, void* stream) {
   AR_REQUIRE(tab && plan && other_hat && c && dy && stepc && rinv && alpha, "ar_rows_update: null pointer");
   AR_REQUIRE(dim_ok(tab->dim), "ar_rows_update: dim %d unsupported", tab->dim);
   AR_REQUIRE(slot >= 0 && slot < plan->n_slots, "ar_rows_update: slot out of range");
   UpdateArgs a{};
   fill_update(a, 0, tab, plan, slot, other_hat, rinv, 0);
-  return launch_update(a, false, c, dy, stepc, alpha, l2, t, replay, sumsq_out, (cudaStream_t)stream);
+  return launch_update(a, false, c, dy, stepc, alpha, l2, t, replay, RegAcc{}, (cudaStream_t)stream);
 }
 
 namespace ar {
@@ -921,6 +1332,13 @@ struct Lookahead {
   cudaEvent_t ev_upd[2] = {nullptr, nullptr};  // "row update of step s is complete" (recorded on the main stream)
   cudaEvent_t ev_ahead = nullptr;              // "look-ahead catch-up for the next step is complete" (side stream)
   cudaEvent_t ev_mid = nullptr;                // peer mode: "forward of step s is queued" (main stream)
+  // single-GPU DAG: A(s) runs on side[s % n_side]; ring of events
+  static constexpr int kRing = AR_SCHED_MAX_DEPTH + 2;
+  cudaStream_t side[AR_SCHED_MAX_DEPTH + 1] = {};
+  cudaEvent_t ev_u[kRing] = {};  // U(s) done (main stream)
+  cudaEvent_t ev_a[kRing] = {};  // A(s) done (side stream)
+  cudaEvent_t ev_begin = nullptr;
+  cudaStream_t cap = nullptr;    // stream the chunk graph is captured on (the caller's may be the legacy default stream)
   bool ok = false;
 };
 static Lookahead* lookahead() {
@@ -930,7 +1348,7 @@ static Lookahead* lookahead() {
   Lookahead& l = la[dev];
   if (!l.ok) {
     // lowest priority: when SM slots free up, the step's own (latency-bound) kernels get them first and the
-    // SFU-bound replay of the NEXT step fills the gaps
+    // SFU-bound replay of the NEXT steps fills the gaps
     int least = 0, greatest = 0;
     cudaDeviceGetStreamPriorityRange(&least, &greatest);
     if (cudaStreamCreateWithPriority(&l.st2, cudaStreamNonBlocking, least) != cudaSuccess) return nullptr;
@@ -938,73 +1356,192 @@ static Lookahead* lookahead() {
       if (cudaEventCreateWithFlags(&l.ev_upd[i], cudaEventDisableTiming) != cudaSuccess) return nullptr;
     if (cudaEventCreateWithFlags(&l.ev_ahead, cudaEventDisableTiming) != cudaSuccess) return nullptr;
     if (cudaEventCreateWithFlags(&l.ev_mid, cudaEventDisableTiming) != cudaSuccess) return nullptr;
+    if (cudaEventCreateWithFlags(&l.ev_begin, cudaEventDisableTiming) != cudaSuccess) return nullptr;
+    if (cudaStreamCreateWithFlags(&l.cap, cudaStreamNonBlocking) != cudaSuccess) return nullptr;
+    for (int i = 0; i <= AR_SCHED_MAX_DEPTH; ++i)
+      if (cudaStreamCreateWithPriority(&l.side[i], cudaStreamNonBlocking, least) != cudaSuccess) return nullptr;
+    for (int i = 0; i < Lookahead::kRing; ++i) {
+      if (cudaEventCreateWithFlags(&l.ev_u[i], cudaEventDisableTiming) != cudaSuccess) return nullptr;
+      if (cudaEventCreateWithFlags(&l.ev_a[i], cudaEventDisableTiming) != cudaSuccess) return nullptr;
+    }
     l.ok = true;
   }
   return &l;
 }
 
-// AR_ADAM_REPLAY overlaps the SFU-bound replay with the memory-bound rest of the step: while step s runs its
-// forward / head / row update on the main stream, the rows of step s+1 that step s does not touch are brought
-// to optimizer step t(s) on a side stream (for them step s is a pure-L2 step too, and alpha[t] is known in
-// advance).  The two row sets are disjoint, so nothing races; rows in BOTH steps need no replay at all after
-// update(s).  Only the first step of a call pays an exposed catch-up.
+static HeadIO head_io(const ar_train_ctx& x) {
+  return HeadIO{x.head, x.head_m, x.head_v, x.bn_moving, x.alpha, x.dy, x.stepc, x.ticket, x.metrics};
+}
+
+// F(s) and U(s) of one slot on `st`; both read the step counter and sample pointers from x.chunk_params.
+static int launch_fwd_head(const ar_train_ctx& x, int slot, cudaStream_t st) {
+  const int dim = x.users.dim;
+  const int32_t* meta_u = x.plan_u.meta + (int64_t)slot * 4;
+  const DevChunk* dc = (const DevChunk*)x.chunk_params;
+  AR_DISPATCH_NV(dim, fwd_head_kernel<NV><<<ceil_div(x.batch, kFwdWarps), kFwdThreads, 0, st>>>(
+                          x.users.W, x.anime.W, dim, dc, slot, x.batch, meta_u, x.uh, x.ah, x.c, x.ru, x.ra, x.fwd_part, head_io(x)));
+  AR_LAUNCH_CHECK();
+  return AR_OK;
+}
+static int launch_update_slot(const ar_train_ctx& x, int slot, bool with_b, cudaStream_t st) {
+  UpdateArgs a{};
+  fill_update(a, 0, &x.users, &x.plan_u, slot, x.ah, x.ru, x.batch);
+  fill_update(a, 1, &x.anime, &x.plan_a, slot, x.uh, x.ra, x.batch);
+  a.dc = (const DevChunk*)x.chunk_params;
+  a.slot = slot;
+  a.use_label = 1;
+  a.batch = x.batch;
+  a.blocks_m = 1;
+  a.metrics = x.metrics;
+  const bool replay = x.mode == AR_ADAM_REPLAY;
+  if (replay) a.health = x.health;
+  if (replay && with_b) {  // B list of slot+1
+    a.blist = x.sched.codes + (int64_t)(slot + 2) * x.sched.cap;
+    a.blist_count = x.sched.counts + (int64_t)(slot + 1) * 4 + 1;
+    a.blocks_b = num_sms();
+  }
+  return launch_update(a, true, x.c, x.dy, x.stepc, x.alpha, x.l2, 0, replay ? 1 : 0, reg_of(x), st);
+}
+
+// The chunk's DAG on streams: main stream F(s) -> U(s); A(s) on low-priority side streams between U(s-depth-1)
+// and F(s).  Capturable (every kernel argument is chunk-invariant; the rest comes from x.chunk_params).
+static int enqueue_chunk(const ar_train_ctx& x, int n_steps, cudaStream_t st, Lookahead* la) {
+  const bool replay = x.mode == AR_ADAM_REPLAY;
+  const int depth = std::max(1, std::min((int)x.depth, AR_SCHED_MAX_DEPTH));
+  const int n_side = depth + 1, R = Lookahead::kRing;
+  int rc;
+  if (replay) AR_CUDA(cudaEventRecord(la->ev_begin, st));  // everything queued before the chunk
+  for (int s = 0; s < n_steps; ++s) {
+    // A(s + depth) may start once U(s - 1) is done; queue the side launches ahead of this step's own kernels
+    if (replay) {
+      const int first = s == 0 ? 0 : s + depth, last = std::min(n_steps - 1, s + depth);
+      for (int a = first; a <= last; ++a) {
+        cudaStream_t sd = la->side[a % n_side];
+        AR_CUDA(cudaStreamWaitEvent(sd, s == 0 ? la->ev_begin : la->ev_u[(s - 1) % R], 0));
+        if ((rc = launch_catchup_list(x, a, sd))) return rc;
+        AR_CUDA(cudaEventRecord(la->ev_a[a % R], sd));
+      }
+      AR_CUDA(cudaStreamWaitEvent(st, la->ev_a[s % R], 0));
+    }
+    if ((rc = launch_fwd_head(x, s, st))) return rc;
+    if ((rc = launch_update_slot(x, s, s + 1 < n_steps, st))) return rc;
+    if (replay) AR_CUDA(cudaEventRecord(la->ev_u[s % R], st));
+  }
+  return AR_OK;
+}
+
+// One instantiated graph per (context, chunk length); a context change (new session, new buffers) rebuilds it.
+struct GraphSlot {
+  ar_train_ctx key;
+  int n_steps = 0;
+  cudaGraphExec_t exec = nullptr;
+  uint64_t stamp = 0;
+};
+static bool same_key(const ar_train_ctx& a, const ar_train_ctx& b) { return memcmp(&a, &b, sizeof(ar_train_ctx)) == 0; }
+static ar_train_ctx graph_key(const ar_train_ctx& x) {
+  ar_train_ctx k;
+  memset(&k, 0, sizeof(k));   // padding bytes too: the key is compared with memcmp
+  k.users = x.users; k.anime = x.anime;
+  k.head = x.head; k.head_m = x.head_m; k.head_v = x.head_v; k.bn_moving = x.bn_moving; k.alpha = x.alpha;
+  k.batch = x.batch; k.l2 = x.l2; k.mode = x.mode;
+  k.plan_u = x.plan_u; k.plan_a = x.plan_a;
+  k.uh = x.uh; k.ah = x.ah; k.c = x.c; k.ru = x.ru; k.ra = x.ra; k.dy = x.dy;
+  k.fwd_part = x.fwd_part; k.head_part = x.head_part; k.stepc = x.stepc; k.ticket = x.ticket; k.metrics = x.metrics;
+  k.reg_acc = x.reg_acc; k.stepw = x.stepw; k.reg_scale = x.reg_scale;
+  k.sched = x.sched; k.depth = x.depth; k.chunk_params = x.chunk_params; k.health = x.health;
+  return k;
+}
+static int chunk_graph(const ar_train_ctx& x, int n_steps, cudaStream_t st, Lookahead* la, cudaGraphExec_t* out) {
+  static GraphSlot cache[64][4];
+  static uint64_t clock_ = 0;
+  int dev = 0;
+  AR_CUDA(cudaGetDevice(&dev));
+  AR_REQUIRE(dev >= 0 && dev < 64, "device index %d out of range", dev);
+  const ar_train_ctx key = graph_key(x);
+  GraphSlot* victim = &cache[dev][0];
+  for (GraphSlot& g : cache[dev]) {
+    if (g.exec && g.n_steps == n_steps && same_key(g.key, key)) {
+      g.stamp = ++clock_;
+      *out = g.exec;
+      return AR_OK;
+    }
+    if (g.stamp < victim->stamp) victim = &g;
+  }
+  cudaGraph_t graph = nullptr;
+  (void)st;
+  AR_CUDA(cudaStreamBeginCapture(la->cap, cudaStreamCaptureModeThreadLocal));
+  int rc = enqueue_chunk(x, n_steps, la->cap, la);
+  cudaError_t e = cudaStreamEndCapture(la->cap, &graph);
+  if (rc) {
+    if (graph) cudaGraphDestroy(graph);
+    return rc;
+  }
+  if (e != cudaSuccess) {
+    ar::set_error("cudaStreamEndCapture: %s", cudaGetErrorString(e));
+    return AR_ERR_CUDA;
+  }
+  cudaGraphExec_t exec = nullptr;
+  e = cudaGraphInstantiate(&exec, graph, 0);
+  cudaGraphDestroy(graph);
+  if (e != cudaSuccess) {
+    ar::set_error("cudaGraphInstantiate: %s", cudaGetErrorString(e));
+    return AR_ERR_CUDA;
+  }
+  if (victim->exec) cudaGraphExecDestroy(victim->exec);
+  victim->key = key;
+  victim->n_steps = n_steps;
+  victim->exec = exec;
+  victim->stamp = ++clock_;
+  *out = exec;
+  return AR_OK;
+}
+
+// Single-GPU step loop.  AR_ADAM_REPLAY and AR_ADAM_TOUCHED go through the chunk DAG (a CUDA graph for chunks of
+// at least kGraphMinSteps steps); AR_ADAM_DENSE and the profiling entry point run stage by stage on one stream.
+constexpr int kGraphMinSteps = 32;
 static int run_steps(const ar_train_ctx& x, int64_t epoch_step0, int32_t slot0, int64_t t0, int32_t n_steps,
                      cudaStream_t st, StageTimer* timer) {
-  const int dim = x.users.dim;
-  static const bool no_overlap = getenv("AR_NO_LOOKAHEAD") != nullptr;
-  Lookahead* la = (x.mode == AR_ADAM_REPLAY && !timer && !no_overlap && x.plan_u.in_prev && x.plan_a.in_prev) ? lookahead() : nullptr;
-  if (la) {
-    AR_CUDA(cudaEventRecord(la->ev_upd[1], st));  // everything queued before this call (stands in for "update(-1)")
+  // steps that actually hold samples
+  int live = 0;
+  for (int s = 0; s < n_steps; ++s)
+    if ((epoch_step0 + s) * (int64_t)x.batch < x.n_samples) live = s + 1;
+  n_steps = live;
+  if (n_steps == 0) return AR_OK;
+  const int64_t base0 = epoch_step0 * (int64_t)x.batch;
+  DevChunk* dc = (DevChunk*)x.chunk_params;
+  set_chunk_kernel<<<1, 1, 0, st>>>(dc, t0, x.iu + base0, x.ia + base0, x.label + base0);
+  AR_LAUNCH_CHECK();
+  const bool replay = x.mode == AR_ADAM_REPLAY;
+  int rc;
+  if (!timer && x.mode != AR_ADAM_DENSE) {
+    AR_REQUIRE(slot0 == 0, "ar_train_steps: slot0 must be 0 (the chunk's kernels index the plans by step)");
+    Lookahead* la = lookahead();
+    AR_REQUIRE(la, "ar_train_steps: could not create the look-ahead streams");
+    static const bool no_graph = getenv("AR_NO_GRAPH") != nullptr;
+    if (!no_graph && n_steps >= kGraphMinSteps) {
+      cudaGraphExec_t exec = nullptr;
+      if ((rc = chunk_graph(x, n_steps, st, la, &exec))) return rc;
+      AR_CUDA(cudaGraphLaunch(exec, st));
+      return AR_OK;
+    }
+    return enqueue_chunk(x, n_steps, st, la);
   }
+  // serial path: dense mode, or per-stage timing (events around every launch)
+  AR_REQUIRE(slot0 == 0, "ar_train_steps: slot0 must be 0");
   for (int s = 0; s < n_steps; ++s) {
-    const int64_t e = epoch_step0 + s;
-    const int64_t base = e * (int64_t)x.batch;
-    if (base >= x.n_samples) break;
-    const int n = (int)std::min<int64_t>(x.batch, x.n_samples - base);
-    const int slot = slot0 + s;
     const int64_t t = t0 + s + 1;
-    const int32_t* meta_u = x.plan_u.meta + (int64_t)slot * 4;
-    const bool has_next = (s + 1 < n_steps) && ((e + 1) * (int64_t)x.batch < x.n_samples);
     AR_TICK(0);
-    if (x.mode == AR_ADAM_REPLAY && (!la || s == 0)) {
-      int rc = launch_catchup(&x.users, &x.plan_u, slot, &x.anime, &x.plan_a, slot, x.alpha, x.l2, t - 1, st, false, x.sched_ws);
-      if (rc) return rc;
-    }
-    bool ahead = false;
-    if (la && has_next) {  // queue the look-ahead BEFORE this step's kernels so the GPU can start it at once
-      AR_CUDA(cudaStreamWaitEvent(la->st2, la->ev_upd[(s + 1) & 1], 0));  // update(s-1) done
-      // the look-ahead owns the SECOND half of sched_ws: at s == 0 it runs concurrently with the main-stream catch-up
-      int32_t* ws2 = x.sched_ws ? x.sched_ws + 3 * ((size_t)x.plan_u.batch_cap + x.plan_a.batch_cap) + 4 : nullptr;
-      int rc = launch_catchup(&x.users, &x.plan_u, slot + 1, &x.anime, &x.plan_a, slot + 1, x.alpha, x.l2, t, la->st2, true, ws2);
-      if (rc) return rc;
-      AR_CUDA(cudaEventRecord(la->ev_ahead, la->st2));
-      ahead = true;
-    }
+    if (replay && (rc = launch_catchup_list(x, s, st))) return rc;
     AR_TICK(1);
-    AR_DISPATCH_NV(dim, embed_fwd_kernel<NV><<<ceil_div(n, kRowWarps), kRowThreads, 0, st>>>(
-                            x.users.W, x.anime.W, dim, x.iu + base, x.ia + base, n, meta_u, x.uh, x.ah, x.c, x.ru, x.ra, x.fwd_part));
-    AR_LAUNCH_CHECK();
+    if ((rc = launch_fwd_head(x, s, st))) return rc;
     AR_TICK(2);
-    head_step_kernel<<<ceil_div(n, kHeadThreads), kHeadThreads, 0, st>>>(
-        x.c, x.label + base, n, meta_u, x.fwd_part, x.head, x.head_m, x.head_v, x.bn_moving, x.alpha, t, x.dy,
-        x.head_part, x.stepc, x.ticket, x.metrics + t * 4, 0);
-    AR_LAUNCH_CHECK();
     AR_TICK(3);
-    UpdateArgs a{};
-    fill_update(a, 0, &x.users, &x.plan_u, slot, x.ah, x.ru, n);
-    fill_update(a, 1, &x.anime, &x.plan_a, slot, x.uh, x.ra, n);
-    double* ss = (x.mode == AR_ADAM_DENSE && x.reg_sumsq) ? x.reg_sumsq + t * 32 : nullptr;
-    int rc = launch_update(a, true, x.c, x.dy, x.stepc, x.alpha, x.l2, t, 0, ss, st);
-    if (rc) return rc;
-    if (la) {
-      AR_CUDA(cudaEventRecord(la->ev_upd[s & 1], st));
-      if (ahead) AR_CUDA(cudaStreamWaitEvent(st, la->ev_ahead, 0));  // the next forward needs the look-ahead rows
-    }
+    if ((rc = launch_update_slot(x, s, s + 1 < n_steps, st))) return rc;
     AR_TICK(4);
     if (x.mode == AR_ADAM_DENSE) {
       // every row the batch did not touch takes the same Adam step with the pure L2 gradient
-      if ((rc = launch_flush(&x.users, x.alpha, x.l2, t, ss, st))) return rc;
-      if ((rc = launch_flush(&x.anime, x.alpha, x.l2, t, ss, st))) return rc;
+      if ((rc = launch_flush(&x.users, x.alpha, x.l2, t, reg_of(x), st))) return rc;
+      if ((rc = launch_flush(&x.anime, x.alpha, x.l2, t, reg_of(x), st))) return rc;
     }
     AR_TICK(5);
   }
@@ -1024,12 +1561,24 @@ static int check_ctx(const ar_train_ctx* ctx, int32_t slot0, int32_t n_steps) {
   AR_REQUIRE(x.mode >= AR_ADAM_REPLAY && x.mode <= AR_ADAM_TOUCHED, "ar_train_steps: bad mode %d", x.mode);
   return AR_OK;
 }
+// the single-GPU entry points additionally need the chunk parameters and, in replay mode, the schedule
+static int check_ctx_single(const ar_train_ctx* ctx, int32_t n_steps) {
+  const ar_train_ctx& x = *ctx;
+  AR_REQUIRE(x.chunk_params, "ar_train_steps: null chunk_params");
+  if (x.mode == AR_ADAM_REPLAY) {
+    AR_REQUIRE(x.sched.codes && x.sched.counts, "ar_train_steps: AR_ADAM_REPLAY needs the replay schedule (ar_plan_sched)");
+    AR_REQUIRE(x.sched.n_slots >= n_steps && x.sched.cap >= x.plan_u.batch_cap + x.plan_a.batch_cap, "ar_train_steps: schedule too small");
+    AR_REQUIRE(x.depth >= 1 && x.depth <= AR_SCHED_MAX_DEPTH, "ar_train_steps: depth %d outside [1,%d]", x.depth, AR_SCHED_MAX_DEPTH);
+  }
+  return AR_OK;
+}
 }  // namespace ar
 
 extern "C" int ar_train_steps(const ar_train_ctx* ctx, int64_t epoch_step0, int32_t slot0, int64_t t0,
                               int32_t n_steps, void* stream) {
   int rc = check_ctx(ctx, slot0, n_steps);
   if (rc) return rc;
+  if ((rc = check_ctx_single(ctx, n_steps))) return rc;
   return run_steps(*ctx, epoch_step0, slot0, t0, n_steps, (cudaStream_t)stream, nullptr);
 }
 
@@ -1037,6 +1586,7 @@ extern "C" int ar_train_steps_profile(const ar_train_ctx* ctx, int64_t epoch_ste
                                       int32_t n_steps, float* stage_ms_host, void* stream) {
   int rc = check_ctx(ctx, slot0, n_steps);
   if (rc) return rc;
+  if ((rc = check_ctx_single(ctx, n_steps))) return rc;
   AR_REQUIRE(stage_ms_host, "ar_train_steps_profile: null stage_ms_host");
   StageTimer tm;
   tm.st = (cudaStream_t)stream;
@@ -1082,8 +1632,40 @@ extern "C" int ar_eval_sums(const float* U, const float* A, int32_t dim, const f
   AR_REQUIRE(dim_ok(dim), "ar_eval_sums: dim %d unsupported", dim);
   if (n <= 0) return AR_OK;
   int blocks = (int)std::min<int64_t>(ceil_div(n, kRowWarps), (int64_t)num_sms() * 8);
-  AR_DISPATCH_NV(dim, predict_kernel<NV, true><<<blocks, kRowThreads, 0, (cudaStream_t)stream>>>(
-                          U, A, dim, head, bn_moving, iu, ia, label, n, nullptr, sums));
+  cudaStream_t st = (cudaStream_t)stream;
+  double* part = nullptr;
+  AR_CUDA(cudaMallocAsync((void**)&part, (size_t)blocks * 2 * sizeof(double), st));
+  AR_DISPATCH_NV(dim, predict_kernel<NV, true><<<blocks, kRowThreads, 0, st>>>(
+                          U, A, dim, head, bn_moving, iu, ia, label, n, nullptr, part));
+  AR_LAUNCH_CHECK();
+  reduce_partials_kernel<<<1, 256, 0, st>>>(part, blocks, 2, sums);
+  AR_LAUNCH_CHECK();
+  AR_CUDA(cudaFreeAsync(part, st));
+  return AR_OK;
+}
+
+namespace ar {
+// MUFU throughput probe: 8 independent sqrt -> add -> reciprocal chains per thread (the two special-function ops
+// of one Adam element-step, adam1()), nothing else competing for the pipe.
+__global__ void __launch_bounds__(256) sfu_probe_kernel(float* __restrict__ out, int iters) {
+  float x[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) x[i] = 1.0f + 0.001f * (float)(threadIdx.x + i);
+#pragma unroll 1
+  for (int it = 0; it < iters; ++it) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) x[i] = rcp_approx(__fadd_rn(sqrt_approx(x[i]), kAdamEps));
+  }
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) s += x[i];
+  out[(size_t)blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+}  // namespace ar
+
+extern "C" int ar_bench_sfu(float* scratch, int32_t blocks, int32_t threads, int32_t iters, void* stream) {
+  AR_REQUIRE(scratch && blocks > 0 && threads > 0 && threads <= 256 && iters > 0, "ar_bench_sfu: bad arguments");
+  ar::sfu_probe_kernel<<<blocks, threads, 0, (cudaStream_t)stream>>>(scratch, iters);
   AR_LAUNCH_CHECK();
   return AR_OK;
 }
@@ -1093,7 +1675,13 @@ extern "C" int ar_sumsq(const float* W, int64_t n_elems, double* out, void* stre
   AR_REQUIRE(n_elems % 4 == 0, "ar_sumsq: n_elems must be a multiple of 4");
   if (n_elems == 0) return AR_OK;
   int blocks = (int)std::min<int64_t>(ceil_div(n_elems / 4, 256), (int64_t)num_sms() * 8);
-  sumsq_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(W, n_elems / 4, out);
+  cudaStream_t st = (cudaStream_t)stream;
+  double* part = nullptr;
+  AR_CUDA(cudaMallocAsync((void**)&part, (size_t)blocks * sizeof(double), st));
+  sumsq_kernel<<<blocks, 256, 0, st>>>(W, n_elems / 4, part);
   AR_LAUNCH_CHECK();
+  reduce_partials_kernel<<<1, 256, 0, st>>>(part, blocks, 1, out);
+  AR_LAUNCH_CHECK();
+  AR_CUDA(cudaFreeAsync(part, st));
   return AR_OK;
 }

@@ -20,11 +20,12 @@ import numpy as np
 import torch
 
 from . import _capi
-from ._capi import ArPlan, ArTable, ArTrainCtx, check, lib, ptr, stream_ptr
+from ._capi import ArPlan, ArSched, ArTable, ArTrainCtx, check, lib, ptr, stream_ptr
 from . import weights_io
 
 BETA1, BETA2 = 0.9, 0.999
 PLAN_CHUNK = 256
+REPLAY_DEPTH = int(os.environ.get("AR_REPLAY_DEPTH", "2"))   # look-ahead depth of the replay schedule
 
 
 def adam_alpha_table(lr, t_first, count):
@@ -108,6 +109,7 @@ class EmbeddingDotModel:
         self.history = None
         self._alpha = None                  # device alpha table, index = global step
         self._alpha_host = np.zeros(1, np.float32)
+        self._stepw = None                  # device step-weight table (samples in step / batch), same indexing
         self.timings = {}
 
     # ------------------------------------------------------------------ state
@@ -125,6 +127,15 @@ class EmbeddingDotModel:
         self.head_m = torch.zeros(4, **f)
         self.head_v = torch.zeros(4, **f)
         self.bn_moving = torch.from_numpy(np.asarray(bn, np.float32)).to(dev)
+        # replay-schedule state (ar_plan_sched): global step of every row's latest planned touch, and the step
+        # of the last full flush
+        self.seenU = torch.zeros(self.n_users, dtype=torch.int32, device=dev)
+        self.seenA = torch.zeros(self.n_anime, dtype=torch.int32, device=dev)
+        self._t_flush = 0
+        # L2-regulariser accumulator of the reported loss (fixed point, see animerec.h ar_train_ctx.reg_acc)
+        self.reg_acc = torch.zeros(1, dtype=torch.int64, device=dev)
+        self.reg_scale = 1.0
+        self._reg_on = False
 
     def _table(self, which):
         t = ArTable()
@@ -144,6 +155,10 @@ class EmbeddingDotModel:
             host[:len(self._alpha_host)] = self._alpha_host
             self._alpha_host = host
             self._alpha = torch.from_numpy(host).to(self.device)
+            sw = torch.ones(n, dtype=torch.float32, device=self.device)
+            if self._stepw is not None:
+                sw[:self._stepw.numel()].copy_(self._stepw)
+            self._stepw = sw
 
     def _set_alpha(self, lr, t_first, count):
         self._ensure_alpha(t_first + count)
@@ -153,13 +168,35 @@ class EmbeddingDotModel:
 
     def _sync_tables(self):
         """In replay mode rows lag behind; replay every row up to the current optimizer step."""
-        if self.adam_mode != "replay" or self.iterations == 0:
+        if self.adam_mode != "replay" or self.iterations == 0 or self._t_flush == self.iterations:
             return
         self._ensure_alpha(self.iterations)
         st = stream_ptr()
+        reg = (ptr(self.reg_acc), ptr(self._stepw), self.reg_scale) if self._reg_on else (None, None, 1.0)
         for which in ("user", "anime"):
             t = self._table(which)
-            check(lib().ar_table_flush(C.byref(t), ptr(self._alpha), self.l2, self.iterations, st), "ar_table_flush")
+            check(lib().ar_table_flush(C.byref(t), ptr(self._alpha), self.l2, self.iterations, *reg, st), "ar_table_flush")
+        self._t_flush = self.iterations
+
+    def _begin_reg(self, steps, batch, n_last):
+        """Arm the regulariser accumulator for an epoch of `steps` steps starting at the current step."""
+        t0 = self.iterations
+        self._ensure_alpha(t0 + steps)
+        self._stepw[t0 + 1:t0 + steps + 1] = 1.0
+        if n_last != batch:
+            self._stepw[t0 + steps] = float(n_last) / float(batch)
+        ss = self.reg_sumsq()
+        bound = max(1.0, float(steps) * (4.0 * ss + 1.0))
+        self.reg_scale = float(2.0 ** min(40, int(math.floor(61 - math.log2(bound)))))
+        self.reg_acc.zero_()
+        self._reg_on = True
+        return ss
+
+    def _end_reg(self):
+        """sum over the epoch's steps t of stepw[t] * (sum U_{t-1}^2 + sum A_{t-1}^2); tables are flushed first."""
+        self._sync_tables()
+        self._reg_on = False
+        return float(self.reg_acc.item()) / self.reg_scale
 
     def reg_sumsq(self):
         """sum U^2 + sum A^2 of the current (synchronised) tables, float64 on host."""
@@ -277,7 +314,6 @@ class EmbeddingDotModel:
         self._check_range(iu_all, ia_all)
         steps = (N + B - 1) // B
         sess = TrainSession(self, B, total_steps=max(0, epochs - initial_epoch) * steps)
-        dense = self.adam_mode == "dense"
 
         callbacks = list(callbacks or [])
         for cb in callbacks:
@@ -320,11 +356,12 @@ class EmbeddingDotModel:
                     torch.cuda.synchronize()
                     tick.append((name, time.perf_counter()))
             _tk("start")
-            reg0 = None if dense else self.l2 * self.reg_sumsq()
+            reg0 = self.l2 * self._begin_reg(steps, B, N - (steps - 1) * B)
             _tk("reg0")
             sess.run(iu_e, ia_e, y_e, lr)
             _tk("steps")
-            self._sync_tables()
+            acc = self._end_reg()          # flushes the tables, then reads the accumulator
+            sess.check_health()
             _tk("flush")
 
             m = sess.metrics[t0 + 1:t0 + steps + 1].cpu().numpy().astype(np.float64)
@@ -332,11 +369,12 @@ class EmbeddingDotModel:
             bce = float((m[:, 0] * w).sum() / N)
             mse = float((m[:, 1] * w).sum() / N)
             reg1 = self.l2 * self.reg_sumsq()
-            if dense:
-                r = self.l2 * sess.reg_ss[t0 + 1:t0 + steps + 1].sum(dim=1).cpu().numpy()
-                reg = float((r * w).sum() / N)
+            if self.adam_mode == "touched":
+                reg = 0.5 * (reg0 + reg1)   # not the reference's arithmetic anyway: end-point average
             else:
-                reg = 0.5 * (reg0 + reg1)   # regulariser is only evaluated at the epoch's flush points
+                # Keras: loss_t = BCE_t + l2*(sum U^2 + sum A^2) with the weights BEFORE step t, averaged with the
+                # step's sample count as weight (neural_network.py:73,78,85; oracle fit())
+                reg = self.l2 * acc * B / N
             logs = dict(loss=bce + reg, mse=mse)
             if val is not None:
                 sums = torch.zeros(2, dtype=torch.float64, device=dev)
@@ -381,8 +419,9 @@ class EmbeddingDotModel:
 
 
 class TrainSession:
-    """Device-side buffers of one training run: dedup plans (PLAN_CHUNK steps at a time), the per-step
-    scratch, the per-step metrics and the ar_train_ctx handed to libanimerec."""
+    """Device-side buffers of one training run: two sets of dedup plans + replay schedules (PLAN_CHUNK steps at a
+    time; chunk i+1 is planned on a side stream while chunk i trains), the per-step scratch, the per-step
+    metrics and the ar_train_ctx handed to libanimerec."""
 
     def __init__(self, model, batch, total_steps, plan_cap=None):
         self.model, self.B = model, int(batch)
@@ -398,16 +437,19 @@ class TrainSession:
         self.c, self.ru, self.ra, self.dy = (torch.empty(P, **f) for _ in range(4))
         self.fwd_part = torch.zeros(2 * ((P + 7) // 8), dtype=torch.float64, device=dev)
         self.head_part = torch.zeros(8 * ((P + 255) // 256), dtype=torch.float64, device=dev)
-        self.stepc = torch.zeros(8, **f)
+        self.stepc = torch.zeros(16, **f)
         self.ticket = torch.zeros(1, dtype=torch.int32, device=dev)
         self.sched_ws = torch.zeros(2 * (3 * 2 * P + 4), dtype=torch.int32, device=dev)
+        self.chunk_params = torch.zeros(16, dtype=torch.int64, device=dev)
+        self.health = torch.zeros(4, dtype=torch.int32, device=dev)
+        self.depth = max(1, min(REPLAY_DEPTH, _capi.AR_SCHED_MAX_DEPTH))
         self.t_cap = model.iterations + int(total_steps)
         model._ensure_alpha(self.t_cap)
         self.metrics = torch.zeros((self.t_cap + 1, 4), **f)
-        self.reg_ss = (torch.zeros((self.t_cap + 1, 32), dtype=torch.float64, device=dev)
-                       if model.adam_mode == "dense" else None)
         self.launches = 0
         self.enqueue_s = 0.0    # host time spent inside ar_train_steps* (queueing the launches)
+        self._sets = None       # single-GPU path: [set 0, set 1] of (plans, schedule, events), made on first run()
+        self.plan_stream = None
 
     @staticmethod
     def _make_plan(n_slots, batch, dev):
@@ -424,6 +466,32 @@ class TrainSession:
             setattr(p, k, v.data_ptr())
         return p, bufs
 
+    @staticmethod
+    def _make_sched(n_slots, batch, dev):
+        i32 = dict(dtype=torch.int32, device=dev)
+        bufs = dict(codes=torch.zeros((n_slots, 2 * batch), **i32), counts=torch.zeros((n_slots, 4), **i32),
+                    gap_u=torch.zeros((n_slots, batch), **i32), gap_a=torch.zeros((n_slots, batch), **i32),
+                    bounds=torch.zeros((n_slots, _capi.AR_SCHED_PARTS + 1), **i32))
+        sc = ArSched()
+        sc.cap, sc.n_slots = 2 * batch, n_slots
+        for k, v in bufs.items():
+            setattr(sc, k, v.data_ptr())
+        return sc, bufs
+
+    def _make_sets(self):
+        dev = self.model.device
+        self._sets = []
+        for k in range(2):
+            if k == 0:
+                pu, ku, pa, ka = self.plan_u, self._keep_u, self.plan_a, self._keep_a
+            else:
+                pu, ku = self._make_plan(self.n_slots, self.P, dev)
+                pa, ka = self._make_plan(self.n_slots, self.P, dev)
+            sc, ks = self._make_sched(self.n_slots, self.P, dev)
+            self._sets.append(dict(plan_u=pu, plan_a=pa, keep=(ku, ka, ks), sched=sc,
+                                   planned=torch.cuda.Event(), consumed=torch.cuda.Event()))
+        self.plan_stream = torch.cuda.Stream(device=dev)
+
     def _ctx(self, iu, ia, y):
         m = self.model
         ctx = ArTrainCtx()
@@ -439,9 +507,23 @@ class TrainSession:
         ctx.fwd_part, ctx.head_part = self.fwd_part.data_ptr(), self.head_part.data_ptr()
         ctx.stepc, ctx.ticket = self.stepc.data_ptr(), self.ticket.data_ptr()
         ctx.metrics = self.metrics.data_ptr()
-        ctx.reg_sumsq = self.reg_ss.data_ptr() if self.reg_ss is not None else None
+        if m._reg_on:
+            ctx.reg_acc, ctx.stepw, ctx.reg_scale = m.reg_acc.data_ptr(), m._stepw.data_ptr(), m.reg_scale
         ctx.sched_ws = self.sched_ws.data_ptr() if os.environ.get("AR_NO_LPT") is None else None
+        ctx.depth = self.depth
+        ctx.chunk_params, ctx.health = self.chunk_params.data_ptr(), self.health.data_ptr()
         return ctx
+
+    def _plan_chunk(self, st, iu, ia, s0, ns, t0):
+        """Queue the planning of steps [s0, s0+ns) (global steps t0+s0+1 ..) into set `st` on the CURRENT stream."""
+        m, L, sp = self.model, lib(), stream_ptr()
+        N = iu.numel()
+        check(L.ar_plan_build(ptr(iu), N, self.B, s0, ns, C.byref(st["plan_u"]), sp), "ar_plan_build(users)")
+        check(L.ar_plan_build(ptr(ia), N, self.B, s0, ns, C.byref(st["plan_a"]), sp), "ar_plan_build(anime)")
+        if m.adam_mode == "replay":
+            check(L.ar_plan_sched(C.byref(st["plan_u"]), C.byref(st["plan_a"]), ns, t0 + s0, m._t_flush,
+                                  ptr(m.seenU), m.n_users, ptr(m.seenA), m.n_anime, self.depth,
+                                  C.byref(st["sched"]), sp), "ar_plan_sched")
 
     def run(self, iu, ia, y, lr, profile=None):
         """Train on every sample of (iu, ia, y) (device int32/int32/float32, visit order) at learning
@@ -455,28 +537,53 @@ class TrainSession:
             raise _capi.AnimerecError("TrainSession sized for %d optimizer steps, %d requested" % (
                 self.t_cap, t0 + steps))
         m._set_alpha(lr, t0 + 1, steps)
+        if self._sets is None:
+            self._make_sets()
         ctx = self._ctx(iu, ia, y)
-        st, L = stream_ptr(), lib()
-        per_step = {"replay": 5 if ctx.sched_ws else 4, "dense": 5, "touched": 3}[m.adam_mode]
-        for s0 in range(0, steps, self.n_slots):
-            ns = min(self.n_slots, steps - s0)
-            check(L.ar_plan_build(ptr(iu), N, B, s0, ns, C.byref(self.plan_u), st), "ar_plan_build(users)")
-            check(L.ar_plan_build(ptr(ia), N, B, s0, ns, C.byref(self.plan_a), st), "ar_plan_build(anime)")
-            if m.adam_mode == "replay":
-                for pl in (self.plan_u, self.plan_a):
-                    check(L.ar_plan_link(C.byref(pl), ns, None, None, 1, st), "ar_plan_link")
+        main, L, S = torch.cuda.current_stream(), lib(), self.n_slots
+        per_step = {"replay": 3, "dense": 4, "touched": 2}[m.adam_mode]
+        chunks = [(s0, min(S, steps - s0)) for s0 in range(0, steps, S)]
+        self.plan_stream.wait_stream(main)                 # the inputs (H2D copies, the shuffle) are queued on `main`
+        with torch.cuda.stream(self.plan_stream):
+            self._plan_chunk(self._sets[0], iu, ia, *chunks[0], t0)
+            self._sets[0]["planned"].record()
+        for i, (s0, ns) in enumerate(chunks):
+            st = self._sets[i % 2]
+            if i + 1 < len(chunks):                        # plan the next chunk while this one runs
+                nxt = self._sets[(i + 1) % 2]
+                with torch.cuda.stream(self.plan_stream):
+                    if i >= 1:
+                        self.plan_stream.wait_event(nxt["consumed"])   # chunk i-1 no longer reads that set
+                    self._plan_chunk(nxt, iu, ia, *chunks[i + 1], t0)
+                    nxt["planned"].record()
+            main.wait_event(st["planned"])
+            ctx.plan_u, ctx.plan_a, ctx.sched = st["plan_u"], st["plan_a"], st["sched"]
+            sp = stream_ptr(main)
             if profile is None:
                 tq = time.perf_counter()
-                check(L.ar_train_steps(C.byref(ctx), s0, 0, t0 + s0, ns, st), "ar_train_steps")
+                check(L.ar_train_steps(C.byref(ctx), s0, 0, t0 + s0, ns, sp), "ar_train_steps")
                 self.enqueue_s += time.perf_counter() - tq
             else:
                 ms = (C.c_float * 5)()
-                check(L.ar_train_steps_profile(C.byref(ctx), s0, 0, t0 + s0, ns, ms, st), "ar_train_steps_profile")
-                for i in range(5):
-                    profile[i] += ms[i]
-            self.launches += (4 if m.adam_mode == "replay" else 2) + ns * per_step
+                check(L.ar_train_steps_profile(C.byref(ctx), s0, 0, t0 + s0, ns, ms, sp), "ar_train_steps_profile")
+                for k in range(5):
+                    profile[k] += ms[k]
+            st["consumed"].record(main)
+            self.launches += 1 + ns * per_step             # chunk parameters + (A, F, U) per step; planning is on the side stream
+        main.wait_stream(self.plan_stream)                 # nothing of this call is left on the side stream
         m.iterations = t0 + steps
+        self._last_set = self._sets[(len(chunks) - 1) % 2]
         return steps
+
+    def check_health(self):
+        """Raise if a row update found a row behind schedule (replay schedule and plans out of step)."""
+        if self.model.adam_mode != "replay":
+            return
+        bad = int(self.health[0].item())
+        if bad:
+            self.health.zero_()
+            raise _capi.AnimerecError("%d row updates found their row behind the replay schedule; results of this "
+                                      "run are invalid" % bad)
 
 
 def load_model(path, device=None, adam_mode="replay"):

@@ -148,4 +148,5 @@ def load_into(model, path, _pre=None):
         model.head_v.copy_(torch.from_numpy(np.concatenate([ent[o + "v/%s:0" % n] for n in hn])).to(dev))
         model.lastU.fill_(model.iterations)
         model.lastA.fill_(model.iterations)
+        model._t_flush = model.iterations
     return model

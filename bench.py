@@ -23,6 +23,7 @@ if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
 N_USERS, N_ANIME, DIM, BATCH = 350_000, 18_000, 128, 10_000
+TARGET_STEPS = 6000            # timed region: reps * steps >= this many consecutive steps (>= 0.2 s of device time)
 L2 = 1e-4
 LR = 1e-5                      # lrfn(0) of the reference's schedule
 METRIC = "train_samples_per_s"
@@ -38,17 +39,37 @@ def peaks():
     return dict(hbm_gbs=6650.0, bf16_tflops=1590.0, bf16_tflops_sustained=1400.0, source="fallback")
 
 
-def sfu_roofline(stage, mode):
+def measure_sfu_peak(dev):
+    """MUFU (sqrt + reciprocal) throughput of this GPU, measured with the library's own micro-kernel
+    (ar_bench_sfu: 8 independent sqrt->add->rcp chains per thread, nothing else) in this process."""
+    import torch
+    from anime_recommendations_b200._capi import check, lib, ptr, stream_ptr
+    blocks, threads, iters = 148 * 8, 256, 4096
+    scratch = torch.zeros(blocks * threads, device=dev)
+    check(lib().ar_bench_sfu(ptr(scratch), blocks, threads, 64, stream_ptr()), "ar_bench_sfu")
+    best = None
+    for _ in range(3):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        check(lib().ar_bench_sfu(ptr(scratch), blocks, threads, iters, stream_ptr()), "ar_bench_sfu")
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1)
+        best = ms if best is None else min(best, ms)
+    return 2.0 * 8 * blocks * threads * iters / (best * 1e-3)
+
+
+def sfu_roofline(stage, mode, peak):
     """rows_catchup against the SFU peak: in steady state the rows touched per step pay off exactly the replay
     debt all rows accrue per step, i.e. (n_users + n_anime) * dim element-steps of 2 MUFU ops (sqrt, reciprocal)
-    each; the SFU retires 16 lanes/clk/SM.  The stage time includes the classify launch and the launch gaps."""
+    each.  The peak is measured in this process (measure_sfu_peak)."""
     if mode != "replay" or stage["rows_catchup"]["ms_per_step"] <= 0:
         return None
     mufu = 2.0 * (N_USERS + N_ANIME) * DIM
-    peak = 16 * 148 * 1.965e9
     ach = mufu / (stage["rows_catchup"]["ms_per_step"] * 1e-3)
     return dict(bound="sfu", mufu_per_launch=mufu, achieved_mufu_per_s=ach, peak_mufu_per_s=peak, frac=ach / peak,
-                peak_source="16 MUFU lanes/clk/SM x 148 SMs x 1.965 GHz (nominal)")
+                peak_source="measured in this process: sqrt+rcp micro-kernel on all SMs (ar_bench_sfu)",
+                nominal_mufu_per_s=16 * 148 * 1.965e9)
 
 
 def ncu_traffic(kernel, mode):
@@ -223,17 +244,25 @@ def gpu_main(args):
                                      l2_reg_factor=L2, seed=1 + rank, adam_mode=mode, dense_kernel=1.0)
     else:
         model = ar.EmbeddingDotModel(N_USERS, N_ANIME, DIM, l2_reg_factor=L2, seed=1, adam_mode=mode, dense_kernel=1.0)
-    iu, ia, y = synth((W + K) * BATCH, 42 + rank, dev, zipf=args.zipf)
+    # Timed region: the K-step region repeated R times back to back, as ONE run of T = R*K consecutive steps of an
+    # epoch (>= 0.2 s of device time), so chunk planning, graph replay and the replay debts are in the steady
+    # state of a 10 900-step epoch (neural_network.py:210-217).  The untimed warm-up is a run of the SAME shape
+    # (T steps, same chunking, same buffer sizes), so no allocation or first-use setup lands in the timed region.
+    R = args.reps if args.reps > 0 else max(1, -(-TARGET_STEPS // K))
+    T = R * K
+    iu, ia, y = synth(T * BATCH, 42 + rank, dev, zipf=args.zipf)
+    wu, wa, wy = synth(T * BATCH, 1042 + rank, dev, zipf=args.zipf)
     if world > 1:
         from anime_recommendations_b200 import dist as ardist
         cls = {"sharded": ardist.ShardedTrainSession, "peer": ardist.PeerTrainSession,
                "replicated": ardist.DistTrainSession}[args.dist]
-        sess = cls(model, BATCH, total_steps=2 * (W + K) + 8)
+        sess = cls(model, BATCH, total_steps=3 * T + K + 8)
     else:
-        sess = TrainSession(model, BATCH, total_steps=2 * (W + K) + 8)
-    # warm-up (untimed)
-    sess.run(iu[:W * BATCH], ia[:W * BATCH], y[:W * BATCH], LR)
+        sess = TrainSession(model, BATCH, total_steps=3 * T + K + 8)
+    # warm-up (untimed): max(W, T) steps in a call of the timed call's shape
+    sess.run(wu, wa, wy, LR)
     torch.cuda.synchronize()
+    del wu, wa, wy
     if world > 1:
         dist.barrier()
     sampler = ClockSampler(local) if rank == 0 and os.environ.get("AR_BENCH_NO_SAMPLER") is None else None
@@ -247,7 +276,7 @@ def gpu_main(args):
     if sampler:
         sampler.mark_begin()
     e0.record()
-    sess.run(iu[W * BATCH:], ia[W * BATCH:], y[W * BATCH:], LR)
+    sess.run(iu, ia, y, LR)
     e1.record()
     torch.cuda.synchronize()
     if sampler:
@@ -255,17 +284,19 @@ def gpu_main(args):
     ms = e0.elapsed_time(e1)
     if hasattr(sess, "verify"):
         sess.verify()          # peer mode: list-capacity and barrier checks of everything just run
+    sess.check_health()
     launches = sess.launches - l0
-    enqueue_us = (sess.enqueue_s - q0) / K * 1e6   # host time per step spent queueing launches (rank 0)
+    enqueue_us = (sess.enqueue_s - q0) / T * 1e6   # host time per step spent queueing launches (rank 0)
     if world > 1:
         t = torch.tensor([ms], device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms = float(t.item())
         dist.barrier()
     clocks = sampler.stop() if sampler else None
-    value = world * K * BATCH / (ms / 1e3)
+    value = world * T * BATCH / (ms / 1e3)
 
-    line = dict(metric=METRIC, value=value, unit=UNIT, n_gpus=world, steps=K, warmup=W, ms_per_step=ms / K,
+    line = dict(metric=METRIC, value=value, unit=UNIT, n_gpus=world, steps=K, warmup=W, reps=R, steps_timed=T,
+                warmup_steps_run=T, ms_per_step=ms / T,
                 higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f32", data="synthetic",
                 config=workload_config(mode, world), gpu_launches=int(launches), host_enqueue_us_per_step=enqueue_us,
                 clocks=clocks)
@@ -275,22 +306,35 @@ def gpu_main(args):
     if rank == 0 and world == 1:
         # ---- roofline of the dominant kernel: per-stage device time measured live with CUDA events
         prof = [0.0] * 5
-        iu2, ia2, y2 = synth(K * BATCH, 4242, dev, zipf=args.zipf)
+        Kp = 256
+        iu2, ia2, y2 = synth(Kp * BATCH, 4242, dev, zipf=args.zipf)
         sess.run(iu2, ia2, y2, LR, profile=prof)
-        # distinct rows per step, from the library's own dedup plans of the steps just run (meta[slot][0])
-        nslot = min(K, sess.n_slots) if K <= sess.n_slots else (K % sess.n_slots or sess.n_slots)
-        uu = float(sess._keep_u["meta"][:nslot, 0].float().mean().item())
-        ua = float(sess._keep_a["meta"][:nslot, 0].float().mean().item())
-        names = ["rows_catchup", "embed_fwd", "head_step", "rows_update", "dense_flush"]
+        sess.check_health()
+        # distinct rows per step and replay lengths, from the library's own plans / schedule of the steps just run
+        ku, ka, ks = sess._last_set["keep"]
+        nu_s, na_s = ku["meta"][:Kp, 0].long(), ka["meta"][:Kp, 0].long()
+        uu, ua = float(nu_s.float().mean().item()), float(na_s.float().mean().item())
+        col = torch.arange(BATCH, device=dev)[None, :]
+        gu = ks["gap_u"][:Kp].float() * (col < nu_s[:, None])
+        ga = ks["gap_a"][:Kp].float() * (col < na_s[:, None])
+        replay = dict(mean_gap_user_rows=float(gu.sum().item() / max(1, int(nu_s.sum()))),
+                      mean_gap_anime_rows=float(ga.sum().item() / max(1, int(na_s.sum()))),
+                      element_steps_per_step=float((gu.sum() + ga.sum()).item() / Kp * DIM),
+                      depth=sess.depth,
+                      what="gap = steps since the row's previous touch; a row replays gap-1 pure-L2 Adam steps")
+        names = ["rows_catchup", "fwd_head", "unused", "rows_update", "dense_flush"]
         row_b = DIM * 4
         alg = dict(rows_catchup=(uu + ua) * row_b * 6,
-                   embed_fwd=BATCH * row_b * 2 * 2 + BATCH * 20,              # gather 2 rows, save 2 normalised rows
-                   head_step=BATCH * 12,
+                   fwd_head=BATCH * row_b * 2 * 2 + BATCH * 32,               # gather 2 rows, save 2 normalised rows; head
+                   unused=0,
                    rows_update=(uu + ua) * row_b * 6 + BATCH * row_b * 2 + BATCH * 24,
                    dense_flush=(N_USERS + N_ANIME) * row_b * 6)
-        stage = {n: dict(ms_per_step=prof[i] / K, alg_bytes=alg[n],
-                         gbs=(alg[n] / (prof[i] / K * 1e-3) / 1e9 if prof[i] > 0 else 0.0)) for i, n in enumerate(names)}
+        stage = {n: dict(ms_per_step=prof[i] / Kp, alg_bytes=alg[n],
+                         gbs=(alg[n] / (prof[i] / Kp * 1e-3) / 1e9 if prof[i] > 0 else 0.0)) for i, n in enumerate(names)
+                 if n != "unused"}
+        names = [n for n in names if n != "unused"]
         dom = max(names, key=lambda n: stage[n]["ms_per_step"])
+        sfu_peak = measure_sfu_peak(dev)
         # step-level accounting of SURVEY §8(d): touched rows (replay/touched) or dense
         if mode == "dense":
             step_bytes = (N_USERS + N_ANIME) * row_b * 6 + BATCH * row_b * 2 + BATCH * 12
@@ -303,14 +347,18 @@ def gpu_main(args):
                                 note=("replay mode: the dominant kernel replays every row's missed dense-L2 Adam steps in "
                                       "registers and is SFU-bound, not HBM-bound (see `sfu`); extras.train_modes.dense "
                                       "runs the same arithmetic HBM-bound") if mode == "replay" else None,
-                                sfu=sfu_roofline(stage, mode),
-                                step=dict(alg_bytes=step_bytes, gbs=step_bytes / (ms / K * 1e-3) / 1e9,
-                                          frac=step_bytes / (ms / K * 1e-3) / 1e9 / pk["hbm_gbs"],
-                                          unique_user_rows=uu, unique_anime_rows=ua),
-                                stages=stage)
+                                sfu=sfu_roofline(stage, mode, sfu_peak),
+                                step=dict(alg_bytes=step_bytes, gbs=step_bytes / (ms / T * 1e-3) / 1e9,
+                                          frac=step_bytes / (ms / T * 1e-3) / 1e9 / pk["hbm_gbs"],
+                                          unique_user_rows=uu, unique_anime_rows=ua,
+                                          sfu_floor_ms=2.0 * (N_USERS + N_ANIME) * DIM / sfu_peak * 1e3 if mode == "replay" else None),
+                                replay=replay if mode == "replay" else None,
+                                stages=stage,
+                                stages_note="stage times are of a serialised run (events around every launch); in the "
+                                            "timed region the catch-up overlaps the forward and the row update")
 
         # ---- e2e: the public API (Model.fit) fed from pinned HOST buffers, copies inside the timed region
-        line["e2e"] = e2e_fit(ar, dev, mode, K, args.zipf)
+        line["e2e"] = e2e_fit(ar, dev, mode, T, args.zipf)
 
         # ---- CPU baseline (bounded sample) beside the GPU number
         if not args.skip_cpu:
@@ -327,7 +375,7 @@ def gpu_main(args):
                                              if m != mode}
     if world > 1:
         # ---- e2e at N GPUs: every rank feeds its shard of each global batch from pinned HOST memory
-        hu, ha, hy = (t.cpu().pin_memory() for t in synth(K * BATCH, 177 + rank, dev, zipf=args.zipf))
+        hu, ha, hy = (t.cpu().pin_memory() for t in synth(T * BATCH, 177 + rank, dev, zipf=args.zipf))
         model._sync_tables()
         torch.cuda.synchronize()
         dist.barrier()
@@ -338,12 +386,12 @@ def gpu_main(args):
         if hasattr(sess, "verify"):
             sess.verify()
         model._sync_tables()
-        mt = sess.metrics[t_first + 1:t_first + K + 1].cpu()              # D2H of the per-step metrics
+        mt = sess.metrics[t_first + 1:t_first + T + 1].cpu()              # D2H of the per-step metrics
         torch.cuda.synchronize()
         dt = torch.tensor([time.perf_counter() - t0], device=dev)
         dist.all_reduce(dt, op=dist.ReduceOp.MAX)
         dist.barrier()
-        line["e2e"] = dict(value=world * K * BATCH / float(dt.item()), unit=UNIT, h2d_bytes_per_step=BATCH * 12,
+        line["e2e"] = dict(value=world * T * BATCH / float(dt.item()), unit=UNIT, h2d_bytes_per_step=BATCH * 12,
                            d2h_bytes_per_step=16, seconds=float(dt.item()), loss_bce_last=float(mt[-1, 0]),
                            what="per rank: pinned host arrays -> H2D, K data-parallel steps (SyncBN, %s), table flush, D2H of "
                                 "the per-step metrics; max over ranks" % {"peer": "rows pulled over NVLink peer memory",
@@ -365,6 +413,8 @@ def mode_run(ar, dev, mode, K, W):
     m = ar.EmbeddingDotModel(N_USERS, N_ANIME, DIM, l2_reg_factor=L2, seed=1, adam_mode=mode, dense_kernel=1.0)
     iu, ia, y = synth((W + K) * BATCH, 4242, dev)
     sess = TrainSession(m, BATCH, total_steps=W + K + 8)
+    if mode == "dense":
+        m._begin_reg(W + K, BATCH, BATCH)     # the reference-literal step includes the regulariser term of the loss
     sess.run(iu[:W * BATCH], ia[:W * BATCH], y[:W * BATCH], LR)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     torch.cuda.synchronize()
@@ -506,6 +556,7 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=1000)
     ap.add_argument("--warmup", type=int, default=50)
+    ap.add_argument("--reps", type=int, default=0, help="timed region = reps x steps consecutive steps (0: enough for >= 0.2 s)")
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--mode", default="replay", choices=["replay", "dense", "touched"])
     ap.add_argument("--zipf", action="store_true", help="Zipf(1) anime popularity instead of uniform")

@@ -88,6 +88,32 @@ int ar_plan_build_lists(const int32_t* keys, int32_t stride, const int32_t* coun
 int ar_plan_link(const ar_plan* plan, int32_t n_steps, const int32_t* uniq_all, const int32_t* meta_all,
                  int32_t n_ranks, void* stream);
 
+/* Replay schedule of AR_ADAM_REPLAY, built at plan time (ar_plan_sched) for the same slots as the two plans.
+ * With gap = (this step) - (step of the row's previous touch or of the last full flush):
+ *   gap == 1            the previous step's own update leaves the row current;
+ *   2 <= gap <= depth   B list: replayed by the PREVIOUS step's row-update launch (at most depth-1 steps);
+ *   gap > depth         A list, longest replay first: a catch-up launch that may start once step s-depth-1 is done.
+ * Slot 0 has no predecessor inside the chunk: every row with gap >= 2 is on its A list. */
+#define AR_SCHED_MAX_DEPTH 8
+#define AR_SCHED_PARTS 296   /* row-range parts of the plan-time walk (bounds has n_slots*(AR_SCHED_PARTS+1) entries) */
+typedef struct {
+  int32_t cap;        /* stride of codes; >= plan_u.batch_cap + plan_a.batch_cap */
+  int32_t n_slots;
+  int32_t* codes;     /* [slot][cap]  (table << 31) | row; A list from the front, B list from the back */
+  int32_t* counts;    /* [slot][4]    n_A, n_B, 0, 0 */
+  int32_t* gap_u;     /* [slot][plan_u.batch_cap] scratch: gap per distinct user row */
+  int32_t* gap_a;     /* [slot][plan_a.batch_cap] */
+  int32_t* bounds;    /* [n_slots][AR_SCHED_PARTS+1] scratch */
+} ar_sched;
+
+/* Build the schedule of `n_steps` planned slots whose global optimizer steps are t0+1 .. t0+n_steps.
+ * seen_u / seen_a: (n_rows) int32, zero-initialised by the caller once and then only passed back: the global step
+ * of every row's latest planned touch.  t_flush: global step every row was last brought to by ar_table_flush (0 =
+ * never).  Chunks must be scheduled in training order, each exactly once.  Replaces the per-step classify launch. */
+int ar_plan_sched(const ar_plan* plan_u, const ar_plan* plan_a, int32_t n_steps, int64_t t0, int64_t t_flush,
+                  int32_t* seen_u, int32_t n_rows_u, int32_t* seen_a, int32_t n_rows_a, int32_t depth,
+                  const ar_sched* sched, void* stream);
+
 typedef enum {
   AR_ADAM_REPLAY = 0,  /* reference-equivalent: missed dense steps of a row are replayed when it is next touched */
   AR_ADAM_DENSE = 1,   /* reference-literal: every row of both tables is updated every step */
@@ -121,17 +147,32 @@ typedef struct {
   float* dy;           /* (batch) dLoss/dy = (p - t)/n per sample */
   double* fwd_part;    /* (2*ceil(batch/8)) per-CTA (sum c, sum c^2) of the forward kernel */
   double* head_part;   /* (8*ceil(batch/256)) per-CTA partial sums of the head kernel */
-  float* stepc;        /* (8) per-step scalars the head hands to the row update */
+  float* stepc;        /* (16) per-step scalars the head hands to the row update */
   uint32_t* ticket;    /* (1) zero-initialised arrival counter of the head kernel */
   /* per-step outputs, indexed by global step t (1-based): metrics[t*4 + {0: mean BCE, 1: mean
-   * squared error, 2: n, 3: batch mean of z}] ; reg_sumsq[t*32 + j], j<32: partial sums whose total is sum U^2 + sum A^2 BEFORE step t
-   * (written in AR_ADAM_DENSE only; may be null) */
+   * squared error, 2: n, 3: batch mean of z}] */
   float* metrics;
-  double* reg_sumsq;
-  /* optional (AR_ADAM_REPLAY): 2 * (3 * (plan_u.batch_cap + plan_a.batch_cap) + 4) int32 of scratch for the
-   * longest-first schedule of the catch-up kernel (one half per stream: the look-ahead catch-up of the
-   * next step runs concurrently with the current one); null = plan order */
+  /* L2-regulariser term of the reported loss (neural_network.py:73,78,85: `loss` = BCE + l2*(sum U^2 + sum A^2),
+   * evaluated with the weights BEFORE each step).  Every (row, step) pair passes exactly once through a replay
+   * step, a row update or a flush; each adds stepw[t] * ||row before step t||^2 to the fixed-point accumulator
+   * reg_acc[0] (uint64, value * reg_scale; integer adds => order-independent, bit-reproducible).  After the
+   * tables are flushed to step T:  reg_acc / reg_scale = sum_{t<=T} stepw[t] * (sum U_{t-1}^2 + sum A_{t-1}^2).
+   * stepw == null or reg_acc == null: not accumulated. */
+  unsigned long long* reg_acc;
+  const float* stepw;  /* stepw[t], indexed like alpha: weight of global step t (samples in the step / batch) */
+  float reg_scale;     /* power of two */
+  /* optional (multi-GPU paths, AR_ADAM_REPLAY): 2 * (3 * (plan_u.batch_cap + plan_a.batch_cap) + 4) int32 of
+   * scratch for the per-step classify launch of ar_train_steps_dist / _sharded / _peer; null = plan order */
   int32_t* sched_ws;
+  /* single-GPU AR_ADAM_REPLAY: the plan-time replay schedule (ar_plan_sched) and its look-ahead depth; required */
+  ar_sched sched;
+  int32_t depth;
+  /* (16 x int64) device scratch the step kernels read their per-chunk parameters from (lets a whole chunk of
+   * steps be replayed as one CUDA graph) */
+  void* chunk_params;
+  /* (4) int32 device counters, zeroed by the caller: [0] rows a row update found behind schedule (must stay 0 in
+   * AR_ADAM_REPLAY: a non-zero value means the replay schedule and the plans disagree) */
+  int32_t* health;
 } ar_train_ctx;
 
 /* Run `n_steps` consecutive training steps.  Epoch-local step e = epoch_step0 + s reads samples
@@ -263,8 +304,10 @@ int ar_allgather_bytes(void* comm, const void* send, void* recv, int64_t bytes_p
 
 /* Bring every row of the table to optimizer step t_target by replaying its missed pure-L2 steps
  * (no-op per row when last_step >= t_target).  Used at epoch end / before validation, saving and
- * similarity in AR_ADAM_REPLAY, and as the "all other rows" half of a dense step. */
-int ar_table_flush(const ar_table* tab, const float* alpha, float l2, int64_t t_target, void* stream);
+ * similarity in AR_ADAM_REPLAY, and as the "all other rows" half of a dense step.  reg_acc / stepw / reg_scale:
+ * the regulariser accumulator of ar_train_ctx (the replayed steps' share of the reported loss), or null. */
+int ar_table_flush(const ar_table* tab, const float* alpha, float l2, int64_t t_target,
+                   unsigned long long* reg_acc, const float* stepw, float reg_scale, void* stream);
 
 /* Individual stages (the kernels ar_train_steps chains), exported for unit parity tests. */
 int ar_embed_fwd(const float* U, const float* A, int32_t dim, const int32_t* iu, const int32_t* ia,
@@ -276,7 +319,7 @@ int ar_rows_catchup(const ar_table* tab, const ar_plan* plan, int32_t slot, cons
                     float l2, int64_t t, void* stream);
 int ar_rows_update(const ar_table* tab, const ar_plan* plan, int32_t slot, const float* other_hat,
                    const float* c, const float* dy, const float* stepc, const float* rinv,
-                   const float* alpha, float l2, int64_t t, int32_t replay, double* sumsq_out, void* stream);
+                   const float* alpha, float l2, int64_t t, int32_t replay, void* stream);
 
 /* Inference forward, Keras `model.predict([users, animes])` (model_recs.py:394): BN uses the
  * moving statistics.  out: (n) float32 probabilities. */
@@ -289,6 +332,11 @@ int ar_eval_sums(const float* U, const float* A, int32_t dim, const float* head,
                  void* stream);
 /* out[0] += sum of squares of the table (L2 regulariser term, neural_network.py:73). */
 int ar_sumsq(const float* W, int64_t n_elems, double* out, void* stream);
+
+/* Measurement aid (bench.py): launches blocks x threads (<= 256) threads that each run `iters` x 8 independent
+ * sqrt.approx -> add -> rcp.approx chains (the special-function work of one Adam element-step) and write one float
+ * to scratch[blocks*threads].  2*8*blocks*threads*iters MUFU ops per launch; the caller times it. */
+int ar_bench_sfu(float* scratch, int32_t blocks, int32_t threads, int32_t iters, void* stream);
 
 /* ------------------------------------------------------------------ Half B: cosine top-k */
 

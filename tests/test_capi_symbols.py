@@ -42,7 +42,7 @@ def test_struct_layouts_match_header():
     prog = r'''
 #include <stdio.h>
 #include "animerec.h"
-int main(void){ printf("%zu %zu %zu %zu %zu %zu\n", sizeof(ar_table), sizeof(ar_plan), sizeof(ar_train_ctx), sizeof(ar_dist_ctx), sizeof(ar_shard_ctx), sizeof(ar_peer_ctx)); return 0; }
+int main(void){ printf("%zu %zu %zu %zu %zu %zu %zu\n", sizeof(ar_table), sizeof(ar_plan), sizeof(ar_train_ctx), sizeof(ar_dist_ctx), sizeof(ar_shard_ctx), sizeof(ar_peer_ctx), sizeof(ar_sched)); return 0; }
 '''
     with tempfile.TemporaryDirectory() as d:
         c = os.path.join(d, "s.c")
@@ -51,7 +51,8 @@ int main(void){ printf("%zu %zu %zu %zu %zu %zu\n", sizeof(ar_table), sizeof(ar_
         subprocess.check_call(["gcc", "-I" + os.path.join(ROOT, "include"), c, "-o", exe])
         sizes = [int(x) for x in subprocess.check_output([exe]).split()]
     assert sizes == [ctypes.sizeof(_capi.ArTable), ctypes.sizeof(_capi.ArPlan), ctypes.sizeof(_capi.ArTrainCtx),
-                     ctypes.sizeof(_capi.ArDistCtx), ctypes.sizeof(_capi.ArShardCtx), ctypes.sizeof(_capi.ArPeerCtx)]
+                     ctypes.sizeof(_capi.ArDistCtx), ctypes.sizeof(_capi.ArShardCtx), ctypes.sizeof(_capi.ArPeerCtx),
+                     ctypes.sizeof(_capi.ArSched)]
 
 
 def test_no_cpu_fallback_without_gpu():
