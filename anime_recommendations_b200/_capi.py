@@ -10,11 +10,13 @@ import os
 
 PKG = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("ANIMEREC_LIB") or os.path.join(PKG, "lib", "libanimerec.so")   # override: A/B builds
-ABI_VERSION = 13
+ABI_VERSION = 14
 
 AR_MAX_BATCH = 16384
 AR_HEAVY_LEN = 64
-AR_SCHED_MAX_DEPTH = 8
+AR_SCHED_MAX_DEPTH = 4
+AR_SCHED_SUB = AR_SCHED_MAX_DEPTH + 2
+AR_SCHED_SPLIT_GAP = 64
 AR_SCHED_PARTS = 296
 ADAM_REPLAY, ADAM_DENSE, ADAM_TOUCHED = 0, 1, 2
 ADAM_MODES = {"replay": ADAM_REPLAY, "dense": ADAM_DENSE, "touched": ADAM_TOUCHED}
@@ -36,7 +38,8 @@ class ArPlan(C.Structure):
 
 
 class ArSched(C.Structure):
-    _fields_ = [("cap", C.c_int32), ("n_slots", C.c_int32), ("codes", C.c_void_p), ("counts", C.c_void_p),
+    _fields_ = [("cap", C.c_int32), ("n_slots", C.c_int32), ("codes", C.c_void_p), ("glen", C.c_void_p),
+                ("sub", C.c_void_p), ("cursor", C.c_void_p),
                 ("gap_u", C.c_void_p), ("gap_a", C.c_void_p), ("bounds", C.c_void_p)]
 
 
@@ -51,7 +54,7 @@ class ArTrainCtx(C.Structure):
                 ("ra", C.c_void_p), ("dy", C.c_void_p), ("fwd_part", C.c_void_p), ("head_part", C.c_void_p),
                 ("stepc", C.c_void_p), ("ticket", C.c_void_p),
                 ("metrics", C.c_void_p), ("reg_acc", C.c_void_p), ("stepw", C.c_void_p), ("reg_scale", C.c_float),
-                ("sched_ws", C.c_void_p), ("sched", ArSched), ("depth", C.c_int32), ("chunk_params", C.c_void_p),
+                ("sched_ws", C.c_void_p), ("sched", ArSched), ("depth", C.c_int32), ("chunk_ws", C.c_void_p),
                 ("health", C.c_void_p)]
 
 
@@ -100,10 +103,10 @@ SIGNATURES = {
     "ar_plan_build": (C.c_int, [_P, _I64, _I32, _I64, _I32, C.POINTER(ArPlan), _P]),
     "ar_plan_build_lists": (C.c_int, [_P, _I32, _P, _I32, C.POINTER(ArPlan), _P]),
     "ar_plan_link": (C.c_int, [C.POINTER(ArPlan), _I32, _P, _P, _I32, _P]),
-    "ar_plan_sched": (C.c_int, [C.POINTER(ArPlan), C.POINTER(ArPlan), _I32, _I64, _I64, _P, _I32, _P, _I32, _I32,
+    "ar_plan_sched": (C.c_int, [C.POINTER(ArPlan), C.POINTER(ArPlan), _I32, _I64, _I64, _P, _I32, _P, _I32, _I32, _I32,
                                 C.POINTER(ArSched), _P]),
     "ar_train_steps": (C.c_int, [C.POINTER(ArTrainCtx), _I64, _I32, _I64, _I32, _P]),
-    "ar_train_steps_profile": (C.c_int, [C.POINTER(ArTrainCtx), _I64, _I32, _I64, _I32, C.POINTER(C.c_float), _P]),
+    "ar_chunk_ws_info": (C.c_int, [_I32, _I32, _I32, C.POINTER(C.c_int64)]),
     "ar_nccl_unique_id": (C.c_int, [_P]),
     "ar_comm_init": (C.c_int, [_P, _I32, _I32, C.POINTER(C.c_void_p)]),
     "ar_comm_destroy": (C.c_int, [_P]),

@@ -1,0 +1,1291 @@
+// Single-GPU training: ONE persistent kernel per chunk of steps (included by train.cu).
+//
+// One CTA per SM.  Warps 0..AR_STEP_WARPS-1 of every CTA are STEP warps: they walk the chunk step by step,
+//     F        warp per sample (a contiguous share per warp, two samples in flight): wait until both rows of the
+//              sample are at optimizer step t-1 (AR_ADAM_REPLAY: last_step[row] is the readiness flag -- the row
+//              was either updated by the previous step or brought there by a replay item), gather them with
+//              128-bit loads, l2-normalise, dot; normalised rows, c, 1/||u||, 1/||a|| to the step scratch
+//              (double-buffered by step parity); per-CTA (sum c, sum c^2) in a fixed order
+//     -- grid barrier --   the only one per step: BatchNorm needs the statistics of the whole batch
+//     head     every CTA, redundantly and bit-identically: batch statistics from the per-CTA partials, one pass
+//              over the step's (c, label) for the five backward sums, Adam on the four head scalars (kept in
+//              shared memory for the whole chunk), the step scalars; each CTA adds the reported BCE / MSE of ITS
+//              share of the samples
+//     U        warp per distinct row (contiguous share): atomic-free segment reduction over the plan's sorted
+//              samples + L2 term + Adam, one RMW of (W, m, v), then (behind a fence) last_step[row] = t; rows hit by
+//              more than AR_HEAVY_LEN samples are cut into pieces, the last piece to arrive (ticket) adds them
+//              in piece order
+// (AR_ADAM_TOUCHED and AR_ADAM_DENSE have no per-row flags: a second grid barrier follows U; DENSE adds a pass over
+// every other row and a third barrier.)  The other warps are REPLAY warps (AR_ADAM_REPLAY): they pull items of the
+// plan-time schedule (ar_plan_sched: "replay the missed pure-L2 Adam steps of row r up to step t-1"),
+// earliest deadline first, up to `depth` steps ahead of the step warps, and publish last_step[row] behind a fence;
+// the replay is bound by the special-function pipe (sqrt + reciprocal per element-step) and fills it while the
+// step warps are bound by memory latency.  Every wait has a time-out that raises ctl->abort instead of hanging the
+// GPU.  Registers move from the replay warps to the step warps at kernel entry (setmaxnreg).
+//
+// Arithmetic follows oracle/train.py; all sums have a fixed order => bit-reproducible.
+
+namespace ar {
+
+// Build-time knobs (A/B builds: -DAR_STEP_WARPS=... etc.; the defaults are the measured best)
+#ifndef AR_STEP_WARPS
+#define AR_STEP_WARPS 12          // step warps per CTA (a multiple of 4: setmaxnreg works on warpgroups)
+#endif
+#ifndef AR_CHUNK_THREADS
+#define AR_CHUNK_THREADS 768      // NV == 1: step warps + replay warps
+#endif
+#ifndef AR_REGS_LAUNCH
+#define AR_REGS_LAUNCH 64         // NV == 1: registers per thread at launch
+#endif
+#ifndef AR_REGS_REPLAY
+#define AR_REGS_REPLAY 40         // ... the replay warps keep
+#endif
+#ifndef AR_REGS_STEP
+#define AR_REGS_STEP 88           // ... the step warps grow to
+#endif
+#ifndef AR_PAIR_U
+#define AR_PAIR_U 0               // row update: two rows in flight per warp
+#endif
+#ifndef AR_PAIR_F
+#define AR_PAIR_F 1               // forward: two samples in flight per warp
+#endif
+constexpr int kStepWarps = AR_STEP_WARPS;
+constexpr int kStepThreads = kStepWarps * 32;
+static_assert(kStepWarps % 4 == 0 && kStepWarps <= 32, "step warps come in warpgroups");
+constexpr int kMaxCtas = 160;      // B200: 148 SMs
+constexpr int kStamps = 8;
+constexpr unsigned kCodeRowMask = (1u << 26) - 1u;
+constexpr unsigned kCodeSplit = 1u << 30;
+constexpr unsigned long long kWaitTimeoutNs = 4000000000ull;
+
+struct ChunkCtl {            // first 256 bytes of the workspace; zeroed before every launch
+  unsigned int arrive;       // grid-barrier arrivals since launch (monotone)
+  unsigned int gen;          // completed grid barriers
+  int abort;                 // a wait timed out: every loop exits
+  int pad0;
+  unsigned long long stats[8];
+  unsigned long long pad1[22];
+};
+static_assert(sizeof(ChunkCtl) == 256, "ChunkCtl is 256 bytes");
+
+struct ChunkLayout {
+  size_t ctl, htick, fpart, mpart, stamps, hpart, stash1, total, zero_bytes;
+  int n_pieces;              // capacity of hpart / htick per table
+};
+static ChunkLayout chunk_layout(int n_slots, int batch_cap, int dim) {
+  ChunkLayout l;
+  auto up = [](size_t x) { return (x + 255) & ~(size_t)255; };
+  l.n_pieces = 2 * (batch_cap / AR_HEAVY_LEN) + 2;
+  l.ctl = 0;
+  l.htick = 256;
+  l.zero_bytes = up(l.htick + (size_t)2 * l.n_pieces * sizeof(int32_t));
+  l.fpart = l.zero_bytes;
+  l.mpart = up(l.fpart + (size_t)kMaxCtas * 2 * sizeof(double));
+  l.stamps = up(l.mpart + (size_t)n_slots * kMaxCtas * 2 * sizeof(double));
+  l.hpart = up(l.stamps + (size_t)n_slots * kStamps * sizeof(long long));
+  l.stash1 = up(l.hpart + (size_t)2 * l.n_pieces * (dim + 4) * sizeof(float));
+  l.total = up(l.stash1 + (size_t)batch_cap * (2 * dim + 4) * sizeof(float));   // odd steps' uh, ah, c, ru, ra
+  return l;
+}
+
+struct ChunkArgs {
+  ar_table tab[2];
+  ar_plan plan[2];
+  ar_sched sched;
+  const int32_t* iu;         // first sample of the chunk
+  const int32_t* ia;
+  const float* label;
+  int64_t t0;
+  int n_steps, batch, mode, depth;
+  float l2x2;
+  const float* alpha;
+  float* head;
+  float* head_m;
+  float* head_v;
+  float* bn_moving;
+  float* uh[2];              // step scratch, by step parity
+  float* ah[2];
+  float* c[2];
+  float* ru[2];
+  float* ra[2];
+  double* fwd_part;
+  float* metrics;
+  RegAcc reg;
+  int32_t* health;
+  ChunkCtl* ctl;
+  int32_t* htick;
+  double* mpart;
+  long long* stamps;
+  float* hpart;
+  int n_pieces;
+};
+
+__device__ __forceinline__ unsigned ld_acquire_u32(const unsigned* p) {
+  unsigned v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ int ld_acquire_s32(const int* p) {
+  int v;
+  asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release_u32(unsigned* p, unsigned v) {
+  asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ int ld_relaxed_s32(const int* p) {
+  int v;
+  asm volatile("ld.relaxed.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ unsigned long long globaltimer_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+__device__ __forceinline__ void step_bar() { asm volatile("bar.sync 1, %0;" ::"n"(kStepThreads) : "memory"); }
+
+__device__ __forceinline__ float4 ldcg4(const float* p) { return __ldcg(reinterpret_cast<const float4*>(p)); }
+template <int NV>
+__device__ __forceinline__ void tile_load_cg(RowTile<NV>& t, const float* row, int d4, int lane) {
+#pragma unroll
+  for (int k = 0; k < NV; ++k) {
+    const int j = lane + 32 * k;
+    t.x[k] = (j < d4) ? ldcg4(row + 4 * j) : make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+}
+template <int NV>
+__device__ __forceinline__ float tile_partial_dot(const RowTile<NV>& a, const RowTile<NV>& b) {
+  float s = 0.f;
+#pragma unroll
+  for (int k = 0; k < NV; ++k) s += dot4(a.x[k], b.x[k]);
+  return s;
+}
+
+// Thread 0 of the step warps spins until `*p >= want`; false = timed out or aborted elsewhere.
+__device__ __forceinline__ bool spin_until_ge(const int* p, int want, ChunkCtl* ctl) {
+  unsigned spins = 0;
+  unsigned long long t_begin = 0;
+  while (ld_relaxed_s32(p) < want) {
+    __nanosleep(32);
+    if ((++spins & 255u) == 0u) {
+      if (ld_relaxed_s32(&ctl->abort)) return false;
+      const unsigned long long now = globaltimer_ns();
+      if (!t_begin) t_begin = now;
+      else if (now - t_begin > kWaitTimeoutNs) return false;
+    }
+  }
+  return ld_acquire_s32(p) >= want;
+}
+
+// Grid barrier over the step warps of all CTAs.  Arrivals are counted monotonically (no reset race): barrier b
+// completes when arrive == n_ctas * b.  Returns false once the chunk is aborted.
+__device__ __forceinline__ bool grid_bar(ChunkCtl* ctl, unsigned& bar, int n_ctas, volatile int* abort_s) {
+  step_bar();
+  ++bar;
+  if (threadIdx.x == 0) {
+    __threadfence();
+    const unsigned old = atomicAdd(&ctl->arrive, 1u);
+    if (old == (unsigned)n_ctas * bar - 1u) {
+      __threadfence();
+      st_release_u32(&ctl->gen, bar);
+    } else if (!spin_until_ge(reinterpret_cast<const int*>(&ctl->gen), (int)bar, ctl)) {
+      *abort_s = 1;
+      atomicExch(&ctl->abort, 1);
+    }
+    __threadfence();
+  }
+  step_bar();
+  return *abort_s == 0;
+}
+
+// sum over the step warps of NVAL doubles per thread; every thread gets the totals (fixed order)
+template <int NVAL>
+__device__ __forceinline__ void step_block_sum(double (&v)[NVAL], double* smem /* [NVAL][kStepWarps] */) {
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+#pragma unroll
+  for (int i = 0; i < NVAL; ++i) v[i] = warp_sum(v[i]);
+  step_bar();  // protect smem reuse
+  if (lane == 0) {
+#pragma unroll
+    for (int i = 0; i < NVAL; ++i) smem[i * kStepWarps + wid] = v[i];
+  }
+  step_bar();
+#pragma unroll
+  for (int i = 0; i < NVAL; ++i) {
+    double t = 0.0;
+#pragma unroll
+    for (int w = 0; w < kStepWarps; ++w) t += smem[i * kStepWarps + w];
+    v[i] = t;
+  }
+}
+
+// Shared state of a CTA.  The step warps pass every grid barrier, so they know how far the chunk is; the other
+// warps read it here instead of polling global memory (2368 warps polling one L2 line starve everything else).
+constexpr int kWin = 1024;   // alpha / step-weight window kept in shared memory: the chunk's steps and the ~750 before
+struct StepSmem {
+  int steps_done;            // steps whose row update is complete grid-wide (written by thread 0 after the barrier)
+  int dense_go;              // AR_ADAM_DENSE: dense pass of step dense_go-1 may start
+  int dense_arrive;          // AR_ADAM_DENSE: helper warps that finished their share (monotone over the chunk)
+  int quit;                  // the step warps have left the loop (abort)
+  int abort;
+  long long win_base;        // alpha_w[i] = alpha[win_base + i]
+  float head[4], hm[4], hv[4], bn[2];
+  float stepc[K_STEPC + 2];
+  double red[8 * kStepWarps];
+  float alpha_w[kWin];
+  float stepw_w[kWin];
+};
+__device__ __forceinline__ void dense_arrive(StepSmem& sm) { atomicAdd(&sm.dense_arrive, 1); }
+struct StepTabs {            // alpha[t], stepw[t] through the shared-memory window
+  const float* alpha;
+  const float* stepw;        // may be null (weight 1)
+  const StepSmem* sm;
+  __device__ __forceinline__ float a_at(int64_t t) const {
+    const long long i = t - sm->win_base;
+    return (unsigned long long)i < (unsigned long long)kWin ? sm->alpha_w[i] : __ldg(alpha + t);
+  }
+  __device__ __forceinline__ float w_at(int64_t t) const {
+    if (!stepw) return 1.f;
+    const long long i = t - sm->win_base;
+    return (unsigned long long)i < (unsigned long long)kWin ? sm->stepw_w[i] : __ldg(stepw + t);
+  }
+};
+
+// Replay pure-L2 Adam steps (from, to] of a full row held as float4 tiles; regd += the replayed
+// steps' share of the regulariser term.  The common all-weights-one blocks take a shorter path.
+template <int NV>
+__device__ __forceinline__ void replay_tile(RowTile<NV>& w, RowTile<NV>& m, RowTile<NV>& v, const StepTabs& tb,
+                                            int64_t from, int64_t to, float l2x2, int lane, double& regd) {
+#pragma unroll 1
+  for (int64_t t0 = from + 1; t0 <= to; t0 += 32) {
+    const int64_t tl = t0 + lane;
+    const float a_l = (tl <= to) ? tb.a_at(tl) : 0.f;
+    const float w_l = (tl <= to) ? tb.w_at(tl) : 1.f;
+    const int cnt = (int)min((int64_t)32, to - t0 + 1);
+    float accf = 0.f;
+    if (__all_sync(0xffffffffu, w_l == 1.f)) {
+#pragma unroll 2
+      for (int s = 0; s < cnt; ++s) {
+        const float a = __shfl_sync(0xffffffffu, a_l, s);
+#pragma unroll
+        for (int k = 0; k < NV; ++k) {
+          accf = fmaf(w.x[k].x, w.x[k].x, accf);
+          accf = fmaf(w.x[k].y, w.x[k].y, accf);
+          accf = fmaf(w.x[k].z, w.x[k].z, accf);
+          accf = fmaf(w.x[k].w, w.x[k].w, accf);
+          const float4 g = make_float4(__fmul_rn(l2x2, w.x[k].x), __fmul_rn(l2x2, w.x[k].y),
+                                       __fmul_rn(l2x2, w.x[k].z), __fmul_rn(l2x2, w.x[k].w));
+          adam4(w.x[k], m.x[k], v.x[k], g, a);
+        }
+      }
+    } else {
+#pragma unroll 1
+      for (int s = 0; s < cnt; ++s) {
+        const float a = __shfl_sync(0xffffffffu, a_l, s);
+        const float sw = __shfl_sync(0xffffffffu, w_l, s);
+        float p = 0.f;
+#pragma unroll
+        for (int k = 0; k < NV; ++k) {
+          p = fmaf(w.x[k].x, w.x[k].x, p);
+          p = fmaf(w.x[k].y, w.x[k].y, p);
+          p = fmaf(w.x[k].z, w.x[k].z, p);
+          p = fmaf(w.x[k].w, w.x[k].w, p);
+          const float4 g = make_float4(__fmul_rn(l2x2, w.x[k].x), __fmul_rn(l2x2, w.x[k].y),
+                                       __fmul_rn(l2x2, w.x[k].z), __fmul_rn(l2x2, w.x[k].w));
+          adam4(w.x[k], m.x[k], v.x[k], g, a);
+        }
+        accf = fmaf(sw, p, accf);
+      }
+    }
+    regd += (double)accf;
+  }
+}
+// ... of one element per lane (the 32-element parts of a split row)
+__device__ __forceinline__ void replay_lane(float& w, float& m, float& v, const StepTabs& tb, int64_t from, int64_t to,
+                                            float l2x2, int lane, double& regd) {
+#pragma unroll 1
+  for (int64_t t0 = from + 1; t0 <= to; t0 += 32) {
+    const int64_t tl = t0 + lane;
+    const float a_l = (tl <= to) ? tb.a_at(tl) : 0.f;
+    const float w_l = (tl <= to) ? tb.w_at(tl) : 1.f;
+    const int cnt = (int)min((int64_t)32, to - t0 + 1);
+    float accf = 0.f;
+    if (__all_sync(0xffffffffu, w_l == 1.f)) {
+#pragma unroll 4
+      for (int s = 0; s < cnt; ++s) {
+        const float a = __shfl_sync(0xffffffffu, a_l, s);
+        accf = fmaf(w, w, accf);
+        adam1(w, m, v, __fmul_rn(l2x2, w), a);
+      }
+    } else {
+#pragma unroll 1
+      for (int s = 0; s < cnt; ++s) {
+        const float a = __shfl_sync(0xffffffffu, a_l, s);
+        const float sw = __shfl_sync(0xffffffffu, w_l, s);
+        accf = fmaf(sw * w, w, accf);
+        adam1(w, m, v, __fmul_rn(l2x2, w), a);
+      }
+    }
+    regd += (double)accf;
+  }
+}
+
+__device__ __forceinline__ void reg_fix_add(double regd, const RegAcc& reg, unsigned long long& regfix) {
+  // one conversion per row visit; integer adds are associative, so the total is independent of which warp does what
+  regfix += (unsigned long long)__double2ll_rn(regd * (double)reg.scale);
+}
+
+// One schedule item: bring the row (or 32 of its elements) from step t_to-(g-1) to t_to.  The item's (W, m, v) are
+// staged in shared memory with cp.async (no registers while in flight, L2-coherent .cg path): the NEXT item of the
+// batch is on its way while this one is replayed.  The caller publishes last_step[row] behind a fence.
+constexpr int kPartShift = 27;   // split rows: the parts count their arrivals in the top bits of last_step[row]
+__device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((unsigned)__cvta_generic_to_shared(smem)), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+// stage: [3][32*NV] float4 (W, m, v of one row)
+template <int NV>
+__device__ __forceinline__ void item_prefetch(const ChunkArgs& a, int code, float4* stage, int lane) {
+  const bool second = code < 0;
+  const int row = (int)((unsigned)code & kCodeRowMask);
+  const int dim = a.tab[0].dim;
+  const float* W = second ? a.tab[1].W : a.tab[0].W;
+  const float* M = second ? a.tab[1].m : a.tab[0].m;
+  const float* V = second ? a.tab[1].v : a.tab[0].v;
+  if ((unsigned)code & kCodeSplit) {
+    const int e0 = (int)(((unsigned)code >> 26) & 15u) * 32;
+    const size_t o = (size_t)row * dim + e0 + 4 * lane;
+    if (lane < 8 && e0 + 4 * lane < dim) {
+      cp_async16(stage + lane, W + o);
+      cp_async16(stage + 32 * NV + lane, M + o);
+      cp_async16(stage + 64 * NV + lane, V + o);
+    }
+  } else {
+    const int d4 = dim >> 2;
+    const size_t o = (size_t)row * dim;
+#pragma unroll
+    for (int k = 0; k < NV; ++k) {
+      const int j = lane + 32 * k;
+      if (j < d4) {
+        cp_async16(stage + j, W + o + 4 * j);
+        cp_async16(stage + 32 * NV + j, M + o + 4 * j);
+        cp_async16(stage + 64 * NV + j, V + o + 4 * j);
+      }
+    }
+  }
+  cp_async_commit();
+}
+
+template <int NV>
+__device__ __forceinline__ void replay_item(const ChunkArgs& a, const StepTabs& tabs, int code, int g, int64_t t_to,
+                                            const float4* stage, int lane, unsigned long long& regfix) {
+  const bool second = code < 0;
+  const int row = (int)((unsigned)code & kCodeRowMask);
+  const int dim = a.tab[0].dim;
+  float* __restrict__ W = second ? a.tab[1].W : a.tab[0].W;
+  float* __restrict__ M = second ? a.tab[1].m : a.tab[0].m;
+  float* __restrict__ V = second ? a.tab[1].v : a.tab[0].v;
+  const int64_t from = t_to - (int64_t)(g - 1);
+  double regd = 0.0;
+  if ((unsigned)code & kCodeSplit) {
+    const int e = (int)(((unsigned)code >> 26) & 15u) * 32 + lane;
+    const bool live = e < dim;
+    const size_t o = (size_t)row * dim + e;
+    const float* sf = reinterpret_cast<const float*>(stage);
+    float w = 0.f, m = 0.f, v = 0.f;
+    if (live) {
+      w = sf[lane];
+      m = sf[128 * NV + lane];
+      v = sf[256 * NV + lane];
+    }
+    replay_lane(w, m, v, tabs, from, t_to, a.l2x2, lane, regd);
+    if (live) {
+      W[o] = w;
+      M[o] = m;
+      V[o] = v;
+    }
+  } else {
+    const int d4 = dim >> 2;
+    const size_t o = (size_t)row * dim;
+    RowTile<NV> w, m, v;
+#pragma unroll
+    for (int k = 0; k < NV; ++k) {
+      const int j = lane + 32 * k;
+      const bool in = j < d4;
+      w.x[k] = in ? stage[j] : make_float4(0.f, 0.f, 0.f, 0.f);
+      m.x[k] = in ? stage[32 * NV + j] : make_float4(0.f, 0.f, 0.f, 0.f);
+      v.x[k] = in ? stage[64 * NV + j] : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    replay_tile<NV>(w, m, v, tabs, from, t_to, a.l2x2, lane, regd);
+    w.store(W + o, d4, lane);
+    m.store(M + o, d4, lane);
+    v.store(V + o, d4, lane);
+  }
+  if (a.reg.acc) {
+    regd = warp_sum(regd);
+    reg_fix_add(regd, a.reg, regfix);
+  }
+}
+// After a fence: the row is at t_to.  A split row becomes current when its last part arrives.
+__device__ __forceinline__ void publish_item(const ChunkArgs& a, int code, int64_t t_to, int n_parts) {
+  int32_t* ls = (code < 0 ? a.tab[1].last_step : a.tab[0].last_step) + (int)((unsigned)code & kCodeRowMask);
+  if ((unsigned)code & kCodeSplit) {
+    const int old = atomicAdd(ls, 1 << kPartShift);
+    if ((old >> kPartShift) == n_parts - 1) {
+      __threadfence();
+      *(volatile int32_t*)ls = (int32_t)t_to;
+    }
+  } else {
+    *(volatile int32_t*)ls = (int32_t)t_to;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// replay warps
+constexpr int kReplayBatch = 4;  // items per grab
+template <int NV>
+__device__ void replay_role(const ChunkArgs& a, StepSmem& sm, float4* stage_all) {
+  const int lane = threadIdx.x & 31;
+  float4* stage = stage_all + (size_t)((threadIdx.x >> 5) - kStepWarps) * (2 * 96 * NV);   // two row buffers per warp
+  ChunkCtl* ctl = a.ctl;
+  const int D = a.depth, Wd = D + 1;
+  const int aidx = lane / Wd, k = lane - aidx * Wd;
+  const int n_parts = (a.tab[0].dim + 31) / 32;
+  const StepTabs tabs{a.alpha, a.reg.stepw, &sm};
+  unsigned long long regfix = 0, busy = 0, items = 0, elsteps = 0;
+  int sd_idle = -1;            // nothing was available at this many completed steps: wait for the next one
+  int sd_seen = -1;
+  for (;;) {
+    if (*(volatile int*)&sm.quit) break;
+    const int sd = *(volatile int*)&sm.steps_done;
+    if (sd == sd_idle) {
+      __nanosleep(500);
+      continue;
+    }
+    if (sd != sd_seen) {       // order the row loads below after the step warps' barrier acquire
+      __threadfence();
+      sd_seen = sd;
+    }
+    // lane (aidx, k): sublist k of step sd + aidx; released iff aidx <= k.  Lowest lane = earliest deadline.
+    const int sp = sd + aidx;
+    bool ok = lane < Wd * Wd && aidx <= k && sp < a.n_steps;
+    int beg = 0, cnt = 0;
+    if (ok) {
+      const int32_t* sb = a.sched.sub + (size_t)sp * AR_SCHED_SUB;
+      beg = sb[k];
+      cnt = sb[k + 1] - beg;
+      ok = ld_relaxed_s32(a.sched.cursor + (size_t)sp * AR_SCHED_SUB + k) < cnt;
+    }
+    const unsigned mask = __ballot_sync(0xffffffffu, ok);
+    if (!mask) {
+      if (sd >= a.n_steps - 1) break;      // every item of the chunk has been released and handed out
+      sd_idle = sd;                        // cursors only grow: nothing new before the next step completes
+      continue;
+    }
+    const int src = __ffs(mask) - 1;
+    const int sp_s = __shfl_sync(0xffffffffu, sp, src), k_s = __shfl_sync(0xffffffffu, k, src);
+    const int beg_s = __shfl_sync(0xffffffffu, beg, src), cnt_s = __shfl_sync(0xffffffffu, cnt, src);
+    const int R = kReplayBatch;
+    int i0 = 0;
+    if (lane == 0) i0 = atomicAdd(a.sched.cursor + (size_t)sp_s * AR_SCHED_SUB + k_s, R);
+    i0 = __shfl_sync(0xffffffffu, i0, 0);
+    if (i0 >= cnt_s) continue;
+    const int nit = min(R, cnt_s - i0);
+    int code = 0, g = 0;
+    if (lane < nit) {
+      const size_t at = (size_t)sp_s * a.sched.cap + beg_s + i0 + lane;
+      code = a.sched.codes[at];
+      g = a.sched.glen[at];
+    }
+    const long long c0 = clock64();
+    const int64_t t_to = a.t0 + sp_s;
+    __syncwarp();                // the previous batch's shared-memory reads are done
+    item_prefetch<NV>(a, __shfl_sync(0xffffffffu, code, 0), stage, lane);
+    for (int j = 0; j < nit; ++j) {
+      const int cj = __shfl_sync(0xffffffffu, code, j), gj = __shfl_sync(0xffffffffu, g, j);
+      const int cn = __shfl_sync(0xffffffffu, code, (j + 1) & 31);
+      if (j + 1 < nit) {         // next item on its way, then wait for this one only
+        item_prefetch<NV>(a, cn, stage + (size_t)((j + 1) & 1) * (96 * NV), lane);
+        cp_async_wait<1>();
+      } else {
+        cp_async_wait<0>();
+      }
+      __syncwarp();
+      replay_item<NV>(a, tabs, cj, gj, t_to, stage + (size_t)(j & 1) * (96 * NV), lane, regfix);
+      elsteps += (unsigned long long)(gj - 1) * (((unsigned)cj & kCodeSplit) ? 32u : (unsigned)a.tab[0].dim);
+      __syncwarp();              // buffer j&1 is free for item j+2
+    }
+    __syncwarp();
+    __threadfence();             // every lane's row stores before the flags
+    if (lane < nit) publish_item(a, code, t_to, n_parts);
+    busy += (unsigned long long)(clock64() - c0);
+    items += nit;
+  }
+  if (lane == 0) {
+    if (a.reg.acc && regfix) atomicAdd(a.reg.acc, regfix);
+    atomicAdd(&ctl->stats[0], busy);
+    atomicAdd(&ctl->stats[1], items);
+    atomicAdd(&ctl->stats[2], elsteps);
+    atomicAdd(&ctl->stats[4], 1ull);
+  }
+}
+
+// AR_ADAM_DENSE: every row the step did not touch takes the same Adam step with the pure L2 gradient.  All warps
+// of the grid share the rows (32 consecutive rows per warp visit, one coalesced last_step load).
+template <int NV>
+__device__ __forceinline__ void dense_pass(const ChunkArgs& a, const StepTabs& tabs, int64_t t, int gwarp,
+                                           int n_gwarps, int lane, unsigned long long& regfix) {
+  const int dim = a.tab[0].dim, d4 = dim >> 2;
+#pragma unroll 1
+  for (int w = 0; w < 2; ++w) {
+    const ar_table tb = a.tab[w];
+    for (int64_t r0 = (int64_t)gwarp * 32; r0 < tb.n_rows; r0 += (int64_t)n_gwarps * 32) {
+      const int64_t mine = r0 + lane;
+      const int last_l = mine < tb.n_rows ? __ldcg(tb.last_step + mine) : 0x7fffffff;
+      unsigned todo = __ballot_sync(0xffffffffu, (int64_t)last_l < t);
+      while (todo) {
+        const int j = __ffs(todo) - 1;
+        todo &= todo - 1;
+        const int64_t last = __shfl_sync(0xffffffffu, last_l, j);
+        const size_t o = (size_t)(r0 + j) * dim;
+        RowTile<NV> x, m, v;
+        tile_load_cg<NV>(x, tb.W + o, d4, lane);
+        tile_load_cg<NV>(m, tb.m + o, d4, lane);
+        tile_load_cg<NV>(v, tb.v + o, d4, lane);
+        double regd = 0.0;
+        replay_tile<NV>(x, m, v, tabs, last, t, a.l2x2, lane, regd);
+        x.store(tb.W + o, d4, lane);
+        m.store(tb.m + o, d4, lane);
+        v.store(tb.v + o, d4, lane);
+        if (a.reg.acc) {
+          regd = warp_sum(regd);
+          reg_fix_add(regd, a.reg, regfix);
+        }
+      }
+      if (mine < tb.n_rows && (int64_t)last_l < t) tb.last_step[mine] = (int32_t)t;
+    }
+  }
+}
+
+// The non-step warps in AR_ADAM_DENSE: join the dense pass of every step.
+template <int NV>
+__device__ void dense_helper_role(const ChunkArgs& a, StepSmem& sm, int n_threads) {
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const int wpc = n_threads >> 5;
+  const StepTabs tabs{a.alpha, a.reg.stepw, &sm};
+  unsigned long long regfix = 0;
+  for (int s = 0; s < a.n_steps; ++s) {
+    // the dense pass of step s starts when grid barrier 3s+2 has completed
+    bool quit = false;
+    while (*(volatile int*)&sm.dense_go < s + 1) {
+      if (*(volatile int*)&sm.quit) { quit = true; break; }
+      __nanosleep(200);
+    }
+    if (quit) break;
+    __threadfence();
+    dense_pass<NV>(a, tabs, a.t0 + s + 1, blockIdx.x * wpc + wid, gridDim.x * wpc, lane, regfix);
+    __threadfence();
+    if (lane == 0) dense_arrive(sm);
+  }
+  if (lane == 0 && a.reg.acc && regfix) atomicAdd(a.reg.acc, regfix);
+}
+
+// ---------------------------------------------------------------------------------------------
+// step warps
+// finish one row: gradient from the reduced samples + L2 term, Adam step t, store.  w/m/v are already loaded.
+// `pend` (AR_ADAM_REPLAY): last_step entry of the row this warp stored BEFORE this one; its flag is published here,
+// behind a fence that finds those stores long complete, and this row's flag becomes the pending one.
+template <int NV>
+__device__ __forceinline__ void finish_loaded(const ChunkArgs& a, const StepTabs& tabs, const ar_table& tb, int row,
+                                              const RowTile<NV>& acc, float q, float rinv, RowTile<NV>& w,
+                                              RowTile<NV>& m, RowTile<NV>& v, int last, int64_t t, int lane,
+                                              unsigned long long& regfix, int32_t*& pend) {
+  const int d4 = tb.dim >> 2;
+  const size_t o = (size_t)row * tb.dim;
+  const bool flags = a.mode == AR_ADAM_REPLAY;
+  double regd = 0.0;
+  if (flags && (int64_t)last != t - 1) {
+    // the forward has waited for this row to be at t-1: cannot happen unless the schedule and the plans disagree
+    if (lane == 0) atomicAdd(a.health, 1);
+  }
+  if (a.reg.acc) {
+    const float ss = warp_sum(tile_partial_dot<NV>(w, w));
+    if (lane == 0) regd += (double)(tabs.w_at(t) * ss);
+    regd = warp_sum(regd);
+    reg_fix_add(regd, a.reg, regfix);
+  }
+  const float al = tabs.a_at(t);
+#pragma unroll
+  for (int k = 0; k < NV; ++k) {
+    const float4 wk = w.x[k], ak = acc.x[k];
+    float4 g;
+    g.x = __fadd_rn(rinv * (ak.x - q * (wk.x * rinv)), __fmul_rn(a.l2x2, wk.x));
+    g.y = __fadd_rn(rinv * (ak.y - q * (wk.y * rinv)), __fmul_rn(a.l2x2, wk.y));
+    g.z = __fadd_rn(rinv * (ak.z - q * (wk.z * rinv)), __fmul_rn(a.l2x2, wk.z));
+    g.w = __fadd_rn(rinv * (ak.w - q * (wk.w * rinv)), __fmul_rn(a.l2x2, wk.w));
+    adam4(w.x[k], m.x[k], v.x[k], g, al);
+  }
+  if (flags && pend) {
+    __threadfence();
+    if (lane == 0) *(volatile int32_t*)pend = (int32_t)t;
+  }
+  w.store(tb.W + o, d4, lane);
+  m.store(tb.m + o, d4, lane);
+  v.store(tb.v + o, d4, lane);
+  if (flags) pend = tb.last_step + row;
+  else if (lane == 0) tb.last_step[row] = (int32_t)t;
+}
+
+template <int NV>
+__device__ void step_role(const ChunkArgs& a, StepSmem& sm, int n_threads) {
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  const int n_ctas = gridDim.x;
+  const int gw = blockIdx.x * kStepWarps + wid, ngw = n_ctas * kStepWarps;
+  const int dim = a.tab[0].dim, d4 = dim >> 2;
+  const bool flags = a.mode == AR_ADAM_REPLAY, dense = a.mode == AR_ADAM_DENSE;
+  ChunkCtl* ctl = a.ctl;
+  const StepTabs tabs{a.alpha, a.reg.stepw, &sm};
+  const bool stamp = blockIdx.x == 0 && tid == 0;
+  constexpr bool kPairF = AR_PAIR_F && NV <= 2, kPairU = AR_PAIR_U && NV == 1;   // two in flight while the registers allow it
+  unsigned bar = 0;
+  unsigned long long regfix = 0;
+  const unsigned long long wall0 = stamp ? globaltimer_ns() : 0ull;
+  const long long clk0 = stamp ? clock64() : 0ll;
+  if (tid < 4) {
+    sm.head[tid] = a.head[tid];
+    sm.hm[tid] = a.head_m[tid];
+    sm.hv[tid] = a.head_v[tid];
+  }
+  if (tid < 2) sm.bn[tid] = a.bn_moving[tid];
+  step_bar();
+
+  for (int s = 0; s < a.n_steps; ++s) {
+    const int n = min(a.batch, a.plan[0].meta[(size_t)s * 4 + 2]);
+    const int64_t t = a.t0 + s + 1;
+    const int par = s & 1;
+    float* __restrict__ uh = a.uh[par];
+    float* __restrict__ ah = a.ah[par];
+    float* __restrict__ cc = a.c[par];
+    float* __restrict__ ruv = a.ru[par];
+    float* __restrict__ rav = a.ra[par];
+    long long* stamps = a.stamps + (size_t)s * kStamps;
+    if (stamp) stamps[0] = (long long)globaltimer_ns();
+
+    // ---- F: forward of this warp's samples
+    {
+      const int32_t* __restrict__ iu = a.iu + (size_t)s * a.batch;
+      const int32_t* __restrict__ ia = a.ia + (size_t)s * a.batch;
+      const float* __restrict__ U = a.tab[0].W;
+      const float* __restrict__ A = a.tab[1].W;
+      const int RF = (n + ngw - 1) / ngw;
+      const int f0 = min(n, gw * RF), f1 = min(n, f0 + RF);
+      double sc = 0.0, sc2 = 0.0;
+      for (int base = f0; base < f1; base += 32) {
+        const int cnt = min(32, f1 - base);
+        int my_u = 0, my_a = 0;
+        if (lane < cnt) {
+          my_u = iu[base + lane];
+          my_a = ia[base + lane];
+        }
+        if (flags) {
+          // both rows of every sample must be at step t-1: updated by the previous step, or replayed to there
+          const int want = (int)(t - 1);
+          const int32_t* lu = a.tab[0].last_step + my_u;
+          const int32_t* la = a.tab[1].last_step + my_a;
+          bool ready = lane >= cnt || (ld_relaxed_s32(lu) == want && ld_relaxed_s32(la) == want);
+          unsigned spins = 0;
+          unsigned long long t_begin = 0;
+          while (!__all_sync(0xffffffffu, ready)) {
+            __nanosleep(64);
+            if (!ready) ready = ld_relaxed_s32(lu) == want && ld_relaxed_s32(la) == want;
+            if ((++spins & 255u) == 0u) {
+              const unsigned long long now = globaltimer_ns();
+              if (!t_begin) t_begin = now;
+              else if (now - t_begin > kWaitTimeoutNs || ld_relaxed_s32(&ctl->abort)) {
+                sm.abort = 1;            // keep going (the barriers below must stay matched); the loop ends at the barrier
+                atomicExch(&ctl->abort, 1);
+                break;
+              }
+            }
+          }
+          __threadfence();
+        }
+        if (stamp && base == f0) stamps[1] = (long long)globaltimer_ns();
+        for (int j = 0; j < cnt; j += kPairF ? 2 : 1) {
+          const bool two = kPairF && j + 1 < cnt;
+          const int j1 = two ? j + 1 : j;
+          const int u0 = __shfl_sync(0xffffffffu, my_u, j), a0 = __shfl_sync(0xffffffffu, my_a, j);
+          const int u1 = __shfl_sync(0xffffffffu, my_u, j1), a1 = __shfl_sync(0xffffffffu, my_a, j1);
+          RowTile<NV> x0, y0, x1, y1;
+          tile_load_cg<NV>(x0, U + (size_t)u0 * dim, d4, lane);
+          tile_load_cg<NV>(y0, A + (size_t)a0 * dim, d4, lane);
+          if (kPairF) {
+            tile_load_cg<NV>(x1, U + (size_t)u1 * dim, d4, lane);
+            tile_load_cg<NV>(y1, A + (size_t)a1 * dim, d4, lane);
+          }
+          float su0 = tile_partial_dot<NV>(x0, x0), sa0 = tile_partial_dot<NV>(y0, y0);
+          float su1 = kPairF ? tile_partial_dot<NV>(x1, x1) : 1.f, sa1 = kPairF ? tile_partial_dot<NV>(y1, y1) : 1.f;
+#pragma unroll
+          for (int o = 16; o > 0; o >>= 1) {
+            su0 += __shfl_xor_sync(0xffffffffu, su0, o);
+            sa0 += __shfl_xor_sync(0xffffffffu, sa0, o);
+            if (kPairF) {
+              su1 += __shfl_xor_sync(0xffffffffu, su1, o);
+              sa1 += __shfl_xor_sync(0xffffffffu, sa1, o);
+            }
+          }
+          const float ru0 = 1.0f / sqrtf(fmaxf(su0, kL2NormEps)), ra0 = 1.0f / sqrtf(fmaxf(sa0, kL2NormEps));
+          const float ru1 = 1.0f / sqrtf(fmaxf(su1, kL2NormEps)), ra1 = 1.0f / sqrtf(fmaxf(sa1, kL2NormEps));
+#pragma unroll
+          for (int k = 0; k < NV; ++k) {
+            x0.x[k] = scale4(x0.x[k], ru0);
+            y0.x[k] = scale4(y0.x[k], ra0);
+            if (kPairF) {
+              x1.x[k] = scale4(x1.x[k], ru1);
+              y1.x[k] = scale4(y1.x[k], ra1);
+            }
+          }
+          float cs0 = tile_partial_dot<NV>(x0, y0), cs1 = kPairF ? tile_partial_dot<NV>(x1, y1) : 0.f;
+#pragma unroll
+          for (int o = 16; o > 0; o >>= 1) {
+            cs0 += __shfl_xor_sync(0xffffffffu, cs0, o);
+            if (kPairF) cs1 += __shfl_xor_sync(0xffffffffu, cs1, o);
+          }
+          const int s0 = base + j;
+          x0.store(uh + (size_t)s0 * dim, d4, lane);
+          y0.store(ah + (size_t)s0 * dim, d4, lane);
+          if (lane == 0) {
+            cc[s0] = cs0;
+            ruv[s0] = ru0;
+            rav[s0] = ra0;
+          }
+          sc += (double)cs0;
+          sc2 += (double)cs0 * (double)cs0;
+          if (two) {
+            x1.store(uh + (size_t)(s0 + 1) * dim, d4, lane);
+            y1.store(ah + (size_t)(s0 + 1) * dim, d4, lane);
+            if (lane == 0) {
+              cc[s0 + 1] = cs1;
+              ruv[s0 + 1] = ru1;
+              rav[s0 + 1] = ra1;
+            }
+            sc += (double)cs1;
+            sc2 += (double)cs1 * (double)cs1;
+          }
+        }
+      }
+      if (lane == 0) {
+        sm.red[2 * wid] = sc;
+        sm.red[2 * wid + 1] = sc2;
+      }
+      step_bar();
+      if (tid == 0) {
+        double b0 = 0.0, b1 = 0.0;
+#pragma unroll
+        for (int w = 0; w < kStepWarps; ++w) {
+          b0 += sm.red[2 * w];
+          b1 += sm.red[2 * w + 1];
+        }
+        a.fwd_part[2 * blockIdx.x] = b0;
+        a.fwd_part[2 * blockIdx.x + 1] = b1;
+      }
+    }
+    if (!grid_bar(ctl, bar, n_ctas, &sm.abort)) break;
+    // every CTA has finished the row update of step s-1 (it came before this step's forward): release the items
+    // that were waiting for it
+    if (flags && tid == 0) *(volatile int*)&sm.steps_done = s;
+    if (stamp) stamps[2] = (long long)globaltimer_ns();
+
+    // ---- head: identical arithmetic, identical order in every CTA
+    const float* __restrict__ label = a.label + (size_t)s * a.batch;
+    {
+      double s0 = 0.0, s1 = 0.0;
+      {
+        double2 pv[kMaxCtas / 32];
+#pragma unroll
+        for (int r = 0; r < kMaxCtas / 32; ++r) {     // all loads in flight together
+          const int i = lane + 32 * r;
+          pv[r] = i < n_ctas ? __ldcg(reinterpret_cast<const double2*>(a.fwd_part) + i) : make_double2(0.0, 0.0);
+        }
+#pragma unroll
+        for (int r = 0; r < kMaxCtas / 32; ++r) {
+          s0 += pv[r].x;
+          s1 += pv[r].y;
+        }
+      }
+      s0 = warp_sum(s0);
+      s1 = warp_sum(s1);
+      const HeadScalars h = head_scalars(sm.head, s0, s1, n);
+      // the reported metrics: this CTA's share of the samples
+      const int mshare = (n + n_ctas - 1) / n_ctas;
+      const int mlo = blockIdx.x * mshare, mhi = min(n, mlo + mshare);
+      double acc[7];
+#pragma unroll
+      for (int i = 0; i < 7; ++i) acc[i] = 0.0;
+      constexpr int kU = 4;
+      for (int base = 0; base < n; base += kU * kStepThreads) {
+        float cr[kU], tr[kU];
+#pragma unroll
+        for (int k = 0; k < kU; ++k) {
+          const int i = base + k * kStepThreads + tid;
+          cr[k] = i < n ? __ldcg(cc + i) : 0.f;
+          tr[k] = i < n ? __ldg(label + i) : 0.f;
+        }
+        float f[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+        for (int k = 0; k < kU; ++k) {
+          const int i = base + k * kStepThreads + tid;
+          if (i < n) {
+            const float zh = ((h.w * cr[k] + h.b) - h.mu) * h.inv;
+            const float y = h.gamma * zh + h.beta;
+            const float p = sigmoidf_(y);
+            const float dy = (p - tr[k]) * h.rn;
+            f[0] += dy;
+            f[1] = fmaf(dy, zh, f[1]);
+            f[2] += zh;
+            f[3] = fmaf(dy, cr[k], f[3]);
+            f[4] = fmaf(zh, cr[k], f[4]);
+            if (i >= mlo && i < mhi) {
+              acc[5] += (double)bce_logits(y, tr[k]);
+              acc[6] += (double)((tr[k] - p) * (tr[k] - p));
+            }
+          }
+        }
+#pragma unroll
+        for (int i = 0; i < 5; ++i) acc[i] += (double)f[i];
+      }
+      step_block_sum<7>(acc, sm.red);
+      const double S1 = acc[0], S2 = acc[1], Szh = acc[2], Sdyc = acc[3], Szhc = acc[4], Sc = s0;
+      const double ig = (double)h.inv * (double)h.gamma;
+      if (tid < 4) {
+        // oracle head_backward(): dgamma = sum dy*zh, dbeta = sum dy, dz_i = inv*gamma*(dy_i - S1/n - zh_i*S2/n)
+        const float g = tid == 0 ? (float)(ig * (Sdyc - S1 / n * Sc - S2 / n * Szhc))   // dw = sum dz*c
+                      : tid == 1 ? (float)(-ig * (S2 / n) * Szh)                        // db = sum dz
+                      : tid == 2 ? (float)S2 : (float)S1;
+        float th = sm.head[tid], hm = sm.hm[tid], hv = sm.hv[tid];
+        adam1(th, hm, hv, g, tabs.a_at(t));
+        sm.head[tid] = th;
+        sm.hm[tid] = hm;
+        sm.hv[tid] = hv;
+      } else if (tid == 32) {
+        const float mm = sm.bn[0], mv = sm.bn[1];
+        sm.bn[0] = mm - (mm - h.mu) * kBnOneMinusMomentum;
+        sm.bn[1] = mv - (mv - h.var) * kBnOneMinusMomentum;
+      } else if (tid == 64) {
+        sm.stepc[K_COEF] = (float)((double)h.w * ig);
+        sm.stepc[K_S1N] = (float)(S1 / n);
+        sm.stepc[K_S2N] = (float)(S2 / n);
+        sm.stepc[K_MU] = h.mu;
+        sm.stepc[K_INV] = h.inv;
+        sm.stepc[K_W] = h.w;
+        sm.stepc[K_B] = h.b;
+        sm.stepc[K_GAMMA] = h.gamma;
+        sm.stepc[K_BETA] = h.beta;
+        sm.stepc[K_FN] = h.fn;
+        sm.stepc[K_RN] = h.rn;
+        double* mp = a.mpart + ((size_t)s * kMaxCtas + blockIdx.x) * 2;
+        mp[0] = acc[5];
+        mp[1] = acc[6];
+        if (blockIdx.x == 0) {
+          float* row = a.metrics + t * 4;
+          row[2] = h.fn;
+          row[3] = h.mu;
+        }
+      }
+      step_bar();
+    }
+    if (stamp) stamps[3] = (long long)globaltimer_ns();
+
+    // ---- U: this warp's share of the step's distinct rows (users first, then anime)
+    {
+      const float* kk = sm.stepc;   // read at the use sites: shared-memory loads are cheaper than 11 live registers
+      const int nu = a.plan[0].meta[(size_t)s * 4], na = a.plan[1].meta[(size_t)s * 4];
+      const int tot = nu + na;
+      const int RU = (tot + ngw - 1) / ngw;
+      const int r0 = min(tot, gw * RU), r1 = min(tot, r0 + RU);
+      int32_t* pend = nullptr;      // flag of the row stored last, published behind the next row's arithmetic
+      for (int base = r0; base < r1; base += 32) {
+        const int cnt = min(32, r1 - base);
+        // lane j: everything row `base + j` needs before its gathers
+        int row_l = 0, beg_l = 0, len_l = 0, s0_l = 0, last_l = 0;
+        float d0_l = 0.f, c0_l = 0.f, rinv_l = 0.f;
+        const int idx = base + lane;
+        const int which_l = idx >= nu ? 1 : 0;
+        if (lane < cnt) {
+          const ar_plan& pl = a.plan[which_l];
+          const int seg = which_l ? idx - nu : idx;
+          row_l = pl.uniq[(size_t)s * pl.batch_cap + seg];
+          const int32_t* off = pl.off + (size_t)s * (pl.batch_cap + 1);
+          beg_l = off[seg];
+          len_l = off[seg + 1] - beg_l;
+          s0_l = pl.order[(size_t)s * pl.batch_cap + beg_l];
+          c0_l = __ldcg(cc + s0_l);
+          d0_l = dc_of_label(c0_l, __ldg(label + s0_l), kk);
+          rinv_l = __ldcg((which_l ? rav : ruv) + s0_l);
+          last_l = __ldcg(a.tab[which_l].last_step + row_l);
+        }
+        for (int j = 0; j < cnt; j += kPairU ? 2 : 1) {
+          const bool two = kPairU && j + 1 < cnt;
+          const int j1 = two ? j + 1 : j;
+          // row A = j, row B = j1 (B is skipped when !two)
+          const int wA = __shfl_sync(0xffffffffu, which_l, j), wB = __shfl_sync(0xffffffffu, which_l, j1);
+          const int rowA = __shfl_sync(0xffffffffu, row_l, j), rowB = __shfl_sync(0xffffffffu, row_l, j1);
+          const int lenA = __shfl_sync(0xffffffffu, len_l, j), lenB = __shfl_sync(0xffffffffu, len_l, j1);
+          const int sA = __shfl_sync(0xffffffffu, s0_l, j), sB = __shfl_sync(0xffffffffu, s0_l, j1);
+          const bool doA = lenA <= AR_HEAVY_LEN, doB = two && lenB <= AR_HEAVY_LEN;
+          const ar_table& tA = a.tab[wA];
+          const ar_table& tB = a.tab[wB];
+          const float* __restrict__ otherA = wA ? uh : ah;
+          const float* __restrict__ otherB = wB ? uh : ah;
+          RowTile<NV> accA, accB, wa, ma, va, wb, mb, vb;
+          if (doA) {
+            tile_load_cg<NV>(accA, otherA + (size_t)sA * dim, d4, lane);
+            tile_load_cg<NV>(wa, tA.W + (size_t)rowA * dim, d4, lane);
+            tile_load_cg<NV>(ma, tA.m + (size_t)rowA * dim, d4, lane);
+            tile_load_cg<NV>(va, tA.v + (size_t)rowA * dim, d4, lane);
+          }
+          if (doB) {
+            tile_load_cg<NV>(accB, otherB + (size_t)sB * dim, d4, lane);
+            tile_load_cg<NV>(wb, tB.W + (size_t)rowB * dim, d4, lane);
+            tile_load_cg<NV>(mb, tB.m + (size_t)rowB * dim, d4, lane);
+            tile_load_cg<NV>(vb, tB.v + (size_t)rowB * dim, d4, lane);
+          }
+          if (doA) {
+            const float d0 = __shfl_sync(0xffffffffu, d0_l, j), c0 = __shfl_sync(0xffffffffu, c0_l, j);
+            float q = fmaf(d0, c0, 0.f);
+#pragma unroll
+            for (int k = 0; k < NV; ++k) accA.x[k] = fma4(d0, accA.x[k], make_float4(0.f, 0.f, 0.f, 0.f));
+            if (lenA > 1) {
+              const ar_plan& pl = a.plan[wA];
+              const int32_t* order = pl.order + (size_t)s * pl.batch_cap + __shfl_sync(0xffffffffu, beg_l, j);
+              for (int e = 1; e < lenA; ++e) {
+                const int sx = order[e];
+                RowTile<NV> o;
+                tile_load_cg<NV>(o, otherA + (size_t)sx * dim, d4, lane);
+                const float cx = __ldcg(cc + sx);
+                const float dx = dc_of_label(cx, __ldg(label + sx), kk);
+                q = fmaf(dx, cx, q);
+#pragma unroll
+                for (int k = 0; k < NV; ++k) accA.x[k] = fma4(dx, o.x[k], accA.x[k]);
+              }
+            }
+            finish_loaded<NV>(a, tabs, tA, rowA, accA, q, __shfl_sync(0xffffffffu, rinv_l, j), wa, ma, va,
+                              __shfl_sync(0xffffffffu, last_l, j), t, lane, regfix, pend);
+          }
+          if (doB) {
+            const float d0 = __shfl_sync(0xffffffffu, d0_l, j1), c0 = __shfl_sync(0xffffffffu, c0_l, j1);
+            float q = fmaf(d0, c0, 0.f);
+#pragma unroll
+            for (int k = 0; k < NV; ++k) accB.x[k] = fma4(d0, accB.x[k], make_float4(0.f, 0.f, 0.f, 0.f));
+            if (lenB > 1) {
+              const ar_plan& pl = a.plan[wB];
+              const int32_t* order = pl.order + (size_t)s * pl.batch_cap + __shfl_sync(0xffffffffu, beg_l, j1);
+              for (int e = 1; e < lenB; ++e) {
+                const int sx = order[e];
+                RowTile<NV> o;
+                tile_load_cg<NV>(o, otherB + (size_t)sx * dim, d4, lane);
+                const float cx = __ldcg(cc + sx);
+                const float dx = dc_of_label(cx, __ldg(label + sx), kk);
+                q = fmaf(dx, cx, q);
+#pragma unroll
+                for (int k = 0; k < NV; ++k) accB.x[k] = fma4(dx, o.x[k], accB.x[k]);
+              }
+            }
+            finish_loaded<NV>(a, tabs, tB, rowB, accB, q, __shfl_sync(0xffffffffu, rinv_l, j1), wb, mb, vb,
+                              __shfl_sync(0xffffffffu, last_l, j1), t, lane, regfix, pend);
+          }
+        }
+      }
+      // heavy rows: pieces of AR_HEAVY_LEN samples spread over all step warps of the grid
+      for (int w = 0; w < 2; ++w) {
+        const ar_plan& pl = a.plan[w];
+        const int nh = pl.meta[(size_t)s * 4 + 1];
+        if (nh == 0) continue;
+        const ar_table& tb = a.tab[w];
+        const float* __restrict__ other = w ? uh : ah;
+        const int32_t* off = pl.off + (size_t)s * (pl.batch_cap + 1);
+        const int32_t* order = pl.order + (size_t)s * pl.batch_cap;
+        int piece0 = 0;   // pieces of the heavy rows before this round
+        for (int hb = 0; hb < nh; hb += 32) {
+          int seg_l = 0, beg_h = 0, len_h = 0, np_l = 0;
+          if (hb + lane < nh) {
+            seg_l = pl.heavy[(size_t)s * pl.heavy_cap + hb + lane];
+            beg_h = off[seg_l];
+            len_h = off[seg_l + 1] - beg_h;
+            np_l = (len_h + AR_HEAVY_LEN - 1) / AR_HEAVY_LEN;
+          }
+          int incl = np_l;
+#pragma unroll
+          for (int o = 1; o < 32; o <<= 1) {
+            const int x = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += x;
+          }
+          const int excl = incl - np_l + piece0;
+          const int round_total = __shfl_sync(0xffffffffu, incl, 31);
+          // pieces [piece0, piece0 + round_total): mine are those == gw (mod ngw)
+          int p = piece0 + ((gw - piece0) % ngw + ngw) % ngw;
+          for (; p < piece0 + round_total; p += ngw) {
+            const unsigned le = __ballot_sync(0xffffffffu, np_l > 0 && excl <= p);
+            const int owner = 31 - __clz(le);
+            const int seg = __shfl_sync(0xffffffffu, seg_l, owner), beg = __shfl_sync(0xffffffffu, beg_h, owner);
+            const int len = __shfl_sync(0xffffffffu, len_h, owner), np = __shfl_sync(0xffffffffu, np_l, owner);
+            const int first = __shfl_sync(0xffffffffu, excl, owner);
+            const int piece = p - first;
+            const int lo = beg + piece * AR_HEAVY_LEN, hi = min(beg + len, lo + AR_HEAVY_LEN);
+            RowTile<NV> acc;
+            acc.zero();
+            float q = 0.f;
+            for (int e = lo; e < hi; ++e) {
+              const int sx = order[e];
+              RowTile<NV> o;
+              tile_load_cg<NV>(o, other + (size_t)sx * dim, d4, lane);
+              const float cx = __ldcg(cc + sx);
+              const float dx = dc_of_label(cx, __ldg(label + sx), kk);
+              q = fmaf(dx, cx, q);
+#pragma unroll
+              for (int k = 0; k < NV; ++k) acc.x[k] = fma4(dx, o.x[k], acc.x[k]);
+            }
+            const int pslot = min(p, a.n_pieces - 1);
+            float* hp = a.hpart + ((size_t)w * a.n_pieces + pslot) * (dim + 4);
+            acc.store(hp, d4, lane);
+            if (lane == 0) hp[dim] = q;
+            __threadfence();
+            int old = 0;
+            int32_t* tick = a.htick + (size_t)w * a.n_pieces + min(first, a.n_pieces - 1);
+            if (lane == 0) old = atomicAdd(tick, 1);
+            old = __shfl_sync(0xffffffffu, old, 0);
+            if (old == np - 1) {   // last piece of the row: add the pieces in order, finish the row
+              __threadfence();
+              if (lane == 0) *tick = 0;
+              acc.zero();
+              q = 0.f;
+              for (int e = 0; e < np; ++e) {
+                const float* src = a.hpart + ((size_t)w * a.n_pieces + first + e) * (dim + 4);
+                RowTile<NV> pp;
+                tile_load_cg<NV>(pp, src, d4, lane);
+#pragma unroll
+                for (int k = 0; k < NV; ++k) {
+                  acc.x[k].x += pp.x[k].x;
+                  acc.x[k].y += pp.x[k].y;
+                  acc.x[k].z += pp.x[k].z;
+                  acc.x[k].w += pp.x[k].w;
+                }
+                q += __ldcg(src + dim);
+              }
+              const int row = pl.uniq[(size_t)s * pl.batch_cap + seg];
+              RowTile<NV> x, m, v;
+              tile_load_cg<NV>(x, tb.W + (size_t)row * dim, d4, lane);
+              tile_load_cg<NV>(m, tb.m + (size_t)row * dim, d4, lane);
+              tile_load_cg<NV>(v, tb.v + (size_t)row * dim, d4, lane);
+              const float rinv = __ldcg((w ? rav : ruv) + order[beg]);
+              finish_loaded<NV>(a, tabs, tb, row, acc, q, rinv, x, m, v, __ldcg(tb.last_step + row), t, lane, regfix, pend);
+            }
+          }
+          piece0 += round_total;
+        }
+      }
+      if (flags && pend) {          // the last row this warp stored
+        __threadfence();
+        if (lane == 0) *(volatile int32_t*)pend = (int32_t)t;
+      }
+    }
+    if (stamp) stamps[4] = (long long)globaltimer_ns();
+    if (!flags) {                   // no per-row flags: everyone's rows before anyone's next forward
+      if (!grid_bar(ctl, bar, n_ctas, &sm.abort)) break;
+      if (tid == 0 && dense) *(volatile int*)&sm.dense_go = s + 1;
+    }
+    if (stamp) stamps[5] = (long long)globaltimer_ns();
+    if (dense) {
+      const int wpc = n_threads >> 5;
+      dense_pass<NV>(a, tabs, t, blockIdx.x * wpc + wid, n_ctas * wpc, lane, regfix);
+      __threadfence();
+      if (tid == 0) {   // the helper warps of this CTA have finished their share of the pass too
+        const int want = (s + 1) * (wpc - kStepWarps);
+        unsigned spins = 0;
+        unsigned long long t_begin = 0;
+        while (*(volatile int*)&sm.dense_arrive < want) {
+          if ((++spins & 1023u) == 0u) {
+            const unsigned long long now = globaltimer_ns();
+            if (!t_begin) t_begin = now;
+            else if (now - t_begin > kWaitTimeoutNs || ld_relaxed_s32(&ctl->abort)) {
+              sm.abort = 1;
+              atomicExch(&ctl->abort, 1);
+              break;
+            }
+          }
+        }
+      }
+      if (!grid_bar(ctl, bar, n_ctas, &sm.abort)) break;
+      if (stamp) stamps[6] = (long long)globaltimer_ns();
+    }
+  }
+  // the last step's row updates, grid-wide, before the kernel's results are read (and the metrics reduced below)
+  if (flags && !sm.abort) {
+    grid_bar(ctl, bar, n_ctas, &sm.abort);
+    if (tid == 0) *(volatile int*)&sm.steps_done = a.n_steps;
+  }
+
+  // ---- epilogue
+  if (tid == 0 && sm.abort) *(volatile int*)&sm.quit = 1;
+  if (sm.abort) {
+    if (tid == 0) atomicAdd(a.health + 1, 1);
+    if (lane == 0 && a.reg.acc && regfix) atomicAdd(a.reg.acc, regfix);
+    return;
+  }
+  if (blockIdx.x == 0) {
+    if (tid < 4) {
+      a.head[tid] = sm.head[tid];
+      a.head_m[tid] = sm.hm[tid];
+      a.head_v[tid] = sm.hv[tid];
+    }
+    if (tid < 2) a.bn_moving[tid] = sm.bn[tid];
+  }
+  // reported metrics: per-step sums of the per-CTA partials, fixed order
+  for (int s = gw; s < a.n_steps; s += ngw) {
+    const int n = min(a.batch, a.plan[0].meta[(size_t)s * 4 + 2]);
+    double b0 = 0.0, b1 = 0.0;
+    for (int i = lane; i < n_ctas; i += 32) {
+      b0 += __ldcg(a.mpart + ((size_t)s * kMaxCtas + i) * 2);
+      b1 += __ldcg(a.mpart + ((size_t)s * kMaxCtas + i) * 2 + 1);
+    }
+    b0 = warp_sum(b0);
+    b1 = warp_sum(b1);
+    if (lane == 0) {
+      float* row = a.metrics + (a.t0 + s + 1) * 4;
+      row[0] = (float)(b0 / n);
+      row[1] = (float)(b1 / n);
+    }
+  }
+  if (lane == 0 && a.reg.acc && regfix) atomicAdd(a.reg.acc, regfix);
+  if (stamp) {
+    ctl->stats[3] = globaltimer_ns() - wall0;
+    ctl->stats[5] = (unsigned long long)(clock64() - clk0);
+  }
+}
+
+// Register budget.  NV == 1 (dim <= 128, the headline shape): AR_CHUNK_THREADS launched at AR_REGS_LAUNCH; the
+// replay warps shrink to AR_REGS_REPLAY, the step warps grow to AR_REGS_STEP; what the CTA leaves of the SM's 64 K
+// registers (and 1280 of 2048 threads) lets one 512-thread plan CTA of the NEXT chunk run beside it.
+// Larger rows: 768 threads at 80 registers, 56 / 88 after the hand-over (the whole register file).
+template <int NV> struct ChunkRegs {
+  static constexpr int kReplay = NV == 1 ? AR_REGS_REPLAY : 56;
+  static constexpr int kStep = NV == 1 ? AR_REGS_STEP : 88;
+};
+static_assert((AR_CHUNK_THREADS - kStepThreads) * (AR_REGS_LAUNCH - AR_REGS_REPLAY) >= kStepThreads * (AR_REGS_STEP - AR_REGS_LAUNCH),
+              "the replay warps do not free enough registers for the step warps");
+static_assert((768 - kStepThreads) * (80 - 56) >= kStepThreads * (88 - 80), "register hand-over (NV > 1)");
+
+template <int NV, int THREADS, int REGS>
+__global__ void __maxnreg__(REGS) chunk_kernel(const __grid_constant__ ChunkArgs a) {
+  __shared__ StepSmem sm;
+  extern __shared__ float4 stage_all[];   // replay warps: [warp][2][3][32*NV] float4
+  {
+    const long long t_hi = a.t0 + a.n_steps;
+    const long long base = t_hi - kWin + 1 > 0 ? t_hi - kWin + 1 : 0;
+    if (threadIdx.x == 0) {
+      sm.steps_done = 0;
+      sm.dense_go = 0;
+      sm.dense_arrive = 0;
+      sm.quit = 0;
+      sm.abort = 0;
+      sm.win_base = base;
+    }
+    for (int i = threadIdx.x; i < kWin; i += THREADS) {
+      const long long t = base + i;
+      sm.alpha_w[i] = t <= t_hi ? a.alpha[t] : 0.f;
+      sm.stepw_w[i] = (a.reg.stepw && t <= t_hi) ? a.reg.stepw[t] : 1.f;
+    }
+  }
+  __syncthreads();
+  // Register hand-over (setmaxnreg, per warpgroup of 4 warps): the replay loop needs few registers, the step warps
+  // keep two rows / samples and their gathers in flight and were spilling their loads at the kernel-wide 64.
+  constexpr int kRegsReplay = ChunkRegs<NV>::kReplay, kRegsStep = ChunkRegs<NV>::kStep;
+  if (threadIdx.x >= kStepThreads) {
+    if (kRegsReplay) asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kRegsReplay ? kRegsReplay : 24));
+    if (a.mode == AR_ADAM_REPLAY) replay_role<NV>(a, sm, stage_all);
+    else if (a.mode == AR_ADAM_DENSE) dense_helper_role<NV>(a, sm, THREADS);
+    return;
+  }
+  if (kRegsStep) asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(kRegsStep ? kRegsStep : 24));
+  step_role<NV>(a, sm, THREADS);
+}
+
+template <int NV> struct ChunkCfg {
+  static constexpr int kThreads = NV == 1 ? AR_CHUNK_THREADS : 768;
+  static constexpr int kRegs = NV == 1 ? AR_REGS_LAUNCH : 80;
+};
+
+template <int NV>
+static int launch_chunk_nv(const ChunkArgs& a, cudaStream_t st) {
+  constexpr int T = ChunkCfg<NV>::kThreads, R = ChunkCfg<NV>::kRegs;
+  static int max_ctas = -1;
+  const size_t dyn = (size_t)(T / 32 - kStepWarps) * 2 * 96 * NV * sizeof(float4);
+  if (max_ctas < 0) {
+    AR_CUDA(cudaFuncSetAttribute(chunk_kernel<NV, T, R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
+    int per_sm = 0;
+    AR_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, chunk_kernel<NV, T, R>, T, dyn));
+    AR_REQUIRE(per_sm >= 1, "ar_train_steps: the step kernel does not fit on an SM");
+    max_ctas = std::min(num_sms(), kMaxCtas);
+  }
+  chunk_kernel<NV, T, R><<<max_ctas, T, dyn, st>>>(a);
+  AR_LAUNCH_CHECK();
+  return AR_OK;
+}
+
+static int launch_chunk(const ar_train_ctx& x, int64_t epoch_step0, int64_t t0, int n_steps, cudaStream_t st) {
+  const ChunkLayout l = chunk_layout(x.plan_u.n_slots, std::max(x.plan_u.batch_cap, x.plan_a.batch_cap), x.users.dim);
+  char* ws = (char*)x.chunk_ws;
+  ChunkArgs a{};
+  a.tab[0] = x.users;
+  a.tab[1] = x.anime;
+  a.plan[0] = x.plan_u;
+  a.plan[1] = x.plan_a;
+  a.sched = x.sched;
+  const int64_t base0 = epoch_step0 * (int64_t)x.batch;
+  a.iu = x.iu + base0;
+  a.ia = x.ia + base0;
+  a.label = x.label + base0;
+  a.t0 = t0;
+  a.n_steps = n_steps;
+  a.batch = x.batch;
+  a.mode = x.mode;
+  a.depth = std::max(1, std::min((int)x.depth, AR_SCHED_MAX_DEPTH));
+  a.l2x2 = (float)(2.0 * (double)x.l2);
+  a.alpha = x.alpha;
+  a.head = x.head;
+  a.head_m = x.head_m;
+  a.head_v = x.head_v;
+  a.bn_moving = x.bn_moving;
+  const int bc = std::max(x.plan_u.batch_cap, x.plan_a.batch_cap);
+  float* st1 = (float*)(ws + l.stash1);
+  a.uh[0] = x.uh;
+  a.ah[0] = x.ah;
+  a.c[0] = x.c;
+  a.ru[0] = x.ru;
+  a.ra[0] = x.ra;
+  a.uh[1] = st1;
+  a.ah[1] = st1 + (size_t)bc * x.users.dim;
+  a.c[1] = st1 + (size_t)2 * bc * x.users.dim;
+  a.ru[1] = a.c[1] + bc;
+  a.ra[1] = a.ru[1] + bc;
+  a.metrics = x.metrics;
+  a.reg = reg_of(x);
+  a.health = x.health;
+  a.ctl = (ChunkCtl*)(ws + l.ctl);
+  a.htick = (int32_t*)(ws + l.htick);
+  a.fwd_part = (double*)(ws + l.fpart);
+  a.mpart = (double*)(ws + l.mpart);
+  a.stamps = (long long*)(ws + l.stamps);
+  a.hpart = (float*)(ws + l.hpart);
+  a.n_pieces = l.n_pieces;
+  AR_CUDA(cudaMemsetAsync(ws, 0, l.zero_bytes, st));
+  int rc = AR_OK;
+  AR_DISPATCH_NV(x.users.dim, rc = launch_chunk_nv<NV>(a, st));
+  return rc;
+}
+
+}  // namespace ar

@@ -140,7 +140,7 @@ rows_merge_update_kernel(MergeArgs a, const float* __restrict__ alpha, float l2x
     }
     q += __ldg(base + B + pos);
   }
-  finish_row<NV>(tb, id, acc, q, -1.0f, alpha, l2x2, t, replay, reg, nullptr, lane);
+  finish_row<NV>(tb, id, acc, q, -1.0f, alpha, l2x2, t, replay, reg, lane);
 }
 
 static int check_dist(const ar_train_ctx* ctx, const ar_dist_ctx* d) {

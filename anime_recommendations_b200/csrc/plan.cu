@@ -21,9 +21,9 @@ void set_error(const char* fmt, ...) {
   va_end(ap);
 }
 
-constexpr int kPlanThreads = 1024;
+constexpr int kPlanThreads = 512;   // 512 x <=32 registers: a plan CTA fits on an SM beside the persistent step kernel
 
-__global__ void __launch_bounds__(kPlanThreads, 1)
+__global__ void __launch_bounds__(kPlanThreads, 2)
 plan_build_kernel(const int32_t* __restrict__ idx, int64_t n_total, int batch, int64_t step0,
                   ar_plan plan, int pow2, const int32_t* __restrict__ counts) {
   extern __shared__ unsigned long long keys[];  // pow2 entries
@@ -94,14 +94,14 @@ plan_build_kernel(const int32_t* __restrict__ idx, int64_t n_total, int batch, i
   if ((tid & 31) == 31) warp_tot[tid >> 5] = incl;
   __syncthreads();
   if (tid < 32) {
-    int w = warp_tot[tid];
+    int w = tid < kPlanThreads / 32 ? warp_tot[tid] : 0;
     int wi = w;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
       int t = __shfl_up_sync(0xffffffffu, wi, o);
       if (tid >= o) wi += t;
     }
-    warp_tot[tid] = wi - w;  // exclusive
+    if (tid < kPlanThreads / 32) warp_tot[tid] = wi - w;  // exclusive
   }
   __syncthreads();
   int seg = warp_tot[tid >> 5] + incl - cnt;
@@ -221,48 +221,69 @@ plan_gap_kernel(ar_plan plan, int n_steps, int64_t t0, int64_t t_flush, int32_t*
   for (int i = threadIdx.x; i < mine; i += blockDim.x) seen[first + i] = seen_s[i];
 }
 
-// plan_sched_kernel: one CTA per step.  Rows with gap 1 are brought up to date by the previous step's own update;
-// rows with 2 <= gap <= depth go to the B list (replayed by the previous step's update kernel, they need at most
-// depth-1 steps); rows with gap > depth go to the A list, longest replay first (log2 buckets), which a catch-up
-// launch may start as soon as step s-depth-1 has finished.  Slot 0 has no predecessor inside the chunk: all its
-// rows with gap >= 2 go to A.  codes: (table << 31) | row; A from the front of codes[slot], B from the back.
-constexpr int kSchedBuckets = 32;
-__global__ void __launch_bounds__(1024)
+// plan_sched_kernel: one CTA per step.  Every distinct row with gap >= 2 becomes an item (animerec.h: ar_sched):
+// sublist k = min(gap-1, depth, slot), longest replay first inside a sublist (log2 buckets: counting sort over
+// (k, clz(gap)) bins).  Rows with gap >= AR_SCHED_SPLIT_GAP become `nparts` items of 32 elements each when the
+// slot's capacity allows.  Also zeroes the slot's run-time cursors.
+constexpr int kSchedBins = (AR_SCHED_MAX_DEPTH + 1) * 32;
+constexpr int kLongClz = 25;   // clz(gap) <= 25  <=>  gap >= 64 = AR_SCHED_SPLIT_GAP
+static_assert((1 << (31 - kLongClz)) == AR_SCHED_SPLIT_GAP, "split threshold and its clz bucket disagree");
+__global__ void __launch_bounds__(512)
 plan_sched_kernel(ar_plan pu, ar_plan pa, const int32_t* __restrict__ gap_u, const int32_t* __restrict__ gap_a,
-                  int depth, ar_sched sc) {
-  __shared__ int cnt[kSchedBuckets + 1], base[kSchedBuckets + 1];
+                  int depth, int nparts, ar_sched sc) {
+  __shared__ int cnt[kSchedBins], base[kSchedBins];
+  __shared__ int split_s;
   const int slot = blockIdx.x;
   const int nu = pu.meta[(int64_t)slot * 4], na = pa.meta[(int64_t)slot * 4];
-  const int bdepth = slot == 0 ? 1 : depth;
-  if (threadIdx.x <= kSchedBuckets) cnt[threadIdx.x] = 0;
+  for (int i = threadIdx.x; i < kSchedBins; i += blockDim.x) cnt[i] = 0;
   __syncthreads();
-  // bucket kSchedBuckets = B list; bucket b < kSchedBuckets: floor(log2(gap)) == 31 - b  (descending gap)
-  auto bucket_of = [&](int g) { return g <= 1 ? -1 : (g <= bdepth ? kSchedBuckets : __clz(g)); };
+  auto bin_of = [&](int g) { return g <= 1 ? -1 : min(min(g - 1, depth), slot) * 32 + __clz(g); };
   for (int i = threadIdx.x; i < nu + na; i += blockDim.x) {
     const int g = i < nu ? gap_u[(int64_t)slot * pu.batch_cap + i] : gap_a[(int64_t)slot * pa.batch_cap + (i - nu)];
-    const int b = bucket_of(g);
+    const int b = bin_of(g);
     if (b >= 0) atomicAdd(&cnt[b], 1);
   }
   __syncthreads();
   if (threadIdx.x == 0) {
+    int rows = 0, n_long = 0;
+    for (int b = 0; b < kSchedBins; ++b) {
+      rows += cnt[b];
+      if ((b & 31) <= kLongClz) n_long += cnt[b];
+    }
+    const bool split = nparts > 1 && (int64_t)rows + (int64_t)n_long * (nparts - 1) <= (int64_t)sc.cap;
+    split_s = split ? 1 : 0;
+    int32_t* sub = sc.sub + (int64_t)slot * AR_SCHED_SUB;
+    int32_t* cur = sc.cursor + (int64_t)slot * AR_SCHED_SUB;
     int acc = 0;
-    for (int b = 0; b < kSchedBuckets; ++b) { base[b] = acc; acc += cnt[b]; }
-    base[kSchedBuckets] = sc.cap - cnt[kSchedBuckets];
-    int32_t* c = sc.counts + (int64_t)slot * 4;
-    c[0] = acc;
-    c[1] = cnt[kSchedBuckets];
-    c[2] = 0;
-    c[3] = 0;
+    for (int b = 0; b < kSchedBins; ++b) {
+      if ((b & 31) == 0) sub[b >> 5] = acc;
+      base[b] = acc;
+      acc += cnt[b] * ((split && (b & 31) <= kLongClz) ? nparts : 1);
+    }
+    sub[AR_SCHED_MAX_DEPTH + 1] = acc;
+    for (int j = 0; j < AR_SCHED_SUB; ++j) cur[j] = 0;
   }
   __syncthreads();
+  const bool split = split_s != 0;
   int32_t* codes = sc.codes + (int64_t)slot * sc.cap;
+  int32_t* glen = sc.glen + (int64_t)slot * sc.cap;
   for (int i = threadIdx.x; i < nu + na; i += blockDim.x) {
     const bool second = i >= nu;
     const int g = second ? gap_a[(int64_t)slot * pa.batch_cap + (i - nu)] : gap_u[(int64_t)slot * pu.batch_cap + i];
-    const int b = bucket_of(g);
+    const int b = bin_of(g);
     if (b < 0) continue;
     const int row = second ? pa.uniq[(int64_t)slot * pa.batch_cap + (i - nu)] : pu.uniq[(int64_t)slot * pu.batch_cap + i];
-    codes[base[b] + atomicAdd(&cnt[b], -1) - 1] = row | (second ? (int)0x80000000 : 0);
+    const int code = row | (second ? (int)0x80000000 : 0);
+    const int pos = atomicAdd(&cnt[b], -1) - 1;
+    if (split && (b & 31) <= kLongClz) {
+      for (int p = 0; p < nparts; ++p) {
+        codes[base[b] + pos * nparts + p] = code | (1 << 30) | (p << 26);
+        glen[base[b] + pos * nparts + p] = g;
+      }
+    } else {
+      codes[base[b] + pos] = code;
+      glen[base[b] + pos] = g;
+    }
   }
 }
 
@@ -287,14 +308,17 @@ extern "C" int ar_plan_link(const ar_plan* plan, int32_t n_steps, const int32_t*
 
 extern "C" int ar_plan_sched(const ar_plan* plan_u, const ar_plan* plan_a, int32_t n_steps, int64_t t0, int64_t t_flush,
                              int32_t* seen_u, int32_t n_rows_u, int32_t* seen_a, int32_t n_rows_a, int32_t depth,
-                             const ar_sched* sched, void* stream) {
+                             int32_t dim, const ar_sched* sched, void* stream) {
   AR_REQUIRE(plan_u && plan_a && sched && seen_u && seen_a, "ar_plan_sched: null pointer");
-  AR_REQUIRE(sched->codes && sched->counts && sched->gap_u && sched->gap_a && sched->bounds, "ar_plan_sched: null buffer in sched");
+  AR_REQUIRE(sched->codes && sched->glen && sched->sub && sched->cursor && sched->gap_u && sched->gap_a && sched->bounds,
+             "ar_plan_sched: null buffer in sched");
   AR_REQUIRE(n_steps >= 0 && n_steps <= plan_u->n_slots && n_steps <= plan_a->n_slots && n_steps <= sched->n_slots,
              "ar_plan_sched: n_steps %d exceeds the plans / schedule", n_steps);
   AR_REQUIRE(sched->cap >= plan_u->batch_cap + plan_a->batch_cap, "ar_plan_sched: sched.cap too small");
   AR_REQUIRE(depth >= 1 && depth <= AR_SCHED_MAX_DEPTH, "ar_plan_sched: depth %d outside [1, %d]", depth, AR_SCHED_MAX_DEPTH);
-  AR_REQUIRE(t0 + n_steps < 0x7fffffffLL, "ar_plan_sched: step counter exceeds int32");
+  AR_REQUIRE(dim > 0 && dim <= 512, "ar_plan_sched: dim %d unsupported", dim);
+  AR_REQUIRE(n_rows_u <= AR_SCHED_MAX_ROWS && n_rows_a <= AR_SCHED_MAX_ROWS, "ar_plan_sched: more than %d rows", AR_SCHED_MAX_ROWS);
+  AR_REQUIRE(t0 + n_steps < (1LL << 27), "ar_plan_sched: step counter exceeds 2^27 (the top bits of last_step count split-row parts)");
   if (n_steps == 0) return AR_OK;
   cudaStream_t st = (cudaStream_t)stream;
   static bool attr_set = false;
@@ -317,13 +341,13 @@ extern "C" int ar_plan_sched(const ar_plan* plan_u, const ar_plan* plan_a, int32
                                                                         rows_per_part, sched->bounds, gaps[w]);
     AR_LAUNCH_CHECK();
   }
-  ar::plan_sched_kernel<<<n_steps, 1024, 0, st>>>(*plan_u, *plan_a, sched->gap_u, sched->gap_a, depth, *sched);
+  ar::plan_sched_kernel<<<n_steps, 512, 0, st>>>(*plan_u, *plan_a, sched->gap_u, sched->gap_a, depth, ar::ceil_div(dim, 32), *sched);
   AR_LAUNCH_CHECK();
   return AR_OK;
 }
 
 extern "C" const char* ar_last_error(void) { return ar::g_err; }
-extern "C" int ar_abi_version(void) { return 13; }
+extern "C" int ar_abi_version(void) { return 14; }
 
 extern "C" int ar_check_device(void) {
   int dev = 0;

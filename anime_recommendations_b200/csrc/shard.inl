@@ -180,7 +180,7 @@ shard_merge_update_kernel(ShardServeArgs a, const float* __restrict__ alpha, flo
     }
     q += __ldg(g + dim);
   }
-  finish_row<NV>(a.tab, id / a.G, acc, q, -1.0f, alpha, l2x2, t, 0, reg, nullptr, lane);
+  finish_row<NV>(a.tab, id / a.G, acc, q, -1.0f, alpha, l2x2, t, 0, reg, lane);
 }
 
 static int shard_alltoall(NcclApi* nc, ncclComm_t comm, int G, const void* send, void* recv, size_t stride_bytes,

@@ -1,21 +1,15 @@
 // Half A: the training step of the neural_network.py embedding model on sm_100a.
 //
-// Step s of a chunk (global optimizer step t, 1-based) is three launches (single GPU):
-//   A(s) rows_catchup  (AR_ADAM_REPLAY only, side streams) bring the step's distinct rows whose previous touch
-//                      lies more than `depth` steps back to optimizer step t-1 by replaying their missed pure-L2
-//                      Adam steps in registers, longest replay first (plan-time schedule, ar_plan_sched); it
-//                      may start as soon as step s-depth-1 is done, i.e. it has `depth` step periods to finish
-//   F(s) fwd_head      warp per sample: gather both rows (128-bit loads), l2-normalise, dot; the LAST CTA to
-//                      finish (ticket) runs the head over the whole batch: Dense(1) + BatchNorm(train) +
-//                      sigmoid + BCE, dLoss/dy per sample, Adam on the 4 head scalars, moving statistics,
-//                      metrics -- fixed summation order, no atomics on data => bit-reproducible
-//   U(s) rows_update   warp per distinct row: atomic-free segment reduction of the row gradient over the
-//                      plan's sorted samples + L2 term + Adam, one RMW of (W, m, v); extra warps replay the
-//                      B list of step s+1 (rows last touched 2..depth steps ago)
-// Dependencies: A(s) -> F(s) -> U(s) -> F(s+1), U(s-depth-1) -> A(s).  The kernels read the chunk's step counter
-// and sample pointers from device memory, so a full chunk is captured once as a CUDA graph and replayed.
+// Single GPU (ar_train_steps): one persistent kernel per chunk of steps, chunk.inl.
+// The multi-GPU paths (dist.inl, shard.inl, peer.inl) chain the stage kernels of this file per step:
+//   rows_classify / rows_catchup  (AR_ADAM_REPLAY) bring the step's distinct rows to optimizer step t-1 by replaying
+//                      their missed pure-L2 Adam steps in registers
+//   embed_fwd          warp per sample: gather both rows (128-bit loads), l2-normalise, dot
+//   head_step          Dense(1) + BatchNorm(train) + sigmoid + BCE, dLoss/dy per sample, Adam on the 4 head scalars,
+//                      moving statistics, metrics -- ticketed last CTA, fixed summation order
+//   rows_update        warp per distinct row: atomic-free segment reduction of the row gradient over the plan's
+//                      sorted samples + L2 term + Adam, one RMW of (W, m, v)
 // AR_ADAM_DENSE appends a flush of every other row to step t (the reference-literal dense Adam).
-// The multi-GPU paths (dist.inl, shard.inl, peer.inl) keep the separate embed_fwd / head_step launches.
 //
 // Arithmetic follows oracle/train.py (the restatement of neural_network.py:66-106 under
 // Keras-2.12 semantics); citations there.
@@ -80,23 +74,6 @@ __device__ __forceinline__ void reg_commit(double regd, const RegAcc& reg, int l
   if (lane == 0 && regd != 0.0) atomicAdd(reg.acc, (unsigned long long)__double2ll_rn(regd * (double)reg.scale));
 }
 
-// Per-chunk parameters in device memory (ar_train_ctx.chunk_params): step `slot` of the chunk is global step
-// t0 + slot + 1 and reads its samples at iu/ia/label + slot*batch.
-struct DevChunk {
-  int64_t t0;
-  const int32_t* iu;
-  const int32_t* ia;
-  const float* label;
-  int64_t pad[12];
-};
-static_assert(sizeof(DevChunk) == 128, "DevChunk is 16 x int64");
-__global__ void set_chunk_kernel(DevChunk* dc, int64_t t0, const int32_t* iu, const int32_t* ia, const float* label) {
-  dc->t0 = t0;
-  dc->iu = iu;
-  dc->ia = ia;
-  dc->label = label;
-}
-
 // Replay pure-L2 Adam steps (from, to] of one row held in registers.  regd += sum over the replayed
 // steps t of stepw[t] * (this lane's share of ||w before step t||^2).
 template <int NV>
@@ -147,12 +124,6 @@ struct CatchupArgs {
   // bucket b at sched + b*cap, their fill counts at sched + 3*cap
   int32_t* sched;
   int cap;
-  // plan-time schedule (single GPU): rows (table << 31 | row) at list[0 .. *list_count), already longest first;
-  // the target step comes from the chunk parameters: t_target = dc->t0 + t_off
-  const int32_t* list;
-  const int32_t* list_count;
-  const DevChunk* dc;
-  int t_off;
   RegAcc reg;
 };
 constexpr int kLongReplay = 128, kMidReplay = 32;
@@ -231,13 +202,7 @@ rows_catchup_kernel(CatchupArgs a, const float* __restrict__ alpha, float l2x2, 
   const int unit = blockIdx.x;
   bool second;
   int row;
-  if (a.list) {  // plan-time schedule
-    if (unit >= a.list_count[0]) return;
-    const int code = a.list[unit];
-    second = code < 0;
-    row = code & 0x7fffffff;
-    t_target = a.dc->t0 + a.t_off;
-  } else if (a.sched) {  // bucket order: long rows first
+  if (a.sched) {  // bucket order: long rows first
     const int32_t* counts = a.sched + 3 * (size_t)a.cap;
     const int n0 = counts[0], n1 = counts[1], n2 = counts[2];
     int b = unit, code;
@@ -397,10 +362,11 @@ __device__ __forceinline__ void block_sum(double (&v)[NVAL], double* smem /* [NV
   }
 }
 
+// numerically stable sigmoid without a branch: e = exp(-|y|) <= 1;  y >= 0: 1/(1+e),  y < 0: e/(1+e)
 __device__ __forceinline__ float sigmoidf_(float y) {
-  if (y >= 0.f) return 1.0f / (1.0f + expf(-y));
-  float e = expf(y);
-  return e / (1.0f + e);
+  const float e = expf(-fabsf(y));
+  const float r = 1.0f / (1.0f + e);
+  return y >= 0.f ? r : e * r;
 }
 __device__ __forceinline__ float bce_logits(float y, float t) {
   return fmaxf(y, 0.f) - y * t + log1pf(expf(-fabsf(y)));
@@ -408,7 +374,7 @@ __device__ __forceinline__ float bce_logits(float y, float t) {
 
 // Per-step scalars the head hands to the row-update kernel: dc_s = K_COEF*(dy_s - K_S1N - zh_s*K_S2N),
 // zh_s = ((w*c_s + b) - mu)*inv   (oracle head_backward(): dz, dc)
-enum { K_COEF = 0, K_S1N, K_S2N, K_MU, K_INV, K_W, K_B, K_GAMMA, K_BETA, K_FN, K_STEPC };  // 16 floats reserved
+enum { K_COEF = 0, K_S1N, K_S2N, K_MU, K_INV, K_W, K_B, K_GAMMA, K_BETA, K_FN, K_RN, K_STEPC };  // 16 floats reserved
 constexpr int kHeadSums = 7;  // sum bce, sq err, dy, dy*zh, zh, dy*c, zh*c
 
 __device__ __forceinline__ float dc_of(float dy, float c, const float* __restrict__ k) {
@@ -418,15 +384,15 @@ __device__ __forceinline__ float dc_of(float dy, float c, const float* __restric
 // dLoss/dy of one sample from its cosine and label: the SAME expression sequence wherever it is evaluated (the
 // head's sums and the row update's per-sample factor must see identical bits)
 __device__ __forceinline__ float dy_of(float c, float tg, float w, float b, float mu, float inv, float gamma,
-                                       float beta, float fn, float* zh_out) {
+                                       float beta, float rn, float* zh_out) {
   const float zh = ((w * c + b) - mu) * inv;
   const float y = gamma * zh + beta;
   *zh_out = zh;
-  return (sigmoidf_(y) - tg) / fn;
+  return (sigmoidf_(y) - tg) * rn;      // rn = 1/n: (p - t)/n up to one rounding
 }
 __device__ __forceinline__ float dc_of_label(float c, float tg, const float* __restrict__ k) {
   float zh;
-  const float dy = dy_of(c, tg, k[K_W], k[K_B], k[K_MU], k[K_INV], k[K_GAMMA], k[K_BETA], k[K_FN], &zh);
+  const float dy = dy_of(c, tg, k[K_W], k[K_B], k[K_MU], k[K_INV], k[K_GAMMA], k[K_BETA], k[K_RN], &zh);
   return k[K_COEF] * (dy - k[K_S1N] - zh * k[K_S2N]);
 }
 
@@ -443,13 +409,14 @@ struct HeadIO {
   float* metrics;   // base of the per-step metrics table (row t is written), or null
 };
 struct HeadScalars {
-  float w, b, gamma, beta, mu, var, inv, fn;
+  float w, b, gamma, beta, mu, var, inv, fn, rn;
 };
 // batch statistics of z = w*c + b from (sum c, sum c^2)
 __device__ __forceinline__ HeadScalars head_scalars(const float* __restrict__ head, double sum_c, double sum_c2, int n) {
   HeadScalars h;
   h.w = head[0]; h.b = head[1]; h.gamma = head[2]; h.beta = head[3];
   h.fn = (float)n;
+  h.rn = 1.0f / h.fn;
   const double mean_c = sum_c / n;
   const double var_c = fmax(sum_c2 / n - mean_c * mean_c, 0.0);
   h.mu = (float)((double)h.w * mean_c + (double)h.b);
@@ -462,7 +429,7 @@ __device__ __forceinline__ float head_sample(float ci, float tg, const HeadScala
   const float zh = ((h.w * ci + h.b) - h.mu) * h.inv;
   const float y = h.gamma * zh + h.beta;
   const float p = sigmoidf_(y);
-  const float dy = (p - tg) / h.fn;
+  const float dy = (p - tg) * h.rn;
   s1[0] += (double)bce_logits(y, tg);
   s1[1] += (double)((tg - p) * (tg - p));
   s1[2] += (double)dy;
@@ -503,6 +470,7 @@ __device__ __forceinline__ void head_finalize(const HeadScalars& h, const double
   io.stepc[K_GAMMA] = h.gamma;
   io.stepc[K_BETA] = h.beta;
   io.stepc[K_FN] = h.fn;
+  io.stepc[K_RN] = h.rn;
   if (io.metrics) {
     float* row = io.metrics + t * 4;
     row[0] = (float)(s2[0] / n);
@@ -562,184 +530,6 @@ head_step_kernel(const float* __restrict__ c, const float* __restrict__ label, i
   if (tid == 0) head_finalize(h, s2, s0[0], n, io, t);
 }
 
-// F(s): the forward with the head's batch reductions folded into the last CTA to finish (ticket).  The tail only
-// does what the row update needs: batch statistics, the five backward sums, Adam on the 4 head scalars, moving
-// statistics and the step scalars; dLoss/dy per sample is recomputed by the row update from (c, label) and the
-// reported BCE / MSE by one extra CTA of the row-update launch -- both off this kernel's critical path.
-constexpr int kFwdThreads = 256;
-constexpr int kFwdWarps = kFwdThreads / 32;
-constexpr int kHeadUnroll = 16;     // samples per thread whose loads are in flight together in the tail
-constexpr int kTailSums = 5;        // sum dy, dy*zh, zh, dy*c, zh*c
-template <int NV>
-__global__ void __launch_bounds__(kFwdThreads)
-fwd_head_kernel(const float* __restrict__ U, const float* __restrict__ A, int dim, const DevChunk* __restrict__ dc,
-                int slot, int batch, const int32_t* __restrict__ meta_n, float* __restrict__ uh,
-                float* __restrict__ ah, float* __restrict__ c, float* __restrict__ ru, float* __restrict__ ra,
-                double* __restrict__ fwd_part, HeadIO io) {
-  __shared__ double red[kHeadSums * 32];
-  __shared__ float cs_s[kFwdWarps];
-  __shared__ int is_last;
-  const int n = min(batch, meta_n[2]);
-  if (n <= 0) return;
-  const int nblk = (n + kFwdWarps - 1) / kFwdWarps;
-  if ((int)blockIdx.x >= nblk) return;
-  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-  const int s = blockIdx.x * kFwdWarps + wid;
-  float cs = 0.f;
-  if (s < n) {
-    const int32_t* __restrict__ iu = dc->iu + (size_t)slot * batch;
-    const int32_t* __restrict__ ia = dc->ia + (size_t)slot * batch;
-    const int d4 = dim >> 2;
-    RowTile<NV> u, a;
-    u.load(U + (size_t)iu[s] * dim, d4, lane);
-    a.load(A + (size_t)ia[s] * dim, d4, lane);
-    const float su = tile_dot<NV>(u, u);
-    const float sa = tile_dot<NV>(a, a);
-    const float r_u = 1.0f / sqrtf(fmaxf(su, kL2NormEps));
-    const float r_a = 1.0f / sqrtf(fmaxf(sa, kL2NormEps));
-#pragma unroll
-    for (int k = 0; k < NV; ++k) {
-      u.x[k] = scale4(u.x[k], r_u);
-      a.x[k] = scale4(a.x[k], r_a);
-    }
-    cs = tile_dot<NV>(u, a);
-    u.store(uh + (size_t)s * dim, d4, lane);
-    a.store(ah + (size_t)s * dim, d4, lane);
-    if (lane == 0) {
-      c[s] = cs;
-      ru[s] = r_u;
-      ra[s] = r_a;
-    }
-  }
-  if (lane == 0) cs_s[wid] = cs;
-  __syncthreads();
-  if (tid == 0) {  // (sum c, sum c^2) of this CTA's samples in a fixed order; padding samples contribute 0
-    double a0 = 0.0, a1 = 0.0;
-#pragma unroll
-    for (int i = 0; i < kFwdWarps; ++i) {
-      const double x = (double)cs_s[i];
-      a0 += x;
-      a1 += x * x;
-    }
-    fwd_part[2 * blockIdx.x] = a0;
-    fwd_part[2 * blockIdx.x + 1] = a1;
-    __threadfence();  // cumulative: also orders the c[] stores of the other warps (observed through the barrier)
-    const unsigned int old = atomicAdd(io.ticket, 1u);
-    is_last = (old == (unsigned int)(nblk - 1));
-  }
-  __syncthreads();
-  if (!is_last) return;
-  __threadfence();
-
-  // ---- tail, this CTA alone, every sum in a fixed order.  All loads that do not depend on the statistics are
-  // issued first: the forward partials, the first samples, the head state.
-  const float* __restrict__ label = dc->label + (size_t)slot * batch;
-  const int64_t t = dc->t0 + slot + 1;
-  float hst[3] = {0.f, 0.f, 0.f};   // thread k < 4: head[k], head_m[k], head_v[k]
-  float alpha_t = 0.f;
-  if (tid < 4) {
-    hst[0] = io.head[tid];
-    hst[1] = io.head_m[tid];
-    hst[2] = io.head_v[tid];
-    alpha_t = io.alpha[t];
-  }
-  float cr[kHeadUnroll], tr[kHeadUnroll];
-#pragma unroll
-  for (int k = 0; k < kHeadUnroll; ++k) {
-    const int i = k * kFwdThreads + tid;
-    cr[k] = i < n ? __ldcg((const float*)c + i) : 0.f;
-    tr[k] = i < n ? __ldg(label + i) : 0.f;
-  }
-  double s0[2] = {0.0, 0.0};
-  for (int i = tid; i < nblk; i += kFwdThreads) {
-    s0[0] += __ldcg(fwd_part + 2 * i);
-    s0[1] += __ldcg(fwd_part + 2 * i + 1);
-  }
-  block_sum<2>(s0, red);
-  const HeadScalars h = head_scalars(io.head, s0[0], s0[1], n);
-  double s1[kTailSums];
-#pragma unroll
-  for (int i = 0; i < kTailSums; ++i) s1[i] = 0.0;
-  for (int base = 0; base < n; base += kHeadUnroll * kFwdThreads) {
-    if (base) {
-#pragma unroll
-      for (int k = 0; k < kHeadUnroll; ++k) {
-        const int i = base + k * kFwdThreads + tid;
-        cr[k] = i < n ? __ldcg((const float*)c + i) : 0.f;
-        tr[k] = i < n ? __ldg(label + i) : 0.f;
-      }
-    }
-    // fp32 partial sums over the chunk's <= kHeadUnroll samples, one conversion per chunk and sum
-    float f[kTailSums] = {0.f, 0.f, 0.f, 0.f, 0.f};
-#pragma unroll
-    for (int k = 0; k < kHeadUnroll; ++k) {
-      const int i = base + k * kFwdThreads + tid;
-      if (i < n) {
-        float zh;
-        const float dy = dy_of(cr[k], tr[k], h.w, h.b, h.mu, h.inv, h.gamma, h.beta, h.fn, &zh);
-        f[0] += dy;
-        f[1] = fmaf(dy, zh, f[1]);
-        f[2] += zh;
-        f[3] = fmaf(dy, cr[k], f[3]);
-        f[4] = fmaf(zh, cr[k], f[4]);
-      }
-    }
-#pragma unroll
-    for (int i = 0; i < kTailSums; ++i) s1[i] += (double)f[i];
-  }
-  block_sum<kTailSums>(s1, red);
-  // every thread holds the totals; threads 0..3 each own one head scalar
-  const double S1 = s1[0], S2 = s1[1], Szh = s1[2], Sdyc = s1[3], Szhc = s1[4], Sc = s0[0];
-  const double ig = (double)h.inv * (double)h.gamma;
-  if (tid < 4) {
-    // oracle head_backward(): dgamma = sum dy*zh, dbeta = sum dy, dz_i = inv*gamma*(dy_i - S1/n - zh_i*S2/n)
-    const float g = tid == 0 ? (float)(ig * (Sdyc - S1 / n * Sc - S2 / n * Szhc))   // dw = sum dz*c
-                  : tid == 1 ? (float)(-ig * (S2 / n) * Szh)                        // db = sum dz (0 up to rounding)
-                  : tid == 2 ? (float)S2 : (float)S1;
-    adam1(hst[0], hst[1], hst[2], g, alpha_t);
-    io.head[tid] = hst[0];
-    io.head_m[tid] = hst[1];
-    io.head_v[tid] = hst[2];
-  } else if (tid == 32) {
-    const float mm = io.bn_moving[0], mv = io.bn_moving[1];
-    io.bn_moving[0] = mm - (mm - h.mu) * kBnOneMinusMomentum;
-    io.bn_moving[1] = mv - (mv - h.var) * kBnOneMinusMomentum;
-  } else if (tid == 64) {
-    io.stepc[K_COEF] = (float)((double)h.w * ig);
-    io.stepc[K_S1N] = (float)(S1 / n);
-    io.stepc[K_S2N] = (float)(S2 / n);
-    io.stepc[K_MU] = h.mu;
-    io.stepc[K_INV] = h.inv;
-    io.stepc[K_W] = h.w;
-    io.stepc[K_B] = h.b;
-    io.stepc[K_GAMMA] = h.gamma;
-    io.stepc[K_BETA] = h.beta;
-    io.stepc[K_FN] = h.fn;
-    *io.ticket = 0u;  // ready for the next step
-  }
-}
-
-// Reported metrics of one step (Keras: mean BCE from logits, mean squared error), by one CTA of the row-update
-// launch: nothing on the step's critical path needs them.
-__device__ __forceinline__ void step_metrics(const float* __restrict__ c, const float* __restrict__ label, int n,
-                                             const float* __restrict__ k, float* __restrict__ metrics_row, double* red) {
-  double s[2] = {0.0, 0.0};
-  for (int i = threadIdx.x; i < n; i += blockDim.x) {
-    const float zh = ((k[K_W] * c[i] + k[K_B]) - k[K_MU]) * k[K_INV];
-    const float y = k[K_GAMMA] * zh + k[K_BETA];
-    const float p = sigmoidf_(y), tg = label[i];
-    s[0] += (double)bce_logits(y, tg);
-    s[1] += (double)((tg - p) * (tg - p));
-  }
-  block_sum<2>(s, red);
-  if (threadIdx.x == 0) {
-    metrics_row[0] = (float)(s[0] / n);
-    metrics_row[1] = (float)(s[1] / n);
-    metrics_row[2] = (float)n;
-    metrics_row[3] = k[K_MU];
-  }
-}
-
 // helpers behind the stand-alone ar_head_step entry point (unit tests): partials from c, dc from dy
 __global__ void c_partials_kernel(const float* __restrict__ c, int n, double* __restrict__ fwd_part) {
   const int blk = blockIdx.x * blockDim.x + threadIdx.x;
@@ -787,27 +577,13 @@ struct UpdateArgs {
   // peer mode: the plan's sample ids index this rank's selection list; samp maps them to the position in the
   // GLOBAL batch that c / dy are indexed by (`other` and `rinv` stay indexed by the plan's own sample id)
   const int32_t* samp[2];
-  // single GPU, AR_ADAM_REPLAY: blocks_b extra CTAs replay the B list of the NEXT step (rows last touched
-  // 2..depth steps ago, not touched by this step) to this step's t; the step counter comes from dc
-  const int32_t* blist;        // end of the next slot's codes (the B list is stored back to front)
-  const int32_t* blist_count;  // &counts[next slot][1]
-  int blocks_b;
-  const DevChunk* dc;
-  int slot;
-  // single GPU: dLoss/dy is recomputed per sample from (c, label) and the step scalars instead of being read
-  // from `dy`; labels at dc->label + slot*batch.  blocks_m (0 or 1) extra CTAs write the step's reported metrics
-  int use_label;
-  int batch;
-  int blocks_m;
-  float* metrics;
-  int32_t* health;
   RegAcc reg;
 };
 
 template <int NV>
 __device__ __forceinline__ void finish_row(const ar_table& tb, int row, RowTile<NV>& acc, float q,
                                            float rinv, const float* __restrict__ alpha, float l2x2,
-                                           int64_t t, int replay, const RegAcc& reg, int32_t* health, int lane) {
+                                           int64_t t, int replay, const RegAcc& reg, int lane) {
   const int d4 = tb.dim >> 2;
   const size_t o = (size_t)row * tb.dim;
   RowTile<NV> w, m, v;
@@ -817,11 +593,7 @@ __device__ __forceinline__ void finish_row(const ar_table& tb, int row, RowTile<
   double regd = 0.0;
   if (replay) {
     const int64_t last = tb.last_step[row];
-    if (last < t - 1) {
-      // with a replay schedule the row must already be current (the forward has read it): count it
-      if (health && lane == 0) atomicAdd(health, 1);
-      replay_l2<NV>(w, m, v, alpha, reg.stepw, last, t - 1, l2x2, lane, regd);
-    }
+    if (last < t - 1) replay_l2<NV>(w, m, v, alpha, reg.stepw, last, t - 1, l2x2, lane, regd);
   }
   if (reg.acc || rinv < 0.f) {
     const float ss = tile_dot<NV>(w, w);
@@ -851,42 +623,7 @@ rows_update_kernel(UpdateArgs a, const float* __restrict__ c, const float* __res
                    const float* __restrict__ stepc, const float* __restrict__ alpha, float l2x2, int64_t t,
                    int replay) {
   extern __shared__ float red[];  // heavy path: [kRowWarps][dim] + [kRowWarps]
-  if (a.dc) t = a.dc->t0 + a.slot + 1;
-  const float* __restrict__ label = a.use_label ? a.dc->label + (size_t)a.slot * a.batch : nullptr;
   int b = blockIdx.x;
-  if (b < a.blocks_m) {  // reported BCE / MSE of the step
-    __shared__ double mred[2 * 32];
-    step_metrics(c, label, min(a.batch, a.meta[0][2]), stepc, a.metrics + t * 4, mred);
-    return;
-  }
-  b -= a.blocks_m;
-  if (b < a.blocks_b) {  // B list of the next step: a short replay to t (these rows are not in this step)
-    const int lane = threadIdx.x & 31;
-    const int nb = a.blist_count[0];
-    for (int i = b * kRowWarps + (threadIdx.x >> 5); i < nb; i += a.blocks_b * kRowWarps) {
-      const int code = a.blist[-1 - i];
-      const bool second = code < 0;
-      const int row = code & 0x7fffffff;
-      const ar_table& tb = second ? a.tab[1] : a.tab[0];
-      const int64_t last = tb.last_step[row];
-      if (last >= t) continue;
-      const int d4 = tb.dim >> 2;
-      const size_t o = (size_t)row * tb.dim;
-      RowTile<NV> w, m, v;
-      w.load(tb.W + o, d4, lane);
-      m.load(tb.m + o, d4, lane);
-      v.load(tb.v + o, d4, lane);
-      double regd = 0.0;
-      replay_l2<NV>(w, m, v, alpha, a.reg.stepw, last, t, l2x2, lane, regd);
-      w.store(tb.W + o, d4, lane);
-      m.store(tb.m + o, d4, lane);
-      v.store(tb.v + o, d4, lane);
-      if (lane == 0) tb.last_step[row] = (int32_t)t;
-      reg_commit(regd, a.reg, lane);
-    }
-    return;
-  }
-  b -= a.blocks_b;
   int which, heavy_path;
   if (b < a.blocks_norm[0]) { which = 0; heavy_path = 0; }
   else if ((b -= a.blocks_norm[0]) < a.blocks_norm[1]) { which = 1; heavy_path = 0; }
@@ -937,8 +674,8 @@ rows_update_kernel(UpdateArgs a, const float* __restrict__ c, const float* __res
       o1.load(other + (size_t)s1 * dim, d4, lane);
       const int g0 = samp ? samp[s0] : s0, g1 = samp ? samp[s1] : s1;
       const float c0 = c[g0], c1 = c[g1];
-      const float d0 = label ? dc_of_label(c0, label[g0], kk) : dc_of(dy[g0], c0, kk);
-      const float d1 = label ? dc_of_label(c1, label[g1], kk) : dc_of(dy[g1], c1, kk);
+      const float d0 = dc_of(dy[g0], c0, kk);
+      const float d1 = dc_of(dy[g1], c1, kk);
       q = fmaf(d0, c0, q);
       q = fmaf(d1, c1, q);
 #pragma unroll
@@ -953,7 +690,7 @@ rows_update_kernel(UpdateArgs a, const float* __restrict__ c, const float* __res
       o0.load(other + (size_t)s0 * dim, d4, lane);
       const int g0 = samp ? samp[s0] : s0;
       const float c0 = c[g0];
-      const float d0 = label ? dc_of_label(c0, label[g0], kk) : dc_of(dy[g0], c0, kk);
+      const float d0 = dc_of(dy[g0], c0, kk);
       q = fmaf(d0, c0, q);
 #pragma unroll
       for (int k = 0; k < NV; ++k) acc.x[k] = fma4(d0, o0.x[k], acc.x[k]);
@@ -972,7 +709,7 @@ rows_update_kernel(UpdateArgs a, const float* __restrict__ c, const float* __res
       }
       return;
     }
-    finish_row<NV>(tb, uniq[seg], acc, q, rinv[order[beg]], alpha, l2x2, t, replay, a.reg, a.health, lane);
+    finish_row<NV>(tb, uniq[seg], acc, q, rinv[order[beg]], alpha, l2x2, t, replay, a.reg, lane);
     return;
   }
 
@@ -989,7 +726,7 @@ rows_update_kernel(UpdateArgs a, const float* __restrict__ c, const float* __res
     o0.load(other + (size_t)s0 * dim, d4, lane);
     const int g0 = samp ? samp[s0] : s0;
     const float c0 = c[g0];
-    const float d0 = label ? dc_of_label(c0, label[g0], kk) : dc_of(dy[g0], c0, kk);
+    const float d0 = dc_of(dy[g0], c0, kk);
     q = fmaf(d0, c0, q);
 #pragma unroll
     for (int k = 0; k < NV; ++k) acc.x[k] = fma4(d0, o0.x[k], acc.x[k]);
@@ -1024,7 +761,7 @@ rows_update_kernel(UpdateArgs a, const float* __restrict__ c, const float* __res
     }
     return;
   }
-  finish_row<NV>(tb, uniq[seg], acc, q, rinv[order[beg]], alpha, l2x2, t, replay, a.reg, a.health, lane);
+  finish_row<NV>(tb, uniq[seg], acc, q, rinv[order[beg]], alpha, l2x2, t, replay, a.reg, lane);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -1177,23 +914,6 @@ static int launch_catchup(const ar_table* t0, const ar_plan* p0, int slot0, cons
   return AR_OK;
 }
 
-// A(s): catch-up from the plan-time schedule of `slot`, to global step dc->t0 + slot (= t(s) - 1).
-static int launch_catchup_list(const ar_train_ctx& x, int slot, cudaStream_t st) {
-  CatchupArgs a{};
-  a.tab[0] = x.users;
-  a.tab[1] = x.anime;
-  a.list = x.sched.codes + (int64_t)slot * x.sched.cap;
-  a.list_count = x.sched.counts + (int64_t)slot * 4;
-  a.dc = (const DevChunk*)x.chunk_params;
-  a.t_off = slot;
-  a.reg = reg_of(x);
-  const int units = x.plan_u.batch_cap + x.plan_a.batch_cap;
-  const float l2x2 = (float)(2.0 * (double)x.l2);
-  rows_catchup_kernel<<<units, catch_threads(x.users.dim), 0, st>>>(a, x.alpha, l2x2, 0);
-  AR_LAUNCH_CHECK();
-  return AR_OK;
-}
-
 static void fill_update(UpdateArgs& a, int w, const ar_table* tab, const ar_plan* p, int slot,
                         const float* other, const float* rinv, int batch_hint) {
   a.tab[w] = *tab;
@@ -1213,7 +933,7 @@ static int launch_update(UpdateArgs& a, bool two, const float* c, const float* d
                          const float* alpha, float l2, int64_t t, int replay, RegAcc reg, cudaStream_t st) {
   if (!two) { a.blocks_norm[1] = 0; a.blocks_heavy[1] = 0; a.tab[1] = a.tab[0]; }
   a.reg = reg;
-  int blocks = a.blocks_m + a.blocks_b + a.blocks_norm[0] + a.blocks_norm[1] + a.blocks_heavy[0] + a.blocks_heavy[1];
+  int blocks = a.blocks_norm[0] + a.blocks_norm[1] + a.blocks_heavy[0] + a.blocks_heavy[1];
   const int dim = a.tab[0].dim;
   size_t smem = (size_t)kRowWarps * dim * sizeof(float) + kRowWarps * sizeof(float);
   const float l2x2 = (float)(2.0 * (double)l2);
@@ -1308,37 +1028,12 @@ extern "C" int ar_rows_update(const ar_table* tab, const ar_plan* plan, int32_t 
 }
 
 namespace ar {
-// Optional per-stage timing: events bracket every launch of the step (bench.py roofline leg).
-struct StageTimer {
-  std::vector<cudaEvent_t> ev;  // per step: 0 start, 1 after catch-up, 2 after fwd, 3 after head, 4 after update, 5 after dense flush
-  cudaStream_t st;
-  int rec(int) {
-    cudaEvent_t e;
-    AR_CUDA(cudaEventCreate(&e));
-    AR_CUDA(cudaEventRecord(e, st));
-    ev.push_back(e);
-    return AR_OK;
-  }
-};
-#define AR_TICK(i)                          \
-  if (timer) {                              \
-    int rc__ = timer->rec(i);               \
-    if (rc__) return rc__;                  \
-  }
-
 // Side stream + events of the look-ahead catch-up (one set per device, created on first use).
 struct Lookahead {
   cudaStream_t st2 = nullptr;
   cudaEvent_t ev_upd[2] = {nullptr, nullptr};  // "row update of step s is complete" (recorded on the main stream)
   cudaEvent_t ev_ahead = nullptr;              // "look-ahead catch-up for the next step is complete" (side stream)
   cudaEvent_t ev_mid = nullptr;                // peer mode: "forward of step s is queued" (main stream)
-  // single-GPU DAG: A(s) runs on side[s % n_side]; ring of events
-  static constexpr int kRing = AR_SCHED_MAX_DEPTH + 2;
-  cudaStream_t side[AR_SCHED_MAX_DEPTH + 1] = {};
-  cudaEvent_t ev_u[kRing] = {};  // U(s) done (main stream)
-  cudaEvent_t ev_a[kRing] = {};  // A(s) done (side stream)
-  cudaEvent_t ev_begin = nullptr;
-  cudaStream_t cap = nullptr;    // stream the chunk graph is captured on (the caller's may be the legacy default stream)
   bool ok = false;
 };
 static Lookahead* lookahead() {
@@ -1356,196 +1051,9 @@ static Lookahead* lookahead() {
       if (cudaEventCreateWithFlags(&l.ev_upd[i], cudaEventDisableTiming) != cudaSuccess) return nullptr;
     if (cudaEventCreateWithFlags(&l.ev_ahead, cudaEventDisableTiming) != cudaSuccess) return nullptr;
     if (cudaEventCreateWithFlags(&l.ev_mid, cudaEventDisableTiming) != cudaSuccess) return nullptr;
-    if (cudaEventCreateWithFlags(&l.ev_begin, cudaEventDisableTiming) != cudaSuccess) return nullptr;
-    if (cudaStreamCreateWithFlags(&l.cap, cudaStreamNonBlocking) != cudaSuccess) return nullptr;
-    for (int i = 0; i <= AR_SCHED_MAX_DEPTH; ++i)
-      if (cudaStreamCreateWithPriority(&l.side[i], cudaStreamNonBlocking, least) != cudaSuccess) return nullptr;
-    for (int i = 0; i < Lookahead::kRing; ++i) {
-      if (cudaEventCreateWithFlags(&l.ev_u[i], cudaEventDisableTiming) != cudaSuccess) return nullptr;
-      if (cudaEventCreateWithFlags(&l.ev_a[i], cudaEventDisableTiming) != cudaSuccess) return nullptr;
-    }
     l.ok = true;
   }
   return &l;
-}
-
-static HeadIO head_io(const ar_train_ctx& x) {
-  return HeadIO{x.head, x.head_m, x.head_v, x.bn_moving, x.alpha, x.dy, x.stepc, x.ticket, x.metrics};
-}
-
-// F(s) and U(s) of one slot on `st`; both read the step counter and sample pointers from x.chunk_params.
-static int launch_fwd_head(const ar_train_ctx& x, int slot, cudaStream_t st) {
-  const int dim = x.users.dim;
-  const int32_t* meta_u = x.plan_u.meta + (int64_t)slot * 4;
-  const DevChunk* dc = (const DevChunk*)x.chunk_params;
-  AR_DISPATCH_NV(dim, fwd_head_kernel<NV><<<ceil_div(x.batch, kFwdWarps), kFwdThreads, 0, st>>>(
-                          x.users.W, x.anime.W, dim, dc, slot, x.batch, meta_u, x.uh, x.ah, x.c, x.ru, x.ra, x.fwd_part, head_io(x)));
-  AR_LAUNCH_CHECK();
-  return AR_OK;
-}
-static int launch_update_slot(const ar_train_ctx& x, int slot, bool with_b, cudaStream_t st) {
-  UpdateArgs a{};
-  fill_update(a, 0, &x.users, &x.plan_u, slot, x.ah, x.ru, x.batch);
-  fill_update(a, 1, &x.anime, &x.plan_a, slot, x.uh, x.ra, x.batch);
-  a.dc = (const DevChunk*)x.chunk_params;
-  a.slot = slot;
-  a.use_label = 1;
-  a.batch = x.batch;
-  a.blocks_m = 1;
-  a.metrics = x.metrics;
-  const bool replay = x.mode == AR_ADAM_REPLAY;
-  if (replay) a.health = x.health;
-  if (replay && with_b) {  // B list of slot+1
-    a.blist = x.sched.codes + (int64_t)(slot + 2) * x.sched.cap;
-    a.blist_count = x.sched.counts + (int64_t)(slot + 1) * 4 + 1;
-    a.blocks_b = num_sms();
-  }
-  return launch_update(a, true, x.c, x.dy, x.stepc, x.alpha, x.l2, 0, replay ? 1 : 0, reg_of(x), st);
-}
-
-// The chunk's DAG on streams: main stream F(s) -> U(s); A(s) on low-priority side streams between U(s-depth-1)
-// and F(s).  Capturable (every kernel argument is chunk-invariant; the rest comes from x.chunk_params).
-static int enqueue_chunk(const ar_train_ctx& x, int n_steps, cudaStream_t st, Lookahead* la) {
-  const bool replay = x.mode == AR_ADAM_REPLAY;
-  const int depth = std::max(1, std::min((int)x.depth, AR_SCHED_MAX_DEPTH));
-  const int n_side = depth + 1, R = Lookahead::kRing;
-  int rc;
-  if (replay) AR_CUDA(cudaEventRecord(la->ev_begin, st));  // everything queued before the chunk
-  for (int s = 0; s < n_steps; ++s) {
-    // A(s + depth) may start once U(s - 1) is done; queue the side launches ahead of this step's own kernels
-    if (replay) {
-      const int first = s == 0 ? 0 : s + depth, last = std::min(n_steps - 1, s + depth);
-      for (int a = first; a <= last; ++a) {
-        cudaStream_t sd = la->side[a % n_side];
-        AR_CUDA(cudaStreamWaitEvent(sd, s == 0 ? la->ev_begin : la->ev_u[(s - 1) % R], 0));
-        if ((rc = launch_catchup_list(x, a, sd))) return rc;
-        AR_CUDA(cudaEventRecord(la->ev_a[a % R], sd));
-      }
-      AR_CUDA(cudaStreamWaitEvent(st, la->ev_a[s % R], 0));
-    }
-    if ((rc = launch_fwd_head(x, s, st))) return rc;
-    if ((rc = launch_update_slot(x, s, s + 1 < n_steps, st))) return rc;
-    if (replay) AR_CUDA(cudaEventRecord(la->ev_u[s % R], st));
-  }
-  return AR_OK;
-}
-
-// One instantiated graph per (context, chunk length); a context change (new session, new buffers) rebuilds it.
-struct GraphSlot {
-  ar_train_ctx key;
-  int n_steps = 0;
-  cudaGraphExec_t exec = nullptr;
-  uint64_t stamp = 0;
-};
-static bool same_key(const ar_train_ctx& a, const ar_train_ctx& b) { return memcmp(&a, &b, sizeof(ar_train_ctx)) == 0; }
-static ar_train_ctx graph_key(const ar_train_ctx& x) {
-  ar_train_ctx k;
-  memset(&k, 0, sizeof(k));   // padding bytes too: the key is compared with memcmp
-  k.users = x.users; k.anime = x.anime;
-  k.head = x.head; k.head_m = x.head_m; k.head_v = x.head_v; k.bn_moving = x.bn_moving; k.alpha = x.alpha;
-  k.batch = x.batch; k.l2 = x.l2; k.mode = x.mode;
-  k.plan_u = x.plan_u; k.plan_a = x.plan_a;
-  k.uh = x.uh; k.ah = x.ah; k.c = x.c; k.ru = x.ru; k.ra = x.ra; k.dy = x.dy;
-  k.fwd_part = x.fwd_part; k.head_part = x.head_part; k.stepc = x.stepc; k.ticket = x.ticket; k.metrics = x.metrics;
-  k.reg_acc = x.reg_acc; k.stepw = x.stepw; k.reg_scale = x.reg_scale;
-  k.sched = x.sched; k.depth = x.depth; k.chunk_params = x.chunk_params; k.health = x.health;
-  return k;
-}
-static int chunk_graph(const ar_train_ctx& x, int n_steps, cudaStream_t st, Lookahead* la, cudaGraphExec_t* out) {
-  static GraphSlot cache[64][4];
-  static uint64_t clock_ = 0;
-  int dev = 0;
-  AR_CUDA(cudaGetDevice(&dev));
-  AR_REQUIRE(dev >= 0 && dev < 64, "device index %d out of range", dev);
-  const ar_train_ctx key = graph_key(x);
-  GraphSlot* victim = &cache[dev][0];
-  for (GraphSlot& g : cache[dev]) {
-    if (g.exec && g.n_steps == n_steps && same_key(g.key, key)) {
-      g.stamp = ++clock_;
-      *out = g.exec;
-      return AR_OK;
-    }
-    if (g.stamp < victim->stamp) victim = &g;
-  }
-  cudaGraph_t graph = nullptr;
-  (void)st;
-  AR_CUDA(cudaStreamBeginCapture(la->cap, cudaStreamCaptureModeThreadLocal));
-  int rc = enqueue_chunk(x, n_steps, la->cap, la);
-  cudaError_t e = cudaStreamEndCapture(la->cap, &graph);
-  if (rc) {
-    if (graph) cudaGraphDestroy(graph);
-    return rc;
-  }
-  if (e != cudaSuccess) {
-    ar::set_error("cudaStreamEndCapture: %s", cudaGetErrorString(e));
-    return AR_ERR_CUDA;
-  }
-  cudaGraphExec_t exec = nullptr;
-  e = cudaGraphInstantiate(&exec, graph, 0);
-  cudaGraphDestroy(graph);
-  if (e != cudaSuccess) {
-    ar::set_error("cudaGraphInstantiate: %s", cudaGetErrorString(e));
-    return AR_ERR_CUDA;
-  }
-  if (victim->exec) cudaGraphExecDestroy(victim->exec);
-  victim->key = key;
-  victim->n_steps = n_steps;
-  victim->exec = exec;
-  victim->stamp = ++clock_;
-  *out = exec;
-  return AR_OK;
-}
-
-// Single-GPU step loop.  AR_ADAM_REPLAY and AR_ADAM_TOUCHED go through the chunk DAG (a CUDA graph for chunks of
-// at least kGraphMinSteps steps); AR_ADAM_DENSE and the profiling entry point run stage by stage on one stream.
-constexpr int kGraphMinSteps = 32;
-static int run_steps(const ar_train_ctx& x, int64_t epoch_step0, int32_t slot0, int64_t t0, int32_t n_steps,
-                     cudaStream_t st, StageTimer* timer) {
-  // steps that actually hold samples
-  int live = 0;
-  for (int s = 0; s < n_steps; ++s)
-    if ((epoch_step0 + s) * (int64_t)x.batch < x.n_samples) live = s + 1;
-  n_steps = live;
-  if (n_steps == 0) return AR_OK;
-  const int64_t base0 = epoch_step0 * (int64_t)x.batch;
-  DevChunk* dc = (DevChunk*)x.chunk_params;
-  set_chunk_kernel<<<1, 1, 0, st>>>(dc, t0, x.iu + base0, x.ia + base0, x.label + base0);
-  AR_LAUNCH_CHECK();
-  const bool replay = x.mode == AR_ADAM_REPLAY;
-  int rc;
-  if (!timer && x.mode != AR_ADAM_DENSE) {
-    AR_REQUIRE(slot0 == 0, "ar_train_steps: slot0 must be 0 (the chunk's kernels index the plans by step)");
-    Lookahead* la = lookahead();
-    AR_REQUIRE(la, "ar_train_steps: could not create the look-ahead streams");
-    static const bool no_graph = getenv("AR_NO_GRAPH") != nullptr;
-    if (!no_graph && n_steps >= kGraphMinSteps) {
-      cudaGraphExec_t exec = nullptr;
-      if ((rc = chunk_graph(x, n_steps, st, la, &exec))) return rc;
-      AR_CUDA(cudaGraphLaunch(exec, st));
-      return AR_OK;
-    }
-    return enqueue_chunk(x, n_steps, st, la);
-  }
-  // serial path: dense mode, or per-stage timing (events around every launch)
-  AR_REQUIRE(slot0 == 0, "ar_train_steps: slot0 must be 0");
-  for (int s = 0; s < n_steps; ++s) {
-    const int64_t t = t0 + s + 1;
-    AR_TICK(0);
-    if (replay && (rc = launch_catchup_list(x, s, st))) return rc;
-    AR_TICK(1);
-    if ((rc = launch_fwd_head(x, s, st))) return rc;
-    AR_TICK(2);
-    AR_TICK(3);
-    if ((rc = launch_update_slot(x, s, s + 1 < n_steps, st))) return rc;
-    AR_TICK(4);
-    if (x.mode == AR_ADAM_DENSE) {
-      // every row the batch did not touch takes the same Adam step with the pure L2 gradient
-      if ((rc = launch_flush(&x.users, x.alpha, x.l2, t, reg_of(x), st))) return rc;
-      if ((rc = launch_flush(&x.anime, x.alpha, x.l2, t, reg_of(x), st))) return rc;
-    }
-    AR_TICK(5);
-  }
-  return AR_OK;
 }
 
 static int check_ctx(const ar_train_ctx* ctx, int32_t slot0, int32_t n_steps) {
@@ -1561,12 +1069,19 @@ static int check_ctx(const ar_train_ctx* ctx, int32_t slot0, int32_t n_steps) {
   AR_REQUIRE(x.mode >= AR_ADAM_REPLAY && x.mode <= AR_ADAM_TOUCHED, "ar_train_steps: bad mode %d", x.mode);
   return AR_OK;
 }
-// the single-GPU entry points additionally need the chunk parameters and, in replay mode, the schedule
+}  // namespace ar
+
+#include "chunk.inl"
+
+namespace ar {
+// the single-GPU entry point additionally needs the workspace and, in replay mode, the schedule
 static int check_ctx_single(const ar_train_ctx* ctx, int32_t n_steps) {
   const ar_train_ctx& x = *ctx;
-  AR_REQUIRE(x.chunk_params, "ar_train_steps: null chunk_params");
+  AR_REQUIRE(x.chunk_ws && ((uintptr_t)x.chunk_ws & 255) == 0, "ar_train_steps: chunk_ws null or not 256-byte aligned");
+  AR_REQUIRE(x.health, "ar_train_steps: null health");
   if (x.mode == AR_ADAM_REPLAY) {
-    AR_REQUIRE(x.sched.codes && x.sched.counts, "ar_train_steps: AR_ADAM_REPLAY needs the replay schedule (ar_plan_sched)");
+    AR_REQUIRE(x.sched.codes && x.sched.glen && x.sched.sub && x.sched.cursor,
+               "ar_train_steps: AR_ADAM_REPLAY needs the replay schedule (ar_plan_sched)");
     AR_REQUIRE(x.sched.n_slots >= n_steps && x.sched.cap >= x.plan_u.batch_cap + x.plan_a.batch_cap, "ar_train_steps: schedule too small");
     AR_REQUIRE(x.depth >= 1 && x.depth <= AR_SCHED_MAX_DEPTH, "ar_train_steps: depth %d outside [1,%d]", x.depth, AR_SCHED_MAX_DEPTH);
   }
@@ -1579,34 +1094,24 @@ extern "C" int ar_train_steps(const ar_train_ctx* ctx, int64_t epoch_step0, int3
   int rc = check_ctx(ctx, slot0, n_steps);
   if (rc) return rc;
   if ((rc = check_ctx_single(ctx, n_steps))) return rc;
-  return run_steps(*ctx, epoch_step0, slot0, t0, n_steps, (cudaStream_t)stream, nullptr);
+  AR_REQUIRE(slot0 == 0, "ar_train_steps: slot0 must be 0 (the step kernel indexes the plans by step)");
+  const ar_train_ctx& x = *ctx;
+  int live = 0;   // steps that actually hold samples
+  for (int s = 0; s < n_steps; ++s)
+    if ((epoch_step0 + s) * (int64_t)x.batch < x.n_samples) live = s + 1;
+  if (live == 0) return AR_OK;
+  return launch_chunk(x, epoch_step0, t0, live, (cudaStream_t)stream);
 }
 
-extern "C" int ar_train_steps_profile(const ar_train_ctx* ctx, int64_t epoch_step0, int32_t slot0, int64_t t0,
-                                      int32_t n_steps, float* stage_ms_host, void* stream) {
-  int rc = check_ctx(ctx, slot0, n_steps);
-  if (rc) return rc;
-  if ((rc = check_ctx_single(ctx, n_steps))) return rc;
-  AR_REQUIRE(stage_ms_host, "ar_train_steps_profile: null stage_ms_host");
-  StageTimer tm;
-  tm.st = (cudaStream_t)stream;
-  rc = run_steps(*ctx, epoch_step0, slot0, t0, n_steps, tm.st, &tm);
-  if (rc == AR_OK) {
-    cudaError_t e = cudaStreamSynchronize(tm.st);
-    if (e != cudaSuccess) { ar::set_error("ar_train_steps_profile: %s", cudaGetErrorString(e)); rc = AR_ERR_CUDA; }
-  }
-  for (int i = 0; i < 5; ++i) stage_ms_host[i] = 0.f;
-  if (rc == AR_OK) {
-    for (size_t b = 0; b + 5 < tm.ev.size() + 0 && b + 5 <= tm.ev.size() - 1; b += 6) {
-      for (int i = 0; i < 5; ++i) {
-        float ms = 0.f;
-        cudaEventElapsedTime(&ms, tm.ev[b + i], tm.ev[b + i + 1]);
-        stage_ms_host[i] += ms;
-      }
-    }
-  }
-  for (cudaEvent_t e : tm.ev) cudaEventDestroy(e);
-  return rc;
+extern "C" int ar_chunk_ws_info(int32_t n_slots, int32_t batch_cap, int32_t dim, int64_t* out_host) {
+  AR_REQUIRE(out_host && n_slots > 0 && batch_cap > 0 && dim_ok(dim), "ar_chunk_ws_info: bad arguments");
+  const ChunkLayout l = chunk_layout(n_slots, batch_cap, dim);
+  for (int i = 0; i < 8; ++i) out_host[i] = 0;
+  out_host[0] = (int64_t)l.total;
+  out_host[1] = (int64_t)l.stamps;
+  out_host[2] = (int64_t)(l.ctl + offsetof(ChunkCtl, stats));
+  out_host[3] = kStamps;
+  return AR_OK;
 }
 
 #include "dist.inl"

@@ -440,7 +440,10 @@ class TrainSession:
         self.stepc = torch.zeros(16, **f)
         self.ticket = torch.zeros(1, dtype=torch.int32, device=dev)
         self.sched_ws = torch.zeros(2 * (3 * 2 * P + 4), dtype=torch.int32, device=dev)
-        self.chunk_params = torch.zeros(16, dtype=torch.int64, device=dev)
+        info = (C.c_int64 * 8)()
+        check(lib().ar_chunk_ws_info(self.n_slots, P, D, info), "ar_chunk_ws_info")
+        self._ws_stamps, self._ws_stats, self._ws_nstamps = int(info[1]), int(info[2]), int(info[3])
+        self.chunk_ws = torch.zeros(int(info[0]) // 8, dtype=torch.int64, device=dev)   # persistent step kernel's workspace
         self.health = torch.zeros(4, dtype=torch.int32, device=dev)
         self.depth = max(1, min(REPLAY_DEPTH, _capi.AR_SCHED_MAX_DEPTH))
         self.t_cap = model.iterations + int(total_steps)
@@ -469,11 +472,14 @@ class TrainSession:
     @staticmethod
     def _make_sched(n_slots, batch, dev):
         i32 = dict(dtype=torch.int32, device=dev)
-        bufs = dict(codes=torch.zeros((n_slots, 2 * batch), **i32), counts=torch.zeros((n_slots, 4), **i32),
+        cap = 4 * batch      # room for the long rows' split items (ar_sched)
+        bufs = dict(codes=torch.zeros((n_slots, cap), **i32), glen=torch.zeros((n_slots, cap), **i32),
+                    sub=torch.zeros((n_slots, _capi.AR_SCHED_SUB), **i32),
+                    cursor=torch.zeros((n_slots, _capi.AR_SCHED_SUB), **i32),
                     gap_u=torch.zeros((n_slots, batch), **i32), gap_a=torch.zeros((n_slots, batch), **i32),
                     bounds=torch.zeros((n_slots, _capi.AR_SCHED_PARTS + 1), **i32))
         sc = ArSched()
-        sc.cap, sc.n_slots = 2 * batch, n_slots
+        sc.cap, sc.n_slots = cap, n_slots
         for k, v in bufs.items():
             setattr(sc, k, v.data_ptr())
         return sc, bufs
@@ -511,7 +517,7 @@ class TrainSession:
             ctx.reg_acc, ctx.stepw, ctx.reg_scale = m.reg_acc.data_ptr(), m._stepw.data_ptr(), m.reg_scale
         ctx.sched_ws = self.sched_ws.data_ptr() if os.environ.get("AR_NO_LPT") is None else None
         ctx.depth = self.depth
-        ctx.chunk_params, ctx.health = self.chunk_params.data_ptr(), self.health.data_ptr()
+        ctx.chunk_ws, ctx.health = self.chunk_ws.data_ptr(), self.health.data_ptr()
         return ctx
 
     def _plan_chunk(self, st, iu, ia, s0, ns, t0):
@@ -522,13 +528,13 @@ class TrainSession:
         check(L.ar_plan_build(ptr(ia), N, self.B, s0, ns, C.byref(st["plan_a"]), sp), "ar_plan_build(anime)")
         if m.adam_mode == "replay":
             check(L.ar_plan_sched(C.byref(st["plan_u"]), C.byref(st["plan_a"]), ns, t0 + s0, m._t_flush,
-                                  ptr(m.seenU), m.n_users, ptr(m.seenA), m.n_anime, self.depth,
+                                  ptr(m.seenU), m.n_users, ptr(m.seenA), m.n_anime, self.depth, m.dim,
                                   C.byref(st["sched"]), sp), "ar_plan_sched")
 
-    def run(self, iu, ia, y, lr, profile=None):
+    def run(self, iu, ia, y, lr):
         """Train on every sample of (iu, ia, y) (device int32/int32/float32, visit order) at learning
-        rate `lr`: ceil(n/B) optimizer steps.  Asynchronous on the current stream unless `profile`
-        (a list) is given, in which case per-stage device times [ms] are accumulated into it."""
+        rate `lr`: ceil(n/B) optimizer steps, one persistent kernel per chunk of PLAN_CHUNK steps.
+        Asynchronous on the current stream."""
         m, B = self.model, self.B
         N = iu.numel()
         steps = (N + B - 1) // B
@@ -541,7 +547,7 @@ class TrainSession:
             self._make_sets()
         ctx = self._ctx(iu, ia, y)
         main, L, S = torch.cuda.current_stream(), lib(), self.n_slots
-        per_step = {"replay": 3, "dense": 4, "touched": 2}[m.adam_mode]
+        plan_launches = 7 if m.adam_mode == "replay" else 2
         chunks = [(s0, min(S, steps - s0)) for s0 in range(0, steps, S)]
         self.plan_stream.wait_stream(main)                 # the inputs (H2D copies, the shuffle) are queued on `main`
         with torch.cuda.stream(self.plan_stream):
@@ -558,32 +564,46 @@ class TrainSession:
                     nxt["planned"].record()
             main.wait_event(st["planned"])
             ctx.plan_u, ctx.plan_a, ctx.sched = st["plan_u"], st["plan_a"], st["sched"]
-            sp = stream_ptr(main)
-            if profile is None:
-                tq = time.perf_counter()
-                check(L.ar_train_steps(C.byref(ctx), s0, 0, t0 + s0, ns, sp), "ar_train_steps")
-                self.enqueue_s += time.perf_counter() - tq
-            else:
-                ms = (C.c_float * 5)()
-                check(L.ar_train_steps_profile(C.byref(ctx), s0, 0, t0 + s0, ns, ms, sp), "ar_train_steps_profile")
-                for k in range(5):
-                    profile[k] += ms[k]
+            tq = time.perf_counter()
+            check(L.ar_train_steps(C.byref(ctx), s0, 0, t0 + s0, ns, stream_ptr(main)), "ar_train_steps")
+            self.enqueue_s += time.perf_counter() - tq
             st["consumed"].record(main)
-            self.launches += 1 + ns * per_step             # chunk parameters + (A, F, U) per step; planning is on the side stream
+            self.launches += 1 + plan_launches             # the step kernel + the chunk's planning kernels (side stream)
+            self._last_ns = ns
         main.wait_stream(self.plan_stream)                 # nothing of this call is left on the side stream
         m.iterations = t0 + steps
         self._last_set = self._sets[(len(chunks) - 1) % 2]
         return steps
 
+    def timeline(self):
+        """In-kernel timeline of the LAST chunk run (synchronises): per-step phase durations [us] from CTA 0's
+        %globaltimer stamps and the replay warps' statistics (ar_chunk_ws_info)."""
+        torch.cuda.synchronize()
+        ns, k = self._last_ns, self._ws_nstamps
+        ws = self.chunk_ws.cpu().numpy()
+        st = ws[self._ws_stamps // 8:self._ws_stamps // 8 + self.n_slots * k].reshape(self.n_slots, k)[:ns].astype(np.float64)
+        stats = ws[self._ws_stats // 8:self._ws_stats // 8 + 8]
+        d = lambda a, b: (st[:, b] - st[:, a]) * 1e-3
+        out = dict(steps=ns, gate_us=d(0, 1), fwd_us=d(1, 2), head_us=d(2, 3), update_us=d(3, 4), barrier2_us=d(4, 5),
+                   step_us=np.r_[np.diff(st[:, 0]) * 1e-3, (st[-1, 5] - st[-1, 0]) * 1e-3],
+                   replay_busy_cycles=int(stats[0]), replay_items=int(stats[1]), replay_element_steps=int(stats[2]),
+                   kernel_ns=int(stats[3]), replay_warps=int(stats[4]), kernel_cycles=int(stats[5]))
+        if self.model.adam_mode == "dense":
+            out["dense_us"] = d(5, 6)
+            out["step_us"] = np.r_[np.diff(st[:, 0]) * 1e-3, (st[-1, 6] - st[-1, 0]) * 1e-3]
+        return out
+
     def check_health(self):
-        """Raise if a row update found a row behind schedule (replay schedule and plans out of step)."""
-        if self.model.adam_mode != "replay":
-            return
-        bad = int(self.health[0].item())
-        if bad:
+        """Raise if a wait inside the step kernel timed out, or a row update found a row behind schedule (replay
+        schedule and plans out of step)."""
+        h = self.health.cpu().tolist()
+        if h[1]:
             self.health.zero_()
-            raise _capi.AnimerecError("%d row updates found their row behind the replay schedule; results of this "
-                                      "run are invalid" % bad)
+            raise _capi.AnimerecError("the step kernel aborted: %d CTAs gave up waiting; results of this run are "
+                                      "invalid" % h[1])
+        if h[0] and self.model.adam_mode == "replay":
+            self.health.zero_()
+            raise _capi.AnimerecError("%d row updates found their row behind the replay schedule" % h[0])
 
 
 def load_model(path, device=None, adam_mode="replay"):

@@ -59,19 +59,6 @@ def measure_sfu_peak(dev):
     return 2.0 * 8 * blocks * threads * iters / (best * 1e-3)
 
 
-def sfu_roofline(stage, mode, peak):
-    """rows_catchup against the SFU peak: in steady state the rows touched per step pay off exactly the replay
-    debt all rows accrue per step, i.e. (n_users + n_anime) * dim element-steps of 2 MUFU ops (sqrt, reciprocal)
-    each.  The peak is measured in this process (measure_sfu_peak)."""
-    if mode != "replay" or stage["rows_catchup"]["ms_per_step"] <= 0:
-        return None
-    mufu = 2.0 * (N_USERS + N_ANIME) * DIM
-    ach = mufu / (stage["rows_catchup"]["ms_per_step"] * 1e-3)
-    return dict(bound="sfu", mufu_per_launch=mufu, achieved_mufu_per_s=ach, peak_mufu_per_s=peak, frac=ach / peak,
-                peak_source="measured in this process: sqrt+rcp micro-kernel on all SMs (ar_bench_sfu)",
-                nominal_mufu_per_s=16 * 148 * 1.965e9)
-
-
 def ncu_traffic(kernel, mode):
     """dram__bytes_read.sum + dram__bytes_write.sum per launch of `kernel` from the committed `ncu --set full`
     capture (profiles/ncu_traffic.json, written by tools/ncu_summary.py); None if that kernel was not captured."""
@@ -304,58 +291,66 @@ def gpu_main(args):
         line["config"]["parallelism"] = "dp%d, %s" % (world, {"peer": "row-sharded tables, NVLink peer-memory pulls + flag barriers", "replicated": "replicated tables, NCCL all-gather", "sharded": "row-sharded tables, NCCL all-to-all"}[args.dist])
 
     if rank == 0 and world == 1:
-        # ---- roofline of the dominant kernel: per-stage device time measured live with CUDA events
-        prof = [0.0] * 5
+        # ---- roofline.  The whole step is ONE persistent kernel per 256-step chunk (csrc/chunk.inl), so the dominant
+        # kernel IS the step: achieved = algorithmic bytes per launch / launch duration = step bytes / step time, both
+        # from the timed region above (CUDA events around back-to-back chunk launches).  The kernel's own
+        # %globaltimer stamps (one more, untimed, chunk) split the step into its phases, and the replay warps'
+        # counters give the special-function-pipe utilisation -- the pipe that actually bounds replay mode.
         Kp = 256
         iu2, ia2, y2 = synth(Kp * BATCH, 4242, dev, zipf=args.zipf)
-        sess.run(iu2, ia2, y2, LR, profile=prof)
+        sess.run(iu2, ia2, y2, LR)
+        tl = sess.timeline()
         sess.check_health()
         # distinct rows per step and replay lengths, from the library's own plans / schedule of the steps just run
         ku, ka, ks = sess._last_set["keep"]
         nu_s, na_s = ku["meta"][:Kp, 0].long(), ka["meta"][:Kp, 0].long()
         uu, ua = float(nu_s.float().mean().item()), float(na_s.float().mean().item())
-        col = torch.arange(BATCH, device=dev)[None, :]
-        gu = ks["gap_u"][:Kp].float() * (col < nu_s[:, None])
-        ga = ks["gap_a"][:Kp].float() * (col < na_s[:, None])
-        replay = dict(mean_gap_user_rows=float(gu.sum().item() / max(1, int(nu_s.sum()))),
-                      mean_gap_anime_rows=float(ga.sum().item() / max(1, int(na_s.sum()))),
-                      element_steps_per_step=float((gu.sum() + ga.sum()).item() / Kp * DIM),
-                      depth=sess.depth,
-                      what="gap = steps since the row's previous touch; a row replays gap-1 pure-L2 Adam steps")
-        names = ["rows_catchup", "fwd_head", "unused", "rows_update", "dense_flush"]
         row_b = DIM * 4
-        alg = dict(rows_catchup=(uu + ua) * row_b * 6,
-                   fwd_head=BATCH * row_b * 2 * 2 + BATCH * 32,               # gather 2 rows, save 2 normalised rows; head
-                   unused=0,
-                   rows_update=(uu + ua) * row_b * 6 + BATCH * row_b * 2 + BATCH * 24,
-                   dense_flush=(N_USERS + N_ANIME) * row_b * 6)
-        stage = {n: dict(ms_per_step=prof[i] / Kp, alg_bytes=alg[n],
-                         gbs=(alg[n] / (prof[i] / Kp * 1e-3) / 1e9 if prof[i] > 0 else 0.0)) for i, n in enumerate(names)
-                 if n != "unused"}
-        names = [n for n in names if n != "unused"]
-        dom = max(names, key=lambda n: stage[n]["ms_per_step"])
+        med = lambda v: float(np.median(v[8:])) if len(v) > 16 else float(np.median(v))
+        stage = dict(gate_wait=med(tl["gate_us"]), forward_and_barrier=med(tl["fwd_us"]), head=med(tl["head_us"]),
+                     row_update=med(tl["update_us"]), barrier_after_update=med(tl["barrier2_us"]), step=med(tl["step_us"]))
+        if "dense_us" in tl:
+            stage["dense_pass_and_barrier"] = med(tl["dense_us"])
         sfu_peak = measure_sfu_peak(dev)
         # step-level accounting of SURVEY §8(d): touched rows (replay/touched) or dense
         if mode == "dense":
             step_bytes = (N_USERS + N_ANIME) * row_b * 6 + BATCH * row_b * 2 + BATCH * 12
         else:
             step_bytes = BATCH * row_b * 2 + (uu + ua) * row_b * 6 + BATCH * 12
-        line["roofline"] = dict(bound="hbm", kernel=dom, achieved=stage[dom]["gbs"], peak=pk["hbm_gbs"], unit="GB/s",
-                                frac=stage[dom]["gbs"] / pk["hbm_gbs"], traffic=ncu_traffic(dom, mode),
-                                peak_source=pk["source"],
-                                accounting="dense" if mode == "dense" else "touched-rows",
-                                note=("replay mode: the dominant kernel replays every row's missed dense-L2 Adam steps in "
-                                      "registers and is SFU-bound, not HBM-bound (see `sfu`); extras.train_modes.dense "
-                                      "runs the same arithmetic HBM-bound") if mode == "replay" else None,
-                                sfu=sfu_roofline(stage, mode, sfu_peak),
-                                step=dict(alg_bytes=step_bytes, gbs=step_bytes / (ms / T * 1e-3) / 1e9,
-                                          frac=step_bytes / (ms / T * 1e-3) / 1e9 / pk["hbm_gbs"],
-                                          unique_user_rows=uu, unique_anime_rows=ua,
-                                          sfu_floor_ms=2.0 * (N_USERS + N_ANIME) * DIM / sfu_peak * 1e3 if mode == "replay" else None),
-                                replay=replay if mode == "replay" else None,
-                                stages=stage,
-                                stages_note="stage times are of a serialised run (events around every launch); in the "
-                                            "timed region the catch-up overlaps the forward and the row update")
+        step_s = ms / T * 1e-3
+        gbs = step_bytes / step_s / 1e9
+        line["roofline"] = dict(bound="hbm", kernel="chunk_kernel (the whole training step; %d steps per launch)" % Kp,
+                                achieved=gbs, peak=pk["hbm_gbs"], unit="GB/s", frac=gbs / pk["hbm_gbs"],
+                                traffic=ncu_traffic("chunk", mode), traffic_note="per launch of %d steps" % Kp,
+                                peak_source=pk["source"], accounting="dense" if mode == "dense" else "touched-rows",
+                                alg_bytes_per_step=step_bytes, alg_bytes_per_launch=step_bytes * Kp,
+                                unique_user_rows=uu, unique_anime_rows=ua,
+                                phases_us=stage,
+                                phases_note="medians over the steps of one chunk, %globaltimer stamps written by CTA 0 "
+                                            "inside the kernel: no events, no profiler")
+        if mode == "replay":
+            col = torch.arange(BATCH, device=dev)[None, :]
+            gu = ks["gap_u"][:Kp].float() * (col < nu_s[:, None])
+            ga = ks["gap_a"][:Kp].float() * (col < na_s[:, None])
+            est = 2.0 * (N_USERS + N_ANIME) * DIM           # steady state: every element of both tables, 2 MUFU per step
+            kern_s = tl["kernel_ns"] * 1e-9
+            ach = 2.0 * tl["replay_element_steps"] / kern_s
+            line["roofline"]["note"] = ("replay mode is bound by the special-function pipe, not HBM: every element of both "
+                                        "tables owes one sqrt + one reciprocal per optimizer step whether its row is touched "
+                                        "or not (dense-L2 Adam, SURVEY H1); see `sfu`")
+            line["roofline"]["sfu"] = dict(
+                bound="sfu", mufu_per_step_steady_state=est, sfu_floor_us_per_step=est / sfu_peak * 1e6,
+                achieved_mufu_per_s=ach, peak_mufu_per_s=sfu_peak, frac=ach / sfu_peak,
+                frac_timed_region=est / step_s / sfu_peak,
+                replay_element_steps_in_chunk=tl["replay_element_steps"], chunk_ms=kern_s * 1e3,
+                replay_warps=tl["replay_warps"],
+                replay_warp_busy_frac=tl["replay_busy_cycles"] / max(1.0, float(tl["replay_warps"]) * tl["kernel_cycles"]),
+                peak_source="measured in this process: sqrt+rcp micro-kernel on all SMs (ar_bench_sfu)",
+                nominal_mufu_per_s=16 * 148 * 1.965e9)
+            line["roofline"]["replay"] = dict(
+                mean_gap_user_rows=float(gu.sum().item() / max(1, int(nu_s.sum()))),
+                mean_gap_anime_rows=float(ga.sum().item() / max(1, int(na_s.sum()))),
+                depth=sess.depth, what="gap = steps since the row's previous touch; a row replays gap-1 pure-L2 Adam steps")
 
         # ---- e2e: the public API (Model.fit) fed from pinned HOST buffers, copies inside the timed region
         line["e2e"] = e2e_fit(ar, dev, mode, T, args.zipf)

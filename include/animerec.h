@@ -89,18 +89,29 @@ int ar_plan_link(const ar_plan* plan, int32_t n_steps, const int32_t* uniq_all, 
                  int32_t n_ranks, void* stream);
 
 /* Replay schedule of AR_ADAM_REPLAY, built at plan time (ar_plan_sched) for the same slots as the two plans.
- * With gap = (this step) - (step of the row's previous touch or of the last full flush):
- *   gap == 1            the previous step's own update leaves the row current;
- *   2 <= gap <= depth   B list: replayed by the PREVIOUS step's row-update launch (at most depth-1 steps);
- *   gap > depth         A list, longest replay first: a catch-up launch that may start once step s-depth-1 is done.
- * Slot 0 has no predecessor inside the chunk: every row with gap >= 2 is on its A list. */
-#define AR_SCHED_MAX_DEPTH 8
+ * With gap = (this step) - (step of the row's previous touch or of the last full flush), a distinct row of slot
+ * s with gap >= 2 becomes one ITEM of slot s (rows with gap == 1 are left current by the previous step's own
+ * update): "replay the row's gap-1 missed pure-L2 Adam steps, up to global step t(s)-1".  The item may be
+ * processed as soon as the row's previous touch is complete, and at most `depth` steps before its own step:
+ *   k = min(gap-1, depth, s)      sublist of the item; it is released when step s-k-1 of the chunk is done
+ *                                 (k == s: before the chunk's first step);
+ * within a sublist items are ordered longest replay first (log2 buckets).  Rows with gap >= AR_SCHED_SPLIT_GAP
+ * are split into ceil(dim/32) items of 32 consecutive elements each when the slot's capacity allows (a long
+ * replay is a serial chain per element; splitting shortens its critical path).
+ * Item code: bit 31 table (0 users, 1 anime) | bit 30 split | bits 29..26 part | bits 25..0 row. */
+#define AR_SCHED_MAX_DEPTH 4
+#define AR_SCHED_SUB (AR_SCHED_MAX_DEPTH + 2)  /* stride of sub / cursor */
+#define AR_SCHED_SPLIT_GAP 64
+#define AR_SCHED_MAX_ROWS (1 << 26)
 #define AR_SCHED_PARTS 296   /* row-range parts of the plan-time walk (bounds has n_slots*(AR_SCHED_PARTS+1) entries) */
 typedef struct {
-  int32_t cap;        /* stride of codes; >= plan_u.batch_cap + plan_a.batch_cap */
+  int32_t cap;        /* stride of codes / glen; >= plan_u.batch_cap + plan_a.batch_cap */
   int32_t n_slots;
-  int32_t* codes;     /* [slot][cap]  (table << 31) | row; A list from the front, B list from the back */
-  int32_t* counts;    /* [slot][4]    n_A, n_B, 0, 0 */
+  int32_t* codes;     /* [slot][cap]  item codes, sublist k at [sub[k], sub[k+1]) */
+  int32_t* glen;      /* [slot][cap]  gap of the item's row */
+  int32_t* sub;       /* [slot][AR_SCHED_SUB]  sublist starts; sub[k] for k > depth = number of items of the slot */
+  int32_t* cursor;    /* [slot][AR_SCHED_SUB]  run-time state of the training kernel, zeroed by ar_plan_sched:
+                         [k] items of sublist k handed out so far, [AR_SCHED_SUB-1] items completed */
   int32_t* gap_u;     /* [slot][plan_u.batch_cap] scratch: gap per distinct user row */
   int32_t* gap_a;     /* [slot][plan_a.batch_cap] */
   int32_t* bounds;    /* [n_slots][AR_SCHED_PARTS+1] scratch */
@@ -109,9 +120,10 @@ typedef struct {
 /* Build the schedule of `n_steps` planned slots whose global optimizer steps are t0+1 .. t0+n_steps.
  * seen_u / seen_a: (n_rows) int32, zero-initialised by the caller once and then only passed back: the global step
  * of every row's latest planned touch.  t_flush: global step every row was last brought to by ar_table_flush (0 =
- * never).  Chunks must be scheduled in training order, each exactly once.  Replaces the per-step classify launch. */
+ * never).  dim: embedding dimension (decides the split).  Chunks must be scheduled in training order, each
+ * exactly once, and a schedule is consumed by exactly one ar_train_steps call. */
 int ar_plan_sched(const ar_plan* plan_u, const ar_plan* plan_a, int32_t n_steps, int64_t t0, int64_t t_flush,
-                  int32_t* seen_u, int32_t n_rows_u, int32_t* seen_a, int32_t n_rows_a, int32_t depth,
+                  int32_t* seen_u, int32_t n_rows_u, int32_t* seen_a, int32_t n_rows_a, int32_t depth, int32_t dim,
                   const ar_sched* sched, void* stream);
 
 typedef enum {
@@ -164,28 +176,35 @@ typedef struct {
   /* optional (multi-GPU paths, AR_ADAM_REPLAY): 2 * (3 * (plan_u.batch_cap + plan_a.batch_cap) + 4) int32 of
    * scratch for the per-step classify launch of ar_train_steps_dist / _sharded / _peer; null = plan order */
   int32_t* sched_ws;
-  /* single-GPU AR_ADAM_REPLAY: the plan-time replay schedule (ar_plan_sched) and its look-ahead depth; required */
+  /* single GPU (ar_train_steps): the plan-time replay schedule (AR_ADAM_REPLAY) and its look-ahead depth */
   ar_sched sched;
   int32_t depth;
-  /* (16 x int64) device scratch the step kernels read their per-chunk parameters from (lets a whole chunk of
-   * steps be replayed as one CUDA graph) */
-  void* chunk_params;
+  /* single GPU: device workspace of the persistent step kernel, ar_chunk_ws_info(...)[0] bytes, 256-byte aligned;
+   * holds the grid-barrier state, per-step metric partials, the in-kernel timeline and the heavy-row partials */
+  void* chunk_ws;
   /* (4) int32 device counters, zeroed by the caller: [0] rows a row update found behind schedule (must stay 0 in
-   * AR_ADAM_REPLAY: a non-zero value means the replay schedule and the plans disagree) */
+   * AR_ADAM_REPLAY: a non-zero value means the replay schedule and the plans disagree), [1] waits that timed out
+   * inside the step kernel (the run's results are invalid) */
   int32_t* health;
 } ar_train_ctx;
 
-/* Run `n_steps` consecutive training steps.  Epoch-local step e = epoch_step0 + s reads samples
- * [e*batch, min(n_samples,(e+1)*batch)) and plan slot `slot0 + s`; its global Adam step is
- * t = t0 + s + 1.  Replaces Keras Model.train_step x n_steps. */
+/* Run `n_steps` consecutive training steps as ONE persistent kernel (one CTA per SM): per step a forward phase,
+ * a grid barrier, the head (redundantly and bit-identically in every CTA), the row-update phase, a grid barrier;
+ * in AR_ADAM_REPLAY the other warps of every CTA work through the replay schedule `depth` steps ahead of the
+ * step warps; AR_ADAM_DENSE adds a third phase that moves every other row.
+ * Epoch-local step e = epoch_step0 + s reads samples [e*batch, min(n_samples,(e+1)*batch)) and plan slot s; its
+ * global Adam step is t = t0 + s + 1.  slot0 must be 0.  Replaces Keras Model.train_step x n_steps. */
 int ar_train_steps(const ar_train_ctx* ctx, int64_t epoch_step0, int32_t slot0, int64_t t0,
                    int32_t n_steps, void* stream);
 
-/* Same as ar_train_steps with CUDA events around every launch; synchronises the stream and writes the
- * summed device time (ms) of the five stages to the HOST array stage_ms_host[5]:
- * 0 catch-up, 1 forward, 2 head, 3 row update, 4 dense flush.  Measurement aid for bench.py. */
-int ar_train_steps_profile(const ar_train_ctx* ctx, int64_t epoch_step0, int32_t slot0, int64_t t0,
-                           int32_t n_steps, float* stage_ms_host, void* stream);
+/* Layout of ar_train_ctx.chunk_ws for plans of `n_slots` slots, `batch_cap` samples per step and rows of `dim`
+ * floats.  Writes to the HOST array out[8]: [0] total bytes, [1] byte offset of the timeline: int64
+ * [n_slots][8] %globaltimer stamps (ns) written by CTA 0 for every step of the last ar_train_steps call:
+ * 0 gate entered (waiting for the step's replay items), 1 forward begins, 2 first grid barrier passed, 3 head done,
+ * 4 row update done (CTA 0's share), 5 second grid barrier passed, 6 dense phase done; [2] byte offset of the
+ * statistics: uint64 [8]: 0 cycles replay warps spent inside items (summed over warps), 1 items, 2 replayed
+ * element-steps, 3 kernel wall time (ns), 4 number of replay warps, 5 SM clock cycles of CTA 0 over the kernel. */
+int ar_chunk_ws_info(int32_t n_slots, int32_t batch_cap, int32_t dim, int64_t* out_host);
 
 /* ---- multi-GPU training, replicated tables (one process per GPU, NCCL over NVLink) ----
  * The reference's only data-parallel path is tf.distribute TPUStrategy (neural_network.py:142-147,

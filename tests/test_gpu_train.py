@@ -64,10 +64,11 @@ def test_plan_build_matches_numpy(batch, n_total, n_rows):
         assert set(b["heavy"][s, :nh].tolist()) == heavy
 
 
-@pytest.mark.parametrize("depth", [1, 2, 4])
-def test_plan_sched_matches_numpy(depth):
-    """ar_plan_sched: gaps, A list (longest first by log2 bucket, gap > depth) and B list (2 <= gap <= depth)."""
-    from anime_recommendations_b200._capi import ArSched
+@pytest.mark.parametrize("depth,dim,cap_mult", [(1, 128, 4), (2, 128, 4), (4, 100, 8), (3, 128, 2)])
+def test_plan_sched_matches_numpy(depth, dim, cap_mult):
+    """ar_plan_sched: gaps, items per sublist k = min(gap-1, depth, slot) ordered longest first by log2 bucket,
+    long rows split into ceil(dim/32) part items when the slot's capacity allows, cursors zeroed."""
+    from anime_recommendations_b200._capi import ArSched, AR_SCHED_SUB, AR_SCHED_MAX_DEPTH, AR_SCHED_SPLIT_GAP
     rng = np.random.RandomState(depth)
     n_rows = (5000, 300)
     batch, steps = 512, 9
@@ -77,43 +78,65 @@ def test_plan_sched_matches_numpy(depth):
     for k in range(2):
         check(lib().ar_plan_build(ptr(d_idx[k]), batch * steps, batch, 0, steps, C.byref(plans[k]), stream_ptr()), "plan")
     i32 = dict(dtype=torch.int32, device=DEV)
-    bufs = dict(codes=torch.full((steps, 2 * batch), -3, **i32), counts=torch.zeros((steps, 4), **i32),
+    cap = cap_mult * batch
+    bufs = dict(codes=torch.full((steps, cap), -3, **i32), glen=torch.full((steps, cap), -3, **i32),
+                sub=torch.full((steps, AR_SCHED_SUB), -3, **i32), cursor=torch.full((steps, AR_SCHED_SUB), 7, **i32),
                 gap_u=torch.zeros((steps, batch), **i32), gap_a=torch.zeros((steps, batch), **i32),
                 bounds=torch.zeros((steps, _capi.AR_SCHED_PARTS + 1), **i32))
     sc = ArSched()
-    sc.cap, sc.n_slots = 2 * batch, steps
+    sc.cap, sc.n_slots = cap, steps
     for k, v in bufs.items():
         setattr(sc, k, v.data_ptr())
-    t0, t_flush = 40, 37
+    t0, t_flush = 400, 37
     seen_np = [np.zeros(n, np.int32) for n in n_rows]
     for k in range(2):
-        seen_np[k][rng.rand(n_rows[k]) < 0.5] = rng.randint(1, 41)      # some rows touched before the flush, some after
+        seen_np[k][rng.rand(n_rows[k]) < 0.5] = rng.randint(1, 401)     # some rows touched before the flush, some after
     seen = [dev(x.copy()) for x in seen_np]
     check(lib().ar_plan_sched(C.byref(plans[0]), C.byref(plans[1]), steps, t0, t_flush, ptr(seen[0]), n_rows[0],
-                              ptr(seen[1]), n_rows[1], depth, C.byref(sc), stream_ptr()), "sched")
+                              ptr(seen[1]), n_rows[1], depth, dim, C.byref(sc), stream_ptr()), "sched")
     torch.cuda.synchronize()
     b = {k: v.cpu().numpy() for k, v in bufs.items()}
+    nparts = (dim + 31) // 32
+    n_split = 0
     for s in range(steps):
         t = t0 + s + 1
-        want_a, want_b = {}, set()
+        want = [dict() for _ in range(depth + 1)]            # sublist -> {row code: gap}
         for k in range(2):
             rows = np.unique(idx[k][s * batch:(s + 1) * batch])
             gap = t - np.maximum(seen_np[k][rows], t_flush)
             np.testing.assert_array_equal(b["gap_u" if k == 0 else "gap_a"][s, :len(rows)], gap)
             seen_np[k][rows] = t
             for r, g in zip(rows, gap):
-                code = int(r) | (k << 31)
-                code = code - (1 << 32) if code >= (1 << 31) else code
-                if g >= 2 and (s == 0 or g > depth):
-                    want_a[code] = int(g)
-                elif g >= 2:
-                    want_b.add(code)
-        na, nb = b["counts"][s, 0], b["counts"][s, 1]
-        got_a = b["codes"][s, :na].tolist()
-        assert sorted(got_a) == sorted(want_a) and na == len(want_a)
-        lg = [int(np.floor(np.log2(want_a[c]))) for c in got_a]
-        assert lg == sorted(lg, reverse=True)                       # longest replay first, by log2 bucket
-        assert set(b["codes"][s, 2 * batch - nb:].tolist()) == want_b and nb == len(want_b)
+                if g >= 2:
+                    want[min(int(g) - 1, depth, s)][int(r) | (k << 31)] = int(g)
+        n_rows_s = sum(len(w) for w in want)
+        n_long = sum(1 for w in want for g in w.values() if g >= AR_SCHED_SPLIT_GAP)
+        split = nparts > 1 and n_rows_s + n_long * (nparts - 1) <= cap
+        sub = b["sub"][s]
+        assert (b["cursor"][s] == 0).all()
+        assert sub[0] == 0 and (sub[depth + 1:] == sub[depth + 1]).all()
+        for k in range(depth + 1):
+            codes = b["codes"][s, sub[k]:sub[k + 1]].astype(np.int64) & 0xffffffff
+            gl = b["glen"][s, sub[k]:sub[k + 1]]
+            got = {}
+            for c, g in zip(codes.tolist(), gl.tolist()):
+                key = c & ~(0x1f << 26) & ~(1 << 30) & 0xffffffff
+                if c & (1 << 30):
+                    assert split and g >= AR_SCHED_SPLIT_GAP
+                    got.setdefault(key, []).append((c >> 26) & 15)
+                else:
+                    assert not (split and g >= AR_SCHED_SPLIT_GAP)
+                    assert key not in got
+                    got[key] = None
+                assert want[k][key] == g
+            assert set(got) == set(want[k])
+            for parts in got.values():
+                if parts is not None:
+                    assert sorted(parts) == list(range(nparts))
+                    n_split += 1
+            lg = [int(np.floor(np.log2(g))) for g in gl.tolist()]
+            assert lg == sorted(lg, reverse=True)                   # longest replay first, by log2 bucket
+    assert (n_split > 0) == (cap_mult >= 4)
     for k in range(2):
         np.testing.assert_array_equal(seen[k].cpu().numpy(), seen_np[k])
 
@@ -255,14 +278,15 @@ def test_fit_matches_reference_arithmetic(mode, dim, heavy):
     assert p.shape == (500, 1) and p.dtype == np.float32
 
 
-@pytest.mark.parametrize("depth", [1, 2, 3])
-def test_graph_chunks_match_oracle(depth, monkeypatch):
-    """Many short steps: full 256-step chunks replayed as CUDA graphs plus a partial chunk, planning double-buffered
-    on the side stream, at several look-ahead depths; rows, slots and the exact epoch loss against the oracle."""
+@pytest.mark.parametrize("depth", [1, 2, 3, 4])
+def test_multi_chunk_epochs_match_oracle(depth, monkeypatch):
+    """Many short steps: a full 256-step chunk plus a partial one per epoch (one persistent kernel each), planning
+    double-buffered on the side stream, at every look-ahead depth; rows, slots and the exact epoch loss against the
+    oracle."""
     from anime_recommendations_b200 import model as model_mod
     monkeypatch.setattr(model_mod, "REPLAY_DEPTH", depth)
     n_users, n_anime, dim, B = 600, 70, 32, 64
-    n = B * 300 + 17                                    # 301 steps / epoch: 256 (graph) + 45 (graph, partial last batch)
+    n = B * 300 + 17                                    # 301 steps / epoch: 256 + 45 (partial last batch)
     iu, ia, y = _problem(51 + depth, n_users, n_anime, n)
     st = ot.init_state(n_users, n_anime, dim, seed=9, w=0.7)
     m = _model_from_state(st, "replay")
