@@ -16,7 +16,7 @@ AR_MAX_BATCH = 16384
 AR_HEAVY_LEN = 64
 AR_SCHED_MAX_DEPTH = 4
 AR_SCHED_SUB = AR_SCHED_MAX_DEPTH + 2
-AR_SCHED_SPLIT_GAP = 64
+AR_SCHED_SPLIT_GAP = 256
 AR_SCHED_PARTS = 296
 ADAM_REPLAY, ADAM_DENSE, ADAM_TOUCHED = 0, 1, 2
 ADAM_MODES = {"replay": ADAM_REPLAY, "dense": ADAM_DENSE, "touched": ADAM_TOUCHED}
@@ -130,6 +130,8 @@ SIGNATURES = {
     "ar_eval_sums": (C.c_int, [_P, _P, _I32, _P, _P, _P, _P, _P, _I64, _P, _P]),
     "ar_sumsq": (C.c_int, [_P, _I64, _P, _P]),
     "ar_bench_sfu": (C.c_int, [_P, _I32, _I32, _I32, _P]),
+    "ar_user_favourites": (C.c_int, [_P, _P, _I32, C.c_double, _P, _P, _P]),
+    "ar_user_recs": (C.c_int, [_P, _P, _P, _I32, _P, _I32, _P, _I32, _I32, _P, _P, _P]),
     "ar_rownorm": (C.c_int, [_P, _I64, _I32, _P, _P]),
     "ar_topk_query_workspace": (C.c_int64, [_I64, _I32]),
     "ar_cosine_topk_query": (C.c_int, [_P, _I64, _I32, _I64, _P, _I64, _I32, _P, _P, _P, _P]),

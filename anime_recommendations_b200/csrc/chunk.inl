@@ -43,12 +43,6 @@ namespace ar {
 #ifndef AR_REGS_STEP
 #define AR_REGS_STEP 88           // ... the step warps grow to
 #endif
-#ifndef AR_PAIR_U
-#define AR_PAIR_U 0               // row update: two rows in flight per warp
-#endif
-#ifndef AR_PAIR_F
-#define AR_PAIR_F 1               // forward: two samples in flight per warp
-#endif
 constexpr int kStepWarps = AR_STEP_WARPS;
 constexpr int kStepThreads = kStepWarps * 32;
 static_assert(kStepWarps % 4 == 0 && kStepWarps <= 32, "step warps come in warpgroups");
@@ -69,7 +63,7 @@ struct ChunkCtl {            // first 256 bytes of the workspace; zeroed before 
 static_assert(sizeof(ChunkCtl) == 256, "ChunkCtl is 256 bytes");
 
 struct ChunkLayout {
-  size_t ctl, htick, fpart, mpart, stamps, hpart, stash1, total, zero_bytes;
+  size_t ctl, htick, fpart, hsum, mpart, stamps, hpart, stash1, total, zero_bytes;
   int n_pieces;              // capacity of hpart / htick per table
 };
 static ChunkLayout chunk_layout(int n_slots, int batch_cap, int dim) {
@@ -80,7 +74,8 @@ static ChunkLayout chunk_layout(int n_slots, int batch_cap, int dim) {
   l.htick = 256;
   l.zero_bytes = up(l.htick + (size_t)2 * l.n_pieces * sizeof(int32_t));
   l.fpart = l.zero_bytes;
-  l.mpart = up(l.fpart + (size_t)kMaxCtas * 2 * sizeof(double));
+  l.hsum = up(l.fpart + (size_t)kMaxCtas * 2 * sizeof(double));
+  l.mpart = up(l.hsum + (size_t)kMaxCtas * 8 * sizeof(double));
   l.stamps = up(l.mpart + (size_t)n_slots * kMaxCtas * 2 * sizeof(double));
   l.hpart = up(l.stamps + (size_t)n_slots * kStamps * sizeof(long long));
   l.stash1 = up(l.hpart + (size_t)2 * l.n_pieces * (dim + 4) * sizeof(float));
@@ -109,6 +104,7 @@ struct ChunkArgs {
   float* ru[2];
   float* ra[2];
   double* fwd_part;
+  double* hsum;              // [cta][8] per-CTA partial sums of the head's second pass
   float* metrics;
   RegAcc reg;
   int32_t* health;
@@ -178,22 +174,19 @@ __device__ __forceinline__ bool spin_until_ge(const int* p, int want, ChunkCtl* 
   return ld_acquire_s32(p) >= want;
 }
 
-// Grid barrier over the step warps of all CTAs.  Arrivals are counted monotonically (no reset race): barrier b
-// completes when arrive == n_ctas * b.  Returns false once the chunk is aborted.
+// Grid barrier over the step warps of all CTAs.  Arrivals are counted monotonically (no reset race): barrier b is
+// complete when arrive == n_ctas * b.  One release-reduction per CTA, everyone polls the counter itself (no
+// "last arriver publishes a generation" hop).  Returns false once the chunk is aborted.
 __device__ __forceinline__ bool grid_bar(ChunkCtl* ctl, unsigned& bar, int n_ctas, volatile int* abort_s) {
   step_bar();
   ++bar;
   if (threadIdx.x == 0) {
-    __threadfence();
-    const unsigned old = atomicAdd(&ctl->arrive, 1u);
-    if (old == (unsigned)n_ctas * bar - 1u) {
-      __threadfence();
-      st_release_u32(&ctl->gen, bar);
-    } else if (!spin_until_ge(reinterpret_cast<const int*>(&ctl->gen), (int)bar, ctl)) {
+    // release: this CTA's writes (ordered before by the CTA barrier above) are visible before the arrival
+    asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(&ctl->arrive) : "memory");
+    if (!spin_until_ge(reinterpret_cast<const int*>(&ctl->arrive), (int)((unsigned)n_ctas * bar), ctl)) {
       *abort_s = 1;
       atomicExch(&ctl->abort, 1);
     }
-    __threadfence();
   }
   step_bar();
   return *abort_s == 0;
@@ -347,6 +340,27 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
+// Rows travel global -> shared with cp.async (no registers while in flight) and are read back by the lane that
+// copied them, so a wait_group is all the synchronisation a TILE needs.  Two buffers per warp while shared memory
+// allows it (the next row / sample pair is in flight during the current one's arithmetic).
+template <int NV> struct StageCfg { static constexpr int kBufs = NV <= 2 ? 2 : 1; };
+template <int NV>
+__device__ __forceinline__ void stage_tile(float4* dst, const float* row, int d4, int lane) {
+#pragma unroll
+  for (int k = 0; k < NV; ++k) {
+    const int j = lane + 32 * k;
+    if (j < d4) cp_async16(dst + j, row + 4 * j);
+  }
+}
+template <int NV>
+__device__ __forceinline__ void tile_from_stage(RowTile<NV>& t, const float4* src, int d4, int lane) {
+#pragma unroll
+  for (int k = 0; k < NV; ++k) {
+    const int j = lane + 32 * k;
+    t.x[k] = (j < d4) ? src[j] : make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+}
+
 // stage: [3][32*NV] float4 (W, m, v of one row)
 template <int NV>
 __device__ __forceinline__ void item_prefetch(const ChunkArgs& a, int code, float4* stage, int lane) {
@@ -450,7 +464,8 @@ constexpr int kReplayBatch = 4;  // items per grab
 template <int NV>
 __device__ void replay_role(const ChunkArgs& a, StepSmem& sm, float4* stage_all) {
   const int lane = threadIdx.x & 31;
-  float4* stage = stage_all + (size_t)((threadIdx.x >> 5) - kStepWarps) * (2 * 96 * NV);   // two row buffers per warp
+  constexpr int kBufs = StageCfg<NV>::kBufs;
+  float4* stage = stage_all + (size_t)((threadIdx.x >> 5) - kStepWarps) * (kBufs * 96 * NV);   // row buffers of this warp
   ChunkCtl* ctl = a.ctl;
   const int D = a.depth, Wd = D + 1;
   const int aidx = lane / Wd, k = lane - aidx * Wd;
@@ -508,14 +523,15 @@ __device__ void replay_role(const ChunkArgs& a, StepSmem& sm, float4* stage_all)
     for (int j = 0; j < nit; ++j) {
       const int cj = __shfl_sync(0xffffffffu, code, j), gj = __shfl_sync(0xffffffffu, g, j);
       const int cn = __shfl_sync(0xffffffffu, code, (j + 1) & 31);
-      if (j + 1 < nit) {         // next item on its way, then wait for this one only
+      if (kBufs == 2 && j + 1 < nit) {   // next item on its way, then wait for this one only
         item_prefetch<NV>(a, cn, stage + (size_t)((j + 1) & 1) * (96 * NV), lane);
         cp_async_wait<1>();
       } else {
+        if (kBufs == 1 && j > 0) item_prefetch<NV>(a, cj, stage, lane);
         cp_async_wait<0>();
       }
       __syncwarp();
-      replay_item<NV>(a, tabs, cj, gj, t_to, stage + (size_t)(j & 1) * (96 * NV), lane, regfix);
+      replay_item<NV>(a, tabs, cj, gj, t_to, stage + (size_t)(j & (kBufs - 1)) * (96 * NV), lane, regfix);
       elsteps += (unsigned long long)(gj - 1) * (((unsigned)cj & kCodeSplit) ? 32u : (unsigned)a.tab[0].dim);
       __syncwarp();              // buffer j&1 is free for item j+2
     }
@@ -641,8 +657,9 @@ __device__ __forceinline__ void finish_loaded(const ChunkArgs& a, const StepTabs
 }
 
 template <int NV>
-__device__ void step_role(const ChunkArgs& a, StepSmem& sm, int n_threads) {
+__device__ void step_role(const ChunkArgs& a, StepSmem& sm, int n_threads, float4* step_stage) {
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  float4* sbuf = step_stage + (size_t)wid * (StageCfg<NV>::kBufs * 128 * NV);
   const int n_ctas = gridDim.x;
   const int gw = blockIdx.x * kStepWarps + wid, ngw = n_ctas * kStepWarps;
   const int dim = a.tab[0].dim, d4 = dim >> 2;
@@ -650,7 +667,7 @@ __device__ void step_role(const ChunkArgs& a, StepSmem& sm, int n_threads) {
   ChunkCtl* ctl = a.ctl;
   const StepTabs tabs{a.alpha, a.reg.stepw, &sm};
   const bool stamp = blockIdx.x == 0 && tid == 0;
-  constexpr bool kPairF = AR_PAIR_F && NV <= 2, kPairU = AR_PAIR_U && NV == 1;   // two in flight while the registers allow it
+  constexpr int kBufs = StageCfg<NV>::kBufs, kBuf4 = 128 * NV;   // staging buffers of 4 tiles (float4 units)
   unsigned bar = 0;
   unsigned long long regfix = 0;
   const unsigned long long wall0 = stamp ? globaltimer_ns() : 0ull;
@@ -715,28 +732,43 @@ __device__ void step_role(const ChunkArgs& a, StepSmem& sm, int n_threads) {
           __threadfence();
         }
         if (stamp && base == f0) stamps[1] = (long long)globaltimer_ns();
-        for (int j = 0; j < cnt; j += kPairF ? 2 : 1) {
-          const bool two = kPairF && j + 1 < cnt;
-          const int j1 = two ? j + 1 : j;
+        // sample pairs through the staging buffers: [u0 | a0 | u1 | a1]
+        const int np = (cnt + 1) >> 1;
+        auto prefetch_pair = [&](int pi, float4* buf) {
+          const int j = 2 * pi, j1 = min(j + 1, cnt - 1);
           const int u0 = __shfl_sync(0xffffffffu, my_u, j), a0 = __shfl_sync(0xffffffffu, my_a, j);
           const int u1 = __shfl_sync(0xffffffffu, my_u, j1), a1 = __shfl_sync(0xffffffffu, my_a, j1);
-          RowTile<NV> x0, y0, x1, y1;
-          tile_load_cg<NV>(x0, U + (size_t)u0 * dim, d4, lane);
-          tile_load_cg<NV>(y0, A + (size_t)a0 * dim, d4, lane);
-          if (kPairF) {
-            tile_load_cg<NV>(x1, U + (size_t)u1 * dim, d4, lane);
-            tile_load_cg<NV>(y1, A + (size_t)a1 * dim, d4, lane);
+          stage_tile<NV>(buf, U + (size_t)u0 * dim, d4, lane);
+          stage_tile<NV>(buf + 32 * NV, A + (size_t)a0 * dim, d4, lane);
+          stage_tile<NV>(buf + 64 * NV, U + (size_t)u1 * dim, d4, lane);
+          stage_tile<NV>(buf + 96 * NV, A + (size_t)a1 * dim, d4, lane);
+          cp_async_commit();
+        };
+        prefetch_pair(0, sbuf);
+        for (int pi = 0; pi < np; ++pi) {
+          const int j = 2 * pi;
+          const bool two = j + 1 < cnt;
+          if (kBufs == 2 && pi + 1 < np) {
+            prefetch_pair(pi + 1, sbuf + (size_t)((pi + 1) & 1) * kBuf4);
+            cp_async_wait<1>();
+          } else {
+            cp_async_wait<0>();
           }
+          const float4* b4 = sbuf + (size_t)(pi & (kBufs - 1)) * kBuf4;
+          RowTile<NV> x0, y0, x1, y1;
+          tile_from_stage<NV>(x0, b4, d4, lane);
+          tile_from_stage<NV>(y0, b4 + 32 * NV, d4, lane);
+          tile_from_stage<NV>(x1, b4 + 64 * NV, d4, lane);
+          tile_from_stage<NV>(y1, b4 + 96 * NV, d4, lane);
+          if (kBufs == 1 && pi + 1 < np) prefetch_pair(pi + 1, sbuf);   // the buffer is in registers now
           float su0 = tile_partial_dot<NV>(x0, x0), sa0 = tile_partial_dot<NV>(y0, y0);
-          float su1 = kPairF ? tile_partial_dot<NV>(x1, x1) : 1.f, sa1 = kPairF ? tile_partial_dot<NV>(y1, y1) : 1.f;
+          float su1 = tile_partial_dot<NV>(x1, x1), sa1 = tile_partial_dot<NV>(y1, y1);
 #pragma unroll
           for (int o = 16; o > 0; o >>= 1) {
             su0 += __shfl_xor_sync(0xffffffffu, su0, o);
             sa0 += __shfl_xor_sync(0xffffffffu, sa0, o);
-            if (kPairF) {
-              su1 += __shfl_xor_sync(0xffffffffu, su1, o);
-              sa1 += __shfl_xor_sync(0xffffffffu, sa1, o);
-            }
+            su1 += __shfl_xor_sync(0xffffffffu, su1, o);
+            sa1 += __shfl_xor_sync(0xffffffffu, sa1, o);
           }
           const float ru0 = 1.0f / sqrtf(fmaxf(su0, kL2NormEps)), ra0 = 1.0f / sqrtf(fmaxf(sa0, kL2NormEps));
           const float ru1 = 1.0f / sqrtf(fmaxf(su1, kL2NormEps)), ra1 = 1.0f / sqrtf(fmaxf(sa1, kL2NormEps));
@@ -744,16 +776,14 @@ __device__ void step_role(const ChunkArgs& a, StepSmem& sm, int n_threads) {
           for (int k = 0; k < NV; ++k) {
             x0.x[k] = scale4(x0.x[k], ru0);
             y0.x[k] = scale4(y0.x[k], ra0);
-            if (kPairF) {
-              x1.x[k] = scale4(x1.x[k], ru1);
-              y1.x[k] = scale4(y1.x[k], ra1);
-            }
+            x1.x[k] = scale4(x1.x[k], ru1);
+            y1.x[k] = scale4(y1.x[k], ra1);
           }
-          float cs0 = tile_partial_dot<NV>(x0, y0), cs1 = kPairF ? tile_partial_dot<NV>(x1, y1) : 0.f;
+          float cs0 = tile_partial_dot<NV>(x0, y0), cs1 = tile_partial_dot<NV>(x1, y1);
 #pragma unroll
           for (int o = 16; o > 0; o >>= 1) {
             cs0 += __shfl_xor_sync(0xffffffffu, cs0, o);
-            if (kPairF) cs1 += __shfl_xor_sync(0xffffffffu, cs1, o);
+            cs1 += __shfl_xor_sync(0xffffffffu, cs1, o);
           }
           const int s0 = base + j;
           x0.store(uh + (size_t)s0 * dim, d4, lane);
@@ -800,8 +830,52 @@ __device__ void step_role(const ChunkArgs& a, StepSmem& sm, int n_threads) {
     if (flags && tid == 0) *(volatile int*)&sm.steps_done = s;
     if (stamp) stamps[2] = (long long)globaltimer_ns();
 
-    // ---- head: identical arithmetic, identical order in every CTA
+    // ---- U, part 0: what this warp's rows need that does not depend on the head -- issued now, so that the loads
+    // (and the first row's gathers) are in flight while the head is computed
     const float* __restrict__ label = a.label + (size_t)s * a.batch;
+    const int nu = a.plan[0].meta[(size_t)s * 4], na = a.plan[1].meta[(size_t)s * 4];
+    const int tot = nu + na;
+    const int RU = (tot + ngw - 1) / ngw;
+    const int r0 = min(tot, gw * RU), r1 = min(tot, r0 + RU);
+    // lane j: everything row `base + j` needs before its gathers
+    int row_l = 0, beg_l = 0, len_l = 0, s0_l = 0, last_l = 0, which_l = 0;
+    float lab_l = 0.f, c0_l = 0.f, rinv_l = 0.f;
+    auto load_meta = [&](int base, int cnt) {
+      const int idx = base + lane;
+      which_l = idx >= nu ? 1 : 0;
+      if (lane < cnt) {
+        const ar_plan& pl = a.plan[which_l];
+        const int seg = which_l ? idx - nu : idx;
+        row_l = pl.uniq[(size_t)s * pl.batch_cap + seg];
+        const int32_t* off = pl.off + (size_t)s * (pl.batch_cap + 1);
+        beg_l = off[seg];
+        len_l = off[seg + 1] - beg_l;
+        s0_l = pl.order[(size_t)s * pl.batch_cap + beg_l];
+        c0_l = __ldcg(cc + s0_l);
+        lab_l = __ldg(label + s0_l);
+        rinv_l = __ldcg((which_l ? rav : ruv) + s0_l);
+        last_l = __ldcg(a.tab[which_l].last_step + row_l);
+      }
+    };
+    // row j of the block -> staging buffer [other row of its first sample | W | m | v]
+    auto prefetch_row = [&](int j, float4* buf) {
+      const int w = __shfl_sync(0xffffffffu, which_l, j), row = __shfl_sync(0xffffffffu, row_l, j);
+      const int len = __shfl_sync(0xffffffffu, len_l, j), sx = __shfl_sync(0xffffffffu, s0_l, j);
+      if (len <= AR_HEAVY_LEN) {
+        const ar_table& tj = a.tab[w];
+        stage_tile<NV>(buf, (w ? uh : ah) + (size_t)sx * dim, d4, lane);
+        stage_tile<NV>(buf + 32 * NV, tj.W + (size_t)row * dim, d4, lane);
+        stage_tile<NV>(buf + 64 * NV, tj.m + (size_t)row * dim, d4, lane);
+        stage_tile<NV>(buf + 96 * NV, tj.v + (size_t)row * dim, d4, lane);
+      }
+      cp_async_commit();
+    };
+    if (r0 < r1) {
+      load_meta(r0, min(32, r1 - r0));
+      prefetch_row(0, sbuf);
+    }
+
+    // ---- head: identical arithmetic, identical order in every CTA
     {
       double s0 = 0.0, s1 = 0.0;
       {
@@ -820,45 +894,50 @@ __device__ void step_role(const ChunkArgs& a, StepSmem& sm, int n_threads) {
       s0 = warp_sum(s0);
       s1 = warp_sum(s1);
       const HeadScalars h = head_scalars(sm.head, s0, s1, n);
-      // the reported metrics: this CTA's share of the samples
+      // second pass, distributed: this CTA's share of the samples (one per thread) -> 5 backward sums + the reported
+      // BCE / squared error; per-CTA partials, a second grid barrier, then every CTA adds them in CTA order
       const int mshare = (n + n_ctas - 1) / n_ctas;
-      const int mlo = blockIdx.x * mshare, mhi = min(n, mlo + mshare);
       double acc[7];
 #pragma unroll
       for (int i = 0; i < 7; ++i) acc[i] = 0.0;
-      constexpr int kU = 4;
-      for (int base = 0; base < n; base += kU * kStepThreads) {
-        float cr[kU], tr[kU];
-#pragma unroll
-        for (int k = 0; k < kU; ++k) {
-          const int i = base + k * kStepThreads + tid;
-          cr[k] = i < n ? __ldcg(cc + i) : 0.f;
-          tr[k] = i < n ? __ldg(label + i) : 0.f;
-        }
-        float f[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
-#pragma unroll
-        for (int k = 0; k < kU; ++k) {
-          const int i = base + k * kStepThreads + tid;
-          if (i < n) {
-            const float zh = ((h.w * cr[k] + h.b) - h.mu) * h.inv;
-            const float y = h.gamma * zh + h.beta;
-            const float p = sigmoidf_(y);
-            const float dy = (p - tr[k]) * h.rn;
-            f[0] += dy;
-            f[1] = fmaf(dy, zh, f[1]);
-            f[2] += zh;
-            f[3] = fmaf(dy, cr[k], f[3]);
-            f[4] = fmaf(zh, cr[k], f[4]);
-            if (i >= mlo && i < mhi) {
-              acc[5] += (double)bce_logits(y, tr[k]);
-              acc[6] += (double)((tr[k] - p) * (tr[k] - p));
-            }
-          }
-        }
-#pragma unroll
-        for (int i = 0; i < 5; ++i) acc[i] += (double)f[i];
+      for (int i = blockIdx.x * mshare + tid; i < min(n, (blockIdx.x + 1) * mshare); i += kStepThreads) {
+        const float ci = __ldcg(cc + i), ti = __ldg(label + i);
+        const float zh = ((h.w * ci + h.b) - h.mu) * h.inv;
+        const float y = h.gamma * zh + h.beta;
+        const float p = sigmoidf_(y);
+        const float dy = (p - ti) * h.rn;
+        acc[0] += (double)dy;
+        acc[1] += (double)(dy * zh);
+        acc[2] += (double)zh;
+        acc[3] += (double)(dy * ci);
+        acc[4] += (double)(zh * ci);
+        acc[5] += (double)bce_logits(y, ti);
+        acc[6] += (double)((ti - p) * (ti - p));
       }
       step_block_sum<7>(acc, sm.red);
+      if (tid < 7) a.hsum[(size_t)blockIdx.x * 8 + tid] = acc[tid];
+      if (tid == 64) {
+        double* mp = a.mpart + ((size_t)s * kMaxCtas + blockIdx.x) * 2;
+        mp[0] = acc[5];
+        mp[1] = acc[6];
+      }
+      if (!grid_bar(ctl, bar, n_ctas, &sm.abort)) break;
+      if (wid < 5) {            // warp i adds sum i over the CTAs, in CTA order
+        double pv[kMaxCtas / 32];
+#pragma unroll
+        for (int r = 0; r < kMaxCtas / 32; ++r) {     // all loads in flight together
+          const int c = lane + 32 * r;
+          pv[r] = c < n_ctas ? __ldcg(a.hsum + (size_t)c * 8 + wid) : 0.0;
+        }
+        double t5 = 0.0;
+#pragma unroll
+        for (int r = 0; r < kMaxCtas / 32; ++r) t5 += pv[r];
+        t5 = warp_sum(t5);
+        if (lane == 0) sm.red[wid] = t5;
+      }
+      step_bar();
+#pragma unroll
+      for (int i = 0; i < 5; ++i) acc[i] = sm.red[i];
       const double S1 = acc[0], S2 = acc[1], Szh = acc[2], Sdyc = acc[3], Szhc = acc[4], Sc = s0;
       const double ig = (double)h.inv * (double)h.gamma;
       if (tid < 4) {
@@ -887,9 +966,6 @@ __device__ void step_role(const ChunkArgs& a, StepSmem& sm, int n_threads) {
         sm.stepc[K_BETA] = h.beta;
         sm.stepc[K_FN] = h.fn;
         sm.stepc[K_RN] = h.rn;
-        double* mp = a.mpart + ((size_t)s * kMaxCtas + blockIdx.x) * 2;
-        mp[0] = acc[5];
-        mp[1] = acc[6];
         if (blockIdx.x == 0) {
           float* row = a.metrics + t * 4;
           row[2] = h.fn;
@@ -900,61 +976,36 @@ __device__ void step_role(const ChunkArgs& a, StepSmem& sm, int n_threads) {
     }
     if (stamp) stamps[3] = (long long)globaltimer_ns();
 
-    // ---- U: this warp's share of the step's distinct rows (users first, then anime)
+    // ---- U: this warp's share of the step's distinct rows (users first, then anime), through the staging buffers
     {
       const float* kk = sm.stepc;   // read at the use sites: shared-memory loads are cheaper than 11 live registers
-      const int nu = a.plan[0].meta[(size_t)s * 4], na = a.plan[1].meta[(size_t)s * 4];
-      const int tot = nu + na;
-      const int RU = (tot + ngw - 1) / ngw;
-      const int r0 = min(tot, gw * RU), r1 = min(tot, r0 + RU);
       int32_t* pend = nullptr;      // flag of the row stored last, published behind the next row's arithmetic
       for (int base = r0; base < r1; base += 32) {
         const int cnt = min(32, r1 - base);
-        // lane j: everything row `base + j` needs before its gathers
-        int row_l = 0, beg_l = 0, len_l = 0, s0_l = 0, last_l = 0;
-        float d0_l = 0.f, c0_l = 0.f, rinv_l = 0.f;
-        const int idx = base + lane;
-        const int which_l = idx >= nu ? 1 : 0;
-        if (lane < cnt) {
-          const ar_plan& pl = a.plan[which_l];
-          const int seg = which_l ? idx - nu : idx;
-          row_l = pl.uniq[(size_t)s * pl.batch_cap + seg];
-          const int32_t* off = pl.off + (size_t)s * (pl.batch_cap + 1);
-          beg_l = off[seg];
-          len_l = off[seg + 1] - beg_l;
-          s0_l = pl.order[(size_t)s * pl.batch_cap + beg_l];
-          c0_l = __ldcg(cc + s0_l);
-          d0_l = dc_of_label(c0_l, __ldg(label + s0_l), kk);
-          rinv_l = __ldcg((which_l ? rav : ruv) + s0_l);
-          last_l = __ldcg(a.tab[which_l].last_step + row_l);
+        if (base != r0) {
+          load_meta(base, cnt);
+          prefetch_row(0, sbuf);
         }
-        for (int j = 0; j < cnt; j += kPairU ? 2 : 1) {
-          const bool two = kPairU && j + 1 < cnt;
-          const int j1 = two ? j + 1 : j;
-          // row A = j, row B = j1 (B is skipped when !two)
-          const int wA = __shfl_sync(0xffffffffu, which_l, j), wB = __shfl_sync(0xffffffffu, which_l, j1);
-          const int rowA = __shfl_sync(0xffffffffu, row_l, j), rowB = __shfl_sync(0xffffffffu, row_l, j1);
-          const int lenA = __shfl_sync(0xffffffffu, len_l, j), lenB = __shfl_sync(0xffffffffu, len_l, j1);
-          const int sA = __shfl_sync(0xffffffffu, s0_l, j), sB = __shfl_sync(0xffffffffu, s0_l, j1);
-          const bool doA = lenA <= AR_HEAVY_LEN, doB = two && lenB <= AR_HEAVY_LEN;
-          const ar_table& tA = a.tab[wA];
-          const ar_table& tB = a.tab[wB];
-          const float* __restrict__ otherA = wA ? uh : ah;
-          const float* __restrict__ otherB = wB ? uh : ah;
-          RowTile<NV> accA, accB, wa, ma, va, wb, mb, vb;
-          if (doA) {
-            tile_load_cg<NV>(accA, otherA + (size_t)sA * dim, d4, lane);
-            tile_load_cg<NV>(wa, tA.W + (size_t)rowA * dim, d4, lane);
-            tile_load_cg<NV>(ma, tA.m + (size_t)rowA * dim, d4, lane);
-            tile_load_cg<NV>(va, tA.v + (size_t)rowA * dim, d4, lane);
+        const float d0_l = dc_of_label(c0_l, lab_l, kk);
+        for (int j = 0; j < cnt; ++j) {
+          if (kBufs == 2 && j + 1 < cnt) {
+            prefetch_row(j + 1, sbuf + (size_t)((j + 1) & 1) * kBuf4);
+            cp_async_wait<1>();
+          } else {
+            cp_async_wait<0>();
           }
-          if (doB) {
-            tile_load_cg<NV>(accB, otherB + (size_t)sB * dim, d4, lane);
-            tile_load_cg<NV>(wb, tB.W + (size_t)rowB * dim, d4, lane);
-            tile_load_cg<NV>(mb, tB.m + (size_t)rowB * dim, d4, lane);
-            tile_load_cg<NV>(vb, tB.v + (size_t)rowB * dim, d4, lane);
-          }
-          if (doA) {
+          const float4* b4 = sbuf + (size_t)(j & (kBufs - 1)) * kBuf4;
+          const int wA = __shfl_sync(0xffffffffu, which_l, j), rowA = __shfl_sync(0xffffffffu, row_l, j);
+          const int lenA = __shfl_sync(0xffffffffu, len_l, j);
+          if (lenA <= AR_HEAVY_LEN) {
+            RowTile<NV> accA, wa, ma, va;
+            tile_from_stage<NV>(accA, b4, d4, lane);
+            tile_from_stage<NV>(wa, b4 + 32 * NV, d4, lane);
+            tile_from_stage<NV>(ma, b4 + 64 * NV, d4, lane);
+            tile_from_stage<NV>(va, b4 + 96 * NV, d4, lane);
+            if (kBufs == 1 && j + 1 < cnt) prefetch_row(j + 1, sbuf);   // the buffer is in registers now
+            const ar_table& tA = a.tab[wA];
+            const float* __restrict__ otherA = wA ? uh : ah;
             const float d0 = __shfl_sync(0xffffffffu, d0_l, j), c0 = __shfl_sync(0xffffffffu, c0_l, j);
             float q = fmaf(d0, c0, 0.f);
 #pragma unroll
@@ -975,28 +1026,8 @@ __device__ void step_role(const ChunkArgs& a, StepSmem& sm, int n_threads) {
             }
             finish_loaded<NV>(a, tabs, tA, rowA, accA, q, __shfl_sync(0xffffffffu, rinv_l, j), wa, ma, va,
                               __shfl_sync(0xffffffffu, last_l, j), t, lane, regfix, pend);
-          }
-          if (doB) {
-            const float d0 = __shfl_sync(0xffffffffu, d0_l, j1), c0 = __shfl_sync(0xffffffffu, c0_l, j1);
-            float q = fmaf(d0, c0, 0.f);
-#pragma unroll
-            for (int k = 0; k < NV; ++k) accB.x[k] = fma4(d0, accB.x[k], make_float4(0.f, 0.f, 0.f, 0.f));
-            if (lenB > 1) {
-              const ar_plan& pl = a.plan[wB];
-              const int32_t* order = pl.order + (size_t)s * pl.batch_cap + __shfl_sync(0xffffffffu, beg_l, j1);
-              for (int e = 1; e < lenB; ++e) {
-                const int sx = order[e];
-                RowTile<NV> o;
-                tile_load_cg<NV>(o, otherB + (size_t)sx * dim, d4, lane);
-                const float cx = __ldcg(cc + sx);
-                const float dx = dc_of_label(cx, __ldg(label + sx), kk);
-                q = fmaf(dx, cx, q);
-#pragma unroll
-                for (int k = 0; k < NV; ++k) accB.x[k] = fma4(dx, o.x[k], accB.x[k]);
-              }
-            }
-            finish_loaded<NV>(a, tabs, tB, rowB, accB, q, __shfl_sync(0xffffffffu, rinv_l, j1), wb, mb, vb,
-                              __shfl_sync(0xffffffffu, last_l, j1), t, lane, regfix, pend);
+          } else if (kBufs == 1 && j + 1 < cnt) {
+            prefetch_row(j + 1, sbuf);
           }
         }
       }
@@ -1182,7 +1213,7 @@ static_assert((768 - kStepThreads) * (80 - 56) >= kStepThreads * (88 - 80), "reg
 template <int NV, int THREADS, int REGS>
 __global__ void __maxnreg__(REGS) chunk_kernel(const __grid_constant__ ChunkArgs a) {
   __shared__ StepSmem sm;
-  extern __shared__ float4 stage_all[];   // replay warps: [warp][2][3][32*NV] float4
+  extern __shared__ float4 stage_all[];   // replay warps: [warp][kBufs][3 tiles]; then step warps: [warp][kBufs][4 tiles]
   {
     const long long t_hi = a.t0 + a.n_steps;
     const long long base = t_hi - kWin + 1 > 0 ? t_hi - kWin + 1 : 0;
@@ -1211,7 +1242,7 @@ __global__ void __maxnreg__(REGS) chunk_kernel(const __grid_constant__ ChunkArgs
     return;
   }
   if (kRegsStep) asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(kRegsStep ? kRegsStep : 24));
-  step_role<NV>(a, sm, THREADS);
+  step_role<NV>(a, sm, THREADS, stage_all + (size_t)(THREADS / 32 - kStepWarps) * (StageCfg<NV>::kBufs * 96 * NV));
 }
 
 template <int NV> struct ChunkCfg {
@@ -1223,7 +1254,7 @@ template <int NV>
 static int launch_chunk_nv(const ChunkArgs& a, cudaStream_t st) {
   constexpr int T = ChunkCfg<NV>::kThreads, R = ChunkCfg<NV>::kRegs;
   static int max_ctas = -1;
-  const size_t dyn = (size_t)(T / 32 - kStepWarps) * 2 * 96 * NV * sizeof(float4);
+  const size_t dyn = ((size_t)(T / 32 - kStepWarps) * 96 + (size_t)kStepWarps * 128) * StageCfg<NV>::kBufs * NV * sizeof(float4);
   if (max_ctas < 0) {
     AR_CUDA(cudaFuncSetAttribute(chunk_kernel<NV, T, R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
     int per_sm = 0;
@@ -1278,6 +1309,7 @@ static int launch_chunk(const ar_train_ctx& x, int64_t epoch_step0, int64_t t0, 
   a.ctl = (ChunkCtl*)(ws + l.ctl);
   a.htick = (int32_t*)(ws + l.htick);
   a.fwd_part = (double*)(ws + l.fpart);
+  a.hsum = (double*)(ws + l.hsum);
   a.mpart = (double*)(ws + l.mpart);
   a.stamps = (long long*)(ws + l.stamps);
   a.hpart = (float*)(ws + l.hpart);

@@ -226,7 +226,7 @@ plan_gap_kernel(ar_plan plan, int n_steps, int64_t t0, int64_t t_flush, int32_t*
 // (k, clz(gap)) bins).  Rows with gap >= AR_SCHED_SPLIT_GAP become `nparts` items of 32 elements each when the
 // slot's capacity allows.  Also zeroes the slot's run-time cursors.
 constexpr int kSchedBins = (AR_SCHED_MAX_DEPTH + 1) * 32;
-constexpr int kLongClz = 25;   // clz(gap) <= 25  <=>  gap >= 64 = AR_SCHED_SPLIT_GAP
+constexpr int kLongClz = 23;   // clz(gap) <= 23  <=>  gap >= 256 = AR_SCHED_SPLIT_GAP
 static_assert((1 << (31 - kLongClz)) == AR_SCHED_SPLIT_GAP, "split threshold and its clz bucket disagree");
 __global__ void __launch_bounds__(512)
 plan_sched_kernel(ar_plan pu, ar_plan pa, const int32_t* __restrict__ gap_u, const int32_t* __restrict__ gap_a,

@@ -101,7 +101,7 @@ int ar_plan_link(const ar_plan* plan, int32_t n_steps, const int32_t* uniq_all, 
  * Item code: bit 31 table (0 users, 1 anime) | bit 30 split | bits 29..26 part | bits 25..0 row. */
 #define AR_SCHED_MAX_DEPTH 4
 #define AR_SCHED_SUB (AR_SCHED_MAX_DEPTH + 2)  /* stride of sub / cursor */
-#define AR_SCHED_SPLIT_GAP 64
+#define AR_SCHED_SPLIT_GAP 256
 #define AR_SCHED_MAX_ROWS (1 << 26)
 #define AR_SCHED_PARTS 296   /* row-range parts of the plan-time walk (bounds has n_slots*(AR_SCHED_PARTS+1) entries) */
 typedef struct {
@@ -356,6 +356,24 @@ int ar_sumsq(const float* W, int64_t n_elems, double* out, void* stream);
  * sqrt.approx -> add -> rcp.approx chains (the special-function work of one Adam element-step) and write one float
  * to scratch[blocks*threads].  2*8*blocks*threads*iters MUFU ops per launch; the caller times it. */
 int ar_bench_sfu(float* scratch, int32_t blocks, int32_t threads, int32_t iters, void* stream);
+
+/* ------------------------------------------------------------------ user_recs: collaborative aggregation
+ * Ratings as a CSR by user: indptr (n_users+1) int64, anime_idx / rating aligned with it. */
+
+/* fav_flag[j] = 1 iff rating j is at or above its user's `percentile`-th percentile (np.percentile, linear
+ * interpolation, evaluated in double) -- the "favourites" of user_recs.py:359-361 / 380-382 (percentile = 80) and
+ * similar_users.py:216 (75).  thr_out (n_users) doubles: the thresholds, or null. */
+int ar_user_favourites(const int64_t* indptr, const float* rating, int32_t n_users, double percentile,
+                       uint8_t* fav_flag, double* thr_out, void* stream);
+
+/* For every query user q (row index into the CSR): count how many of q's similar users sim_users[q][0..k_sim)
+ * (row indices; < 0 = padding) hold each anime among their favourites, drop q's own favourites, and emit the
+ * n_recs anime with the highest counts, ties by lower anime index (user_recs.py:761-774 value_counts; the
+ * reference's order among equal counts is pandas-version dependent).  out_idx / out_cnt: [n_query][n_recs],
+ * idx = -1 past the last recommendation. */
+int ar_user_recs(const int64_t* indptr, const int32_t* anime_idx, const uint8_t* fav_flag, int32_t n_anime,
+                 const int32_t* query_users, int32_t n_query, const int32_t* sim_users, int32_t k_sim,
+                 int32_t n_recs, int32_t* out_idx, int32_t* out_cnt, void* stream);
 
 /* ------------------------------------------------------------------ Half B: cosine top-k */
 

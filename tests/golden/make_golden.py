@@ -196,9 +196,36 @@ def golden_preprocess():
               open(os.path.join(OUT, "preprocess.json"), "w"))
 
 
+def golden_user_recs():
+    """similar_user_recs / fave_genres / fave_sources / get_fave_df (user_recs.py:348-404, 708-794) executed on the
+    synthetic world; metadata decoration (get_anime_frame, get_sypnopsis) runs unmodified too."""
+    tables, anime_df, syn, df, anime_ids, user_ids = make_world()
+    anime_df = anime_df.copy()
+    anime_df["sources"] = anime_df["Source"]
+    args = types.SimpleNamespace(user_recs_fn="recs.csv", ID_spec_genres=False)
+    ur = lift("user_recs/user_recs.py", dict(args=args))
+    out = dict(query=[], sim=[], rec_anime_id=[], rec_count=[], fav_user=[], fav_names=[])
+    rng = np.random.RandomState(17)
+    for q in (user_ids[2], user_ids[11], user_ids[30]):
+        sims = [int(x) for x in rng.choice([u for u in user_ids if u != q], 6, replace=False)]
+        sim_df = pd.DataFrame(dict(similar_users=sims, similarity=np.linspace(0.9, 0.5, 6)))
+        pref = ur["get_fave_df"](ur["fave_genres"](q, df, anime_df), ur["fave_sources"](q, df, anime_df))
+        frame, fname = ur["similar_user_recs"](q, sim_df, syn, df, None, None, anime_df, 12, None, None, pref)
+        out["query"].append(q)
+        out["sim"].append(sims)
+        out["rec_anime_id"].append(frame["anime_id"].tolist())
+        out["rec_count"].append(frame["n_user_prefs"].tolist())
+    for u in user_ids[:8]:
+        fav = ur["fave_genres"](u, df, anime_df)
+        out["fav_user"].append(u)
+        out["fav_names"].append(sorted(fav["eng_version"].tolist()))
+    json.dump(out, open(os.path.join(OUT, "user_recs.json"), "w"))
+
+
 if __name__ == "__main__":
     golden_lrfn()
     golden_sample_perm()
     golden_similarity()
     golden_preprocess()
+    golden_user_recs()
     print("golden fixtures written to", OUT)
