@@ -619,21 +619,17 @@ template <int NV>
 __device__ __forceinline__ void finish_loaded(const ChunkArgs& a, const StepTabs& tabs, const ar_table& tb, int row,
                                               const RowTile<NV>& acc, float q, float rinv, RowTile<NV>& w,
                                               RowTile<NV>& m, RowTile<NV>& v, int last, int64_t t, int lane,
-                                              unsigned long long& regfix, int32_t*& pend) {
+                                              double& reg_lane, int32_t*& pend) {
   const int d4 = tb.dim >> 2;
   const size_t o = (size_t)row * tb.dim;
   const bool flags = a.mode == AR_ADAM_REPLAY;
-  double regd = 0.0;
   if (flags && (int64_t)last != t - 1) {
     // the forward has waited for this row to be at t-1: cannot happen unless the schedule and the plans disagree
     if (lane == 0) atomicAdd(a.health, 1);
   }
-  if (a.reg.acc) {
-    const float ss = warp_sum(tile_partial_dot<NV>(w, w));
-    if (lane == 0) regd += (double)(tabs.w_at(t) * ss);
-    regd = warp_sum(regd);
-    reg_fix_add(regd, a.reg, regfix);
-  }
+  // regulariser term of the step: this lane's share; the warp adds its lanes once per step (its rows are a fixed
+  // share of the plan, so the order of the sum is fixed)
+  if (a.reg.acc) reg_lane += (double)(tabs.w_at(t) * tile_partial_dot<NV>(w, w));
   const float al = tabs.a_at(t);
 #pragma unroll
   for (int k = 0; k < NV; ++k) {
@@ -980,6 +976,7 @@ __device__ void step_role(const ChunkArgs& a, StepSmem& sm, int n_threads, float
     {
       const float* kk = sm.stepc;   // read at the use sites: shared-memory loads are cheaper than 11 live registers
       int32_t* pend = nullptr;      // flag of the row stored last, published behind the next row's arithmetic
+      double reg_lane = 0.0;
       for (int base = r0; base < r1; base += 32) {
         const int cnt = min(32, r1 - base);
         if (base != r0) {
@@ -1025,7 +1022,7 @@ __device__ void step_role(const ChunkArgs& a, StepSmem& sm, int n_threads, float
               }
             }
             finish_loaded<NV>(a, tabs, tA, rowA, accA, q, __shfl_sync(0xffffffffu, rinv_l, j), wa, ma, va,
-                              __shfl_sync(0xffffffffu, last_l, j), t, lane, regfix, pend);
+                              __shfl_sync(0xffffffffu, last_l, j), t, lane, reg_lane, pend);
           } else if (kBufs == 1 && j + 1 < cnt) {
             prefetch_row(j + 1, sbuf);
           }
@@ -1113,7 +1110,7 @@ __device__ void step_role(const ChunkArgs& a, StepSmem& sm, int n_threads, float
               tile_load_cg<NV>(m, tb.m + (size_t)row * dim, d4, lane);
               tile_load_cg<NV>(v, tb.v + (size_t)row * dim, d4, lane);
               const float rinv = __ldcg((w ? rav : ruv) + order[beg]);
-              finish_loaded<NV>(a, tabs, tb, row, acc, q, rinv, x, m, v, __ldcg(tb.last_step + row), t, lane, regfix, pend);
+              finish_loaded<NV>(a, tabs, tb, row, acc, q, rinv, x, m, v, __ldcg(tb.last_step + row), t, lane, reg_lane, pend);
             }
           }
           piece0 += round_total;
@@ -1123,6 +1120,7 @@ __device__ void step_role(const ChunkArgs& a, StepSmem& sm, int n_threads, float
         __threadfence();
         if (lane == 0) *(volatile int32_t*)pend = (int32_t)t;
       }
+      if (a.reg.acc) reg_fix_add(warp_sum(reg_lane), a.reg, regfix);
     }
     if (stamp) stamps[4] = (long long)globaltimer_ns();
     if (!flags) {                   // no per-row flags: everyone's rows before anyone's next forward

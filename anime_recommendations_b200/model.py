@@ -25,7 +25,7 @@ from . import weights_io
 
 BETA1, BETA2 = 0.9, 0.999
 PLAN_CHUNK = 256
-REPLAY_DEPTH = int(os.environ.get("AR_REPLAY_DEPTH", "2"))   # look-ahead depth of the replay schedule
+REPLAY_DEPTH = int(os.environ.get("AR_REPLAY_DEPTH", "3"))   # look-ahead depth of the replay schedule
 
 
 def adam_alpha_table(lr, t_first, count):

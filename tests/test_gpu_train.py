@@ -136,7 +136,7 @@ def test_plan_sched_matches_numpy(depth, dim, cap_mult):
                     n_split += 1
             lg = [int(np.floor(np.log2(g))) for g in gl.tolist()]
             assert lg == sorted(lg, reverse=True)                   # longest replay first, by log2 bucket
-    assert (n_split > 0) == (cap_mult >= 4)
+    assert n_split > 0 or cap_mult < 4          # the roomy schedules do split their long rows
     for k in range(2):
         np.testing.assert_array_equal(seen[k].cpu().numpy(), seen_np[k])
 
