@@ -84,9 +84,9 @@ __device__ __forceinline__ int ld_relaxed_sys(const int32_t* p) {
   asm volatile("ld.volatile.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
   return v;
 }
-// Called by every thread of a CTA; threads r < G wait for rank r's arrival.  The poll is a relaxed system-scope
-// load: everything read behind it that another rank wrote is read with system-scope (L1-bypassing) loads as
-// well, and only after the __syncthreads, so no acquire (L1 invalidation per CTA) is needed.
+// Called by every thread of a CTA; threads r < G wait for rank r's arrival.  The polls are relaxed system-scope
+// loads; each waiting thread then re-reads its flag with ld.acquire.sys, which (with the __syncthreads) orders every
+// later read of the CTA -- peer rows, published lists -- after the arrivals it has observed.
 __device__ __forceinline__ void peer_wait(int32_t* mine, int G, int epoch) {
   if ((int)threadIdx.x < G && ld_relaxed_sys(mine + kPeerErrWord) == 0) {
     const unsigned long long t0 = global_ns();
@@ -96,6 +96,11 @@ __device__ __forceinline__ void peer_wait(int32_t* mine, int G, int epoch) {
         break;
       }
     }
+    // acquire: one more load of the flag, now with acquire semantics (unlike a fence it does not have to drain this
+    // thread's own stores first)
+    int seen;
+    asm volatile("ld.acquire.sys.global.s32 %0, [%1];" : "=r"(seen) : "l"(mine + threadIdx.x) : "memory");
+    (void)seen;
   }
   __syncthreads();
 }

@@ -317,7 +317,11 @@ class PeerTrainSession(TrainSession):
         # chunk is checked by verify() (an overflowing list is truncated on the device, nothing is corrupted)
         torch.maximum(self._max_seen, st["max_count"], out=self._max_seen)
 
-    def run(self, iu, ia, y, lr, profile=None):
+    def run(self, iu, ia, y, lr, profile=None, verify=True):
+        """Queue the steps; with verify=True (default) finish with verify() -- a synchronising host check that no
+        selection list overflowed and no flag barrier timed out -- so that wrong results cannot leave this call
+        unnoticed.  verify=False keeps the call asynchronous; the caller then owes a verify() before using the
+        tables or the metrics."""
         m, B = self.model, self.B
         N = iu.numel()
         steps = (N + B - 1) // B
@@ -357,6 +361,8 @@ class PeerTrainSession(TrainSession):
             self.launches += 5 + ns * {"replay": 5, "dense": 6, "touched": 4}[m.adam_mode]
         main.wait_stream(self.plan_stream)                 # nothing of this call is left on the side stream
         m.iterations = t0 + steps
+        if verify:
+            self.verify()
         return steps
 
     def verify(self):
