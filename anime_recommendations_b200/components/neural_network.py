@@ -2,8 +2,12 @@
 the same files out (model, best weights, history json/csv); training runs on libanimerec.so.
 
 Differences forced by the environment, all outside the arithmetic: inputs come from local files instead of
-W&B artifacts; `--TPU_INIT` selects multi-GPU data parallelism when launched under torchrun (the reference's
-TPUStrategy path, neural_network.py:142-147,173-182); no loss plot is uploaded."""
+W&B artifacts; no loss plot is uploaded.  `--TPU_INIT True` is the reference's distribution-strategy switch
+(neural_network.py:142-147,173-182): here it selects multi-GPU data parallelism and must be launched with one
+process per GPU (`python -m torch.distributed.run --nproc-per-node N -m
+anime_recommendations_b200.components.neural_network ...`); as in the reference the global batch is
+batch_size x replicas and max_lr is scaled by the replica count.  Without torchrun it is an error, not a silent
+single-GPU run."""
 from __future__ import annotations
 
 import argparse
@@ -34,7 +38,23 @@ def get_df(args):
     return enc
 
 
-def build_model(args, n_users, n_anime):
+def init_strategy(args):
+    """neural_network.py:142-147: -> number of replicas (1 without --TPU_INIT)."""
+    if not C.strtobool(args.TPU_INIT):
+        return 1
+    import torch
+    import torch.distributed as dist
+    if not dist.is_initialized():
+        if "RANK" not in os.environ or "WORLD_SIZE" not in os.environ:
+            raise RuntimeError("--TPU_INIT True selects multi-GPU training: launch one process per GPU with "
+                               "`python -m torch.distributed.run --nproc-per-node N ...`")
+        local = int(os.environ.get("LOCAL_RANK", "0"))
+        torch.cuda.set_device(local)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    return dist.get_world_size()
+
+
+def build_model(args, n_users, n_anime, replicas=1):
     """neural_network.py:66-106.  Only the configuration the reference ships is implemented in CUDA."""
     if args.model_loss != "binary_crossentropy" or args.activation_function != "sigmoid" or \
             str(args.optimizer).lower() != "adam":
@@ -44,6 +64,15 @@ def build_model(args, n_users, n_anime):
     if list(metrics) != ["mse"]:
         raise ValueError("only model_metrics ['mse'] (config.yaml:88) is implemented")
     seed = int(args.seed) if str(getattr(args, "seed", "")).strip() else None
+    if replicas > 1:
+        from ..dist_fit import DistributedEmbeddingDotModel
+        if seed is None:
+            seed = 0          # every rank must draw the same initial weights
+        return DistributedEmbeddingDotModel(n_users, n_anime, int(args.embedding_size),
+                                            l2_reg_factor=float(args.l2_reg_factor),
+                                            kernel_initializer=args.kernel_initializer, ID_emb_name=args.ID_emb_name,
+                                            anime_emb_name=args.anime_emb_name, merged_name=args.merged_name, seed=seed,
+                                            adam_mode=getattr(args, "adam_mode", "replay"))
     return EmbeddingDotModel(n_users, n_anime, int(args.embedding_size), l2_reg_factor=float(args.l2_reg_factor),
                              kernel_initializer=args.kernel_initializer, ID_emb_name=args.ID_emb_name,
                              anime_emb_name=args.anime_emb_name, merged_name=args.merged_name, seed=seed,
@@ -54,8 +83,14 @@ def go(args):
     enc = get_df(args)
     logger.info("Data frame loaded")
     (x_train, y_train), (x_test, y_test) = data.train_test_split_tail(enc, int(args.test_size))
-    model = build_model(args, enc.n_users, enc.n_anime)
-    sched = LearningRateScheduler(lambda epoch: lrfn(epoch, args.start_lr, args.min_lr, args.max_lr,
+    replicas = init_strategy(args)
+    rank0 = True
+    if replicas > 1:
+        import torch.distributed as dist
+        rank0 = dist.get_rank() == 0
+    model = build_model(args, enc.n_users, enc.n_anime, replicas)
+    max_lr = float(args.max_lr) * replicas                      # neural_network.py:177
+    sched = LearningRateScheduler(lambda epoch: lrfn(epoch, args.start_lr, args.min_lr, max_lr,
                                                      args.rampup_epochs, args.sustain_epochs, args.exp_decay), verbose=0)
     ckpt = ModelCheckpoint(filepath=args.weights_artifact, save_weights_only=C.strtobool(args.save_weights_only),
                            monitor=args.checkpoint_metric, save_freq=args.save_freq, mode=args.mode,
@@ -69,6 +104,8 @@ def go(args):
         model.save(args.model_name)
     logger.info("model trained and saved!")
     hist = history.history
+    if not rank0:                                              # the files are written once, by rank 0
+        return model, history
     with open("history.json", "w") as f:                      # DataFrame.to_json layout: {column: {row: value}}
         json.dump({k: {str(i): v for i, v in enumerate(vals)} for k, vals in hist.items()}, f)
     cols = list(hist.keys())

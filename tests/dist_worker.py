@@ -35,6 +35,67 @@ def sim_main(shard, dev, rank, world):
         print("DIST_OK", shard)
 
 
+def score_main(dev, rank, world):
+    """cfg4 scoring with the users sharded over the ranks == the single-process result (gathered on every rank)."""
+    import anime_recommendations_b200 as ar
+    from anime_recommendations_b200 import similarity as sim, similarity_dist as sd
+    from anime_recommendations_b200.dist import Comm
+    rng = np.random.RandomState(21)
+    nu, na, k = 600, 1800, 20
+    m = ar.EmbeddingDotModel(nu, na, 128, seed=3, dense_kernel=0.9)
+    users = rng.choice(nu, 301, replace=False)
+    counts = rng.randint(100, 700, len(users))
+    indptr = np.r_[0, np.cumsum(counts)]
+    widx = np.concatenate([rng.choice(na, c, replace=False) for c in counts]).astype(np.int32)
+    comm = Comm()
+    gi, gp = sd.score_topk_sharded(m, users, indptr, widx, k, rank, world, comm=comm, gather=True)
+    wi, wp = sim.score_topk(m, users, indptr, widx, k)
+    np.testing.assert_array_equal(gi, wi)
+    np.testing.assert_array_equal(gp, wp)
+    comm.close()
+    if rank == 0:
+        print("DIST_OK score")
+
+
+def fit_main(dev, rank, world):
+    """DistributedEmbeddingDotModel.fit on `world` GPUs == EmbeddingDotModel.fit on one GPU with batch world*B:
+    history (loss incl. the exact L2 term, mse, val_loss, val_mse, lr), checkpoint callback, gathered tables."""
+    import tempfile
+    import anime_recommendations_b200 as ar
+    from anime_recommendations_b200.dist_fit import DistributedEmbeddingDotModel
+    nu, na, D, B = 3001, 403, 128, 500
+    rng = np.random.RandomState(31)
+    n = world * B * 5 + world * 123                                # 6 global steps / epoch, the last one partial
+    iu, ia = rng.randint(0, nu, n), rng.randint(0, na, n)
+    y = rng.randint(0, 11, n) / 10.0
+    vu, va, vy = rng.randint(0, nu, 400), rng.randint(0, na, 400), rng.randint(0, 11, 400) / 10.0
+    lr_kw = dict(start_lr=1e-3, min_lr=1e-3, max_lr=3e-3, rampup_epochs=2, sustain_epochs=0, exp_decay=0.8)
+    tmp = tempfile.mkdtemp() if rank == 0 else None
+    box = [tmp]
+    dist.broadcast_object_list(box, src=0)
+    ck = os.path.join(box[0], "best_weights.h5")
+    dm = DistributedEmbeddingDotModel(nu, na, D, seed=7, dense_kernel=0.8)
+    cbs = [ar.LearningRateScheduler(lambda e: ar.lrfn(e, **lr_kw)),
+           ar.ModelCheckpoint(ck, save_weights_only=True, monitor="val_loss", mode="min", save_best_only=True),
+           ar.EarlyStopping(patience=3, monitor="val_loss", mode="min", restore_best_weights=True)]
+    h = dm.fit([iu, ia], y, batch_size=B, epochs=3, validation_data=([vu, va], vy), callbacks=cbs, shuffle_seed=4)
+    w = dm.get_weights()
+    p = dm.predict([vu, va])
+    if rank == 0:
+        m1 = ar.EmbeddingDotModel(nu, na, D, seed=7, dense_kernel=0.8)
+        h1 = m1.fit([iu, ia], y, batch_size=world * B, epochs=3, validation_data=([vu, va], vy),
+                    callbacks=[ar.LearningRateScheduler(lambda e: ar.lrfn(e, **lr_kw))], shuffle_seed=4)
+        for k in ("loss", "mse", "val_loss", "val_mse", "lr"):
+            np.testing.assert_allclose(h.history[k], h1.history[k], rtol=1e-4, atol=2e-6, err_msg=k)
+        w1 = m1.get_weights()
+        np.testing.assert_allclose(w[0], w1[0], rtol=1e-4, atol=3e-6)
+        np.testing.assert_allclose(w[1], w1[1], rtol=1e-4, atol=3e-6)
+        np.testing.assert_allclose(p, m1.predict([vu, va]), rtol=0, atol=2e-4)
+        best = ar.load_model(ck)                                   # what the checkpoint callback wrote (rank 0)
+        assert best.get_weights()[0].shape == (nu, D)
+        print("DIST_OK fit", h.history["loss"])
+
+
 def shard_main(mode, dev, rank, world, peer=False):
     """Row-sharded training (NCCL all-to-all, or NVLink peer memory) == single-GPU training on the concatenated batch."""
     import anime_recommendations_b200 as ar
@@ -113,6 +174,16 @@ def main(mode):
     dist.init_process_group("nccl", device_id=dev)
     if mode.startswith("shard_") or mode.startswith("peer_"):
         shard_main(mode.split("_", 1)[1], dev, rank, world, peer=mode.startswith("peer_"))
+        dist.barrier()
+        dist.destroy_process_group()
+        return
+    if mode == "fit":
+        fit_main(dev, rank, world)
+        dist.barrier()
+        dist.destroy_process_group()
+        return
+    if mode == "score":
+        score_main(dev, rank, world)
         dist.barrier()
         dist.destroy_process_group()
         return

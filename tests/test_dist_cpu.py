@@ -84,3 +84,23 @@ def test_shard_range_tiles_rows_on_aligned_boundaries():
                 assert edges[0][0] == 0 and edges[-1][1] == n
                 for (a, b), (c, d) in zip(edges[:-1], edges[1:]):
                     assert b == c and a <= b and (b % align == 0 or b == n)
+
+
+def test_shard_csr_tiles_the_watched_lists():
+    """cfg4 scoring shards the query users: the per-rank CSR slices re-based to 0 tile the original lists."""
+    from anime_recommendations_b200.similarity_dist import shard_csr
+    rng = np.random.RandomState(0)
+    n = 103
+    counts = rng.randint(0, 9, n)
+    indptr = np.r_[0, np.cumsum(counts)].astype(np.int64)
+    idx = rng.randint(0, 50, indptr[-1]).astype(np.int32)
+    for world in (1, 2, 3, 8):
+        got_counts, got_idx = [], []
+        for r in range(world):
+            lo, hi = shard_range(n, r, world)
+            ip, ix = shard_csr(indptr, idx, lo, hi)
+            assert ip[0] == 0 and len(ip) == hi - lo + 1 and ip[-1] == len(ix)
+            got_counts.append(np.diff(ip))
+            got_idx.append(ix)
+        np.testing.assert_array_equal(np.concatenate(got_counts), counts)
+        np.testing.assert_array_equal(np.concatenate(got_idx), idx)

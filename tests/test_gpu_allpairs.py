@@ -141,6 +141,27 @@ def test_score_topk_matches_oracle_model_recs(w):
         assert cand_mask[gi[j]].all()
 
 
+@pytest.mark.parametrize("world", [2, 3])
+def test_score_topk_sharded_over_users_equals_unsharded(world):
+    """BASELINE cfg4 / SURVEY 8e row 4: the query users are split over ranks, nothing else is shared -- the ranks'
+    results laid end to end are the unsharded result (here the ranks run one after the other on this GPU; the
+    2-process version is tests/test_gpu_dist.py::test_two_rank_sharded_scoring)."""
+    from anime_recommendations_b200 import similarity_dist as sd
+    rng = np.random.RandomState(5)
+    nu, na, k = 400, 1500, 20
+    m = ar.EmbeddingDotModel(nu, na, 128, seed=0, dense_kernel=-0.7)
+    users = rng.choice(nu, 257, replace=False)
+    counts = rng.randint(100, 600, len(users))
+    indptr = np.r_[0, np.cumsum(counts)]
+    widx = np.concatenate([rng.choice(na, c, replace=False) for c in counts]).astype(np.int32)
+    wi, wp = sim.score_topk(m, users, indptr, widx, k)
+    parts = [sd.score_topk_sharded(m, users, indptr, widx, k, r, world) for r in range(world)]
+    assert parts[0][0] == 0 and parts[-1][1] == len(users)
+    assert all(parts[r][1] == parts[r + 1][0] for r in range(world - 1))
+    np.testing.assert_array_equal(np.concatenate([p[2] for p in parts]), wi)
+    np.testing.assert_array_equal(np.concatenate([p[3] for p in parts]), wp)
+
+
 def test_allpairs_full_user_table_sampled_against_oracle():
     """cfg3 at full size (350 000 x 128): every 5000th row checked against the single-query oracle."""
     rng = np.random.RandomState(7)

@@ -64,3 +64,35 @@ def test_one_rank_peer_memory_training_equals_single_gpu():
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
     assert "DIST_OK" in r.stdout
+
+
+def test_two_rank_sharded_scoring():
+    """cfg4 (model_recs over many users): users sharded over 2 GPUs, gathered result == single-GPU result."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr",
+           "127.0.0.1", "--master-port", "29551", os.path.join(ROOT, "tests", "dist_worker.py"), "score"]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
+    assert "DIST_OK" in r.stdout
+
+
+def test_two_rank_distributed_fit_equals_single_gpu_fit():
+    """dist_fit.DistributedEmbeddingDotModel.fit (epochs, seeded shuffle, validation, callbacks, sharded tables)
+    against EmbeddingDotModel.fit with the global batch on one GPU: histories to 1e-4."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr",
+           "127.0.0.1", "--master-port", "29553", os.path.join(ROOT, "tests", "dist_worker.py"), "fit"]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
+    assert "DIST_OK" in r.stdout
+
+
+def test_one_rank_distributed_fit_equals_single_gpu_fit():
+    """The same with a world of one rank: runs on a single-GPU box."""
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "1", "--master-addr",
+           "127.0.0.1", "--master-port", "29555", os.path.join(ROOT, "tests", "dist_worker.py"), "fit"]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
+    assert "DIST_OK" in r.stdout
