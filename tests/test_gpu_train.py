@@ -359,6 +359,28 @@ def test_early_stopping_checkpoint_and_container_roundtrip(tmp_path):
     assert m2.iterations == m.iterations
     np.testing.assert_array_equal(m2.get_layer("user_embedding").get_weights()[0], m.get_weights()[0])
     np.testing.assert_array_equal(m.predict([vu, va]), m2.predict([vu, va]))
+    # the files are HDF5 in the Keras-2.12 layout: groups, attributes, tensor names
+    from anime_recommendations_b200 import minih5
+    assert open(full, "rb").read(8) == b"\x89HDF\r\n\x1a\n" and open(ck, "rb").read(8) == b"\x89HDF\r\n\x1a\n"
+    d, a = minih5.read(full)
+    assert a[""]["keras_version"].tobytes() == b"2.12.0" and a[""]["backend"].tobytes() == b"tensorflow"
+    import json
+    cfg = json.loads(a[""]["model_config"].tobytes().decode())
+    assert cfg["class_name"] == "Functional" and [l["name"] for l in cfg["config"]["layers"]] == [
+        "user", "anime", "user_embedding", "anime_embedding", "dot_product", "flatten", "dense", "batch_normalization",
+        "activation"]
+    assert [x.decode() for x in a["/model_weights"]["layer_names"].tolist()] == [l["name"] for l in cfg["config"]["layers"]]
+    assert a["/model_weights/user_embedding"]["weight_names"].tolist() == [b"user_embedding/embeddings:0"]
+    assert d["/model_weights/user_embedding/user_embedding/embeddings:0"].shape == (n_users, 16)
+    assert d["/model_weights/dense/dense/kernel:0"].shape == (1, 1)
+    assert int(d["/optimizer_weights/iteration:0"]) == m.iterations
+    assert a["/optimizer_weights"]["weight_names"].tolist()[:3] == [b"iteration:0", b"Adam/m/user_embedding/embeddings:0",
+                                                                    b"Adam/v/user_embedding/embeddings:0"]
+    dw, aw = minih5.read(ck)                                       # weights-only file: layer groups at the root
+    assert "layer_names" in aw[""] and "/user_embedding/user_embedding/embeddings:0" in dw
+    npz = str(tmp_path / "twin.npz")
+    m.save(npz)
+    np.testing.assert_array_equal(ar.load_model(npz).get_weights()[1], m.get_weights()[1])
     with pytest.raises(ValueError):
         m.get_layer("nope")
 
