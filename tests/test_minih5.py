@@ -91,3 +91,15 @@ def test_h5py_reads_the_file(tmp_path):
         assert list(f["model_weights"].attrs["layer_names"]) == [b"user", b"user_embedding", b"dense"]
         np.testing.assert_array_equal(f["model_weights/dense/dense/kernel:0"][()], [[1.25]])
         assert len(f["wide"]) == 19 and int(f["optimizer_weights/iteration:0"][()]) == 1234
+
+
+def test_reads_a_keras_written_file():
+    """tests/golden/tf_model_keras.h5 is what Keras 2.12 + h5py write for the reference's model (produced by
+    tests/golden/make_tf_golden.py wherever TensorFlow exists); the reader must find the Keras tensor names in it."""
+    import os
+    p = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "tf_model_keras.h5")
+    if not os.path.exists(p):
+        pytest.skip("no Keras-written file (run tests/golden/make_tf_golden.py where TF 2.12 exists)")
+    d, a = minih5.read(p)
+    assert d["/model_weights/user_embedding/user_embedding/embeddings:0"].ndim == 2
+    assert [x.decode() for x in a["/model_weights"]["layer_names"].tolist()][:2] == ["user", "anime"]

@@ -163,3 +163,28 @@ def test_torch_cpu_port_matches_numpy_oracle():
         assert abs(m0["loss"] - m1["loss"]) < 2e-6 and abs(m0["mse"] - m1["mse"]) < 2e-6
     np.testing.assert_allclose(ts.U.numpy(), st.U, rtol=2e-5, atol=2e-7)
     np.testing.assert_allclose(ts.A.numpy(), st.A, rtol=2e-5, atol=2e-7)
+
+
+def test_oracle_matches_tensorflow_dump(golden_dir):
+    """Half A against TensorFlow itself: consumes tests/golden/tf_train.npz when someone has produced it with
+    tests/golden/make_tf_golden.py on a machine that has TensorFlow 2.12 (not installable in the build image).
+    Until then Half A's parity is UNPINNED: the oracle encodes eight Keras-2.12 assumptions (oracle/train.py) that
+    only the lrfn KAT and the torch-autograd cross-check constrain."""
+    import os
+    path = os.path.join(golden_dir, "tf_train.npz")
+    if not os.path.exists(path):
+        pytest.skip("parity unpinned: no TensorFlow dump (run tests/golden/make_tf_golden.py where TF 2.12 exists)")
+    z = np.load(path)
+    st = ot.State(U=z["U0"].copy(), A=z["A0"].copy(), head=z["head0"].copy())
+    lr, l2 = float(z["lr"]), float(z["l2"])
+    for s in range(z["iu"].shape[0]):
+        out = ot.train_step(st, z["iu"][s], z["ia"][s], z["y"][s], lr, l2)
+        assert abs(out["loss"] - z["loss"][s]) <= 2e-6 + 2e-6 * abs(z["loss"][s])
+        assert abs(out["mse"] - z["mse"][s]) <= 2e-6
+    np.testing.assert_allclose(st.U, z["U"], rtol=2e-5, atol=2e-7)
+    np.testing.assert_allclose(st.A, z["A"], rtol=2e-5, atol=2e-7)
+    np.testing.assert_allclose(np.delete(st.head, 1), np.delete(z["head"], 1), rtol=1e-4, atol=1e-7)
+    np.testing.assert_allclose([st.mov_mean, st.mov_var], z["moving"], rtol=1e-5, atol=1e-6)
+    np.testing.assert_allclose(ot.predict(st, z["pred_u"], z["pred_a"]).reshape(-1), z["pred"].reshape(-1), atol=2e-5)
+    np.testing.assert_allclose(st.mU, z["slot__Adam__m__user_embedding__embeddings:0"], rtol=5e-5, atol=1e-7)
+    np.testing.assert_allclose(st.vA, z["slot__Adam__v__anime_embedding__embeddings:0"], rtol=1e-4, atol=1e-11)
