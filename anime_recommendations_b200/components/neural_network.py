@@ -33,7 +33,8 @@ logger = logging.getLogger("neural_network")
 def get_df(args):
     """neural_network.py:25-63 -> data.EncodedRatings (first-appearance vocabulary, sample(random_state=42))."""
     u, a, r = C.read_ratings(C.artifact_path(args.input_data))
-    enc = data.encode_ratings(u, a, r)
+    from .. import data_gpu
+    enc = data_gpu.encode_ratings(u, a, r)        # vocabulary + seeded shuffle on the device, same result as data.py
     logger.info("Final df shape is %s", (len(enc.user), 3))
     return enc
 
