@@ -35,13 +35,9 @@ def go(args):
     import pandas as pd
     df = pd.read_parquet(C.artifact_path(args.raw_stats))
     cols = {c: df[c].to_numpy() for c in data.RAW_COLUMNS}
-    import torch
-    if torch.cuda.is_available():      # the filters on the GPU (data_gpu: bit-equal to the host path, ~60x faster per row)
-        from .. import data_gpu
-        idx = data_gpu.drop_useless(cols, int(args.num_reviews), C.strtobool(args.drop_unwatched),
-                                    C.strtobool(args.drop_plan)).cpu().numpy()
-    else:                              # data preparation, not the hot path: the NumPy twin works without a GPU
-        idx = data.drop_useless(cols, int(args.num_reviews), C.strtobool(args.drop_unwatched), C.strtobool(args.drop_plan))
+    from .. import data_gpu            # the filters run on the GPU (bit-equal to data.py, the NumPy statement of the same rules)
+    idx = data_gpu.drop_useless(cols, int(args.num_reviews), C.strtobool(args.drop_unwatched),
+                                C.strtobool(args.drop_plan)).cpu().numpy()
     cols = {c: np.asarray(v)[idx] for c, v in cols.items()}
     logger.info("Useless data dropped!")
     if C.strtobool(args.drop_half_watched):

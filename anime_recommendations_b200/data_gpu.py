@@ -20,7 +20,13 @@ from .data import RAW_COLUMNS, EncodedRatings, sample_permutation
 
 
 def _dev(device):
-    return torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device())
+    if device is not None:
+        return torch.device(device)
+    if not torch.cuda.is_available():
+        from ._capi import AnimerecError
+        raise AnimerecError("data_gpu needs a CUDA device; there is no CPU fallback (data.py is the NumPy statement of "
+                            "the same rules, used by the tests)")
+    return torch.device("cuda", torch.cuda.current_device())
 
 
 def _i64(x):
