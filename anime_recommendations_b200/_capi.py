@@ -134,6 +134,7 @@ SIGNATURES = {
     "ar_user_recs": (C.c_int, [_P, _P, _P, _I32, _P, _I32, _P, _I32, _I32, _P, _P, _P]),
     "ar_rownorm": (C.c_int, [_P, _I64, _I32, _P, _P]),
     "ar_topk_query_workspace": (C.c_int64, [_I64, _I32]),
+    "ar_cosine_topk_queries": (C.c_int, [_P, _I64, _I32, _I64, _I64, _P, _I32, _P, _P, _P, _P]),
     "ar_cosine_topk_query": (C.c_int, [_P, _I64, _I32, _I64, _P, _I64, _I32, _P, _P, _P, _P]),
     "ar_topk_merge": (C.c_int, [_P, _P, _I32, _I64, _I32, _I32, _I32, _P, _P, _P]),
     "ar_cosine_rerank": (C.c_int, [_P, _I64, _I64, _P, _I32, _P, _P, _P, _I32, _I32, _I32, _F, _P, _P, _P, _P, _P]),

@@ -67,7 +67,7 @@ def anime_recs(args, name, count, anime_df, model=None):
         if gm is None:
             return None, translated + ".csv", translated
         mask &= gm
-    idx, sims = similarity.cosine_topk_query(W, q, min(int(count), similarity._capi.MAX_K), mask=mask, exclude=q)
+    idx, sims = similarity.cosine_topk_query(W, q, int(count), mask=mask, exclude=q)   # any count: multi-pass above 32
     out = []
     for i, s in zip(idx, sims):
         aid = int(anime_ids[i])

@@ -451,6 +451,21 @@ extern "C" int ar_cosine_topk_query(const float* W, int64_t n_rows, int32_t dim,
   return AR_OK;
 }
 
+// Many exact fp32 queries in one call (embedding sizes the tensor-core pass is not built for): query i is row
+// q0 + i, excluded from its own result; the launches are queued back to back on the stream from C, so a whole
+// table costs no host round trips (similarity.allpairs_topk used to loop in Python here).
+extern "C" int ar_cosine_topk_queries(const float* W, int64_t n_rows, int32_t dim, int64_t q0, int64_t n_queries,
+                                      const uint32_t* cand_mask, int32_t k, int32_t* out_idx, float* out_score,
+                                      void* workspace, void* stream) {
+  AR_REQUIRE(q0 >= 0 && n_queries >= 0 && q0 + n_queries <= n_rows, "ar_cosine_topk_queries: query range outside the table");
+  for (int64_t i = 0; i < n_queries; ++i) {
+    const int rc = ar_cosine_topk_query(W, n_rows, dim, q0 + i, cand_mask, q0 + i, k, out_idx + i * k, out_score + i * k,
+                                        workspace, stream);
+    if (rc) return rc;
+  }
+  return AR_OK;
+}
+
 extern "C" int ar_topk_merge(const int32_t* idx, const float* score, int32_t n_lists, int64_t n_queries,
                              int32_t k_in, int32_t k_out, int32_t lists_sorted, int32_t* out_idx, float* out_score,
                              void* stream) {

@@ -60,8 +60,25 @@ def cosine_topk_query(W, q, k, mask=None, exclude=None):
     q = int(q)
     if not 0 <= q < n:
         raise KeyError("query row %d outside [0, %d)" % (q, n))
-    if not 0 < k <= _capi.MAX_K:
-        raise ValueError("k must be in [1, %d]" % _capi.MAX_K)
+    if k <= 0:
+        raise ValueError("k must be positive")
+    if k > _capi.MAX_K:
+        # the kernel ranks up to MAX_K rows per pass: take the best MAX_K, strike them from the candidates, repeat
+        # (the reference returns Frame[:count] for any count, similar_anime.py:468)
+        cand = np.ones(n, bool) if mask is None else np.asarray(mask, bool).copy()
+        if exclude is not None:
+            cand[int(exclude)] = False
+        out_i, out_s = [], []
+        while sum(len(x) for x in out_i) < k and cand.any():
+            i, sc = cosine_topk_query(W, q, min(_capi.MAX_K, k - sum(len(x) for x in out_i)), mask=cand)
+            if len(i) == 0:
+                break
+            cand[i] = False
+            out_i.append(i)
+            out_s.append(sc)
+        if not out_i:
+            return np.zeros(0, np.int32), np.zeros(0, np.float32)
+        return np.concatenate(out_i), np.concatenate(out_s)
     L = lib()
     ws = torch.empty(max(8, L.ar_topk_query_workspace(n, k)), dtype=torch.uint8, device=W.device)
     oi = torch.empty(k, dtype=torch.int32, device=W.device)
@@ -300,11 +317,15 @@ def allpairs_topk(W, k=10, kprime=16, q0=0, nq=None, stats=None):
     W = as_table(W)
     n = W.shape[0]
     nq = n - q0 if nq is None else nq
-    if W.shape[1] != TENSOR_DIM:                              # other embedding sizes: the fp32 single-query kernel per row
+    if W.shape[1] < TENSOR_DIM:                               # smaller embeddings: zero columns change no cosine
+        W = torch.nn.functional.pad(W, (0, TENSOR_DIM - W.shape[1])).contiguous()
+    if W.shape[1] > TENSOR_DIM:                               # larger ones: exact fp32 queries, one C call for all rows
+        L = lib()
         oi = torch.empty((nq, k), dtype=torch.int32, device=W.device)
         os_ = torch.empty((nq, k), dtype=torch.float32, device=W.device)
-        for r in range(nq):
-            oi[r], os_[r] = cosine_topk_query_device(W, q0 + r, k, exclude=q0 + r)
+        ws = torch.empty(max(8, L.ar_topk_query_workspace(n, k)), dtype=torch.uint8, device=W.device)
+        check(L.ar_cosine_topk_queries(ptr(W), n, W.shape[1], q0, nq, None, k, ptr(oi), ptr(os_), ptr(ws), stream_ptr()),
+              "ar_cosine_topk_queries")
         return oi, os_
     Wn, res = normalize_rows_bf16(W, with_resid=True)
     res = torch.nan_to_num(res, nan=1.0)
@@ -349,15 +370,23 @@ def score_topk(model, users, watched_indptr, watched_idx, k, cand_mask=None, kpr
     Uq = (model.U[users_t] * sign).contiguous()               # query rows (negated when the map decreases)
     wb = watched_bits(watched_indptr, watched_idx, nq, na, dev, cand_mask)
 
-    def exact_row(r):
-        return _query_vs_table(Uq[r], model.A, k, wb[r])
+    A_t = model.A
+    if model.dim < TENSOR_DIM:                                # zero columns change no cosine: pad to the tensor-core width
+        Uq = torch.nn.functional.pad(Uq, (0, TENSOR_DIM - model.dim)).contiguous()
+        A_t = torch.nn.functional.pad(model.A, (0, TENSOR_DIM - model.dim)).contiguous()
+    aug = []                                                  # the anime table + one scratch row, built on first use
 
-    if model.dim == TENSOR_DIM:
-        (Qn, qres), (Cn, cres) = normalize_rows_bf16(Uq, True), normalize_rows_bf16(model.A, True)
+    def exact_row(r):
+        if not aug:
+            aug.append(torch.cat([A_t, torch.zeros((1, A_t.shape[1]), dtype=A_t.dtype, device=dev)], dim=0).contiguous())
+        return _query_vs_table(Uq[r], aug[0], k, wb[r])
+
+    if model.dim <= TENSOR_DIM:
+        (Qn, qres), (Cn, cres) = normalize_rows_bf16(Uq, True), normalize_rows_bf16(A_t, True)
         qres, cres = torch.nan_to_num(qres, nan=1.0), torch.nan_to_num(cres, nan=1.0)
-        oi, os_ = _certified_topk(Uq, Qn, qres, model.A, Cn, float(cres.max().item()), k, kprime, False, None, wb,
+        oi, os_ = _certified_topk(Uq, Qn, qres, A_t, Cn, float(cres.max().item()), k, kprime, False, None, wb,
                                   stats, exact_row)
-    else:                                                     # other embedding sizes: fp32 GEMV + top-k per user
+    else:                                                     # larger embeddings: exact fp32 GEMV + top-k per user
         oi = torch.empty((nq, k), dtype=torch.int32, device=dev)
         os_ = torch.empty((nq, k), dtype=torch.float32, device=dev)
         for r in range(nq):
@@ -376,12 +405,13 @@ def score_topk(model, users, watched_indptr, watched_idx, k, cand_mask=None, kpr
     return oi.cpu().numpy(), pred.cpu().numpy()
 
 
-def _query_vs_table(qrow, C, k, drop_bits):
-    """fp32 fallback for one scoring row: append the query to the table and use the single-query kernel."""
-    T = torch.cat([C, qrow.reshape(1, -1)], dim=0).contiguous()
-    n = C.shape[0]
+def _query_vs_table(qrow, T, k, drop_bits):
+    """fp32 fallback for one scoring row.  T is the candidate table with one scratch row appended (built once by the
+    caller): the query is written there and ranked against the rest by the single-query kernel."""
+    n = T.shape[0] - 1
+    T[n].copy_(qrow)
     words = (n + 1 + 31) // 32
-    keep = torch.zeros(words, dtype=torch.int32, device=C.device)
+    keep = torch.zeros(words, dtype=torch.int32, device=T.device)
     keep[:drop_bits.numel()] = ~drop_bits
     return cosine_topk_query_device(T, n, k, mask_bits=keep, exclude=n)
 

@@ -390,6 +390,12 @@ int ar_cosine_topk_query(const float* W, int64_t n_rows, int32_t dim, int64_t q,
                          const uint32_t* cand_mask, int64_t exclude, int32_t k, int32_t* out_idx,
                          float* out_score, void* workspace, void* stream);
 
+/* n_queries single-query top-k's in one call: query i is row q0+i, excluded from its own list; out_idx / out_score
+ * are [n_queries][k].  Exact fp32; used for embedding sizes above 128, which the tensor-core pass is not built for. */
+int ar_cosine_topk_queries(const float* W, int64_t n_rows, int32_t dim, int64_t q0, int64_t n_queries,
+                           const uint32_t* cand_mask, int32_t k, int32_t* out_idx, float* out_score,
+                           void* workspace, void* stream);
+
 /* Merge `n_lists` partial top-k lists per query (lists[l][query][k], global row ids) into one.
  * lists_sorted != 0: every list is sorted best first (the output order of the top-k entry points), which lets
  * the kernel drop everything below the largest k_out-th entry of any list before merging. */

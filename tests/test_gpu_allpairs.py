@@ -162,6 +162,49 @@ def test_score_topk_sharded_over_users_equals_unsharded(world):
     np.testing.assert_array_equal(np.concatenate([p[3] for p in parts]), wp)
 
 
+@pytest.mark.parametrize("dim,expect_tensor", [(64, True), (100, True), (256, False)])
+def test_allpairs_other_embedding_sizes(dim, expect_tensor):
+    """config.yaml:63 makes the embedding size a knob: smaller sizes ride the tensor-core pass zero-padded to 128
+    (zero columns change no cosine), larger ones take the exact fp32 kernel for every row in ONE C call."""
+    rng = np.random.RandomState(dim)
+    n = 1500
+    W = rng.standard_normal((n, dim)).astype(np.float32)
+    st = {}
+    gi, gs = sim.allpairs_topk(W, k=10, stats=st)
+    gi, gs = gi.cpu().numpy(), gs.cpu().numpy()
+    oi, os_ = osim.allpairs_topk_fast(W, 10)
+    np.testing.assert_allclose(gs, os_, rtol=0, atol=3e-6)
+    Wn = osim.get_weights(W)
+    for r in np.nonzero((gi != oi).any(axis=1))[0]:
+        assert_topk_close(gi[r], gs[r], oi[r], os_[r], Wn @ Wn[r])
+    assert ("uncertified" in st) == expect_tensor             # the certified tensor-core pipeline ran (or not)
+
+
+def test_score_topk_small_embedding_uses_the_tensor_path():
+    rng = np.random.RandomState(9)
+    nu, na, k, D = 300, 1200, 20, 64
+    st = ot.init_state(nu, na, D, seed=4, w=1.1)
+    st.U[:] = rng.standard_normal(st.U.shape).astype(np.float32)
+    st.A[:] = rng.standard_normal(st.A.shape).astype(np.float32)
+    st.head[:] = [1.1, 0.05, 0.8, -0.1]
+    st.mov_mean, st.mov_var = np.float32(0.02), np.float32(0.03)
+    m = ar.EmbeddingDotModel(nu, na, D, seed=0, dense_kernel=1.0)
+    m.set_weights([st.U, st.A, st.head[0:1], st.head[1:2], st.head[2:3], st.head[3:4],
+                   np.array([st.mov_mean]), np.array([st.mov_var])])
+    users = rng.choice(nu, 150, replace=False)
+    counts = rng.randint(100, 500, len(users))
+    indptr = np.r_[0, np.cumsum(counts)]
+    widx = np.concatenate([rng.choice(na, c, replace=False) for c in counts]).astype(np.int32)
+    stats = {}
+    gi, gp = sim.score_topk(m, users, indptr, widx, k, stats=stats)
+    oi, op = osim.score_topk(st, users, indptr, widx, k)
+    assert "uncertified" in stats
+    np.testing.assert_allclose(gp, op, rtol=0, atol=2e-6)
+    for r in np.nonzero((gi != oi).any(axis=1))[0]:
+        full = osim.model_scores(st, users[r], np.arange(na))
+        assert_topk_close(gi[r], gp[r], oi[r], op[r], full, tol=2e-6)
+
+
 def test_allpairs_full_user_table_sampled_against_oracle():
     """cfg3 at full size (350 000 x 128): every 5000th row checked against the single-query oracle."""
     rng = np.random.RandomState(7)

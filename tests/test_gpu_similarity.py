@@ -55,7 +55,8 @@ def test_similar_anime_golden(world):
 
 
 @pytest.mark.parametrize("n,dim,k", [(50000, 128, 10), (17560, 128, 32), (3000, 16, 7), (2000, 100, 11),
-                                     (4000, 256, 10), (1500, 512, 5), (33, 64, 32), (5, 8, 10)])
+                                     (4000, 256, 10), (1500, 512, 5), (33, 64, 32), (5, 8, 10),
+                                     (3000, 128, 100), (70, 32, 90)])          # k > 32: several passes of the kernel
 def test_query_topk_random(n, dim, k):
     rng = np.random.RandomState(n + dim)
     W = rng.standard_normal((n, dim)).astype(np.float32)
