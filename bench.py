@@ -568,7 +568,7 @@ def e2e_fit(ar, dev, mode, K, zipf):
     torch.cuda.synchronize()
     dt = time.perf_counter() - t0
     return dict(value=K * BATCH / dt, unit=UNIT, h2d_bytes_per_step=BATCH * 12, d2h_bytes_per_step=16,
-                seconds=dt, loss=h.history["loss"][0],
+                seconds=dt, loss=h.history["loss"][0], epoch_seconds=m2.timings.get("epoch_s", [None])[-1],
                 what="Model.fit([users, animes], ratings) from pinned host arrays: H2D of the step inputs, "
                      "plan build, K steps, end-of-epoch flush + L2 term, D2H of per-step metrics")
 
