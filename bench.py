@@ -581,24 +581,43 @@ def extras(dev, pk):
     g = torch.Generator(device=dev)
     g.manual_seed(7)
     Wt = torch.randn((N_USERS, DIM), generator=g, device=dev)
-    flush = torch.empty(256 * 1024 * 1024 // 4, device=dev)
+    Wt2 = torch.randn((N_USERS, DIM), generator=g, device=dev)
     qs = [int(x) for x in np.random.RandomState(0).randint(0, N_USERS, 20)]
     sim.cosine_topk_query(Wt, qs[0], 11)
+    sim.cosine_topk_query(Wt2, qs[0], 11)
+    # 20 queries back to back, alternating between two 179 MB tables (each evicts the other from the 126 MB L2), one
+    # pair of events around the batch: the GPU never waits for the Python launch path, which a per-call timing of a
+    # ~40 us kernel pair would mostly measure
+    best = None
+    for _ in range(3):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        e0.record()
+        for i, q in enumerate(qs):
+            sim.cosine_topk_query_device(Wt if i % 2 == 0 else Wt2, q, 11)
+        e1.record()
+        torch.cuda.synchronize()
+        t = e0.elapsed_time(e1) / len(qs)
+        best = t if best is None else min(best, t)
+    # ... and one query at a time behind a 256 MB L2 flush, the latency a caller of the single-query API sees
+    flush = torch.empty(256 * 1024 * 1024 // 4, device=dev)
     ts = []
-    for q in qs:
-        flush.fill_(0.0)                                # write 256 MB > L2 between timed iterations
+    for q in qs[:10]:
+        flush.fill_(0.0)
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         sim.cosine_topk_query_device(Wt, q, 11)
         e1.record()
         torch.cuda.synchronize()
         ts.append(e0.elapsed_time(e1))
-    ms = float(np.median(ts))
+    del flush, Wt2
+    ms = float(best)
     by = N_USERS * DIM * 4
     out["query_topk_users"] = dict(rows=N_USERS, dim=DIM, k=11, ms=ms, rows_per_s=N_USERS / (ms / 1e3),
                                    gbs=by / (ms / 1e3) / 1e9, frac_hbm=by / (ms / 1e3) / 1e9 / pk["hbm_gbs"],
-                                   bound="hbm", l2_flush="256 MB write between iterations")
-    del flush
+                                   bound="hbm", ms_single_call_after_l2_flush=float(np.median(ts)),
+                                   l2_flush="inputs larger than L2: 20 queries back to back alternating between two "
+                                            "179 MB tables; ms = batch time / 20 (scan + merge kernels)")
     # ---- all-pairs cosine top-10 (BASELINE cfg3): tensor-core candidate pass + fp32 re-rank + recovery
     for name, n in (("allpairs_users", N_USERS), ("allpairs_anime", N_ANIME)):
         Wn = Wt[:n].contiguous()
