@@ -242,9 +242,104 @@ topk_merge_kernel(const int* __restrict__ idx, const float* __restrict__ score, 
   __syncthreads();
   const float bound = bound_s;
   __syncthreads();
+  const int total = n_lists * k_in;
+  // Fast path (everything a single-query scan or an all-gather merge produces: total <= 8192 entries): an exact
+  // radix select of the k_out-th largest score over order-preserving keys held in registers (8 passes of 4 bits,
+  // 16-bin shared-memory histograms), then the few entries at or above it are ranked by counting how many beat them
+  // (score desc, row id asc -- a strict order, every row sits in one list only).  No serial list insertion: the
+  // per-list bound above still leaves thousands of entries when hundreds of short lists are merged.
+  constexpr int kPerT = 8, kCap = 1024;
+  __shared__ unsigned hist[16];
+  __shared__ unsigned sel_prefix, sel_need;
+  __shared__ float cand_s[kCap];
+  __shared__ int cand_i[kCap];
+  __shared__ int cand_n;
+  if (total <= kMergeThreads * kPerT) {
+    unsigned key[kPerT];
+    int cid[kPerT];
+    float csc[kPerT];
+#pragma unroll
+    for (int u = 0; u < kPerT; ++u) {
+      const int e = u * kMergeThreads + threadIdx.x;
+      key[u] = 0u;
+      cid[u] = -1;
+      csc[u] = -CUDART_INF_F;
+      if (e < total) {
+        const int l = e / k_in, j = e - l * k_in;
+        const int64_t o = ((int64_t)l * n_queries + qy) * k_in + j;
+        cid[u] = idx[o];
+        csc[u] = score[o];
+        if (cid[u] >= 0 && csc[u] == csc[u] && csc[u] >= bound) {
+          const unsigned b = __float_as_uint(csc[u]);
+          key[u] = ((b & 0x80000000u) ? ~b : (b | 0x80000000u)) | 1u;   // valid keys are never 0 (lowest bit is noise)
+        } else {
+          cid[u] = -1;
+        }
+      }
+    }
+    if (threadIdx.x == 0) {
+      sel_prefix = 0u;
+      sel_need = (unsigned)k_out;
+      cand_n = 0;
+    }
+    __syncthreads();
+    for (int shift = 28; shift >= 0; shift -= 4) {
+      if (threadIdx.x < 16) hist[threadIdx.x] = 0u;
+      __syncthreads();
+      const unsigned prefix = sel_prefix;
+#pragma unroll
+      for (int u = 0; u < kPerT; ++u)
+        if (key[u] && (shift == 28 || (key[u] >> (shift + 4)) == (prefix >> (shift + 4))))
+          atomicAdd(&hist[(key[u] >> shift) & 15u], 1u);
+      __syncthreads();
+      if (threadIdx.x == 0) {
+        unsigned need = sel_need, d = 0;
+        for (int dd = 15; dd >= 0; --dd) {
+          if (hist[dd] >= need) { d = (unsigned)dd; break; }
+          need -= hist[dd];
+          if (dd == 0) { d = 0; need = 0; }      // fewer valid entries than k_out: keep them all
+        }
+        sel_need = need;
+        sel_prefix = prefix | (d << shift);
+      }
+      __syncthreads();
+    }
+    const unsigned kth = sel_need ? sel_prefix : 0u;
+#pragma unroll
+    for (int u = 0; u < kPerT; ++u)
+      if (key[u] && key[u] >= (kth & ~1u)) {       // the key's lowest bit was forced: compare without it
+        const int pos = atomicAdd(&cand_n, 1);
+        if (pos < kCap) {
+          cand_s[pos] = csc[u];
+          cand_i[pos] = cid[u];
+        }
+      }
+    __syncthreads();
+    const int m = cand_n;
+    if (m <= kCap) {
+      if ((int)threadIdx.x < m) {
+        const float cs = cand_s[threadIdx.x];
+        const int ci = cand_i[threadIdx.x];
+        int rank = 0;
+        for (int j = 0; j < m; ++j) {
+          const float os = cand_s[j];
+          rank += (os > cs || (os == cs && cand_i[j] < ci)) ? 1 : 0;
+        }
+        if (rank < k_out) {
+          out_idx[qy * k_out + rank] = ci;
+          out_score[qy * k_out + rank] = cs;
+        }
+      }
+      for (int r = m + threadIdx.x; r < k_out; r += kMergeThreads) {
+        out_idx[qy * k_out + r] = -1;
+        out_score[qy * k_out + r] = -CUDART_INF_F;
+      }
+      return;
+    }
+    __syncthreads();
+  }
   WarpList wl;
   wl.init();
-  const int total = n_lists * k_in;
   // every thread fetches its (up to 8) entries of a pass BEFORE any is ranked: one exposed load latency per
   // pass instead of one per entry (the 592 x 11 lists of a single-query scan are one pass of 1024 threads)
   constexpr int kPer = 8;

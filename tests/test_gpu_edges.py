@@ -86,7 +86,10 @@ def test_query_topk_edges():
     with pytest.raises(KeyError):
         sim.cosine_topk_query(W, 300, 3)
     with pytest.raises(ValueError):
-        sim.cosine_topk_query(W, 0, 33)
+        sim.cosine_topk_query(W, 0, 0)
+    idx, sc = sim.cosine_topk_query(W, 0, 33)             # above the kernel's 32 per pass: several passes, same answer
+    oi, os_ = osim.rank_desc(osim.query_scores(osim.get_weights(W), 0), 33)
+    assert idx.tolist() == oi.tolist()
 
 
 def test_allpairs_tiny_and_ragged_tables():
