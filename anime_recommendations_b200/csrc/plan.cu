@@ -21,16 +21,29 @@ void set_error(const char* fmt, ...) {
   va_end(ap);
 }
 
-constexpr int kPlanThreads = 512;   // 512 x <=32 registers: a plan CTA fits on an SM beside the persistent step kernel
+constexpr int kPlanThreads = 256;   // 256 x <=64 registers = 16 K: a plan CTA fits on an SM beside the persistent step kernel
+constexpr int kPlanWarps = kPlanThreads / 32;
+constexpr int kRadixBits = 4, kRadix = 1 << kRadixBits;
 
-__global__ void __launch_bounds__(kPlanThreads, 2)
+// One CTA sorts one step's samples by row, STABLY (samples of a row keep their order), with an LSD radix sort of
+// the sample permutation in shared memory: 4-bit digits, every thread owns a contiguous run of positions (blocked
+// arrangement => stable), per-thread digit counts -> one block-wide exclusive scan in digit-major order -> scatter.
+// ceil(bits(max row)/4) passes of O(n) instead of the 105 compare-exchange stages of a 16 K bitonic network (the
+// round-1 kernel: 400 us per step-plan at 512 threads, 9 % of a training chunk; this one: see profiles/).
+// Dynamic shared memory: rows[batch] u32 | perm A[batch] u16 | perm B[batch] u16 | counts[16][512] u16.
+__global__ void __launch_bounds__(kPlanThreads, 4)
 plan_build_kernel(const int32_t* __restrict__ idx, int64_t n_total, int batch, int64_t step0,
-                  ar_plan plan, int pow2, const int32_t* __restrict__ counts) {
-  extern __shared__ unsigned long long keys[];  // pow2 entries
-  __shared__ int warp_tot[kPlanThreads / 32];
-  __shared__ int n_heavy_s;
+                  ar_plan plan, const int32_t* __restrict__ counts) {
+  extern __shared__ unsigned char smem_raw[];
+  uint32_t* rows = reinterpret_cast<uint32_t*>(smem_raw);
+  uint16_t* perm_a = reinterpret_cast<uint16_t*>(rows + batch);
+  uint16_t* perm_b = perm_a + batch + (batch & 1);
+  uint16_t* cnt = perm_b + batch + (batch & 1);            // [kRadix][kPlanThreads]
+  __shared__ int warp_tot[kPlanWarps];
+  __shared__ int n_heavy_s, n_uniq_s;
+  __shared__ uint32_t max_row_s;
   const int slot = blockIdx.x;
-  const int tid = threadIdx.x;
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   int64_t base = (step0 + slot) * (int64_t)batch;
   int n = 0;
   if (counts) {  // list form (ar_plan_build_lists): slot's keys at idx[slot*batch ...], counts[slot] of them
@@ -39,98 +52,146 @@ plan_build_kernel(const int32_t* __restrict__ idx, int64_t n_total, int batch, i
   } else if (base < n_total) {
     n = (int)min((int64_t)batch, n_total - base);
   }
-
-  for (int i = tid; i < pow2; i += kPlanThreads) {
-    unsigned long long k = ~0ull;
-    if (i < n) k = ((unsigned long long)(uint32_t)idx[base + i] << 32) | (uint32_t)i;
-    keys[i] = k;
+  if (tid == 0) {
+    n_heavy_s = 0;
+    max_row_s = 0u;
   }
-  if (tid == 0) n_heavy_s = 0;
   __syncthreads();
-
-  // bitonic sort, ascending; (row, sample) packed so equal rows keep sample order
-  for (int k = 2; k <= pow2; k <<= 1) {
-    for (int j = k >> 1; j > 0; j >>= 1) {
-      for (int p = tid; p < (pow2 >> 1); p += kPlanThreads) {
-        // p-th compare-exchange pair of this stage
-        int i = ((p & ~(j - 1)) << 1) | (p & (j - 1));
-        int l = i | j;
-        bool up = ((i & k) == 0);
-        unsigned long long a = keys[i], b = keys[l];
-        if ((a > b) == up) {
-          keys[i] = b;
-          keys[l] = a;
-        }
-      }
-      __syncthreads();
-    }
+  uint32_t mx = 0u;
+  for (int i = tid; i < n; i += kPlanThreads) {
+    const uint32_t r = (uint32_t)idx[base + i];
+    rows[i] = r;
+    perm_a[i] = (uint16_t)i;
+    mx = max(mx, r);
   }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+  if (lane == 0) atomicMax(&max_row_s, mx);
+  __syncthreads();
+  const int bits = 32 - __clz(max_row_s | 1u);
+  const int per = (n + kPlanThreads - 1) / kPlanThreads;     // positions per thread
+  const int lo = min(n, tid * per), hi = min(n, lo + per);
+  uint16_t* pin = perm_a;
+  uint16_t* pout = perm_b;
+  for (int shift = 0; shift < bits; shift += kRadixBits) {
+    int c[kRadix];
+#pragma unroll
+    for (int d = 0; d < kRadix; ++d) c[d] = 0;
+    for (int i = lo; i < hi; ++i) {
+      const int dgt = (rows[pin[i]] >> shift) & (kRadix - 1);
+#pragma unroll
+      for (int d = 0; d < kRadix; ++d) c[d] += (dgt == d) ? 1 : 0;
+    }
+#pragma unroll
+    for (int d = 0; d < kRadix; ++d) cnt[d * kPlanThreads + tid] = (uint16_t)c[d];
+    __syncthreads();
+    // exclusive scan of the kRadix*kPlanThreads counters in digit-major order: thread t owns 16 consecutive ones
+    int own[kRadix];
+    int sum = 0;
+#pragma unroll
+    for (int j = 0; j < kRadix; ++j) {
+      own[j] = cnt[tid * kRadix + j];
+      sum += own[j];
+    }
+    int incl = sum;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int t = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl += t;
+    }
+    if (lane == 31) warp_tot[wid] = incl;
+    __syncthreads();
+    if (tid < 32) {
+      const int w = tid < kPlanWarps ? warp_tot[tid] : 0;
+      int wi = w;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int t = __shfl_up_sync(0xffffffffu, wi, o);
+        if (tid >= o) wi += t;
+      }
+      if (tid < kPlanWarps) warp_tot[tid] = wi - w;  // exclusive
+    }
+    __syncthreads();
+    int run = warp_tot[wid] + incl - sum;
+#pragma unroll
+    for (int j = 0; j < kRadix; ++j) {
+      cnt[tid * kRadix + j] = (uint16_t)run;     // n <= 16384 fits 16 bits
+      run += own[j];
+    }
+    __syncthreads();
+    int off[kRadix];
+#pragma unroll
+    for (int d = 0; d < kRadix; ++d) off[d] = cnt[d * kPlanThreads + tid];
+    for (int i = lo; i < hi; ++i) {
+      const uint16_t item = pin[i];
+      const int dgt = (rows[item] >> shift) & (kRadix - 1);
+      int pos = 0;
+#pragma unroll
+      for (int d = 0; d < kRadix; ++d)
+        if (dgt == d) pos = off[d]++;
+      pout[pos] = item;
+    }
+    __syncthreads();
+    uint16_t* t = pin;
+    pin = pout;
+    pout = t;
+  }
+  // pin: samples sorted by (row, sample)
 
   int32_t* order = plan.order + (int64_t)slot * plan.batch_cap;
   int32_t* uniq = plan.uniq + (int64_t)slot * plan.batch_cap;
-  int32_t* off = plan.off + (int64_t)slot * (plan.batch_cap + 1);
+  int32_t* off_o = plan.off + (int64_t)slot * (plan.batch_cap + 1);
   int32_t* meta = plan.meta + (int64_t)slot * 4;
   int32_t* heavy = plan.heavy + (int64_t)slot * plan.heavy_cap;
 
-  // segment heads: blocked arrangement, per = pow2 / threads consecutive elements per thread
-  const int per = (pow2 + kPlanThreads - 1) / kPlanThreads;
-  const int lo = tid * per;
-  int cnt = 0;
-  for (int e = 0; e < per; ++e) {
-    int i = lo + e;
-    if (i < n) {
-      uint32_t r = (uint32_t)(keys[i] >> 32);
-      bool head = (i == 0) || ((uint32_t)(keys[i - 1] >> 32) != r);
-      cnt += head ? 1 : 0;
-    }
+  // segment heads over the same blocked arrangement
+  int cnt_heads = 0;
+  for (int i = lo; i < hi; ++i) {
+    const uint32_t r = rows[pin[i]];
+    cnt_heads += (i == 0 || rows[pin[i - 1]] != r) ? 1 : 0;
   }
-  // block exclusive scan of cnt
-  int incl = cnt;
+  int incl = cnt_heads;
 #pragma unroll
   for (int o = 1; o < 32; o <<= 1) {
-    int t = __shfl_up_sync(0xffffffffu, incl, o);
-    if ((tid & 31) >= o) incl += t;
+    const int t = __shfl_up_sync(0xffffffffu, incl, o);
+    if (lane >= o) incl += t;
   }
-  if ((tid & 31) == 31) warp_tot[tid >> 5] = incl;
+  if (lane == 31) warp_tot[wid] = incl;
   __syncthreads();
   if (tid < 32) {
-    int w = tid < kPlanThreads / 32 ? warp_tot[tid] : 0;
+    const int w = tid < kPlanWarps ? warp_tot[tid] : 0;
     int wi = w;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
-      int t = __shfl_up_sync(0xffffffffu, wi, o);
+      const int t = __shfl_up_sync(0xffffffffu, wi, o);
       if (tid >= o) wi += t;
     }
-    if (tid < kPlanThreads / 32) warp_tot[tid] = wi - w;  // exclusive
+    if (tid < kPlanWarps) warp_tot[tid] = wi - w;  // exclusive
   }
   __syncthreads();
-  int seg = warp_tot[tid >> 5] + incl - cnt;
-  for (int e = 0; e < per; ++e) {
-    int i = lo + e;
-    if (i < n) {
-      unsigned long long kv = keys[i];
-      uint32_t r = (uint32_t)(kv >> 32);
-      bool head = (i == 0) || ((uint32_t)(keys[i - 1] >> 32) != r);
-      order[i] = (int32_t)(uint32_t)kv;
-      if (head) {
-        uniq[seg] = (int32_t)r;
-        off[seg] = i;
-        ++seg;
-      }
+  int seg = warp_tot[wid] + incl - cnt_heads;
+  for (int i = lo; i < hi; ++i) {
+    const int item = pin[i];
+    const uint32_t r = rows[item];
+    order[i] = item;
+    if (i == 0 || rows[pin[i - 1]] != r) {
+      uniq[seg] = (int32_t)r;
+      off_o[seg] = i;
+      ++seg;
     }
   }
-  __shared__ int n_uniq_s;
   if (tid == kPlanThreads - 1) {
-    n_uniq_s = seg;  // last thread's running count == total
-    off[seg] = n;
+    n_uniq_s = seg;  // the last thread's running count == total
+    off_o[seg] = n;
   }
   __syncthreads();
   const int n_uniq = n_uniq_s;
-  for (int s = tid; s < n_uniq; s += kPlanThreads) {
-    int len = off[s + 1] - off[s];
+  __threadfence_block();
+  for (int sg = tid; sg < n_uniq; sg += kPlanThreads) {
+    const int len = off_o[sg + 1] - off_o[sg];
     if (len > AR_HEAVY_LEN) {
-      int pos = atomicAdd(&n_heavy_s, 1);
-      if (pos < plan.heavy_cap) heavy[pos] = s;
+      const int pos = atomicAdd(&n_heavy_s, 1);
+      if (pos < plan.heavy_cap) heavy[pos] = sg;
     }
   }
   __syncthreads();
@@ -383,15 +444,15 @@ static int plan_build_impl(const int32_t* idx, int64_t n_total, int32_t batch, i
   AR_REQUIRE(n_steps >= 0 && n_steps <= plan->n_slots, "ar_plan_build: n_steps %d > plan.n_slots %d", n_steps, plan->n_slots);
   AR_REQUIRE(plan->heavy_cap >= batch / AR_HEAVY_LEN + 1, "ar_plan_build: heavy_cap too small");
   if (n_steps == 0) return AR_OK;
-  int pow2 = 2;
-  while (pow2 < batch) pow2 <<= 1;
-  size_t smem = (size_t)pow2 * sizeof(unsigned long long);
+  const size_t be = (size_t)batch + (batch & 1);
+  const size_t smem = (size_t)batch * 4 + 2 * be * 2 + (size_t)ar::kRadix * ar::kPlanThreads * 2;
   static bool attr_set = false;
   if (!attr_set) {
-    AR_CUDA(cudaFuncSetAttribute(ar::plan_build_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, AR_MAX_BATCH * 8));
+    AR_CUDA(cudaFuncSetAttribute(ar::plan_build_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 AR_MAX_BATCH * 8 + ar::kRadix * ar::kPlanThreads * 2));
     attr_set = true;
   }
-  ar::plan_build_kernel<<<n_steps, ar::kPlanThreads, smem, (cudaStream_t)stream>>>(idx, n_total, batch, step0, *plan, pow2, counts);
+  ar::plan_build_kernel<<<n_steps, ar::kPlanThreads, smem, (cudaStream_t)stream>>>(idx, n_total, batch, step0, *plan, counts);
   AR_LAUNCH_CHECK();
   return AR_OK;
 }
