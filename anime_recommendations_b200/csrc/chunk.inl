@@ -29,7 +29,7 @@ namespace ar {
 
 // Build-time knobs (A/B builds: -DAR_STEP_WARPS=... etc.; the defaults are the measured best)
 #ifndef AR_STEP_WARPS
-#define AR_STEP_WARPS 12          // step warps per CTA (a multiple of 4: setmaxnreg works on warpgroups)
+#define AR_STEP_WARPS 16          // step warps per CTA (a multiple of 4: setmaxnreg works on warpgroups)
 #endif
 #ifndef AR_CHUNK_THREADS
 #define AR_CHUNK_THREADS 768      // NV == 1: step warps + replay warps
@@ -41,7 +41,7 @@ namespace ar {
 #define AR_REGS_REPLAY 40         // ... the replay warps keep
 #endif
 #ifndef AR_REGS_STEP
-#define AR_REGS_STEP 88           // ... the step warps grow to
+#define AR_REGS_STEP 72           // ... the step warps grow to
 #endif
 constexpr int kStepWarps = AR_STEP_WARPS;
 constexpr int kStepThreads = kStepWarps * 32;
@@ -831,13 +831,15 @@ __device__ void step_role(const ChunkArgs& a, StepSmem& sm, int n_threads, float
     const float* __restrict__ label = a.label + (size_t)s * a.batch;
     const int nu = a.plan[0].meta[(size_t)s * 4], na = a.plan[1].meta[(size_t)s * 4];
     const int tot = nu + na;
-    const int RU = (tot + ngw - 1) / ngw;
-    const int r0 = min(tot, gw * RU), r1 = min(tot, r0 + RU);
+    // item k of this warp is segment gw + k*ngw (users first, then anime): popular rows have neighbouring ids, a
+    // contiguous share would hand all of them to one warp
+    const int RU = tot > gw ? (tot - gw + ngw - 1) / ngw : 0;
+    const int r0 = 0, r1 = RU;
     // lane j: everything row `base + j` needs before its gathers
     int row_l = 0, beg_l = 0, len_l = 0, s0_l = 0, last_l = 0, which_l = 0;
     float lab_l = 0.f, c0_l = 0.f, rinv_l = 0.f;
     auto load_meta = [&](int base, int cnt) {
-      const int idx = base + lane;
+      const int idx = gw + (base + lane) * ngw;
       which_l = idx >= nu ? 1 : 0;
       if (lane < cnt) {
         const ar_plan& pl = a.plan[which_l];
@@ -977,58 +979,8 @@ __device__ void step_role(const ChunkArgs& a, StepSmem& sm, int n_threads, float
       const float* kk = sm.stepc;   // read at the use sites: shared-memory loads are cheaper than 11 live registers
       int32_t* pend = nullptr;      // flag of the row stored last, published behind the next row's arithmetic
       double reg_lane = 0.0;
-      for (int base = r0; base < r1; base += 32) {
-        const int cnt = min(32, r1 - base);
-        if (base != r0) {
-          load_meta(base, cnt);
-          prefetch_row(0, sbuf);
-        }
-        const float d0_l = dc_of_label(c0_l, lab_l, kk);
-        for (int j = 0; j < cnt; ++j) {
-          if (kBufs == 2 && j + 1 < cnt) {
-            prefetch_row(j + 1, sbuf + (size_t)((j + 1) & 1) * kBuf4);
-            cp_async_wait<1>();
-          } else {
-            cp_async_wait<0>();
-          }
-          const float4* b4 = sbuf + (size_t)(j & (kBufs - 1)) * kBuf4;
-          const int wA = __shfl_sync(0xffffffffu, which_l, j), rowA = __shfl_sync(0xffffffffu, row_l, j);
-          const int lenA = __shfl_sync(0xffffffffu, len_l, j);
-          if (lenA <= AR_HEAVY_LEN) {
-            RowTile<NV> accA, wa, ma, va;
-            tile_from_stage<NV>(accA, b4, d4, lane);
-            tile_from_stage<NV>(wa, b4 + 32 * NV, d4, lane);
-            tile_from_stage<NV>(ma, b4 + 64 * NV, d4, lane);
-            tile_from_stage<NV>(va, b4 + 96 * NV, d4, lane);
-            if (kBufs == 1 && j + 1 < cnt) prefetch_row(j + 1, sbuf);   // the buffer is in registers now
-            const ar_table& tA = a.tab[wA];
-            const float* __restrict__ otherA = wA ? uh : ah;
-            const float d0 = __shfl_sync(0xffffffffu, d0_l, j), c0 = __shfl_sync(0xffffffffu, c0_l, j);
-            float q = fmaf(d0, c0, 0.f);
-#pragma unroll
-            for (int k = 0; k < NV; ++k) accA.x[k] = fma4(d0, accA.x[k], make_float4(0.f, 0.f, 0.f, 0.f));
-            if (lenA > 1) {
-              const ar_plan& pl = a.plan[wA];
-              const int32_t* order = pl.order + (size_t)s * pl.batch_cap + __shfl_sync(0xffffffffu, beg_l, j);
-              for (int e = 1; e < lenA; ++e) {
-                const int sx = order[e];
-                RowTile<NV> o;
-                tile_load_cg<NV>(o, otherA + (size_t)sx * dim, d4, lane);
-                const float cx = __ldcg(cc + sx);
-                const float dx = dc_of_label(cx, __ldg(label + sx), kk);
-                q = fmaf(dx, cx, q);
-#pragma unroll
-                for (int k = 0; k < NV; ++k) accA.x[k] = fma4(dx, o.x[k], accA.x[k]);
-              }
-            }
-            finish_loaded<NV>(a, tabs, tA, rowA, accA, q, __shfl_sync(0xffffffffu, rinv_l, j), wa, ma, va,
-                              __shfl_sync(0xffffffffu, last_l, j), t, lane, reg_lane, pend);
-          } else if (kBufs == 1 && j + 1 < cnt) {
-            prefetch_row(j + 1, sbuf);
-          }
-        }
-      }
-      // heavy rows: pieces of AR_HEAVY_LEN samples spread over all step warps of the grid
+      // heavy rows FIRST (their flags are what the next forward waits for longest): pieces of AR_HEAVY_LEN samples
+      // spread over all step warps of the grid, the last piece to arrive finishes the row
       for (int w = 0; w < 2; ++w) {
         const ar_plan& pl = a.plan[w];
         const int nh = pl.meta[(size_t)s * 4 + 1];
@@ -1114,6 +1066,57 @@ __device__ void step_role(const ChunkArgs& a, StepSmem& sm, int n_threads, float
             }
           }
           piece0 += round_total;
+        }
+      }
+      for (int base = r0; base < r1; base += 32) {
+        const int cnt = min(32, r1 - base);
+        if (base != r0) {
+          load_meta(base, cnt);
+          prefetch_row(0, sbuf);
+        }
+        const float d0_l = dc_of_label(c0_l, lab_l, kk);
+        for (int j = 0; j < cnt; ++j) {
+          if (kBufs == 2 && j + 1 < cnt) {
+            prefetch_row(j + 1, sbuf + (size_t)((j + 1) & 1) * kBuf4);
+            cp_async_wait<1>();
+          } else {
+            cp_async_wait<0>();
+          }
+          const float4* b4 = sbuf + (size_t)(j & (kBufs - 1)) * kBuf4;
+          const int wA = __shfl_sync(0xffffffffu, which_l, j), rowA = __shfl_sync(0xffffffffu, row_l, j);
+          const int lenA = __shfl_sync(0xffffffffu, len_l, j);
+          if (lenA <= AR_HEAVY_LEN) {
+            RowTile<NV> accA, wa, ma, va;
+            tile_from_stage<NV>(accA, b4, d4, lane);
+            tile_from_stage<NV>(wa, b4 + 32 * NV, d4, lane);
+            tile_from_stage<NV>(ma, b4 + 64 * NV, d4, lane);
+            tile_from_stage<NV>(va, b4 + 96 * NV, d4, lane);
+            if (kBufs == 1 && j + 1 < cnt) prefetch_row(j + 1, sbuf);   // the buffer is in registers now
+            const ar_table& tA = a.tab[wA];
+            const float* __restrict__ otherA = wA ? uh : ah;
+            const float d0 = __shfl_sync(0xffffffffu, d0_l, j), c0 = __shfl_sync(0xffffffffu, c0_l, j);
+            float q = fmaf(d0, c0, 0.f);
+#pragma unroll
+            for (int k = 0; k < NV; ++k) accA.x[k] = fma4(d0, accA.x[k], make_float4(0.f, 0.f, 0.f, 0.f));
+            if (lenA > 1) {
+              const ar_plan& pl = a.plan[wA];
+              const int32_t* order = pl.order + (size_t)s * pl.batch_cap + __shfl_sync(0xffffffffu, beg_l, j);
+              for (int e = 1; e < lenA; ++e) {
+                const int sx = order[e];
+                RowTile<NV> o;
+                tile_load_cg<NV>(o, otherA + (size_t)sx * dim, d4, lane);
+                const float cx = __ldcg(cc + sx);
+                const float dx = dc_of_label(cx, __ldg(label + sx), kk);
+                q = fmaf(dx, cx, q);
+#pragma unroll
+                for (int k = 0; k < NV; ++k) accA.x[k] = fma4(dx, o.x[k], accA.x[k]);
+              }
+            }
+            finish_loaded<NV>(a, tabs, tA, rowA, accA, q, __shfl_sync(0xffffffffu, rinv_l, j), wa, ma, va,
+                              __shfl_sync(0xffffffffu, last_l, j), t, lane, reg_lane, pend);
+          } else if (kBufs == 1 && j + 1 < cnt) {
+            prefetch_row(j + 1, sbuf);
+          }
         }
       }
       if (flags && pend) {          // the last row this warp stored
