@@ -554,24 +554,44 @@ __device__ void replay_role(const ChunkArgs& a, StepSmem& sm, float4* stage_all)
 // of the grid share the rows (32 consecutive rows per warp visit, one coalesced last_step load).
 template <int NV>
 __device__ __forceinline__ void dense_pass(const ChunkArgs& a, const StepTabs& tabs, int64_t t, int gwarp,
-                                           int n_gwarps, int lane, unsigned long long& regfix) {
+                                           int n_gwarps, int lane, unsigned long long& regfix, float4* stage) {
+  // stage: this warp's staging buffers, kBufs x [W | m | v]; the next row is on its way (cp.async) while the current
+  // one takes its step -- the pass is a pure HBM stream (1.13 GB per step at cfg2) and wants bytes in flight
+  constexpr int kBufs = StageCfg<NV>::kBufs, kRow4 = 96 * NV;
   const int dim = a.tab[0].dim, d4 = dim >> 2;
 #pragma unroll 1
   for (int w = 0; w < 2; ++w) {
     const ar_table tb = a.tab[w];
+    auto prefetch = [&](int64_t row, float4* buf) {
+      const size_t o = (size_t)row * dim;
+      stage_tile<NV>(buf, tb.W + o, d4, lane);
+      stage_tile<NV>(buf + 32 * NV, tb.m + o, d4, lane);
+      stage_tile<NV>(buf + 64 * NV, tb.v + o, d4, lane);
+      cp_async_commit();
+    };
     for (int64_t r0 = (int64_t)gwarp * 32; r0 < tb.n_rows; r0 += (int64_t)n_gwarps * 32) {
       const int64_t mine = r0 + lane;
       const int last_l = mine < tb.n_rows ? __ldcg(tb.last_step + mine) : 0x7fffffff;
       unsigned todo = __ballot_sync(0xffffffffu, (int64_t)last_l < t);
+      int k = 0;
+      if (todo) prefetch(r0 + __ffs(todo) - 1, stage);
       while (todo) {
         const int j = __ffs(todo) - 1;
         todo &= todo - 1;
         const int64_t last = __shfl_sync(0xffffffffu, last_l, j);
         const size_t o = (size_t)(r0 + j) * dim;
+        if (kBufs == 2 && todo) {
+          prefetch(r0 + __ffs(todo) - 1, stage + (size_t)((k + 1) & 1) * kRow4);
+          cp_async_wait<1>();
+        } else {
+          cp_async_wait<0>();
+        }
+        const float4* b4 = stage + (size_t)(k & (kBufs - 1)) * kRow4;
         RowTile<NV> x, m, v;
-        tile_load_cg<NV>(x, tb.W + o, d4, lane);
-        tile_load_cg<NV>(m, tb.m + o, d4, lane);
-        tile_load_cg<NV>(v, tb.v + o, d4, lane);
+        tile_from_stage<NV>(x, b4, d4, lane);
+        tile_from_stage<NV>(m, b4 + 32 * NV, d4, lane);
+        tile_from_stage<NV>(v, b4 + 64 * NV, d4, lane);
+        if (kBufs == 1 && todo) prefetch(r0 + __ffs(todo) - 1, stage);
         double regd = 0.0;
         replay_tile<NV>(x, m, v, tabs, last, t, a.l2x2, lane, regd);
         x.store(tb.W + o, d4, lane);
@@ -581,6 +601,7 @@ __device__ __forceinline__ void dense_pass(const ChunkArgs& a, const StepTabs& t
           regd = warp_sum(regd);
           reg_fix_add(regd, a.reg, regfix);
         }
+        ++k;
       }
       if (mine < tb.n_rows && (int64_t)last_l < t) tb.last_step[mine] = (int32_t)t;
     }
@@ -589,7 +610,7 @@ __device__ __forceinline__ void dense_pass(const ChunkArgs& a, const StepTabs& t
 
 // The non-step warps in AR_ADAM_DENSE: join the dense pass of every step.
 template <int NV>
-__device__ void dense_helper_role(const ChunkArgs& a, StepSmem& sm, int n_threads) {
+__device__ void dense_helper_role(const ChunkArgs& a, StepSmem& sm, int n_threads, float4* stage_all) {
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   const int wpc = n_threads >> 5;
   const StepTabs tabs{a.alpha, a.reg.stepw, &sm};
@@ -603,7 +624,8 @@ __device__ void dense_helper_role(const ChunkArgs& a, StepSmem& sm, int n_thread
     }
     if (quit) break;
     __threadfence();
-    dense_pass<NV>(a, tabs, a.t0 + s + 1, blockIdx.x * wpc + wid, gridDim.x * wpc, lane, regfix);
+    dense_pass<NV>(a, tabs, a.t0 + s + 1, blockIdx.x * wpc + wid, gridDim.x * wpc, lane, regfix,
+                   stage_all + (size_t)(wid - kStepWarps) * (StageCfg<NV>::kBufs * 96 * NV));
     __threadfence();
     if (lane == 0) dense_arrive(sm);
   }
@@ -1133,7 +1155,7 @@ __device__ void step_role(const ChunkArgs& a, StepSmem& sm, int n_threads, float
     if (stamp) stamps[5] = (long long)globaltimer_ns();
     if (dense) {
       const int wpc = n_threads >> 5;
-      dense_pass<NV>(a, tabs, t, blockIdx.x * wpc + wid, n_ctas * wpc, lane, regfix);
+      dense_pass<NV>(a, tabs, t, blockIdx.x * wpc + wid, n_ctas * wpc, lane, regfix, sbuf);
       __threadfence();
       if (tid == 0) {   // the helper warps of this CTA have finished their share of the pass too
         const int want = (s + 1) * (wpc - kStepWarps);
@@ -1239,7 +1261,7 @@ __global__ void __maxnreg__(REGS) chunk_kernel(const __grid_constant__ ChunkArgs
   if (threadIdx.x >= kStepThreads) {
     if (kRegsReplay) asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kRegsReplay ? kRegsReplay : 24));
     if (a.mode == AR_ADAM_REPLAY) replay_role<NV>(a, sm, stage_all);
-    else if (a.mode == AR_ADAM_DENSE) dense_helper_role<NV>(a, sm, THREADS);
+    else if (a.mode == AR_ADAM_DENSE) dense_helper_role<NV>(a, sm, THREADS, stage_all);
     return;
   }
   if (kRegsStep) asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(kRegsStep ? kRegsStep : 24));
