@@ -10,7 +10,7 @@ import os
 
 PKG = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("ANIMEREC_LIB") or os.path.join(PKG, "lib", "libanimerec.so")   # override: A/B builds
-ABI_VERSION = 14
+ABI_VERSION = 15
 
 AR_MAX_BATCH = 16384
 AR_HEAVY_LEN = 64
@@ -85,7 +85,9 @@ class ArPeerCtx(C.Structure):
                 ("flags_peer", C.c_void_p * PEER_MAX_RANKS), ("sel_cap", C.c_int32),
                 ("sel_key", C.c_void_p * 2), ("sel_samp", C.c_void_p * 2), ("sel_oth", C.c_void_p * 2),
                 ("sel_cnt", C.c_void_p * 2), ("max_count", C.c_void_p), ("label_step", C.c_void_p),
-                ("c_all", C.c_void_p), ("dy_all", C.c_void_p), ("fwd_part_all", C.c_void_p), ("head_part_all", C.c_void_p)]
+                ("c_all", C.c_void_p), ("dy_all", C.c_void_p), ("fwd_part_all", C.c_void_p), ("head_part_all", C.c_void_p),
+                ("rowflag_peer", (C.c_void_p * PEER_MAX_RANKS) * 2), ("pairs_peer", C.c_void_p * PEER_MAX_RANKS),
+                ("hdrin_peer", C.c_void_p * PEER_MAX_RANKS), ("sel_lab", C.c_void_p * 2)]
 
 
 class AnimerecError(RuntimeError):

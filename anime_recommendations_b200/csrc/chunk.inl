@@ -116,6 +116,69 @@ struct ChunkArgs {
   int n_pieces;
 };
 
+// Multi-GPU (peer-memory) extension of the same kernel, csrc/peer.inl: the tables are row-sharded, this rank works on
+// the samples of the GLOBAL batch that touch its rows (two selection lists per step) and reads the other table's row
+// -- and its readiness flag -- straight from the owner's HBM over NVLink.
+constexpr int kPeerRanks = AR_PEER_MAX_RANKS;
+constexpr int kPeerErrWordC = 32;         // flags[32]: sticky "a cross-rank wait timed out" (shared with the staged path)
+constexpr int kPeerLenWord = 56;          // flags[56 + parity]: length of the list this rank sent two steps ago (local)
+constexpr unsigned long long kPeerWaitTimeoutNs = 20000000000ull;
+// Tagged words: one 64-bit store carries the payload and the step it belongs to, so the reader needs neither a flag
+// nor a fence -- it polls the word itself.  Pair word: low half = position in the global batch (18 bits) | tag << 18,
+// high half = the cosine's bits; the tag tells step t from step t-2, the only other step whose word can still sit in
+// the slot (a slot that drops out of the list is overwritten with kPairInvalid).  Header word: low half = 32 bits of
+// payload, high half = the optimizer step.
+constexpr int kPairPosBits = 18;
+constexpr unsigned kPairPosMask = (1u << kPairPosBits) - 1u;
+constexpr unsigned long long kPairInvalid = ~0ull;
+static_assert(AR_PEER_MAX_RANKS * AR_MAX_BATCH < (int)kPairPosMask, "positions of the global batch must fit the pair word");
+constexpr int kHdrWords = 8;              // 5 used: list length, sum c (lo, hi), sum c^2 (lo, hi)
+__device__ __forceinline__ unsigned pair_tag(int64_t t) { return (unsigned)((t >> 1) & ((1u << (32 - kPairPosBits)) - 1u)); }
+struct PeerExt {
+  const float* W_peer[2][kPeerRanks];          // [table][rank] shard bases (own entry = local pointer)
+  int32_t* rowflag_peer[2][kPeerRanks];        // [table][rank] per-row "at step" words the owners publish for the peers
+  unsigned long long* pairs_peer[kPeerRanks];  // [rank] its inbox of pair words: [2 parities][G senders][cap]
+  unsigned long long* hdrin_peer[kPeerRanks];  // [rank] its inbox of header words: [2 parities][G senders][kHdrWords]
+  int32_t* flags;                              // my flag words (error word, kPeerLenWord)
+  const int32_t* key[2];                       // selection lists of the chunk, [slot][cap]: local row of my table
+  const int32_t* oth[2];                       // ... global row of the other table
+  const int32_t* samp0;                        // ... position in the global batch (user side)
+  const int32_t* cnt[2];                       // [slot]
+  const float* lab[2];                         // [slot][cap] label of the listed sample
+  const float* label_step;                     // [slot][G*B] labels in global-batch order
+  float* cl1[2];                               // [parity][cap] cosines of the anime-side list (the user side's, the
+                                               // normalised other rows and 1/||my row|| live in ChunkArgs' c, ah/uh, ru/ra)
+  int G, me, cap, gb;                          // gb = G * per-rank batch
+  int strict;                                  // 1: system-scope fences in front of the row words (see below)
+};
+__device__ __forceinline__ int ld_sys_s32(const int32_t* p) {
+  int v;
+  asm volatile("ld.relaxed.sys.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ int ld_acquire_sys_s32(const int32_t* p) {
+  int v;
+  asm volatile("ld.acquire.sys.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ unsigned long long ld_sys_u64(const unsigned long long* p) {
+  unsigned long long v;
+  asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_sys_u64(unsigned long long* p, unsigned long long v) {
+  asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ void st_sys_s32(int32_t* p, int v) { asm volatile("st.relaxed.sys.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
+// Row flags in peer mode: last_step[row] is the LOCAL flag; the peers poll rowflag[row] (own array, so that the two
+// can be published differently) and then read the row from the owner's HBM with loads that bypass their own caches.
+//   default   both words are written behind the same DEVICE-scope fence.  The row lives in the owner's memory: once
+//             the fence has completed, the row's stores have been performed at the owner's L2, which is where every
+//             reader of that memory -- local SM or NVLink peer -- is served from, so a peer that sees the word reads
+//             the new row.  This is an argument about the hardware; the PTX model asks for a system-scope fence here.
+//   strict    (AR_PEER_STRICT=1) the PTX-conformant version: rowflag[row] is written behind a SYSTEM-scope fence -- one
+//             per step warp and step (after its last row), one per batch of replay items.  MEMBAR.SYS stalls far more
+//             than the warp that issues it: measured 93.7 us/step against 57.8 (1 rank, cfg2 shapes).
 __device__ __forceinline__ unsigned ld_acquire_u32(const unsigned* p) {
   unsigned v;
   asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
@@ -226,6 +289,8 @@ struct StepSmem {
   float head[4], hm[4], hv[4], bn[2];
   float stepc[K_STEPC + 2];
   double red[8 * kStepWarps];
+  int pcnt[kPeerRanks];      // peer mode: every rank's published list length / batch sums of the current step
+  double ps0[kPeerRanks], ps1[kPeerRanks];
   float alpha_w[kWin];
   float stepw_w[kWin];
 };
@@ -445,24 +510,29 @@ __device__ __forceinline__ void replay_item(const ChunkArgs& a, const StepTabs& 
   }
 }
 // After a fence: the row is at t_to.  A split row becomes current when its last part arrives.
-__device__ __forceinline__ void publish_item(const ChunkArgs& a, int code, int64_t t_to, int n_parts) {
-  int32_t* ls = (code < 0 ? a.tab[1].last_step : a.tab[0].last_step) + (int)((unsigned)code & kCodeRowMask);
+template <bool PEER>
+__device__ __forceinline__ void publish_item(const ChunkArgs& a, const PeerExt* px, int code, int64_t t_to, int n_parts) {
+  const int row = (int)((unsigned)code & kCodeRowMask);
+  int32_t* ls = (code < 0 ? a.tab[1].last_step : a.tab[0].last_step) + row;
+  bool current = true;
   if ((unsigned)code & kCodeSplit) {
     const int old = atomicAdd(ls, 1 << kPartShift);
-    if ((old >> kPartShift) == n_parts - 1) {
-      __threadfence();
-      *(volatile int32_t*)ls = (int32_t)t_to;
+    current = (old >> kPartShift) == n_parts - 1;
+    if (current) {   // (the other parts' stores: ordered before their arrivals by their fences, cumulative through this one)
+      if (PEER && px->strict) __threadfence_system(); else __threadfence();
     }
-  } else {
+  }
+  if (current) {
     *(volatile int32_t*)ls = (int32_t)t_to;
+    if (PEER) st_sys_s32(px->rowflag_peer[code < 0 ? 1 : 0][px->me] + row, (int32_t)t_to);
   }
 }
 
 // ---------------------------------------------------------------------------------------------
 // replay warps
 constexpr int kReplayBatch = 4;  // items per grab
-template <int NV>
-__device__ void replay_role(const ChunkArgs& a, StepSmem& sm, float4* stage_all) {
+template <int NV, bool PEER>
+__device__ void replay_role(const ChunkArgs& a, const PeerExt* px, StepSmem& sm, float4* stage_all) {
   const int lane = threadIdx.x & 31;
   constexpr int kBufs = StageCfg<NV>::kBufs;
   float4* stage = stage_all + (size_t)((threadIdx.x >> 5) - kStepWarps) * (kBufs * 96 * NV);   // row buffers of this warp
@@ -536,8 +606,8 @@ __device__ void replay_role(const ChunkArgs& a, StepSmem& sm, float4* stage_all)
       __syncwarp();              // buffer j&1 is free for item j+2
     }
     __syncwarp();
-    __threadfence();             // every lane's row stores before the flags
-    if (lane < nit) publish_item(a, code, t_to, n_parts);
+    if (PEER && px->strict) __threadfence_system(); else __threadfence();   // every lane's row stores before the flags
+    if (lane < nit) publish_item<PEER>(a, px, code, t_to, n_parts);
     busy += (unsigned long long)(clock64() - c0);
     items += nit;
   }
@@ -637,11 +707,12 @@ __device__ void dense_helper_role(const ChunkArgs& a, StepSmem& sm, int n_thread
 // finish one row: gradient from the reduced samples + L2 term, Adam step t, store.  w/m/v are already loaded.
 // `pend` (AR_ADAM_REPLAY): last_step entry of the row this warp stored BEFORE this one; its flag is published here,
 // behind a fence that finds those stores long complete, and this row's flag becomes the pending one.
-template <int NV>
+template <int NV, bool PEER>
 __device__ __forceinline__ void finish_loaded(const ChunkArgs& a, const StepTabs& tabs, const ar_table& tb, int row,
                                               const RowTile<NV>& acc, float q, float rinv, RowTile<NV>& w,
                                               RowTile<NV>& m, RowTile<NV>& v, int last, int64_t t, int lane,
-                                              double& reg_lane, int32_t*& pend) {
+                                              double& reg_lane, int32_t*& pend, int32_t*& pend_peer,
+                                              int32_t* rowflag = nullptr) {
   const int d4 = tb.dim >> 2;
   const size_t o = (size_t)row * tb.dim;
   const bool flags = a.mode == AR_ADAM_REPLAY;
@@ -665,19 +736,184 @@ __device__ __forceinline__ void finish_loaded(const ChunkArgs& a, const StepTabs
   }
   if (flags && pend) {
     __threadfence();
-    if (lane == 0) *(volatile int32_t*)pend = (int32_t)t;
+    if (lane == 0) {
+      *(volatile int32_t*)pend = (int32_t)t;
+      if (PEER && pend_peer) st_sys_s32(pend_peer, (int32_t)t);
+    }
   }
   w.store(tb.W + o, d4, lane);
   m.store(tb.m + o, d4, lane);
   v.store(tb.v + o, d4, lane);
   if (flags) pend = tb.last_step + row;
+  if (PEER) pend_peer = rowflag ? rowflag + row : nullptr;
   else if (lane == 0) tb.last_step[row] = (int32_t)t;
 }
 
+// pair buffers of the peer forward per step warp (each 4 row tiles); dim <= 128: 3 x 2 KB x 16 warps = 96 KB
+template <int NV> struct PeerCfg { static constexpr int kPairBufs = NV == 1 ? 3 : StageCfg<NV>::kBufs; };
+static_assert(PeerCfg<1>::kPairBufs <= 4, "peer_forward waits on at most 3 younger groups");
+template <int NV, bool PEER> struct StepStage {   // float4 per step warp
+  static constexpr int k4 = (PEER ? PeerCfg<NV>::kPairBufs : StageCfg<NV>::kBufs) * 128 * NV;
+};
+
+// Peer mode, forward of step s: this warp's share of the rank's two selection lists (entries of the user-side list
+// first).  Entry = (my row, local) + (the sample's row of the OTHER table, in its owner's HBM): wait until both are at
+// step t-1 (the owner's per-row flags are polled over NVLink), gather, normalise, dot.  Kept for the row update: the
+// normalised other row, 1/||my row|| and the cosine, per list entry; the user side also appends (position, cosine) to
+// the list the other ranks read, and only its cosines enter the batch sums (every sample once).
 template <int NV>
-__device__ void step_role(const ChunkArgs& a, StepSmem& sm, int n_threads, float4* step_stage) {
+__device__ __forceinline__ void peer_forward(const ChunkArgs& a, const PeerExt& px, StepSmem& sm, int s, int64_t t, int par,
+                                             int gw, int ngw, int lane, int wid, float4* sbuf, long long* stamps) {
+  constexpr int NB = PeerCfg<NV>::kPairBufs, kBuf4 = 128 * NV;
+  const int dim = a.tab[0].dim, d4 = dim >> 2;
+  const int G = px.G;
+  const int cu = min(px.cnt[0][s], px.cap), ca = min(px.cnt[1][s], px.cap);
+  const int tot = cu + ca;
+  const int RF = (tot + ngw - 1) / ngw;
+  const int f0 = min(tot, gw * RF), f1 = min(tot, f0 + RF);
+  const size_t my_box = ((size_t)par * G + px.me) * px.cap;   // my sender slot in every rank's inbox of this parity
+  const unsigned tag = pair_tag(t) << kPairPosBits;
+  {
+    // slots that held a word two steps ago and are past the end of this step's list: invalid from now on
+    const int prev = __ldcg(px.flags + kPeerLenWord + par);
+    for (int k = cu + gw * 32 + lane; k < min(prev, px.cap); k += ngw * 32)
+      for (int d = 0; d < G; ++d) st_sys_u64(px.pairs_peer[d] + my_box + k, kPairInvalid);
+  }
+  float* __restrict__ cl0 = a.c[par];
+  float* __restrict__ cl1 = px.cl1[par];
+  double sc = 0.0, sc2 = 0.0;
+  for (int base = f0; base < f1; base += 32) {
+    const int cnt = min(32, f1 - base);
+    int T_l = 0, k_l = 0, key_l = 0, own_l = px.me, ol_l = 0, samp_l = -1;
+    if (lane < cnt) {
+      const int e = base + lane;
+      T_l = e >= cu ? 1 : 0;
+      k_l = T_l ? e - cu : e;
+      const size_t at = (size_t)s * px.cap + k_l;
+      key_l = px.key[T_l][at];
+      const int og = px.oth[T_l][at];
+      own_l = og % G;
+      ol_l = og / G;
+      if (!T_l) samp_l = px.samp0[at];
+    }
+    {
+      const int want = (int)(t - 1);
+      const int32_t* lmine = a.tab[T_l].last_step + key_l;
+      const int32_t* lpeer = px.rowflag_peer[1 - T_l][own_l] + ol_l;
+      // (the peer's word is read with an acquire load: the row reads below come after it, at system scope, and a
+      // word that is already there costs one NVLink round trip, not two)
+      bool ready = lane >= cnt || (ld_acquire_sys_s32(lpeer) == want && ld_relaxed_s32(lmine) == want);
+      unsigned spins = 0;
+      unsigned long long t_begin = 0;
+      while (!__all_sync(0xffffffffu, ready)) {
+        __nanosleep(64);
+        if (!ready) ready = ld_acquire_sys_s32(lpeer) == want && ld_relaxed_s32(lmine) == want;
+        if ((++spins & 255u) == 0u) {
+          const unsigned long long now = globaltimer_ns();
+          if (!t_begin) t_begin = now;
+          else if (now - t_begin > kPeerWaitTimeoutNs || ld_relaxed_s32(&a.ctl->abort)) {
+            sm.abort = 1;            // keep going (the barriers must stay matched); the loop ends at the barrier
+            atomicExch(&a.ctl->abort, 1);
+            st_sys_s32(px.flags + kPeerErrWordC, (int)t);
+            break;
+          }
+        }
+      }
+      __threadfence();
+    }
+    if (stamps && base == f0) stamps[1] = (long long)globaltimer_ns();
+    // entry pairs through the staging buffers: [mine0 | other0 | mine1 | other1]
+    const int np = (cnt + 1) >> 1;
+    auto prefetch_pair = [&](int pi, float4* buf) {
+      const int j = 2 * pi, j1 = min(j + 1, cnt - 1);
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const int jj = h ? j1 : j;
+        const int T = __shfl_sync(0xffffffffu, T_l, jj), key = __shfl_sync(0xffffffffu, key_l, jj);
+        const int q = __shfl_sync(0xffffffffu, own_l, jj), ol = __shfl_sync(0xffffffffu, ol_l, jj);
+        stage_tile<NV>(buf + (2 * h) * 32 * NV, a.tab[T].W + (size_t)key * dim, d4, lane);
+        stage_tile<NV>(buf + (2 * h + 1) * 32 * NV, px.W_peer[1 - T][q] + (size_t)ol * dim, d4, lane);
+      }
+      cp_async_commit();
+    };
+    // ring of NB pair buffers, one cp.async group per pair: the rows come over NVLink (microseconds away), so as many
+    // pairs as shared memory allows are requested before the first one is waited for
+    for (int pi = 0; pi < min(NB, np); ++pi) prefetch_pair(pi, sbuf + (size_t)pi * kBuf4);
+    for (int pi = 0; pi < np; ++pi) {
+      const int j = 2 * pi;
+      const bool two = j + 1 < cnt;
+      const int pending = min(np, pi + NB) - (pi + 1);   // younger groups that may stay in flight
+      if (pending <= 0) cp_async_wait<0>();
+      else if (pending == 1) cp_async_wait<1>();
+      else if (pending == 2) cp_async_wait<2>();
+      else cp_async_wait<3>();
+      const float4* b4 = sbuf + (size_t)(pi % NB) * kBuf4;
+      RowTile<NV> x0, y0, x1, y1;   // x = my row, y = the other table's row
+      tile_from_stage<NV>(x0, b4, d4, lane);
+      tile_from_stage<NV>(y0, b4 + 32 * NV, d4, lane);
+      tile_from_stage<NV>(x1, b4 + 64 * NV, d4, lane);
+      tile_from_stage<NV>(y1, b4 + 96 * NV, d4, lane);
+      if (pi + NB < np) prefetch_pair(pi + NB, sbuf + (size_t)(pi % NB) * kBuf4);   // the buffer is in registers now
+      float sx0 = tile_partial_dot<NV>(x0, x0), sy0 = tile_partial_dot<NV>(y0, y0);
+      float sx1 = tile_partial_dot<NV>(x1, x1), sy1 = tile_partial_dot<NV>(y1, y1);
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        sx0 += __shfl_xor_sync(0xffffffffu, sx0, o);
+        sy0 += __shfl_xor_sync(0xffffffffu, sy0, o);
+        sx1 += __shfl_xor_sync(0xffffffffu, sx1, o);
+        sy1 += __shfl_xor_sync(0xffffffffu, sy1, o);
+      }
+      const float rx0 = 1.0f / sqrtf(fmaxf(sx0, kL2NormEps)), ry0 = 1.0f / sqrtf(fmaxf(sy0, kL2NormEps));
+      const float rx1 = 1.0f / sqrtf(fmaxf(sx1, kL2NormEps)), ry1 = 1.0f / sqrtf(fmaxf(sy1, kL2NormEps));
+#pragma unroll
+      for (int k = 0; k < NV; ++k) {
+        x0.x[k] = scale4(x0.x[k], rx0);
+        y0.x[k] = scale4(y0.x[k], ry0);
+        x1.x[k] = scale4(x1.x[k], rx1);
+        y1.x[k] = scale4(y1.x[k], ry1);
+      }
+      // (the products commute, so the anime side gets the very bits the user side publishes)
+      float cs0 = tile_partial_dot<NV>(x0, y0), cs1 = tile_partial_dot<NV>(x1, y1);
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        cs0 += __shfl_xor_sync(0xffffffffu, cs0, o);
+        cs1 += __shfl_xor_sync(0xffffffffu, cs1, o);
+      }
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        if (h && !two) break;
+        const int jj = j + h;
+        const int T = __shfl_sync(0xffffffffu, T_l, jj), k = __shfl_sync(0xffffffffu, k_l, jj);
+        const int sp = __shfl_sync(0xffffffffu, samp_l, jj);
+        const float cs = h ? cs1 : cs0, rx = h ? rx1 : rx0;
+        float* stash = (T ? a.uh[par] : a.ah[par]) + (size_t)k * dim;
+        if (h) y1.store(stash, d4, lane); else y0.store(stash, d4, lane);
+        if (lane == 0) {
+          (T ? a.ra[par] : a.ru[par])[k] = rx;
+          (T ? cl1 : cl0)[k] = cs;
+        }
+        if (!T && lane < G) {   // to every rank's inbox: position, tag and cosine in ONE 64-bit store
+          const unsigned long long word = (unsigned long long)(((unsigned)sp & kPairPosMask) | tag) |
+                                          ((unsigned long long)__float_as_uint(cs) << 32);
+          st_sys_u64(px.pairs_peer[lane] + my_box + k, word);
+        }
+        if (!T) {
+          sc += (double)cs;
+          sc2 += (double)cs * (double)cs;
+        }
+      }
+    }
+  }
+  if (lane == 0) {
+    sm.red[2 * wid] = sc;
+    sm.red[2 * wid + 1] = sc2;
+  }
+}
+
+template <int NV, bool PEER>
+__device__ void step_role(const ChunkArgs& a, const PeerExt* px, StepSmem& sm, int n_threads, float4* step_stage) {
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-  float4* sbuf = step_stage + (size_t)wid * (StageCfg<NV>::kBufs * 128 * NV);
+  float4* sbuf = step_stage + (size_t)wid * StepStage<NV, PEER>::k4;
   const int n_ctas = gridDim.x;
   const int gw = blockIdx.x * kStepWarps + wid, ngw = n_ctas * kStepWarps;
   const int dim = a.tab[0].dim, d4 = dim >> 2;
@@ -701,7 +937,8 @@ __device__ void step_role(const ChunkArgs& a, StepSmem& sm, int n_threads, float
   for (int s = 0; s < a.n_steps; ++s) {
     const int n = min(a.batch, a.plan[0].meta[(size_t)s * 4 + 2]);
     const int64_t t = a.t0 + s + 1;
-    const int par = s & 1;
+    // scratch parity: by chunk step on one GPU; by optimizer step in peer mode (the published lists outlive a launch)
+    const int par = PEER ? (int)(t & 1) : (s & 1);
     float* __restrict__ uh = a.uh[par];
     float* __restrict__ ah = a.ah[par];
     float* __restrict__ cc = a.c[par];
@@ -711,7 +948,9 @@ __device__ void step_role(const ChunkArgs& a, StepSmem& sm, int n_threads, float
     if (stamp) stamps[0] = (long long)globaltimer_ns();
 
     // ---- F: forward of this warp's samples
-    {
+    if constexpr (PEER) {
+      peer_forward<NV>(a, *px, sm, s, t, par, gw, ngw, lane, wid, sbuf, stamp ? stamps : nullptr);
+    } else {
       const int32_t* __restrict__ iu = a.iu + (size_t)s * a.batch;
       const int32_t* __restrict__ ia = a.ia + (size_t)s * a.batch;
       const float* __restrict__ U = a.tab[0].W;
@@ -830,17 +1069,17 @@ __device__ void step_role(const ChunkArgs& a, StepSmem& sm, int n_threads, float
         sm.red[2 * wid] = sc;
         sm.red[2 * wid + 1] = sc2;
       }
-      step_bar();
-      if (tid == 0) {
-        double b0 = 0.0, b1 = 0.0;
+    }
+    step_bar();
+    if (tid == 0) {
+      double b0 = 0.0, b1 = 0.0;
 #pragma unroll
-        for (int w = 0; w < kStepWarps; ++w) {
-          b0 += sm.red[2 * w];
-          b1 += sm.red[2 * w + 1];
-        }
-        a.fwd_part[2 * blockIdx.x] = b0;
-        a.fwd_part[2 * blockIdx.x + 1] = b1;
+      for (int w = 0; w < kStepWarps; ++w) {
+        b0 += sm.red[2 * w];
+        b1 += sm.red[2 * w + 1];
       }
+      a.fwd_part[2 * blockIdx.x] = b0;
+      a.fwd_part[2 * blockIdx.x + 1] = b1;
     }
     if (!grid_bar(ctl, bar, n_ctas, &sm.abort)) break;
     // every CTA has finished the row update of step s-1 (it came before this step's forward): release the items
@@ -850,7 +1089,11 @@ __device__ void step_role(const ChunkArgs& a, StepSmem& sm, int n_threads, float
 
     // ---- U, part 0: what this warp's rows need that does not depend on the head -- issued now, so that the loads
     // (and the first row's gathers) are in flight while the head is computed
-    const float* __restrict__ label = a.label + (size_t)s * a.batch;
+    const float* __restrict__ label = PEER ? nullptr : a.label + (size_t)s * a.batch;
+    // per listed sample: cosine and label.  One GPU: both tables index the batch.  Peer mode: each table has its own
+    // selection list (the anime side computed the same cosine bits itself)
+    auto cc_of = [&](int w) -> const float* { return PEER ? (w ? px->cl1[par] : cc) : cc; };
+    auto lab_of = [&](int w) -> const float* { return PEER ? px->lab[w] + (size_t)s * px->cap : label; };
     const int nu = a.plan[0].meta[(size_t)s * 4], na = a.plan[1].meta[(size_t)s * 4];
     const int tot = nu + na;
     // item k of this warp is segment gw + k*ngw (users first, then anime): popular rows have neighbouring ids, a
@@ -871,8 +1114,8 @@ __device__ void step_role(const ChunkArgs& a, StepSmem& sm, int n_threads, float
         beg_l = off[seg];
         len_l = off[seg + 1] - beg_l;
         s0_l = pl.order[(size_t)s * pl.batch_cap + beg_l];
-        c0_l = __ldcg(cc + s0_l);
-        lab_l = __ldg(label + s0_l);
+        c0_l = __ldcg(cc_of(which_l) + s0_l);
+        lab_l = __ldg(lab_of(which_l) + s0_l);
         rinv_l = __ldcg((which_l ? rav : ruv) + s0_l);
         last_l = __ldcg(a.tab[which_l].last_step + row_l);
       }
@@ -898,7 +1141,8 @@ __device__ void step_role(const ChunkArgs& a, StepSmem& sm, int n_threads, float
     // ---- head: identical arithmetic, identical order in every CTA
     {
       double s0 = 0.0, s1 = 0.0;
-      {
+      int nh = n;               // samples the batch statistics run over (peer mode: the global batch)
+      if (!PEER || (blockIdx.x == 0 && wid == 0)) {
         double2 pv[kMaxCtas / 32];
 #pragma unroll
         for (int r = 0; r < kMaxCtas / 32; ++r) {     // all loads in flight together
@@ -913,6 +1157,64 @@ __device__ void step_role(const ChunkArgs& a, StepSmem& sm, int n_threads, float
       }
       s0 = warp_sum(s0);
       s1 = warp_sum(s1);
+      if constexpr (PEER) {
+        // Cross-rank exchange, no flags and no fences: CTA 0 sends this rank's list length and batch sums to every
+        // rank's header inbox as step-tagged words; everyone polls its own inbox until all ranks' words of step t
+        // are there.  (The pair words were sent during the forward and are validated one by one below.)
+        const int G = px->G;
+        if (blockIdx.x == 0 && tid == 0) {
+          const unsigned long long b0 = (unsigned long long)__double_as_longlong(s0);
+          const unsigned long long b1 = (unsigned long long)__double_as_longlong(s1);
+          const int cu = min(px->cnt[0][s], px->cap);
+          const unsigned pay[5] = {(unsigned)cu, (unsigned)b0, (unsigned)(b0 >> 32), (unsigned)b1, (unsigned)(b1 >> 32)};
+          const unsigned long long tg = (unsigned long long)(unsigned)t << 32;
+          for (int d = 0; d < G; ++d) {
+            unsigned long long* box = px->hdrin_peer[d] + ((size_t)par * G + px->me) * kHdrWords;
+#pragma unroll
+            for (int i = 0; i < 5; ++i) st_sys_u64(box + i, (unsigned long long)pay[i] | tg);
+          }
+          px->flags[kPeerLenWord + par] = cu;   // what the forward of step t+2 has to invalidate behind
+        }
+        if (tid < G) {
+          const unsigned long long* box = px->hdrin_peer[px->me] + ((size_t)par * G + tid) * kHdrWords;
+          unsigned long long w[5];
+          unsigned spins = 0;
+          unsigned long long t_begin = 0;
+          for (;;) {
+            bool all = true;
+#pragma unroll
+            for (int i = 0; i < 5; ++i) {
+              w[i] = ld_sys_u64(box + i);
+              all = all && (unsigned)(w[i] >> 32) == (unsigned)t;
+            }
+            if (all) break;
+            if ((++spins & 63u) == 0u) {
+              const unsigned long long now = globaltimer_ns();
+              if (!t_begin) t_begin = now;
+              else if (now - t_begin > kPeerWaitTimeoutNs || ld_relaxed_s32(&ctl->abort)) {
+                st_sys_s32(px->flags + kPeerErrWordC, (int)t);
+                sm.abort = 1;          // the barriers below stay matched; the loop ends at the next one
+                atomicExch(&ctl->abort, 1);
+                break;
+              }
+            }
+          }
+          sm.pcnt[tid] = (int)(unsigned)w[0];
+          sm.ps0[tid] = __longlong_as_double((long long)((w[1] & 0xffffffffull) | (w[2] << 32)));
+          sm.ps1[tid] = __longlong_as_double((long long)((w[3] & 0xffffffffull) | (w[4] << 32)));
+        }
+        step_bar();
+        s0 = 0.0;
+        s1 = 0.0;
+        nh = 0;
+        for (int r = 0; r < G; ++r) {   // rank order: identical sums on every rank
+          s0 += sm.ps0[r];
+          s1 += sm.ps1[r];
+          nh += min(max(sm.pcnt[r], 0), px->cap);
+        }
+        nh = max(nh, 1);
+      }
+      const int n = nh;   // (shadows the per-rank count from here to the end of the head)
       const HeadScalars h = head_scalars(sm.head, s0, s1, n);
       // second pass, distributed: this CTA's share of the samples (one per thread) -> 5 backward sums + the reported
       // BCE / squared error; per-CTA partials, a second grid barrier, then every CTA adds them in CTA order
@@ -920,8 +1222,45 @@ __device__ void step_role(const ChunkArgs& a, StepSmem& sm, int n_threads, float
       double acc[7];
 #pragma unroll
       for (int i = 0; i < 7; ++i) acc[i] = 0.0;
-      for (int i = blockIdx.x * mshare + tid; i < min(n, (blockIdx.x + 1) * mshare); i += kStepThreads) {
-        const float ci = __ldcg(cc + i), ti = __ldg(label + i);
+      // peer mode: the samples are every rank's published (position, cosine) pairs, read over NVLink; CTA b takes
+      // pairs [b*share, (b+1)*share) of every list, flattened over (rank, pair) so that the loads are in flight together
+      int shmax = 0;
+      if constexpr (PEER) {
+        for (int r = 0; r < px->G; ++r) shmax = max(shmax, (min(max(sm.pcnt[r], 0), px->cap) + n_ctas - 1) / n_ctas);
+      }
+      const int i_lo = PEER ? tid : blockIdx.x * mshare + tid;
+      const int i_hi = PEER ? px->G * shmax : min(n, (blockIdx.x + 1) * mshare);
+      for (int i = i_lo; i < i_hi; i += kStepThreads) {
+        float ci, ti;
+        if constexpr (PEER) {
+          const int r = i / shmax, k = blockIdx.x * shmax + (i - r * shmax);
+          if (k >= min(sm.pcnt[r], px->cap)) continue;
+          const unsigned long long* pp = px->pairs_peer[px->me] + ((size_t)par * px->G + r) * px->cap + k;
+          const unsigned want = pair_tag(t);
+          unsigned long long pw = ld_sys_u64(pp);
+          unsigned spins = 0;
+          unsigned long long t_begin = 0;
+          // valid = this step's tag and a position inside the global batch (an invalidated slot has neither)
+          while ((unsigned)pw >> kPairPosBits != want || ((unsigned)pw & kPairPosMask) >= (unsigned)px->gb) {
+            if ((++spins & 63u) == 0u) {
+              const unsigned long long now = globaltimer_ns();
+              if (!t_begin) t_begin = now;
+              else if (now - t_begin > kPeerWaitTimeoutNs || ld_relaxed_s32(&ctl->abort)) {
+                st_sys_s32(px->flags + kPeerErrWordC, (int)t);
+                sm.abort = 1;
+                atomicExch(&ctl->abort, 1);
+                break;
+              }
+            }
+            pw = ld_sys_u64(pp);
+          }
+          const int j = (int)min((unsigned)pw & kPairPosMask, (unsigned)px->gb - 1u);
+          ci = __uint_as_float((unsigned)(pw >> 32));
+          ti = __ldg(px->label_step + (size_t)s * px->gb + j);
+        } else {
+          ci = __ldcg(cc + i);
+          ti = __ldg(label + i);
+        }
         const float zh = ((h.w * ci + h.b) - h.mu) * h.inv;
         const float y = h.gamma * zh + h.beta;
         const float p = sigmoidf_(y);
@@ -1001,6 +1340,10 @@ __device__ void step_role(const ChunkArgs& a, StepSmem& sm, int n_threads, float
       const float* kk = sm.stepc;   // read at the use sites: shared-memory loads are cheaper than 11 live registers
       int32_t* pend = nullptr;      // flag of the row stored last, published behind the next row's arithmetic
       double reg_lane = 0.0;
+      int hv_n = 0, hv_row = 0;     // strict peer mode: heavy rows this warp finished (lane i: the i-th; bit 31 = anime)
+      int32_t* pend_peer = nullptr; // default peer mode: the pending row's word for the peers
+      const bool strict = PEER && px->strict;
+      auto rowflag_of = [&](int w) -> int32_t* { return (PEER && !strict) ? px->rowflag_peer[w][px->me] : nullptr; };
       // heavy rows FIRST (their flags are what the next forward waits for longest): pieces of AR_HEAVY_LEN samples
       // spread over all step warps of the grid, the last piece to arrive finishes the row
       for (int w = 0; w < 2; ++w) {
@@ -1009,6 +1352,8 @@ __device__ void step_role(const ChunkArgs& a, StepSmem& sm, int n_threads, float
         if (nh == 0) continue;
         const ar_table& tb = a.tab[w];
         const float* __restrict__ other = w ? uh : ah;
+        const float* __restrict__ ccw = cc_of(w);
+        const float* __restrict__ labw = lab_of(w);
         const int32_t* off = pl.off + (size_t)s * (pl.batch_cap + 1);
         const int32_t* order = pl.order + (size_t)s * pl.batch_cap;
         int piece0 = 0;   // pieces of the heavy rows before this round
@@ -1045,8 +1390,8 @@ __device__ void step_role(const ChunkArgs& a, StepSmem& sm, int n_threads, float
               const int sx = order[e];
               RowTile<NV> o;
               tile_load_cg<NV>(o, other + (size_t)sx * dim, d4, lane);
-              const float cx = __ldcg(cc + sx);
-              const float dx = dc_of_label(cx, __ldg(label + sx), kk);
+              const float cx = __ldcg(ccw + sx);
+              const float dx = dc_of_label(cx, __ldg(labw + sx), kk);
               q = fmaf(dx, cx, q);
 #pragma unroll
               for (int k = 0; k < NV; ++k) acc.x[k] = fma4(dx, o.x[k], acc.x[k]);
@@ -1084,7 +1429,17 @@ __device__ void step_role(const ChunkArgs& a, StepSmem& sm, int n_threads, float
               tile_load_cg<NV>(m, tb.m + (size_t)row * dim, d4, lane);
               tile_load_cg<NV>(v, tb.v + (size_t)row * dim, d4, lane);
               const float rinv = __ldcg((w ? rav : ruv) + order[beg]);
-              finish_loaded<NV>(a, tabs, tb, row, acc, q, rinv, x, m, v, __ldcg(tb.last_step + row), t, lane, reg_lane, pend);
+              finish_loaded<NV, PEER>(a, tabs, tb, row, acc, q, rinv, x, m, v, __ldcg(tb.last_step + row), t, lane, reg_lane, pend,
+                                      pend_peer, rowflag_of(w));
+              if (strict) {
+                if (hv_n == 32) {   // (never in practice: a warp finishing more than 32 heavy rows of one step)
+                  __threadfence_system();
+                  st_sys_s32(px->rowflag_peer[hv_row < 0 ? 1 : 0][px->me] + (hv_row & 0x7fffffff), (int32_t)t);
+                  hv_n = 0;
+                }
+                if (lane == hv_n) hv_row = row | (w ? (int)0x80000000 : 0);
+                ++hv_n;
+              }
             }
           }
           piece0 += round_total;
@@ -1116,6 +1471,8 @@ __device__ void step_role(const ChunkArgs& a, StepSmem& sm, int n_threads, float
             if (kBufs == 1 && j + 1 < cnt) prefetch_row(j + 1, sbuf);   // the buffer is in registers now
             const ar_table& tA = a.tab[wA];
             const float* __restrict__ otherA = wA ? uh : ah;
+            const float* __restrict__ ccA = cc_of(wA);
+            const float* __restrict__ labA = lab_of(wA);
             const float d0 = __shfl_sync(0xffffffffu, d0_l, j), c0 = __shfl_sync(0xffffffffu, c0_l, j);
             float q = fmaf(d0, c0, 0.f);
 #pragma unroll
@@ -1127,15 +1484,15 @@ __device__ void step_role(const ChunkArgs& a, StepSmem& sm, int n_threads, float
                 const int sx = order[e];
                 RowTile<NV> o;
                 tile_load_cg<NV>(o, otherA + (size_t)sx * dim, d4, lane);
-                const float cx = __ldcg(cc + sx);
-                const float dx = dc_of_label(cx, __ldg(label + sx), kk);
+                const float cx = __ldcg(ccA + sx);
+                const float dx = dc_of_label(cx, __ldg(labA + sx), kk);
                 q = fmaf(dx, cx, q);
 #pragma unroll
                 for (int k = 0; k < NV; ++k) accA.x[k] = fma4(dx, o.x[k], accA.x[k]);
               }
             }
-            finish_loaded<NV>(a, tabs, tA, rowA, accA, q, __shfl_sync(0xffffffffu, rinv_l, j), wa, ma, va,
-                              __shfl_sync(0xffffffffu, last_l, j), t, lane, reg_lane, pend);
+            finish_loaded<NV, PEER>(a, tabs, tA, rowA, accA, q, __shfl_sync(0xffffffffu, rinv_l, j), wa, ma, va,
+                              __shfl_sync(0xffffffffu, last_l, j), t, lane, reg_lane, pend, pend_peer, rowflag_of(wA));
           } else if (kBufs == 1 && j + 1 < cnt) {
             prefetch_row(j + 1, sbuf);
           }
@@ -1143,7 +1500,27 @@ __device__ void step_role(const ChunkArgs& a, StepSmem& sm, int n_threads, float
       }
       if (flags && pend) {          // the last row this warp stored
         __threadfence();
-        if (lane == 0) *(volatile int32_t*)pend = (int32_t)t;
+        if (lane == 0) {
+          *(volatile int32_t*)pend = (int32_t)t;
+          if (PEER && pend_peer) st_sys_s32(pend_peer, (int32_t)t);
+        }
+      }
+      if (strict) {
+        // for the peers: ONE system-scope fence behind all of this warp's rows of the step, then their row words
+        __threadfence_system();
+        if (lane < hv_n) st_sys_s32(px->rowflag_peer[hv_row < 0 ? 1 : 0][px->me] + (hv_row & 0x7fffffff), (int32_t)t);
+        for (int base = r0; base < r1; base += 32) {
+          const int k = base + lane;
+          if (k < r1) {
+            const int idx = gw + k * ngw;
+            const int w = idx >= nu ? 1 : 0;
+            const ar_plan& pl = a.plan[w];
+            const int seg = w ? idx - nu : idx;
+            const int32_t* off = pl.off + (size_t)s * (pl.batch_cap + 1);
+            if (off[seg + 1] - off[seg] <= AR_HEAVY_LEN)
+              st_sys_s32(px->rowflag_peer[w][px->me] + pl.uniq[(size_t)s * pl.batch_cap + seg], (int32_t)t);
+          }
+        }
       }
       if (a.reg.acc) reg_fix_add(warp_sum(reg_lane), a.reg, regfix);
     }
@@ -1200,7 +1577,9 @@ __device__ void step_role(const ChunkArgs& a, StepSmem& sm, int n_threads, float
   }
   // reported metrics: per-step sums of the per-CTA partials, fixed order
   for (int s = gw; s < a.n_steps; s += ngw) {
-    const int n = min(a.batch, a.plan[0].meta[(size_t)s * 4 + 2]);
+    // (peer mode: the global batch's size, as CTA 0 recorded it with the step's statistics)
+    const int n = PEER ? max(1, (int)__ldcg(a.metrics + (a.t0 + s + 1) * 4 + 2))
+                       : min(a.batch, a.plan[0].meta[(size_t)s * 4 + 2]);
     double b0 = 0.0, b1 = 0.0;
     for (int i = lane; i < n_ctas; i += 32) {
       b0 += __ldcg(a.mpart + ((size_t)s * kMaxCtas + i) * 2);
@@ -1233,8 +1612,8 @@ static_assert((AR_CHUNK_THREADS - kStepThreads) * (AR_REGS_LAUNCH - AR_REGS_REPL
               "the replay warps do not free enough registers for the step warps");
 static_assert((768 - kStepThreads) * (80 - 56) >= kStepThreads * (88 - 80), "register hand-over (NV > 1)");
 
-template <int NV, int THREADS, int REGS>
-__global__ void __maxnreg__(REGS) chunk_kernel(const __grid_constant__ ChunkArgs a) {
+template <int NV, int THREADS, bool PEER>
+__device__ __forceinline__ void chunk_body(const ChunkArgs& a, const PeerExt* px) {
   __shared__ StepSmem sm;
   extern __shared__ float4 stage_all[];   // replay warps: [warp][kBufs][3 tiles]; then step warps: [warp][kBufs][4 tiles]
   {
@@ -1260,12 +1639,22 @@ __global__ void __maxnreg__(REGS) chunk_kernel(const __grid_constant__ ChunkArgs
   constexpr int kRegsReplay = ChunkRegs<NV>::kReplay, kRegsStep = ChunkRegs<NV>::kStep;
   if (threadIdx.x >= kStepThreads) {
     if (kRegsReplay) asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kRegsReplay ? kRegsReplay : 24));
-    if (a.mode == AR_ADAM_REPLAY) replay_role<NV>(a, sm, stage_all);
-    else if (a.mode == AR_ADAM_DENSE) dense_helper_role<NV>(a, sm, THREADS, stage_all);
+    if (a.mode == AR_ADAM_REPLAY) replay_role<NV, PEER>(a, px, sm, stage_all);
+    else if (!PEER && a.mode == AR_ADAM_DENSE) dense_helper_role<NV>(a, sm, THREADS, stage_all);
     return;
   }
   if (kRegsStep) asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(kRegsStep ? kRegsStep : 24));
-  step_role<NV>(a, sm, THREADS, stage_all + (size_t)(THREADS / 32 - kStepWarps) * (StageCfg<NV>::kBufs * 96 * NV));
+  step_role<NV, PEER>(a, px, sm, THREADS, stage_all + (size_t)(THREADS / 32 - kStepWarps) * (StageCfg<NV>::kBufs * 96 * NV));
+}
+
+template <int NV, int THREADS, int REGS>
+__global__ void __maxnreg__(REGS) chunk_kernel(const __grid_constant__ ChunkArgs a) {
+  chunk_body<NV, THREADS, false>(a, nullptr);
+}
+// the same kernel over row-sharded tables and NVLink peer memory (AR_ADAM_REPLAY only), csrc/peer.inl
+template <int NV, int THREADS, int REGS>
+__global__ void __maxnreg__(REGS) peer_chunk_kernel(const __grid_constant__ ChunkArgs a, const __grid_constant__ PeerExt px) {
+  chunk_body<NV, THREADS, true>(a, &px);
 }
 
 template <int NV> struct ChunkCfg {
@@ -1274,23 +1663,37 @@ template <int NV> struct ChunkCfg {
 };
 
 template <int NV>
-static int launch_chunk_nv(const ChunkArgs& a, cudaStream_t st) {
+static int launch_chunk_nv(const ChunkArgs& a, const PeerExt* px, cudaStream_t st) {
   constexpr int T = ChunkCfg<NV>::kThreads, R = ChunkCfg<NV>::kRegs;
-  static int max_ctas = -1;
-  const size_t dyn = ((size_t)(T / 32 - kStepWarps) * 96 + (size_t)kStepWarps * 128) * StageCfg<NV>::kBufs * NV * sizeof(float4);
-  if (max_ctas < 0) {
-    AR_CUDA(cudaFuncSetAttribute(chunk_kernel<NV, T, R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
+  static int max_ctas[2] = {-1, -1};
+  const size_t dyn = ((size_t)(T / 32 - kStepWarps) * 96 * StageCfg<NV>::kBufs * NV +
+                      (size_t)kStepWarps * (px ? StepStage<NV, true>::k4 : StepStage<NV, false>::k4)) * sizeof(float4);
+  const int which = px ? 1 : 0;
+  if (max_ctas[which] < 0) {
     int per_sm = 0;
-    AR_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, chunk_kernel<NV, T, R>, T, dyn));
+    if (px) {
+      AR_CUDA(cudaFuncSetAttribute(peer_chunk_kernel<NV, T, R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
+      AR_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, peer_chunk_kernel<NV, T, R>, T, dyn));
+    } else {
+      AR_CUDA(cudaFuncSetAttribute(chunk_kernel<NV, T, R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
+      AR_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, chunk_kernel<NV, T, R>, T, dyn));
+    }
     AR_REQUIRE(per_sm >= 1, "ar_train_steps: the step kernel does not fit on an SM");
-    max_ctas = std::min(num_sms(), kMaxCtas);
+    max_ctas[which] = std::min(num_sms(), kMaxCtas);
   }
-  chunk_kernel<NV, T, R><<<max_ctas, T, dyn, st>>>(a);
+  // peer mode leaves a few SMs to the side stream: the next chunk's planning (an NCCL all-gather, the selection and
+  // the plan sorts, whose CTAs do not fit beside a step CTA) then overlaps this chunk instead of following it
+  static const int reserve = getenv("AR_PEER_RESERVE_SMS") ? atoi(getenv("AR_PEER_RESERVE_SMS")) : 20;
+  const int peer_ctas = std::max(1, max_ctas[which] - std::max(0, reserve));
+  if (px) peer_chunk_kernel<NV, T, R><<<peer_ctas, T, dyn, st>>>(a, *px);
+  else chunk_kernel<NV, T, R><<<max_ctas[which], T, dyn, st>>>(a);
   AR_LAUNCH_CHECK();
   return AR_OK;
 }
 
-static int launch_chunk(const ar_train_ctx& x, int64_t epoch_step0, int64_t t0, int n_steps, cudaStream_t st) {
+// px != null: peer mode (the caller fills everything of *px but cl1)
+static int launch_chunk(const ar_train_ctx& x, int64_t epoch_step0, int64_t t0, int n_steps, cudaStream_t st,
+                        PeerExt* px = nullptr) {
   const ChunkLayout l = chunk_layout(x.plan_u.n_slots, std::max(x.plan_u.batch_cap, x.plan_a.batch_cap), x.users.dim);
   char* ws = (char*)x.chunk_ws;
   ChunkArgs a{};
@@ -1300,9 +1703,9 @@ static int launch_chunk(const ar_train_ctx& x, int64_t epoch_step0, int64_t t0, 
   a.plan[1] = x.plan_a;
   a.sched = x.sched;
   const int64_t base0 = epoch_step0 * (int64_t)x.batch;
-  a.iu = x.iu + base0;
-  a.ia = x.ia + base0;
-  a.label = x.label + base0;
+  a.iu = px ? nullptr : x.iu + base0;      // peer mode works from the selection lists
+  a.ia = px ? nullptr : x.ia + base0;
+  a.label = px ? nullptr : x.label + base0;
   a.t0 = t0;
   a.n_steps = n_steps;
   a.batch = x.batch;
@@ -1326,6 +1729,10 @@ static int launch_chunk(const ar_train_ctx& x, int64_t epoch_step0, int64_t t0, 
   a.c[1] = st1 + (size_t)2 * bc * x.users.dim;
   a.ru[1] = a.c[1] + bc;
   a.ra[1] = a.ru[1] + bc;
+  if (px) {
+    px->cl1[0] = x.dy;                     // (sel_cap) scratch the staged kernels use for dy
+    px->cl1[1] = a.ra[1] + bc;             // the fourth per-sample vector of the odd-parity stash
+  }
   a.metrics = x.metrics;
   a.reg = reg_of(x);
   a.health = x.health;
@@ -1339,7 +1746,7 @@ static int launch_chunk(const ar_train_ctx& x, int64_t epoch_step0, int64_t t0, 
   a.n_pieces = l.n_pieces;
   AR_CUDA(cudaMemsetAsync(ws, 0, l.zero_bytes, st));
   int rc = AR_OK;
-  AR_DISPATCH_NV(x.users.dim, rc = launch_chunk_nv<NV>(a, st));
+  AR_DISPATCH_NV(x.users.dim, rc = launch_chunk_nv<NV>(a, px, st));
   return rc;
 }
 

@@ -186,6 +186,7 @@ struct PeerSelArgs {
   int32_t* cnt[2];         // [slot]
   int32_t* max_count;      // [2]
   float* lab_step;         // [slot][G*B]
+  float* lab_list[2];      // [slot][cap] label of the listed sample (may be null)
 };
 constexpr int kSelThreads = 1024;
 
@@ -200,11 +201,13 @@ __global__ void __launch_bounds__(kSelThreads, 1) peer_select_kernel(PeerSelArgs
   int32_t* samp = a.samp[T] + (int64_t)slot * a.cap;
   int32_t* oth = a.oth[T] + (int64_t)slot * a.cap;
   float* lab = a.lab_step + (int64_t)slot * a.G * a.B;
+  float* labl = a.lab_list[T] ? a.lab_list[T] + (int64_t)slot * a.cap : nullptr;
   int running = 0;
   for (int base = 0; base < ng; base += kSelThreads) {
     const int j = base + tid;
     bool mine = false;
     int k_own = 0, k_oth = 0;
+    float lab_j = 0.f;
     if (j < ng) {
       const int r = j / n, i = j - r * n;
       const int64_t src = (int64_t)r * a.rank_stride + first + i;
@@ -212,7 +215,8 @@ __global__ void __launch_bounds__(kSelThreads, 1) peer_select_kernel(PeerSelArgs
       k_own = T ? ka : ku;
       k_oth = T ? ku : ka;
       mine = (k_own % a.G) == a.me;
-      if (T == 0) lab[j] = a.lab_all[src];
+      lab_j = a.lab_all[src];
+      if (T == 0) lab[j] = lab_j;
     }
     const unsigned bal = __ballot_sync(0xffffffffu, mine);
     if (lane == 0) warp_tot[wid] = __popc(bal);
@@ -235,6 +239,7 @@ __global__ void __launch_bounds__(kSelThreads, 1) peer_select_kernel(PeerSelArgs
         key[pos] = k_own / a.G;
         samp[pos] = j;
         oth[pos] = k_oth;
+        if (labl) labl[pos] = lab_j;
       }
     }
     running += tile_tot;
@@ -426,6 +431,8 @@ extern "C" int ar_peer_plan(const int32_t* iu_all, const int32_t* ia_all, const 
   }
   a.max_count = h->max_count;
   a.lab_step = h->label_step;
+  a.lab_list[0] = h->sel_lab[0];
+  a.lab_list[1] = h->sel_lab[1];
   peer_select_kernel<<<dim3(n_steps, 2), kSelThreads, 0, st>>>(a);
   AR_LAUNCH_CHECK();
   const ar_plan* plans[2] = {plan_u, plan_a};
@@ -449,6 +456,43 @@ extern "C" int ar_train_steps_peer(const ar_train_ctx* ctx, const ar_peer_ctx* h
   AR_REQUIRE(t0 + n_steps < (1ll << 29), "ar_train_steps_peer: optimizer step too large for the barrier epochs");
   cudaStream_t st = (cudaStream_t)stream;
   const int dim = x.users.dim, G = h->n_ranks, B = x.batch;
+  // AR_ADAM_REPLAY with a replay schedule and the peer views of the readiness flags: the persistent kernel of the
+  // single-GPU path, extended over peer memory (chunk.inl) -- one launch for the whole chunk
+  static const bool staged = getenv("AR_PEER_STAGED") != nullptr;
+  if (!staged && x.mode == AR_ADAM_REPLAY && x.sched.codes && x.chunk_ws && x.health && h->hdrin_peer[h->rank] &&
+      h->sel_lab[0] && h->sel_lab[1]) {
+    AR_REQUIRE(slot0 == 0, "ar_train_steps_peer: slot0 must be 0 (the step kernel indexes the plans by step)");
+    if ((rc = check_ctx_single(ctx, n_steps))) return rc;
+    AR_REQUIRE(t0 + n_steps < (1ll << 27), "ar_train_steps_peer: optimizer step too large for the row flags");
+    int live = 0;
+    for (int s = 0; s < n_steps; ++s)
+      if ((epoch_step0 + s) * (int64_t)B < x.n_samples) live = s + 1;
+    if (live == 0) return AR_OK;
+    PeerExt px{};
+    for (int r = 0; r < G; ++r) {
+      AR_REQUIRE(h->rowflag_peer[0][r] && h->rowflag_peer[1][r] && h->pairs_peer[r] && h->hdrin_peer[r],
+                 "ar_train_steps_peer: inboxes / row flags of rank %d missing", r);
+      for (int k = 0; k < 2; ++k) {
+        px.W_peer[k][r] = h->W_peer[k][r];
+        px.rowflag_peer[k][r] = h->rowflag_peer[k][r];
+      }
+      px.pairs_peer[r] = reinterpret_cast<unsigned long long*>(h->pairs_peer[r]);
+      px.hdrin_peer[r] = reinterpret_cast<unsigned long long*>(h->hdrin_peer[r]);
+    }
+    px.flags = h->flags_peer[h->rank];
+    static const bool strict = getenv("AR_PEER_STRICT") != nullptr;
+    px.strict = strict ? 1 : 0;
+    for (int k = 0; k < 2; ++k) {
+      px.key[k] = h->sel_key[k];
+      px.oth[k] = h->sel_oth[k];
+      px.cnt[k] = h->sel_cnt[k];
+      px.lab[k] = h->sel_lab[k];
+    }
+    px.samp0 = h->sel_samp[0];
+    px.label_step = h->label_step;
+    px.G = G; px.me = h->rank; px.cap = cap; px.gb = G * B;
+    return launch_chunk(x, epoch_step0, t0, live, st, &px);
+  }
   static const bool no_overlap = getenv("AR_NO_LOOKAHEAD") != nullptr;
   // where the look-ahead catch-up of step s+1 starts: behind the forward of step s (default) -- the forward is
   // what the OTHER ranks wait for, so it gets the SMs to itself and the replay overlaps the pull, the head and

@@ -408,7 +408,7 @@ extern "C" int ar_plan_sched(const ar_plan* plan_u, const ar_plan* plan_a, int32
 }
 
 extern "C" const char* ar_last_error(void) { return ar::g_err; }
-extern "C" int ar_abi_version(void) { return 14; }
+extern "C" int ar_abi_version(void) { return 15; }
 
 extern "C" int ar_check_device(void) {
   int dev = 0;

@@ -9,6 +9,7 @@ issued from libanimerec on the kernels' stream.
 from __future__ import annotations
 
 import ctypes as C
+import os
 import time
 
 import numpy as np
@@ -202,19 +203,35 @@ class PeerTrainSession(TrainSession):
             raise _capi.AnimerecError("peer-memory training supports up to %d ranks" % _capi.PEER_MAX_RANKS)
         cap = peer_plan_cap(int(batch), G)
         super().__init__(model, batch, total_steps, plan_cap=cap)
+        # replay mode: ONE persistent kernel per chunk (csrc/chunk.inl over peer memory); AR_PEER_STAGED=1 and the
+        # other Adam modes chain the per-step stage kernels of csrc/peer.inl
+        self.persistent = model.adam_mode == "replay" and os.environ.get("AR_PEER_STAGED") is None
         self.comm = comm or Comm()
         B, D, dev, S = self.B, model.dim, model.device, self.n_slots
         f = dict(dtype=torch.float32, device=dev)
         i32 = dict(dtype=torch.int32, device=dev)
-        # everything the other ranks read or write lives in ONE allocation: [U | A | published list | flags]
+        # everything the other ranks read or write lives in ONE allocation:
+        # [U | A | published list (staged path) | flags | row words U | row words A | pair inbox | header inbox]
         nU, nA = model.U.numel(), model.A.numel()
-        words = nU + nA + 2 * cap + PEER_FLAG_WORDS
+        up4 = lambda n: (n + 3) // 4 * 4       # noqa: E731  (16-byte aligned regions)
+        nFU, nFA = up4(model.lastU.numel()), up4(model.lastA.numel())
+        nPairs = 2 * G * cap * 2               # [2 parities][G senders][cap] 64-bit words, in 32-bit units
+        nHdr = 2 * G * 8 * 2                   # [2][G][8] 64-bit words
+        words = nU + nA + 2 * cap + PEER_FLAG_WORDS + nFU + nFA + nPairs + nHdr
         self.arena = torch.zeros(words, **f)
         o = 0
         U = self.arena[o:o + nU].view_as(model.U); o += nU
         A = self.arena[o:o + nA].view_as(model.A); o += nA
         self.pub = self.arena[o:o + 2 * cap]; o += 2 * cap
-        self.flags = self.arena[o:o + PEER_FLAG_WORDS].view(torch.int32)
+        self.flags = self.arena[o:o + PEER_FLAG_WORDS].view(torch.int32); o += PEER_FLAG_WORDS
+        # per row: the optimizer step the row is at, as the PEERS may rely on it (written behind a system-scope fence;
+        # model.lastU / lastA stay the local flags).  Refreshed from the local flags at the start of every run().
+        self.rowflag = [self.arena[o:o + model.lastU.numel()].view(torch.int32),
+                        self.arena[o + nFU:o + nFU + model.lastA.numel()].view(torch.int32)]
+        o += nFU + nFA
+        self.pair_inbox = self.arena[o:o + nPairs].view(torch.int32); o += nPairs
+        self.pair_inbox.fill_(-1)              # every slot invalid
+        self.hdr_inbox = self.arena[o:o + nHdr]; o += nHdr
         U.copy_(model.U)
         A.copy_(model.A)
         model.U, model.A = U, A                # the model's tables now live in the exported arena
@@ -240,13 +257,19 @@ class PeerTrainSession(TrainSession):
                 base = p.value
             self.peer_base.append(base)
         # shard sizes differ by at most one row between ranks, so every rank reports its own layout
-        lay = torch.tensor([nU, nA], dtype=torch.int64, device=dev)
+        lay = torch.tensor([nU, nA, nFU, nFA], dtype=torch.int64, device=dev)
         lays = self.comm.allgather(lay).cpu().tolist()
         for r in range(G):
-            h.W_peer[0][r] = self.peer_base[r]
-            h.W_peer[1][r] = self.peer_base[r] + 4 * lays[r][0]
-            h.pub_peer[r] = self.peer_base[r] + 4 * (lays[r][0] + lays[r][1])
-            h.flags_peer[r] = self.peer_base[r] + 4 * (lays[r][0] + lays[r][1] + 2 * cap)
+            base, (rU, rA, rFU, rFA) = self.peer_base[r], lays[r]
+            o = rU + rA
+            h.W_peer[0][r] = base
+            h.W_peer[1][r] = base + 4 * rU
+            h.pub_peer[r] = base + 4 * o; o += 2 * cap
+            h.flags_peer[r] = base + 4 * o; o += PEER_FLAG_WORDS
+            h.rowflag_peer[0][r] = base + 4 * o
+            h.rowflag_peer[1][r] = base + 4 * (o + rFU); o += rFU + rFA
+            h.pairs_peer[r] = base + 4 * o; o += nPairs
+            h.hdrin_peer[r] = base + 4 * o
         self.c_all = torch.zeros(G * B, **f)
         self.dy_all = torch.empty(G * B, **f)
         self.fwd_part_all = torch.zeros(2 * G * ((cap + 1023) // 1024), dtype=torch.float64, device=dev)
@@ -266,7 +289,9 @@ class PeerTrainSession(TrainSession):
             st["sel"] = dict(sel_key=[torch.zeros((S, cap), **i32) for _ in range(2)],
                              sel_samp=[torch.zeros((S, cap), **i32) for _ in range(2)],
                              sel_oth=[torch.zeros((S, cap), **i32) for _ in range(2)],
-                             sel_cnt=[torch.zeros(S, **i32) for _ in range(2)])
+                             sel_cnt=[torch.zeros(S, **i32) for _ in range(2)],
+                             sel_lab=[torch.zeros((S, cap), **f) for _ in range(2)])
+            st["sched"], st["keep_sched"] = self._make_sched(S, cap, dev)   # replay schedule of the persistent kernel
             st["max_count"] = torch.zeros(2, **i32)
             st["label_step"] = torch.zeros((S, G * B), **f)
             st["gather"] = [torch.empty((G, S * B), **i32), torch.empty((G, S * B), **i32), torch.empty((G, S * B), **f)]
@@ -299,8 +324,8 @@ class PeerTrainSession(TrainSession):
         dist.barrier()
         check(lib().ar_peer_close_all(), "ar_peer_close_all")
 
-    def _plan_chunk(self, st, iu, ia, y, s0, ns):
-        """Queue the planning of steps [s0, s0+ns) into set `st` on the CURRENT stream."""
+    def _plan_chunk(self, st, iu, ia, y, s0, ns, t0):
+        """Queue the planning of steps [s0, s0+ns) (optimizer steps t0+s0+1 ..) into set `st` on the CURRENT stream."""
         B, S, L, sp = self.B, self.n_slots, lib(), stream_ptr()
         N = iu.numel()
         lo, hi = s0 * B, min(N, (s0 + ns) * B)
@@ -313,6 +338,12 @@ class PeerTrainSession(TrainSession):
         g = st["gather"]
         check(L.ar_peer_plan(ptr(g[0]), ptr(g[1]), ptr(g[2]), S * B, hi - lo, B, ns, C.byref(st["plan_u"]),
                              C.byref(st["plan_a"]), C.byref(st["pctx"]), sp), "ar_peer_plan")
+        m = self.model
+        if self.persistent:
+            # the replay schedule over MY rows (local ids), exactly as on one GPU
+            check(L.ar_plan_sched(C.byref(st["plan_u"]), C.byref(st["plan_a"]), ns, t0 + s0, m._t_flush,
+                                  ptr(m.seenU), m.n_users, ptr(m.seenA), m.n_anime, self.depth, m.dim,
+                                  C.byref(st["sched"]), sp), "ar_plan_sched")
         # no host round trip per chunk: the grids are sized for the list capacity, and the longest list of every
         # chunk is checked by verify() (an overflowing list is truncated on the device, nothing is corrupted)
         torch.maximum(self._max_seen, st["max_count"], out=self._max_seen)
@@ -330,15 +361,21 @@ class PeerTrainSession(TrainSession):
             raise _capi.AnimerecError("PeerTrainSession sized for %d optimizer steps, %d requested" % (self.t_cap, t0 + steps))
         m._set_alpha(lr, t0 + 1, steps)
         ctx = self._ctx(iu, ia, y)
+        if self.persistent:
+            # what happened to the rows outside this session (a flush, restored weights) reaches the peers' view here;
+            # no rank polls these words between runs, and the values only grow
+            self.rowflag[0].copy_(m.lastU)
+            self.rowflag[1].copy_(m.lastA)
         # plan-order catch-up: with the rows sharded a row's replay is ~G times shorter than on one GPU, and the
         # longest-first schedule's two extra launches per step cost more than its balance gains (2 GPUs: 72.0 vs
         # 78.5 us/step)
         ctx.sched_ws = None
         main, L, S = torch.cuda.current_stream(), lib(), self.n_slots
+        per_step = {"replay": 5, "dense": 6, "touched": 4}[m.adam_mode]
         chunks = [(s0, min(S, steps - s0)) for s0 in range(0, steps, S)]
         self.plan_stream.wait_stream(main)                 # the inputs (H2D copies) are queued on `main`
         with torch.cuda.stream(self.plan_stream):
-            self._plan_chunk(self.sets[0], iu, ia, y, *chunks[0])
+            self._plan_chunk(self.sets[0], iu, ia, y, *chunks[0], t0)
             self.sets[0]["planned"].record()
         for i, (s0, ns) in enumerate(chunks):
             st = self.sets[i % 2]
@@ -347,18 +384,22 @@ class PeerTrainSession(TrainSession):
                 with torch.cuda.stream(self.plan_stream):
                     if i >= 1:
                         self.plan_stream.wait_event(nxt["consumed"])   # chunk i-1 no longer reads that set
-                    self._plan_chunk(nxt, iu, ia, y, *chunks[i + 1])
+                    self._plan_chunk(nxt, iu, ia, y, *chunks[i + 1], t0)
                     nxt["planned"].record()
             main.wait_event(st["planned"])
             ctx.plan_u, ctx.plan_a = st["plan_u"], st["plan_a"]
+            if self.persistent:
+                ctx.sched = st["sched"]
             tq = time.perf_counter()
             check(L.ar_train_steps_peer(C.byref(ctx), C.byref(st["pctx"]), s0, 0, t0 + s0, ns, self.P, stream_ptr(main)),
                   "ar_train_steps_peer")
             self.enqueue_s += time.perf_counter() - tq
             st["consumed"].record(main)
-            # per chunk: select, 2 plan sorts, 2 plan links; per step: forward, pull, head, row update and
-            # (replay) catch-up or (dense) two table flushes
-            self.launches += 5 + ns * {"replay": 5, "dense": 6, "touched": 4}[m.adam_mode]
+            # per chunk: select, 2 plan sorts, 2 plan links (+ 5 schedule kernels and ONE step kernel when the
+            # persistent kernel runs); else per step: forward, pull, head, row update and (replay) catch-up or
+            # (dense) two table flushes
+            self.launches += 5 + (6 if self.persistent else ns * per_step)
+            self._last_ns = ns
         main.wait_stream(self.plan_stream)                 # nothing of this call is left on the side stream
         m.iterations = t0 + steps
         if verify:
@@ -377,3 +418,4 @@ class PeerTrainSession(TrainSession):
             raise _capi.AnimerecError("peer mode: %d samples of one step touch one rank's rows, capacity %d; the "
                                       "results of this run are invalid -- use ShardedTrainSession for this data" % (mc, self.P))
         self.check_flags()
+        self.check_health()        # the persistent kernel's own time-outs and schedule checks

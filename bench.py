@@ -289,7 +289,7 @@ def gpu_main(args):
                 config=workload_config(mode, world), gpu_launches=int(launches), host_enqueue_us_per_step=enqueue_us,
                 clocks=clocks)
     if world > 1:
-        line["config"]["parallelism"] = "dp%d, %s" % (world, {"peer": "row-sharded tables, NVLink peer-memory pulls + flag barriers", "replicated": "replicated tables, NCCL all-gather", "sharded": "row-sharded tables, NCCL all-to-all"}[args.dist])
+        line["config"]["parallelism"] = "dp%d, %s" % (world, {"peer": "row-sharded tables, one persistent kernel per 256 steps: rows pulled over NVLink peer memory behind per-row step words, cosines exchanged as step-tagged words", "replicated": "replicated tables, NCCL all-gather", "sharded": "row-sharded tables, NCCL all-to-all"}[args.dist])
 
     if rank == 0 and world == 1:
         # ---- roofline.  The whole step is ONE persistent kernel per 256-step chunk (csrc/chunk.inl), so the dominant
@@ -369,6 +369,15 @@ def gpu_main(args):
             line["extras"] = extras(dev, pk)
             line["extras"]["train_modes"] = {m: mode_run(ar, dev, m, min(K, 100), W) for m in ("dense", "touched")
                                              if m != mode}
+    if world > 1 and getattr(sess, "persistent", False):
+        # CTA 0's %globaltimer stamps of the last chunk (rank 0): where a multi-GPU step spends its time
+        tl = sess.timeline() if rank == 0 else None
+        if tl is not None:
+            line["peer_step_phases_us"] = {k: float(np.mean(tl[k + "_us"][4:])) for k in ("gate", "fwd", "head", "update", "step")}
+            line["peer_step_phases_us"]["what"] = ("gate = wait for the rows of the first samples (local + NVLink row words), fwd = "
+                                                   "forward incl. the NVLink row pulls + grid barrier, head = cross-rank exchange + "
+                                                   "head + second barrier, update = row updates")
+            line["peer_step_phases_us"]["replay_warp_busy_frac"] = tl["replay_busy_cycles"] / max(1.0, float(tl["replay_warps"]) * tl["kernel_cycles"])
     if world > 1:
         # ---- e2e at N GPUs: every rank feeds its shard of each global batch from pinned HOST memory
         hu, ha, hy = (t.cpu().pin_memory() for t in synth(T * BATCH, 177 + rank, dev, zipf=args.zipf))

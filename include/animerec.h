@@ -288,7 +288,8 @@ typedef struct {
   float* W_peer[2][AR_PEER_MAX_RANKS];          /* [0 users | 1 anime][rank]: base of that rank's shard; the own
                                                    entry is the local pointer (= ctx->users.W / ctx->anime.W) */
   float* pub_peer[AR_PEER_MAX_RANKS];           /* every rank's published (sample, cosine) list: sel_cap pairs of
-                                                   (int32 position in the global batch, float c) */
+                                                   (int32 position in the global batch, float c); two such lists
+                                                   back to back (by step parity) for the persistent kernel */
   int32_t* flags_peer[AR_PEER_MAX_RANKS];       /* every rank's AR_PEER_FLAG_WORDS int32, zero-initialised before
                                                    any rank's first step; word 32 != 0: a barrier timed out */
   int32_t sel_cap;                              /* capacity of one selection list = batch_cap of both plans */
@@ -303,6 +304,16 @@ typedef struct {
   float* dy_all;                                /* (n_ranks*batch) */
   double* fwd_part_all;                         /* (2 * n_ranks * ceil(sel_cap/1024)) */
   double* head_part_all;
+  /* persistent peer kernel (AR_ADAM_REPLAY with a replay schedule; all of these set, else the staged kernels run).
+   * Nothing here needs a fence on the step's critical path: cosines and batch sums travel as 64-bit words that carry
+   * their own step tag (written with one store, valid when the tag matches), rows are guarded by per-row step words. */
+  int32_t* rowflag_peer[2][AR_PEER_MAX_RANKS];  /* [table][rank] per row of that rank's shard: the optimizer step the
+                                                   row is at, written (behind a system-scope fence) by its owner */
+  uint64_t* pairs_peer[AR_PEER_MAX_RANKS];      /* [rank] that rank's inbox of (position, cosine) words:
+                                                   [2 step parities][n_ranks senders][sel_cap], initialised to ~0 */
+  uint64_t* hdrin_peer[AR_PEER_MAX_RANKS];      /* [rank] that rank's inbox of list headers: [2][n_ranks][8] words
+                                                   (list length, sum c, sum c^2 as 32-bit halves + step tag) */
+  float* sel_lab[2];                            /* [n_slots][sel_cap] label of every listed sample */
 } ar_peer_ctx;
 
 /* Plan a chunk: iu_all / ia_all / label_all hold every rank's samples of the chunk, rank r's at

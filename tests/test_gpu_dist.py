@@ -44,24 +44,37 @@ def test_two_rank_row_sharded_training_equals_single_gpu(mode):
     assert "DIST_OK" in r.stdout
 
 
-@pytest.mark.parametrize("mode", ["replay", "dense", "touched"])
+def _peer_env(mode):
+    """replay_staged: the per-step stage kernels of csrc/peer.inl instead of the persistent kernel."""
+    env = dict(os.environ)
+    env.pop("AR_PEER_STAGED", None)
+    if mode.endswith("_staged"):
+        env["AR_PEER_STAGED"] = "1"
+    return mode.replace("_staged", ""), env
+
+
+@pytest.mark.parametrize("mode", ["replay", "replay_staged", "dense", "touched"])
 def test_two_rank_peer_memory_training_equals_single_gpu(mode):
-    """csrc/peer.inl: owners pull the other table's rows over NVLink, flag barriers instead of collectives."""
+    """csrc/peer.inl + the peer mode of csrc/chunk.inl: owners pull the other table's rows over NVLink, flags
+    instead of collectives."""
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs")
+    mode, env = _peer_env(mode)
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr",
            "127.0.0.1", "--master-port", "29547", os.path.join(ROOT, "tests", "dist_worker.py"), "peer_" + mode]
-    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600, env=env)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
     assert "DIST_OK" in r.stdout
 
 
-def test_one_rank_peer_memory_training_equals_single_gpu():
+@pytest.mark.parametrize("mode", ["replay", "replay_staged"])
+def test_one_rank_peer_memory_training_equals_single_gpu(mode):
     """The peer-memory path with a world of ONE rank (every pull is local): runs on a single-GPU box, so the
-    peer_select / peer_fwd / peer_pull kernels and the chunked planning are covered there too."""
+    persistent peer kernel, peer_select / peer_fwd / peer_pull and the chunked planning are covered there too."""
+    mode, env = _peer_env(mode)
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "1", "--master-addr",
-           "127.0.0.1", "--master-port", "29549", os.path.join(ROOT, "tests", "dist_worker.py"), "peer_replay"]
-    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+           "127.0.0.1", "--master-port", "29549", os.path.join(ROOT, "tests", "dist_worker.py"), "peer_" + mode]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600, env=env)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
     assert "DIST_OK" in r.stdout
 
