@@ -749,9 +749,13 @@ __device__ __forceinline__ void finish_loaded(const ChunkArgs& a, const StepTabs
   else if (lane == 0) tb.last_step[row] = (int32_t)t;
 }
 
-// pair buffers of the peer forward per step warp (each 4 row tiles); dim <= 128: 3 x 2 KB x 16 warps = 96 KB
-template <int NV> struct PeerCfg { static constexpr int kPairBufs = NV == 1 ? 3 : StageCfg<NV>::kBufs; };
-static_assert(PeerCfg<1>::kPairBufs <= 4, "peer_forward waits on at most 3 younger groups");
+// pair buffers of the peer forward per step warp (each 4 row tiles); dim <= 128: 3 x 2 KB x 16 warps = 96 KB (measured:
+// five buffers request a whole share at once but shrink the L1 and slow the head and the row update more than they gain)
+#ifndef AR_PEER_PAIR_BUFS
+#define AR_PEER_PAIR_BUFS 3
+#endif
+template <int NV> struct PeerCfg { static constexpr int kPairBufs = NV == 1 ? AR_PEER_PAIR_BUFS : StageCfg<NV>::kBufs; };
+static_assert(PeerCfg<1>::kPairBufs <= 5, "peer_forward waits on at most 4 younger groups");
 template <int NV, bool PEER> struct StepStage {   // float4 per step warp
   static constexpr int k4 = (PEER ? PeerCfg<NV>::kPairBufs : StageCfg<NV>::kBufs) * 128 * NV;
 };
@@ -768,9 +772,14 @@ __device__ __forceinline__ void peer_forward(const ChunkArgs& a, const PeerExt& 
   const int dim = a.tab[0].dim, d4 = dim >> 2;
   const int G = px.G;
   const int cu = min(px.cnt[0][s], px.cap), ca = min(px.cnt[1][s], px.cap);
-  const int tot = cu + ca;
-  const int RF = (tot + ngw - 1) / ngw;
-  const int f0 = min(tot, gw * RF), f1 = min(tot, f0 + RF);
+  // this warp: a contiguous share of the user-side list, then one of the anime-side list.  The user-side entries
+  // come first because they send words to the other ranks: those stores are long acknowledged when the grid
+  // barrier's release fence has to wait for them
+  const int RFu = (cu + ngw - 1) / ngw, RFa = (ca + ngw - 1) / ngw;
+  const int u0 = min(cu, gw * RFu), u1 = min(cu, u0 + RFu);
+  const int a0 = min(ca, gw * RFa), a1 = min(ca, a0 + RFa);
+  const int nuw = u1 - u0;
+  const int f0 = 0, f1 = nuw + (a1 - a0);
   const size_t my_box = ((size_t)par * G + px.me) * px.cap;   // my sender slot in every rank's inbox of this parity
   const unsigned tag = pair_tag(t) << kPairPosBits;
   {
@@ -787,8 +796,8 @@ __device__ __forceinline__ void peer_forward(const ChunkArgs& a, const PeerExt& 
     int T_l = 0, k_l = 0, key_l = 0, own_l = px.me, ol_l = 0, samp_l = -1;
     if (lane < cnt) {
       const int e = base + lane;
-      T_l = e >= cu ? 1 : 0;
-      k_l = T_l ? e - cu : e;
+      T_l = e >= nuw ? 1 : 0;
+      k_l = T_l ? a0 + (e - nuw) : u0 + e;
       const size_t at = (size_t)s * px.cap + k_l;
       key_l = px.key[T_l][at];
       const int og = px.oth[T_l][at];
@@ -846,7 +855,8 @@ __device__ __forceinline__ void peer_forward(const ChunkArgs& a, const PeerExt& 
       if (pending <= 0) cp_async_wait<0>();
       else if (pending == 1) cp_async_wait<1>();
       else if (pending == 2) cp_async_wait<2>();
-      else cp_async_wait<3>();
+      else if (pending == 3) cp_async_wait<3>();
+      else cp_async_wait<4>();
       const float4* b4 = sbuf + (size_t)(pi % NB) * kBuf4;
       RowTile<NV> x0, y0, x1, y1;   // x = my row, y = the other table's row
       tile_from_stage<NV>(x0, b4, d4, lane);
