@@ -61,8 +61,8 @@ def main():
             world, sess.persistent, zipf, us, world * BATCH / us))
         if sess.persistent:
             tl = sess.timeline()
-            print("  phases us (CTA 0, mean): gate %.1f | fwd+barrier %.1f | head %.1f | update %.1f | step %.1f" % tuple(
-                float(np.mean(tl[k][4:])) for k in ("gate_us", "fwd_us", "head_us", "update_us", "step_us")))
+            print("  phases us (CTA 0, mean): gate %.1f | fwd+barrier %.1f (own forward %.1f) | head %.1f | update %.1f | step %.1f" % tuple(
+                float(np.mean(tl[k][4:])) for k in ("gate_us", "fwd_us", "fwd_own_us", "head_us", "update_us", "step_us")))
             print("  replay: %d items, %d element-steps, busy %.2f of warp-cycles" % (
                 tl["replay_items"], tl["replay_element_steps"],
                 tl["replay_busy_cycles"] / max(1, tl["replay_warps"] * tl["kernel_cycles"])))
