@@ -289,6 +289,7 @@ struct StepSmem {
   float head[4], hm[4], hv[4], bn[2];
   float stepc[K_STEPC + 2];
   double red[8 * kStepWarps];
+  unsigned long long pmbar[kStepWarps][4];   // peer mode: one mbarrier per step warp and pair buffer (bulk copies)
   int pcnt[kPeerRanks];      // peer mode: every rank's published list length / batch sums of the current step
   double ps0[kPeerRanks], ps1[kPeerRanks];
   float alpha_w[kWin];
@@ -749,13 +750,38 @@ __device__ __forceinline__ void finish_loaded(const ChunkArgs& a, const StepTabs
   else if (lane == 0) tb.last_step[row] = (int32_t)t;
 }
 
+// Bulk asynchronous copies (TMA engine, no tensor map): a row travels global -> shared as ONE request that completes on
+// an mbarrier.  The per-lane 16-byte cp.async used elsewhere in this file keeps too few bytes in flight per SM once the
+// source is microseconds away over NVLink (measured: the forward took 27 / 38 / 43 us at 2 / 4 / 8 GPUs with it).
+#ifndef AR_PEER_TMA
+#define AR_PEER_TMA 1
+#endif
+__device__ __forceinline__ unsigned smem_addr32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void bulk_row(unsigned dst, const float* src, unsigned bytes, unsigned bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src),
+               "r"(bytes), "r"(bar)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_expect(unsigned bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try(unsigned bar, unsigned parity) {
+  unsigned ok;
+  asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}"
+               : "=r"(ok)
+               : "r"(bar), "r"(parity)
+               : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async;" ::: "memory"); }
+
 // pair buffers of the peer forward per step warp (each 4 row tiles); dim <= 128: 3 x 2 KB x 16 warps = 96 KB (measured:
 // five buffers request a whole share at once but shrink the L1 and slow the head and the row update more than they gain)
 #ifndef AR_PEER_PAIR_BUFS
 #define AR_PEER_PAIR_BUFS 3
 #endif
 template <int NV> struct PeerCfg { static constexpr int kPairBufs = NV == 1 ? AR_PEER_PAIR_BUFS : StageCfg<NV>::kBufs; };
-static_assert(PeerCfg<1>::kPairBufs <= 5, "peer_forward waits on at most 4 younger groups");
+static_assert(PeerCfg<1>::kPairBufs <= 4, "four mbarriers per step warp");
 template <int NV, bool PEER> struct StepStage {   // float4 per step warp
   static constexpr int k4 = (PEER ? PeerCfg<NV>::kPairBufs : StageCfg<NV>::kBufs) * 128 * NV;
 };
@@ -767,8 +793,12 @@ template <int NV, bool PEER> struct StepStage {   // float4 per step warp
 // the list the other ranks read, and only its cosines enter the batch sums (every sample once).
 template <int NV>
 __device__ __forceinline__ void peer_forward(const ChunkArgs& a, const PeerExt& px, StepSmem& sm, int s, int64_t t, int par,
-                                             int gw, int ngw, int lane, int wid, float4* sbuf, long long* stamps) {
+                                             int gw, int ngw, int lane, int wid, float4* sbuf, long long* stamps,
+                                             unsigned& ring_phase) {
   constexpr int NB = PeerCfg<NV>::kPairBufs, kBuf4 = 128 * NV;
+  const unsigned mb0 = smem_addr32(&sm.pmbar[wid][0]);
+  const unsigned sb0 = smem_addr32(sbuf);
+  const unsigned row_bytes = (unsigned)a.tab[0].dim * 4u;
   const int dim = a.tab[0].dim, d4 = dim >> 2;
   const int G = px.G;
   const int cu = min(px.cnt[0][s], px.cap), ca = min(px.cnt[1][s], px.cap);
@@ -836,35 +866,68 @@ __device__ __forceinline__ void peer_forward(const ChunkArgs& a, const PeerExt& 
     const int np = (cnt + 1) >> 1;
     auto prefetch_pair = [&](int pi, float4* buf) {
       const int j = 2 * pi, j1 = min(j + 1, cnt - 1);
+      const int b = pi % NB;
+#if AR_PEER_TMA
+      if (lane == 0) mbar_expect(mb0 + 8u * b, 4u * row_bytes);
+#endif
 #pragma unroll
       for (int h = 0; h < 2; ++h) {
         const int jj = h ? j1 : j;
         const int T = __shfl_sync(0xffffffffu, T_l, jj), key = __shfl_sync(0xffffffffu, key_l, jj);
         const int q = __shfl_sync(0xffffffffu, own_l, jj), ol = __shfl_sync(0xffffffffu, ol_l, jj);
+#if AR_PEER_TMA
+        if (lane == 0) {
+          const unsigned dst = sb0 + (unsigned)((b * kBuf4 + (2 * h) * 32 * NV) * sizeof(float4));
+          bulk_row(dst, a.tab[T].W + (size_t)key * dim, row_bytes, mb0 + 8u * b);
+          bulk_row(dst + 32u * NV * (unsigned)sizeof(float4), px.W_peer[1 - T][q] + (size_t)ol * dim, row_bytes, mb0 + 8u * b);
+        }
+#else
         stage_tile<NV>(buf + (2 * h) * 32 * NV, a.tab[T].W + (size_t)key * dim, d4, lane);
         stage_tile<NV>(buf + (2 * h + 1) * 32 * NV, px.W_peer[1 - T][q] + (size_t)ol * dim, d4, lane);
+#endif
       }
+#if !AR_PEER_TMA
       cp_async_commit();
+#endif
     };
+#if AR_PEER_TMA
+    fence_proxy_async();   // the bulk copies read what the row words announced (generic-proxy acquire above)
+#endif
     // ring of NB pair buffers, one cp.async group per pair: the rows come over NVLink (microseconds away), so as many
     // pairs as shared memory allows are requested before the first one is waited for
     for (int pi = 0; pi < min(NB, np); ++pi) prefetch_pair(pi, sbuf + (size_t)pi * kBuf4);
     for (int pi = 0; pi < np; ++pi) {
       const int j = 2 * pi;
       const bool two = j + 1 < cnt;
+#if AR_PEER_TMA
+      {
+        const int b = pi % NB;
+        unsigned spins = 0;
+        while (!mbar_try(mb0 + 8u * b, (ring_phase >> b) & 1u)) {
+          if ((++spins & 0xfffffu) == 0u && ld_relaxed_s32(&a.ctl->abort)) break;
+        }
+        ring_phase ^= 1u << b;
+      }
+#else
       const int pending = min(np, pi + NB) - (pi + 1);   // younger groups that may stay in flight
       if (pending <= 0) cp_async_wait<0>();
       else if (pending == 1) cp_async_wait<1>();
       else if (pending == 2) cp_async_wait<2>();
-      else if (pending == 3) cp_async_wait<3>();
-      else cp_async_wait<4>();
+      else cp_async_wait<3>();
+#endif
       const float4* b4 = sbuf + (size_t)(pi % NB) * kBuf4;
       RowTile<NV> x0, y0, x1, y1;   // x = my row, y = the other table's row
       tile_from_stage<NV>(x0, b4, d4, lane);
       tile_from_stage<NV>(y0, b4 + 32 * NV, d4, lane);
       tile_from_stage<NV>(x1, b4 + 64 * NV, d4, lane);
       tile_from_stage<NV>(y1, b4 + 96 * NV, d4, lane);
-      if (pi + NB < np) prefetch_pair(pi + NB, sbuf + (size_t)(pi % NB) * kBuf4);   // the buffer is in registers now
+      if (pi + NB < np) {   // the buffer is in registers now
+#if AR_PEER_TMA
+        __syncwarp();
+        fence_proxy_async();   // every lane's reads of the buffer before the engine writes it again
+#endif
+        prefetch_pair(pi + NB, sbuf + (size_t)(pi % NB) * kBuf4);
+      }
       float sx0 = tile_partial_dot<NV>(x0, x0), sy0 = tile_partial_dot<NV>(y0, y0);
       float sx1 = tile_partial_dot<NV>(x1, x1), sy1 = tile_partial_dot<NV>(y1, y1);
 #pragma unroll
@@ -943,6 +1006,12 @@ __device__ void step_role(const ChunkArgs& a, const PeerExt* px, StepSmem& sm, i
     sm.hv[tid] = a.head_v[tid];
   }
   if (tid < 2) sm.bn[tid] = a.bn_moving[tid];
+  unsigned ring_phase = 0;      // peer mode: phase parity of this warp's pair-buffer mbarriers
+  if (PEER && lane == 0) {
+    for (int b = 0; b < 4; ++b)
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_addr32(&sm.pmbar[wid][b])));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
   step_bar();
 
   for (int s = 0; s < a.n_steps; ++s) {
@@ -960,7 +1029,7 @@ __device__ void step_role(const ChunkArgs& a, const PeerExt* px, StepSmem& sm, i
 
     // ---- F: forward of this warp's samples
     if constexpr (PEER) {
-      peer_forward<NV>(a, *px, sm, s, t, par, gw, ngw, lane, wid, sbuf, stamp ? stamps : nullptr);
+      peer_forward<NV>(a, *px, sm, s, t, par, gw, ngw, lane, wid, sbuf, stamp ? stamps : nullptr, ring_phase);
     } else {
       const int32_t* __restrict__ iu = a.iu + (size_t)s * a.batch;
       const int32_t* __restrict__ ia = a.ia + (size_t)s * a.batch;
