@@ -870,7 +870,7 @@ __device__ __forceinline__ void peer_forward(const ChunkArgs& a, const PeerExt& 
       const int j = 2 * pi, j1 = min(j + 1, cnt - 1);
       const int b = pi % NB;
 #if AR_PEER_TMA
-      if (lane == 0) mbar_expect(mb0 + 8u * b, 4u * row_bytes);
+      if (lane == 0) mbar_expect(mb0 + 8u * b, (AR_PEER_TMA == 2 ? 2u : 4u) * row_bytes);
 #endif
 #pragma unroll
       for (int h = 0; h < 2; ++h) {
@@ -880,15 +880,16 @@ __device__ __forceinline__ void peer_forward(const ChunkArgs& a, const PeerExt& 
 #if AR_PEER_TMA
         if (lane == 0) {
           const unsigned dst = sb0 + (unsigned)((b * kBuf4 + (2 * h) * 32 * NV) * sizeof(float4));
-          bulk_row(dst, a.tab[T].W + (size_t)key * dim, row_bytes, mb0 + 8u * b);
+          if (AR_PEER_TMA != 2) bulk_row(dst, a.tab[T].W + (size_t)key * dim, row_bytes, mb0 + 8u * b);
           bulk_row(dst + 32u * NV * (unsigned)sizeof(float4), px.W_peer[1 - T][q] + (size_t)ol * dim, row_bytes, mb0 + 8u * b);
         }
+        if (AR_PEER_TMA == 2) stage_tile<NV>(buf + (2 * h) * 32 * NV, a.tab[T].W + (size_t)key * dim, d4, lane);
 #else
         stage_tile<NV>(buf + (2 * h) * 32 * NV, a.tab[T].W + (size_t)key * dim, d4, lane);
         stage_tile<NV>(buf + (2 * h + 1) * 32 * NV, px.W_peer[1 - T][q] + (size_t)ol * dim, d4, lane);
 #endif
       }
-#if !AR_PEER_TMA
+#if AR_PEER_TMA != 1
       cp_async_commit();
 #endif
     };
@@ -910,7 +911,8 @@ __device__ __forceinline__ void peer_forward(const ChunkArgs& a, const PeerExt& 
         }
         ring_phase ^= 1u << b;
       }
-#else
+#endif
+#if AR_PEER_TMA != 1
       const int pending = min(np, pi + NB) - (pi + 1);   // younger groups that may stay in flight
       if (pending <= 0) cp_async_wait<0>();
       else if (pending == 1) cp_async_wait<1>();
