@@ -289,11 +289,12 @@ struct StepSmem {
   float head[4], hm[4], hv[4], bn[2];
   float stepc[K_STEPC + 2];
   double red[8 * kStepWarps];
-  unsigned long long pmbar[kStepWarps][4];   // peer mode: one mbarrier per step warp and pair buffer (bulk copies)
-  int pcnt[kPeerRanks];      // peer mode: every rank's published list length / batch sums of the current step
-  double ps0[kPeerRanks], ps1[kPeerRanks];
   float alpha_w[kWin];
   float stepw_w[kWin];
+  // peer mode only (kept behind everything the single-GPU kernel uses)
+  unsigned long long pmbar[kStepWarps][4];   // one mbarrier per step warp and pair buffer (bulk copies)
+  double ps0[kPeerRanks], ps1[kPeerRanks];   // every rank's batch sums / published list length of the current step
+  int pcnt[kPeerRanks];
 };
 __device__ __forceinline__ void dense_arrive(StepSmem& sm) { atomicAdd(&sm.dense_arrive, 1); }
 struct StepTabs {            // alpha[t], stepw[t] through the shared-memory window
@@ -515,15 +516,15 @@ template <bool PEER>
 __device__ __forceinline__ void publish_item(const ChunkArgs& a, const PeerExt* px, int code, int64_t t_to, int n_parts) {
   const int row = (int)((unsigned)code & kCodeRowMask);
   int32_t* ls = (code < 0 ? a.tab[1].last_step : a.tab[0].last_step) + row;
-  bool current = true;
   if ((unsigned)code & kCodeSplit) {
     const int old = atomicAdd(ls, 1 << kPartShift);
-    current = (old >> kPartShift) == n_parts - 1;
-    if (current) {   // (the other parts' stores: ordered before their arrivals by their fences, cumulative through this one)
+    if ((old >> kPartShift) == n_parts - 1) {
+      // (the other parts' stores: ordered before their arrivals by their fences, cumulative through this one)
       if (PEER && px->strict) __threadfence_system(); else __threadfence();
+      *(volatile int32_t*)ls = (int32_t)t_to;
+      if (PEER) st_sys_s32(px->rowflag_peer[code < 0 ? 1 : 0][px->me] + row, (int32_t)t_to);
     }
-  }
-  if (current) {
+  } else {
     *(volatile int32_t*)ls = (int32_t)t_to;
     if (PEER) st_sys_s32(px->rowflag_peer[code < 0 ? 1 : 0][px->me] + row, (int32_t)t_to);
   }
@@ -745,9 +746,9 @@ __device__ __forceinline__ void finish_loaded(const ChunkArgs& a, const StepTabs
   w.store(tb.W + o, d4, lane);
   m.store(tb.m + o, d4, lane);
   v.store(tb.v + o, d4, lane);
-  if (flags) pend = tb.last_step + row;
+  if (flags) pend = tb.last_step + row;                       // published later, behind a fence
+  else if (lane == 0) tb.last_step[row] = (int32_t)t;         // no per-row flags: a grid barrier follows the update
   if (PEER) pend_peer = rowflag ? rowflag + row : nullptr;
-  else if (lane == 0) tb.last_step[row] = (int32_t)t;
 }
 
 // Bulk asynchronous copies (TMA engine, no tensor map): a row travels global -> shared as ONE request that completes on
@@ -1154,7 +1155,7 @@ __device__ void step_role(const ChunkArgs& a, const PeerExt* px, StepSmem& sm, i
         sm.red[2 * wid + 1] = sc2;
       }
     }
-    if (stamp) stamps[7] = (long long)globaltimer_ns();   // this warp's own forward is done; the rest is waiting
+    if (PEER && stamp) stamps[7] = (long long)globaltimer_ns();   // this warp's own forward is done; the rest is waiting
     step_bar();
     if (tid == 0) {
       double b0 = 0.0, b1 = 0.0;
@@ -1313,9 +1314,8 @@ __device__ void step_role(const ChunkArgs& a, const PeerExt* px, StepSmem& sm, i
       if constexpr (PEER) {
         for (int r = 0; r < px->G; ++r) shmax = max(shmax, (min(max(sm.pcnt[r], 0), px->cap) + n_ctas - 1) / n_ctas);
       }
-      const int i_lo = PEER ? tid : blockIdx.x * mshare + tid;
-      const int i_hi = PEER ? px->G * shmax : min(n, (blockIdx.x + 1) * mshare);
-      for (int i = i_lo; i < i_hi; i += kStepThreads) {
+      const unsigned i_hi = PEER ? (unsigned)(px->G * shmax) : min(n, (blockIdx.x + 1) * mshare);
+      for (int i = PEER ? tid : blockIdx.x * mshare + tid; i < i_hi; i += kStepThreads) {
         float ci, ti;
         if constexpr (PEER) {
           const int r = i / shmax, k = blockIdx.x * shmax + (i - r * shmax);
