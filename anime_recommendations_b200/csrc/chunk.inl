@@ -897,8 +897,8 @@ __device__ __forceinline__ void peer_forward(const ChunkArgs& a, const PeerExt& 
 #if AR_PEER_TMA
     fence_proxy_async();   // the bulk copies read what the row words announced (generic-proxy acquire above)
 #endif
-    // ring of NB pair buffers, one cp.async group per pair: the rows come over NVLink (microseconds away), so as many
-    // pairs as shared memory allows are requested before the first one is waited for
+    // ring of NB pair buffers, one mbarrier each: the rows come over NVLink (microseconds away), so as many pairs as
+    // shared memory allows are requested before the first one is waited for
     for (int pi = 0; pi < min(NB, np); ++pi) prefetch_pair(pi, sbuf + (size_t)pi * kBuf4);
     for (int pi = 0; pi < np; ++pi) {
       const int j = 2 * pi;

@@ -584,10 +584,12 @@ class TrainSession:
         st = ws[self._ws_stamps // 8:self._ws_stamps // 8 + self.n_slots * k].reshape(self.n_slots, k)[:ns].astype(np.float64)
         stats = ws[self._ws_stats // 8:self._ws_stats // 8 + 8]
         d = lambda a, b: (st[:, b] - st[:, a]) * 1e-3
-        out = dict(steps=ns, gate_us=d(0, 1), fwd_us=d(1, 2), fwd_own_us=d(1, 7), head_us=d(2, 3), update_us=d(3, 4), barrier2_us=d(4, 5),
+        out = dict(steps=ns, gate_us=d(0, 1), fwd_us=d(1, 2), head_us=d(2, 3), update_us=d(3, 4), barrier2_us=d(4, 5),
                    step_us=np.r_[np.diff(st[:, 0]) * 1e-3, (st[-1, 5] - st[-1, 0]) * 1e-3],
                    replay_busy_cycles=int(stats[0]), replay_items=int(stats[1]), replay_element_steps=int(stats[2]),
                    kernel_ns=int(stats[3]), replay_warps=int(stats[4]), kernel_cycles=int(stats[5]))
+        if getattr(self, "persistent", False):       # peer kernel: stamp 7 = CTA 0's own forward done, the rest of fwd_us is waiting
+            out["fwd_own_us"] = d(1, 7)
         if self.model.adam_mode == "dense":
             out["dense_us"] = d(5, 6)
             out["step_us"] = np.r_[np.diff(st[:, 0]) * 1e-3, (st[-1, 6] - st[-1, 0]) * 1e-3]

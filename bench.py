@@ -373,10 +373,12 @@ def gpu_main(args):
         # CTA 0's %globaltimer stamps of the last chunk (rank 0): where a multi-GPU step spends its time
         tl = sess.timeline() if rank == 0 else None
         if tl is not None:
-            line["peer_step_phases_us"] = {k: float(np.mean(tl[k + "_us"][4:])) for k in ("gate", "fwd", "head", "update", "step")}
+            line["peer_step_phases_us"] = {k: float(np.mean(tl[k + "_us"][4:])) for k in ("gate", "fwd", "fwd_own", "head", "update", "step")
+                                           if k + "_us" in tl}
             line["peer_step_phases_us"]["what"] = ("gate = wait for the rows of the first samples (local + NVLink row words), fwd = "
-                                                   "forward incl. the NVLink row pulls + grid barrier, head = cross-rank exchange + "
-                                                   "head + second barrier, update = row updates")
+                                                   "forward incl. the NVLink row pulls + grid barrier (fwd_own = CTA 0 warp 0's own share of it, the "
+                                                   "rest is waiting for the slowest warp), head = cross-rank exchange + head + second barrier, "
+                                                   "update = row updates")
             line["peer_step_phases_us"]["replay_warp_busy_frac"] = tl["replay_busy_cycles"] / max(1.0, float(tl["replay_warps"]) * tl["kernel_cycles"])
     if world > 1:
         # ---- e2e at N GPUs: every rank feeds its shard of each global batch from pinned HOST memory
