@@ -250,6 +250,29 @@ def _compare_model_state(m, st, check_slots=True, mean_tol=1e-4):
         np.testing.assert_allclose(m.vA.cpu().numpy(), st.vA, rtol=1e-4, atol=1e-11)
 
 
+@pytest.mark.parametrize("dim", [128, 256])
+def test_replay_fit_repeats_agree(dim):
+    """The same small replay-mode fit, many times: every run must land on the same tables.  A synchronisation slip in
+    the step kernel shows up here as occasional rows that are one optimizer step off (this is the test that would
+    have caught the unfenced row flag of round 2 in one run instead of one in four; tools/race_probe.py is its
+    verbose sibling)."""
+    n_users, n_anime, n, B = 700, 90, 5300, 1000
+    iu, ia, y = _problem(11, n_users, n_anime, n)
+    st0 = ot.init_state(n_users, n_anime, dim, seed=5, w=-1.3)
+    lr_kw = dict(start_lr=1e-3, min_lr=1e-3, max_lr=3e-3, rampup_epochs=2, sustain_epochs=0, exp_decay=0.8)
+    first = None
+    for trial in range(16):
+        m = _model_from_state(st0, "replay")
+        m.fit([iu, ia], y, batch_size=B, epochs=3, callbacks=[ar.LearningRateScheduler(lambda e: ar.lrfn(e, **lr_kw))],
+              shuffle="numpy", shuffle_seed=0)
+        w = m.get_weights()
+        if first is None:
+            first = w
+            continue
+        for k in range(2):
+            np.testing.assert_allclose(w[k], first[k], err_msg="trial %d, table %d" % (trial, k), **ROW_TOL)
+
+
 @pytest.mark.parametrize("mode", ["dense", "replay"])
 @pytest.mark.parametrize("dim,heavy", [(128, False), (64, True), (256, False)])
 def test_fit_matches_reference_arithmetic(mode, dim, heavy):
