@@ -270,7 +270,8 @@ def test_replay_fit_repeats_agree(dim):
             first = w
             continue
         for k in range(2):
-            np.testing.assert_allclose(w[k], first[k], err_msg="trial %d, table %d" % (trial, k), **ROW_TOL)
+            # (a slip moves a row by a fraction of an optimizer step, 2e-5 .. 5e-4 here; identical runs agree to the bit)
+            np.testing.assert_allclose(w[k], first[k], err_msg="trial %d, table %d" % (trial, k), rtol=1e-4, atol=1e-5)
 
 
 @pytest.mark.parametrize("mode", ["dense", "replay"])

@@ -1,5 +1,10 @@
 """Developer tool: repeat the small replay-mode fit of tests/test_gpu_train.py::test_fit_matches_reference_arithmetic many
-times and report every trial whose tables differ from the oracle -- which rows, when they were touched, by how much."""
+times and report every trial whose tables differ from the oracle -- which rows, when they were touched, by how much.
+
+    python tools/race_probe.py [dim=256] [trials=30] [mode=replay]        (AR_REPLAY_DEPTH=n to vary the look-ahead)
+
+Round 2: 11-22 of 60 trials differed while a row's flag was published without its fence (a dangling else in
+finish_loaded); dense mode and the previous build: 0 of 60."""
 import os
 import sys
 
