@@ -224,8 +224,9 @@ class PeerTrainSession(TrainSession):
         A = self.arena[o:o + nA].view_as(model.A); o += nA
         self.pub = self.arena[o:o + 2 * cap]; o += 2 * cap
         self.flags = self.arena[o:o + PEER_FLAG_WORDS].view(torch.int32); o += PEER_FLAG_WORDS
-        # per row: the optimizer step the row is at, as the PEERS may rely on it (written behind a system-scope fence;
-        # model.lastU / lastA stay the local flags).  Refreshed from the local flags at the start of every run().
+        # per row: the optimizer step the row is at, as the PEERS see it (written right behind the local flag, or behind
+        # a system-scope fence with AR_PEER_STRICT=1; model.lastU / lastA stay the local flags).  Refreshed from the
+        # local flags at the start of every run().
         self.rowflag = [self.arena[o:o + model.lastU.numel()].view(torch.int32),
                         self.arena[o + nFU:o + nFU + model.lastA.numel()].view(torch.int32)]
         o += nFU + nFA
