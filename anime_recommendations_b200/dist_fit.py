@@ -33,6 +33,23 @@ def shard_of(table, rank, world):
     return out
 
 
+def replica_slice(order, world, batch, rank):
+    """Which samples of an epoch's visit order `order` replica `rank` trains on, in its own visit order.
+
+    Global step s of the epoch covers order[s*G*B : (s+1)*G*B]; replica r takes the r-th run of B of them
+    (`batch_size * strategy.num_replicas_in_sync`, neural_network.py:176).  The order is cut to a multiple of G samples;
+    a last, shorter global step is split evenly.  Concatenating the replicas' slices of a step in rank order gives the
+    step's global batch back -- which is what makes an N-GPU fit equal the 1-GPU fit with batch G*B."""
+    order = np.asarray(order)
+    G, B = int(world), int(batch)
+    n_use = (len(order) // G) * G
+    glob = order[:n_use]
+    F = (n_use // (G * B)) * G * B
+    head = glob[:F].reshape(-1, G, B)[:, rank, :].reshape(-1)
+    tail = glob[F:].reshape(G, -1)[rank] if n_use > F else glob[:0]
+    return np.concatenate([head, tail])
+
+
 class DistributedEmbeddingDotModel:
     """The Keras-like facade of model.EmbeddingDotModel over row-sharded tables.  Collective methods (every rank
     must call them): fit, get_weights, get_layer(...).get_weights, predict, evaluate, save, save_weights."""
@@ -183,10 +200,7 @@ class DistributedEmbeddingDotModel:
                     perm = np.arange(N)
                 else:
                     raise ValueError("shuffle must be 'numpy', 'device' or False")
-                glob = perm[:n_use]
-                F = full_steps * GB
-                mine = np.concatenate([glob[:F].reshape(-1, G, B)[:, r, :].reshape(-1),
-                                       glob[F:].reshape(G, -1)[r] if n_use > F else np.zeros(0, np.int64)])
+                mine = replica_slice(perm, G, B, r)
                 iu = torch.from_numpy(iu_all[mine].astype(np.int32)).to(dev)
                 ia = torch.from_numpy(ia_all[mine].astype(np.int32)).to(dev)
                 yy = torch.from_numpy(y_all[mine]).to(dev)

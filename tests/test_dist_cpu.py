@@ -104,3 +104,23 @@ def test_shard_csr_tiles_the_watched_lists():
             got_idx.append(ix)
         np.testing.assert_array_equal(np.concatenate(got_counts), counts)
         np.testing.assert_array_equal(np.concatenate(got_idx), idx)
+
+
+def test_replica_slices_rebuild_every_global_batch():
+    """dist_fit.replica_slice (the data-parallel split of neural_network.py:176): the replicas' slices of a step, in
+    rank order, are that step's global batch -- full steps and the shorter last one -- and every sample of the cut
+    order is visited exactly once."""
+    from anime_recommendations_b200.dist_fit import replica_slice
+    rng = np.random.RandomState(0)
+    for G, B, N in [(2, 5, 47), (4, 3, 36), (8, 4, 1000), (1, 7, 20), (3, 10, 29), (2, 8, 16), (4, 2, 3)]:
+        order = rng.permutation(N)
+        sl = [replica_slice(order, G, B, r) for r in range(G)]
+        n_use = N // G * G
+        assert all(len(s) == n_use // G for s in sl)
+        assert sorted(np.concatenate(sl).tolist()) == sorted(order[:n_use].tolist())
+        GB = G * B
+        for s in range(-(-n_use // GB)):
+            glob = order[s * GB:min(n_use, (s + 1) * GB)]
+            nb = len(glob) // G
+            got = np.concatenate([sl[r][s * B:s * B + nb] for r in range(G)])
+            assert got.tolist() == glob.tolist(), (G, B, N, s)
