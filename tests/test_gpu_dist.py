@@ -45,15 +45,19 @@ def test_two_rank_row_sharded_training_equals_single_gpu(mode):
 
 
 def _peer_env(mode):
-    """replay_staged: the per-step stage kernels of csrc/peer.inl instead of the persistent kernel."""
+    """replay_staged: the per-step stage kernels of csrc/peer.inl instead of the persistent kernel;
+    replay_strict: the persistent kernel with system-scope fences in front of the row words (AR_PEER_STRICT=1)."""
     env = dict(os.environ)
     env.pop("AR_PEER_STAGED", None)
+    env.pop("AR_PEER_STRICT", None)
     if mode.endswith("_staged"):
         env["AR_PEER_STAGED"] = "1"
-    return mode.replace("_staged", ""), env
+    if mode.endswith("_strict"):
+        env["AR_PEER_STRICT"] = "1"
+    return mode.replace("_staged", "").replace("_strict", ""), env
 
 
-@pytest.mark.parametrize("mode", ["replay", "replay_staged", "dense", "touched"])
+@pytest.mark.parametrize("mode", ["replay", "replay_staged", "replay_strict", "dense", "touched"])
 def test_two_rank_peer_memory_training_equals_single_gpu(mode):
     """csrc/peer.inl + the peer mode of csrc/chunk.inl: owners pull the other table's rows over NVLink, flags
     instead of collectives."""
@@ -67,7 +71,7 @@ def test_two_rank_peer_memory_training_equals_single_gpu(mode):
     assert "DIST_OK" in r.stdout
 
 
-@pytest.mark.parametrize("mode", ["replay", "replay_staged"])
+@pytest.mark.parametrize("mode", ["replay", "replay_staged", "replay_strict"])
 def test_one_rank_peer_memory_training_equals_single_gpu(mode):
     """The peer-memory path with a world of ONE rank (every pull is local): runs on a single-GPU box, so the
     persistent peer kernel, peer_select / peer_fwd / peer_pull and the chunked planning are covered there too."""
